@@ -1,0 +1,100 @@
+"""Pins the BM25 restatement (oracle/bm25_oracle.py) against results produced by the
+reference's own code: SURVEY.md Appendix E and tests/golden/bm25_small.* (oracle/make_golden.py)."""
+import numpy as np
+import pytest
+
+from oracle import bm25_oracle as bo
+from oracle import stub_harness as sh
+import mse_testlib as helpers
+
+
+def test_appendix_e_index_matches_reference_tables():
+    ix, e = helpers.load_appendix_e()
+    built = bo.build_arrays([d for d, _ in e["docs"]],
+                            [{w: t.split().count(w) for w in set(t.split())} for _, t in e["docs"]])
+    assert built.terms == ix.terms
+    np.testing.assert_array_equal(built.term_off, ix.term_off)
+    np.testing.assert_array_equal(built.post_doc, ix.post_doc)
+    np.testing.assert_array_equal(built.post_tf, ix.post_tf)
+    np.testing.assert_array_equal(built.doc_len, ix.doc_len)
+    np.testing.assert_array_equal(built.idf, ix.idf)          # float32(log10(.)) bit-exact
+    assert built.avgdl == 3.5 and built.total_docs == 6.0
+
+
+@pytest.mark.parametrize("fn", [bo.search_faithful, bo.search_fast])
+def test_appendix_e_known_answers(fn):
+    ix, e = helpers.load_appendix_e()
+    for s in e["searches"]:
+        got = fn(ix, s["query"].split(), top_k=s["top_k"], min_score=s["min_score"])
+        want = [(r[0], r[1]) for r in s["result"]]
+        assert [(int(ix.doc_ids[d]), sc) for d, sc in got] == want, s["query"]   # bit-exact float64
+
+
+def test_appendix_e_hand_checked_quirks():
+    ix, e = helpers.load_appendix_e()
+    by = {(s["query"], s["min_score"], s["top_k"]): s["result"] for s in e["searches"]}
+    assert [r[0] for r in by[("alpha", 0.0, 10)]] == [1, 3, 6]          # idf == 0: zero scores kept, id order
+    assert by[("beta", 0.0, 10)] == []                                   # all negative -> dropped
+    assert by[("nonexistent", 0.0, 10)] == []
+    assert by[("gamma delta", 0.0, 1)][0][2] == "N/A: beta gamma gamma gamma delta"
+    assert bo.snippet("", "beta gamma gamma gamma delta") == "N/A: beta gamma gamma gamma delta"
+    assert bo.snippet("T", "x" * 201) == "T: " + "x" * 200 + "..."
+
+
+@pytest.mark.parametrize("fn", [bo.search_faithful, bo.search_fast])
+def test_small_corpus_matches_reference_search(fn):
+    ix, j, _ = helpers.load_bm25_small()
+    assert ix.n_docs == 300
+    n_nonempty = 0
+    for s in j["searches"]:
+        got = fn(ix, s["query"].split(), top_k=s["top_k"], min_score=s["min_score"])
+        assert [int(ix.doc_ids[d]) for d, _ in got] == s["doc_ids"], s["query"]
+        assert [sc for _, sc in got] == s["scores"], s["query"]          # bit-exact float64
+        n_nonempty += bool(got)
+    assert n_nonempty >= 18
+
+
+def test_small_corpus_tables_match_restated_build():
+    ix, j, z = helpers.load_bm25_small()
+    docs = j["docs"]
+    toks = []
+    for d, title, text in docs:
+        t = f"{title or ''} {text or ''}".lower().split()
+        toks.append({w: t.count(w) for w in set(t)})
+    built = bo.build_arrays([d for d, _, _ in docs], toks)
+    assert built.terms == ix.terms
+    np.testing.assert_array_equal(built.term_off, ix.term_off)
+    np.testing.assert_array_equal(built.post_doc, ix.post_doc)
+    np.testing.assert_array_equal(built.post_tf, ix.post_tf)
+    np.testing.assert_array_equal(built.idf, ix.idf)
+    assert built.avgdl == ix.avgdl and built.total_docs == ix.total_docs
+    np.testing.assert_array_equal(np.diff(ix.term_off), z["term_df"])
+
+
+def test_fast_equals_faithful_on_random_queries():
+    ix, _, _ = helpers.load_bm25_small()
+    rng = np.random.default_rng(5)
+    for _ in range(40):
+        terms = rng.integers(0, ix.n_terms, size=int(rng.integers(1, 6))).tolist()
+        a = bo.search_faithful(ix, terms, top_k=30, min_score=-10.0)
+        b = bo.search_fast(ix, terms, top_k=30, min_score=-10.0)
+        assert a == b
+
+
+@pytest.mark.skipif(not sh.reference_available(), reason="reference not mounted (GPU box)")
+def test_live_reference_agrees_with_oracle_on_fresh_corpus():
+    """Runs the unmodified reference now (build container only) on a corpus the fixtures do not hold."""
+    rng = np.random.default_rng(77)
+    words = [f"v{i:02d}" for i in range(60)]
+    docs = [(i + 1, "", " ".join(rng.choice(words, size=int(rng.integers(2, 30))))) for i in range(45)]
+    with sh.hosted_reference() as h:
+        sh.create_urls(h.raw, [(d, f"http://x/{d}", t, x) for d, t, x in docs])
+        bm = h.BM25("x.db", read_only=False)
+        bm.build_index(batch_size=20)
+        toks = [{w: x.split().count(w) for w in set(x.split())} for _, _, x in docs]
+        ix = bo.build_arrays([d for d, _, _ in docs], toks)
+        for _ in range(15):
+            q = rng.choice(words, size=int(rng.integers(1, 5))).tolist()
+            ref = bm.search(" ".join(q), top_k=20, min_score=-5.0)
+            got = bo.search_faithful(ix, q, top_k=20, min_score=-5.0)
+            assert [(r["doc_id"], r["score"]) for r in ref] == [(int(ix.doc_ids[d]), s) for d, s in got]
