@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the retrieval hot path.
+
+Workload (BASELINE.json configs[1]): BM25-only, 1M synthetic docs, Zipf(1.0) vocabulary of 200k,
+~256 tokens/doc (~192M postings), batches of 1024 four-term queries, top-1000, on one B200.
+A "step" = one batch of 1024 queries through prepare -> score -> select (-> all-gather + merge on
+N > 1 GPUs, where the 1M-doc corpus is sharded by doc range: strong scaling).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Prints ONE JSON line (rank 0).  `value` = queries/s with inputs resident in HBM; `e2e` = the same
+through the C ABI with HOST buffers (H2D of the query CSR and D2H of the results inside the timed
+region); `roofline` describes the dominant kernel (bm25_score_kernel) with algorithmic bytes
+12*P_q + 8*k per query; `cpu_baseline` = the oracle port of the reference's Python
+scoring loop (indexer/bm25_indexer.py:435-485) timed on this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_DOCS = 1_000_000
+VOCAB = 200_000
+BATCH = 1024
+TOP_K = 1000
+SEED = 1234
+METRIC = "bm25_queries_per_sec"
+UNIT = "queries/s"
+WORKLOAD = "C2 BM25-only: 1M synthetic docs, Zipf(1.0) vocab 200k, batch 1024 x 4-term queries, top-1000"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed regions run."""
+
+    def __init__(self, index: int, period: float = 0.01):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.sm_max = [], set(), None
+        self._halt = threading.Event()
+        self.active = threading.Event()
+        self.err = None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = int(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            names = {
+                getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+                getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+                getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+            }
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+            while not self._halt.is_set():
+                if self.active.is_set():
+                    self.samples.append(int(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                    r = int(get_reasons(h))
+                    for bit, name in names.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                time.sleep(self.period)
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+
+    def stop(self):
+        self._halt.set()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": 0, "error": self.err}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def gen_corpus(device):
+    from mse_b200 import synthetic
+    return synthetic.make_bm25_corpus(N_DOCS, vocab=VOCAB, seed=SEED, device=device)
+
+
+def shard_corpus(c, rank, world):
+    """Contiguous doc-index range balanced by postings; postings re-based to local doc indices."""
+    import torch
+    if world == 1:
+        return c.term_off, c.post_doc, c.post_tf, c.doc_len, 0
+    per_doc = torch.bincount(c.post_doc.long(), minlength=c.n_docs)
+    cum = torch.cumsum(per_doc, 0)
+    total = int(cum[-1].item())
+    targets = torch.tensor([total * r // world for r in range(1, world)], device=cum.device)
+    cuts = [0] + (torch.searchsorted(cum, targets) + 1).tolist() + [c.n_docs]
+    lo, hi = int(cuts[rank]), int(cuts[rank + 1])
+    keep = (c.post_doc >= lo) & (c.post_doc < hi)
+    df = torch.diff(c.term_off)
+    term_of = torch.repeat_interleave(torch.arange(c.n_terms, device=df.device), df)
+    ndf = torch.bincount(term_of[keep], minlength=c.n_terms)
+    term_off = torch.zeros(c.n_terms + 1, dtype=torch.int64, device=df.device)
+    term_off[1:] = torch.cumsum(ndf, 0)
+    return term_off, (c.post_doc[keep] - lo).contiguous(), c.post_tf[keep].contiguous(), c.doc_len[lo:hi].contiguous(), lo
+
+
+def run_reference_arm(args, rank, world):
+    """The reference's CPU path for this workload: the oracle port of BM25.search's Python loop
+    (the reference is pure Python; nothing compiles to oracle/_ref), one process per host core."""
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    import torch
+    from mse_b200 import synthetic
+    from oracle import bm25_oracle as bo
+    dev = "cuda:0" if torch.cuda.is_available() else "cpu"
+    n_docs = N_DOCS if dev != "cpu" else 50_000          # CPU-only container: tiny corpus just to exercise the arm
+    c = synthetic.make_bm25_corpus(n_docs, vocab=VOCAB, seed=SEED, device=dev)
+    global _REF_IX, _REF_Q
+    _REF_IX = bo.Bm25Arrays(c.term_off.cpu().numpy(), c.post_doc.cpu().numpy(), c.post_tf.cpu().numpy(),
+                            c.doc_len.cpu().numpy(), c.idf.cpu().numpy(), c.avgdl, c.total_docs, c.doc_ids.cpu().numpy())
+    q_off, q_term, q_tf = synthetic.make_bm25_queries(c, BATCH, seed=SEED + 1)
+    _REF_Q = [[int(t) for s in range(q_off[i], q_off[i + 1]) for t in [q_term[s]] * int(q_tf[s])] for i in range(BATCH)]
+    cores = os.cpu_count() or 1
+    per_step = min(BATCH, 2 * cores)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        pool.map(_ref_one, range(min(cores, BATCH)))                       # warm the workers
+        for w in range(args.warmup):
+            pool.map(_ref_one, [(w * per_step + j) % BATCH for j in range(per_step)])
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            pool.map(_ref_one, [((args.warmup + s) * per_step + j) % BATCH for j in range(per_step)])
+        dt = time.perf_counter() - t0
+    value = args.steps * per_step / dt
+    sample = f"{per_step} of the {BATCH} queries per step, full {n_docs}-doc index, faithful Python-loop port"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "queries_per_step": per_step},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+_REF_IX = None
+_REF_Q = None
+
+
+def _ref_one(i):
+    from oracle import bm25_oracle as bo
+    return len(bo.search_faithful(_REF_IX, _REF_Q[i], top_k=TOP_K, min_score=0.0))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=16, help="queries timed by the CPU baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--range-docs", type=int, default=0)
+    ap.add_argument("--queries-per-item", type=int, default=0)
+    ap.add_argument("--cand-cap", type=int, default=0)
+    ap.add_argument("--no-tau", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    import mse_b200  # noqa: F401
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from mse_b200 import _native, synthetic
+    from mse_b200.sharding import ShardedSearcher
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    # ---- corpus + index ------------------------------------------------------------------------
+    t0 = time.perf_counter()
+    c = gen_corpus(dev)
+    term_off, post_doc, post_tf, doc_len, doc_base = shard_corpus(c, rank, world)
+    nat = _native.NativeIndex(local_rank)
+    nat.bm25_load(term_off, post_doc, post_tf, doc_len, c.idf, c.avgdl, doc_base=doc_base)
+    for name, v in (("bm25_range_docs", args.range_docs), ("bm25_queries_per_item", args.queries_per_item),
+                    ("bm25_cand_cap", args.cand_cap)):
+        if v:
+            nat.set_option(name, v)
+    if args.no_tau:
+        nat.set_option("bm25_use_tau", 0)
+    searcher = ShardedSearcher(nat, rank, world)
+    df_global = torch.diff(c.term_off).cpu().numpy()
+    n_postings_local = int(post_doc.numel())
+    setup_s = time.perf_counter() - t0
+
+    # ---- query batches: a different batch every step (no reuse of a step's postings in L2) -------
+    n_batches = args.steps + args.warmup
+    host_batches, dev_batches, postings_per_batch = [], [], []
+    for i in range(n_batches):
+        q_off, q_term, q_tf = synthetic.make_bm25_queries(c, BATCH, seed=SEED + 1 + i)
+        host_batches.append((q_off, q_term, q_tf))
+        dev_batches.append(tuple(torch.from_numpy(a).to(dev) for a in (q_off, q_term, q_tf)))
+        postings_per_batch.append(int(df_global[q_term].sum()))
+    out = (torch.empty((BATCH, TOP_K), dtype=torch.int32, device=dev), torch.empty((BATCH, TOP_K), dtype=torch.float32, device=dev),
+           torch.empty((BATCH,), dtype=torch.int32, device=dev))
+
+    def step_device(i):
+        q_off, q_term, q_tf = dev_batches[i]
+        if world == 1:
+            return nat.bm25_search(q_off, q_term, q_tf, TOP_K, 0.0, out=out)
+        return searcher.bm25_search(q_off, q_term, q_tf, TOP_K, 0.0)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM ----------------------------------------------------------------
+    for i in range(args.warmup):
+        step_device(i)
+    sync_all()
+    nat.set_option("reset_timers", 1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.active.set()
+    e0.record()
+    for s in range(args.steps):
+        res = step_device(args.warmup + s)
+    e1.record()
+    sync_all()
+    sampler.active.clear()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    score_ms, score_n = nat.kernel_time("bm25_score")
+    select_ms, _ = nat.kernel_time("topk_select")
+    prep_ms, _ = nat.kernel_time("bm25_prepare")
+    stats = nat.bm25_stats()
+    value = args.steps * BATCH / (ms / 1000.0)
+
+    # ---- e2e: host buffers through the C ABI (H2D + D2H inside the timed region) ----------------------
+    pin = lambda a: torch.from_numpy(a).pin_memory()
+    host_pinned = [tuple(pin(a) for a in b) for b in host_batches]
+    h_out = (torch.empty((BATCH, TOP_K), dtype=torch.int32).pin_memory(), torch.empty((BATCH, TOP_K), dtype=torch.float32).pin_memory(),
+             torch.empty((BATCH,), dtype=torch.int32).pin_memory())
+
+    def step_host(i):
+        q_off, q_term, q_tf = host_pinned[i]
+        if world == 1:
+            nat.bm25_search(q_off, q_term, q_tf, TOP_K, 0.0, out=h_out)      # MSE_HOST path: copies + sync inside
+        else:
+            d = tuple(t.to(dev, non_blocking=True) for t in (q_off, q_term, q_tf))
+            r = searcher.bm25_search(d[0], d[1], d[2], TOP_K, 0.0)
+            for dst, src in zip(h_out, r):
+                dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step_host(i)
+    sync_all()
+    sampler.active.set()
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        step_host(args.warmup + s)
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+    sampler.active.clear()
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = args.steps * BATCH / e2e_s
+    h2d = int(np.mean([sum(a.nbytes for a in b) for b in host_batches[args.warmup:]]))
+    d2h = BATCH * TOP_K * 8 + BATCH * 4
+    sampler.stop()
+
+    # ---- roofline of the dominant kernel -----------------------------------------------------------------
+    peak, peak_src = measured_peaks()
+    timed_post = postings_per_batch[args.warmup:]
+    # algorithmic bytes per launch: 12 B per posting of THIS rank's shard + 8 B per emitted result
+    frac_local = n_postings_local / max(1, int(c.n_postings))
+    alg_bytes = 12.0 * float(np.mean(timed_post)) * frac_local + 8.0 * TOP_K * BATCH
+    avg_score_ms = score_ms / max(1, score_n)
+    achieved = alg_bytes / (avg_score_ms * 1e-3) / 1e9 if avg_score_ms > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "bm25_score_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    # ---- parity spot-check + CPU baseline (rank 0, N=1) -------------------------------------------------
+    cpu_baseline = None
+    parity = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import bm25_oracle as bo
+        ix = bo.Bm25Arrays(c.term_off.cpu().numpy(), c.post_doc.cpu().numpy(), c.post_tf.cpu().numpy(), c.doc_len.cpu().numpy(),
+                           c.idf.cpu().numpy(), c.avgdl, c.total_docs, c.doc_ids.cpu().numpy())
+        q_off, q_term, q_tf = host_batches[args.warmup]
+        n_s = min(args.cpu_sample, BATCH)
+        qs = [[int(t) for s in range(q_off[i], q_off[i + 1]) for t in [q_term[s]] * int(q_tf[s])] for i in range(n_s)]
+        t0 = time.perf_counter()
+        refs = [bo.search_faithful(ix, q, top_k=TOP_K, min_score=0.0) for q in qs]
+        faithful_s = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        fast = [bo.search_fast(ix, q, top_k=TOP_K, min_score=0.0) for q in qs]
+        fast_s = time.perf_counter() - t0
+        g_doc, g_score, g_count = nat.bm25_search(q_off, q_term, q_tf, TOP_K, 0.0)
+        bad, worst = 0, 0.0
+        for i in range(n_s):
+            rd = np.asarray([d for d, _ in refs[i]]); rs = np.asarray([s for _, s in refs[i]])
+            n = int(g_count[i])
+            if n != len(rd):
+                bad += 1
+                continue
+            scale = bo.abs_contrib_sum(ix, qs[i])[rd] if len(rd) else np.zeros(0)
+            err = np.abs(g_score[i, :n] - rs) / np.maximum(np.maximum(np.abs(rs), scale), 1e-30)
+            worst = max(worst, float(err.max(initial=0.0)))
+            bad += int(np.any(err > 1e-5)) or int(np.mean(g_doc[i, :n] == rd) < 0.99)
+        parity = {"queries_checked": n_s, "queries_failing": bad, "max_rel_err": worst, "tolerance": 1e-5}
+        cpu_baseline = {"value": n_s / faithful_s, "unit": UNIT, "cores": 1, "kind": "port",
+                        "sample": f"{n_s} of the {BATCH} queries of one batch, full 1M-doc index, faithful Python-loop port of "
+                                  f"bm25_indexer.py:435-485 (no SQL cost)",
+                        "vectorised_numpy_value": n_s / fast_s}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "n_docs": N_DOCS, "vocab": VOCAB, "postings": int(c.n_postings), "batch": BATCH,
+                       "top_k": TOP_K, "sharding": f"doc-range x{world}" if world > 1 else "none",
+                       "l2_policy": "inputs larger than L2: 1.5 GB index, a different query batch every step",
+                       "postings_per_query": float(np.mean(timed_post)) / BATCH},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": args.steps * (3 + (1 if world > 1 else 0)),
+            "roofline": {"bound": "hbm", "kernel": "bm25_score_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": avg_score_ms},
+            "cpu_baseline": cpu_baseline,
+            "clocks": sampler.summary(),
+            "breakdown": {"prepare_ms": prep_ms / max(1, score_n), "score_ms": avg_score_ms, "select_ms": select_ms / max(1, score_n),
+                          "candidates_emitted_per_query": stats["emitted"] / BATCH, "rerun_queries": stats["rerun_queries"],
+                          "ranges": stats["ranges"], "score_ctas": stats["ctas"], "setup_s": setup_s},
+            "parity": parity,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,147 @@
+/* mse_b200.h — C ABI of the B200-native retrieval hot path.
+ *
+ * The reference (StephenTaf/Modern-Search-Engines-Project) is pure Python and has no FFI; each
+ * entry point below replaces the inside of one reference function and is what a ctypes binding
+ * in the reference would call (see INTEGRATION.md for the stubs):
+ *
+ *   mse_bm25_load           <- what BM25.__init__ opens: the four bm25_* tables
+ *                              (indexer/bm25_indexer.py:57-80, DDL :82-128)
+ *   mse_bm25_search_batch   <- BM25.search steps 5-8: candidate SQL, grouping, float64 scoring
+ *                              loop, sort, slice (indexer/bm25_indexer.py:435-485)
+ *   mse_dense_load          <- chunks_optimized + embeddings tables (indexer/embedder.py:31-52)
+ *   mse_rerank_batch        <- rerank(): candidate fetch, cosine, min-max, fusion, positional
+ *                              weighting, per-doc max, sort (reranker/reranker_api.py:27-63,273-372)
+ *   mse_dense_scan_batch    <- the removed Retriever.quick_search (call sites search_api.py:60,87)
+ *   mse_topk_merge          <- (new) merge of per-shard top-k lists after the NCCL all-gather
+ *
+ * Conventions: every function returns 0 on success or an MSE_ERR_* code and sets a thread-local
+ * message readable through mse_last_error(); no exception crosses the boundary.  An mse_index
+ * owns all device memory it allocates; callers own every buffer they pass in.  The index is
+ * immutable after load, and search calls may be issued from several host threads (a per-index
+ * workspace is guarded by a mutex).  There is no CPU fallback: without a CUDA device every
+ * compute entry point fails with MSE_ERR_CUDA.
+ *
+ * Document numbering: all kernels work on the dense document index 0..n_docs-1 (ascending
+ * urlsDB id, so "tie -> lower doc id" == "tie -> lower index"); outputs are doc_base + local
+ * index, where doc_base is the first dense index of this shard.
+ */
+#ifndef MSE_B200_H
+#define MSE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSE_ABI_VERSION 1
+
+#define MSE_OK 0
+#define MSE_ERR_INVALID 1      /* bad argument / malformed index (unsorted postings, ...) */
+#define MSE_ERR_CUDA 2         /* CUDA runtime error, or no device */
+#define MSE_ERR_NOMEM 3
+#define MSE_ERR_STATE 4        /* e.g. search before load */
+#define MSE_ERR_UNSUPPORTED 5  /* e.g. top_k above MSE_MAX_TOPK */
+
+#define MSE_MAX_TOPK 4096      /* the reference uses 1000 (config.py:13) and 100 (reranker/config.yaml:30) */
+#define MSE_EMB_DIM 768        /* config.py:2 */
+
+#define MSE_HOST 0             /* buffers are host memory; the call copies and synchronises */
+#define MSE_DEVICE 1           /* buffers are device memory; work is ordered on `stream` */
+
+typedef struct mse_index mse_index;
+
+const char* mse_last_error(void);
+int mse_abi_version(void);
+int mse_device_count(int* n_devices);
+
+int mse_index_create(int device, mse_index** out);
+int mse_index_destroy(mse_index* idx);
+
+/* Tuning knobs (all optional; 0 restores the automatic choice):
+ *   "bm25_range_docs"        docs per shared-memory accumulator range (multiple of 256)
+ *   "bm25_queries_per_item"  queries a CTA scores per scheduled work item
+ *   "bm25_cand_cap"          per-query capacity of the candidate list between scoring and selection
+ *   "bm25_use_tau"           1 (default) = running k-th-score bound filters candidates, 0 = emit all
+ *   "dense_scan_ctas_per_sm" persistent CTAs per SM of the scan kernel
+ *   "reset_timers"           any value: zero the accumulated kernel timers */
+int mse_index_set_option(mse_index* idx, const char* name, int64_t value);
+
+/* ---- BM25 (Stage 1) -------------------------------------------------------------------- */
+
+/* Loads the inverted index of one shard.
+ *   term_off[n_terms+1]  CSR offsets into the posting arrays (bm25_term_freq ORDER BY term, doc_id)
+ *   post_doc[P]          LOCAL dense doc index (0..n_docs-1), strictly ascending inside a term
+ *   post_tf[P]           bm25_term_freq.freq
+ *   doc_len[n_docs]      bm25_doc_stats.doc_length
+ *   idf[n_terms]         bm25_term_stats.idf_score verbatim (float32 log10, may be <= 0; :140)
+ *   avgdl                bm25_corpus_stats 'avg_doc_length' (float32; GLOBAL, never per shard)
+ *   k1, b                BM25.__init__ parameters (:57)
+ * `where` tells whether the five arrays are host (MSE_HOST) or device (MSE_DEVICE) memory. */
+int mse_bm25_load(mse_index* idx, int64_t n_terms, int64_t n_docs, int64_t doc_base,
+                  const int64_t* term_off, const int32_t* post_doc, const int32_t* post_tf,
+                  const int32_t* doc_len, const float* idf, float avgdl, float k1, float b, int where);
+
+/* Scores a batch of tokenised queries and returns, per query, the top_k documents with
+ * score >= min_score among documents holding at least one posting of a valid query term
+ * (:436-456, :480), ordered by score descending, ties by ascending doc (:484).
+ *   q_off[n_queries+1], q_term[], q_tf[]   CSR of DISTINCT term indices per query with their
+ *       query frequency (:405-409); indices < 0 or >= n_terms or with df == 0 are ignored (:430)
+ *   out_doc[n_queries*top_k], out_score[n_queries*top_k], out_count[n_queries]
+ * Scores are computed in float32 (reference: float64 on float32 idf/avgdl). */
+int mse_bm25_search_batch(mse_index* idx, int32_t n_queries, const int32_t* q_off, const int32_t* q_term,
+                          const int32_t* q_tf, int32_t top_k, float min_score,
+                          int32_t* out_doc, float* out_score, int32_t* out_count, int where, void* stream);
+
+/* Counters of the last BM25 call on this index (for the roofline report):
+ * stats[0] = postings traversed (sum of df over valid query terms), stats[1] = candidates
+ * emitted to the selection stage, stats[2] = queries re-run through the unbounded-capacity path,
+ * stats[3] = doc ranges, stats[4] = score-kernel CTAs launched. */
+int mse_bm25_last_stats(mse_index* idx, int64_t stats[8]);
+
+/* Timing hooks: every call brackets its kernels with CUDA events on the launching stream.
+ * Returns the accumulated device time (ms) and the number of launches since the last
+ * "reset_timers".  kernel: 0 = bm25 score, 1 = top-k select, 2 = dense scan, 3 = rerank,
+ * 4 = bm25 prepare. */
+int mse_kernel_time(mse_index* idx, int kernel, double* total_ms, int64_t* launches);
+
+/* ---- dense (Stage 2) ------------------------------------------------------------------- */
+
+/* Loads one shard of chunk embeddings, doc-contiguous in ascending chunk id.
+ *   emb            n_chunks x 768, float32 (emb_is_bf16 = 0; converted to bf16 on load) or bf16
+ *   doc_chunk_off  [n_docs+1] chunk range of every local doc (chunks_optimized ORDER BY doc_id, chunk_id)
+ *   chunk_base     global row number of the first local chunk (chunk ids are sequential, indexer.py:108-111) */
+int mse_dense_load(mse_index* idx, int64_t n_chunks, int64_t n_docs, int64_t doc_base, int64_t chunk_base,
+                   const void* emb, int emb_is_bf16, const int64_t* doc_chunk_off, int where);
+
+/* Exhaustive scan: inner product of each query with every stored chunk, max over the chunks of
+ * a document, top_k documents per query (ties -> lower doc).  q is float32 [n_queries*768]. */
+int mse_dense_scan_batch(mse_index* idx, int32_t n_queries, const float* q, int32_t top_k,
+                         int32_t* out_doc, float* out_score, int32_t* out_count, int where, void* stream);
+
+/* Gathered rerank of BM25 candidates (reranker_api.py:336-372).
+ *   cand_off[n_queries+1], cand_doc[], cand_bm25[]   candidates per query in BM25 order (GLOBAL dense index)
+ *   url_group[n_docs] or NULL   id of the url-up-to-'?' group of each local doc (:44-47); among
+ *       candidates of one group only the lowest doc survives
+ *   q            float32 [n_queries*768], NOT normalised (:355)
+ *   out_*        [n_queries*max_out]: docs sorted by fused score descending; out_orig = min-max'd BM25
+ *                score, out_chunk = global row (== chunk id) of the representative chunk,
+ *                out_rows[n_queries] = fetched chunk rows (`total_documents` of the reference response). */
+int mse_rerank_batch(mse_index* idx, int32_t n_queries, const int32_t* cand_off, const int32_t* cand_doc,
+                     const float* cand_bm25, const int32_t* url_group, const float* q,
+                     float smoothing, int32_t max_chunks, int32_t max_out,
+                     int32_t* out_doc, float* out_score, float* out_orig, int64_t* out_chunk,
+                     int32_t* out_count, int32_t* out_rows, int where, void* stream);
+
+/* ---- shard merge (multi-GPU) ------------------------------------------------------------ */
+
+/* Merges n_lists sorted top-k lists per query (the all-gathered per-rank results, laid out
+ * [n_lists][n_queries][list_k]) into one top_k list per query with the same ordering rule. */
+int mse_topk_merge(mse_index* idx, int32_t n_queries, int32_t n_lists, int32_t list_k,
+                   const int32_t* in_doc, const float* in_score, const int32_t* in_count, int32_t top_k,
+                   int32_t* out_doc, float* out_score, int32_t* out_count, int where, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSE_B200_H */

@@ -1,0 +1,262 @@
+"""ctypes binding of ``csrc/libmsegpu.so`` (C ABI: ``include/mse_b200.h``).
+
+There is deliberately no CPU fallback: if the shared library is missing, or no sm_100a device
+is present, the compute entry points raise ``NativeError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import sys
+from typing import Optional, Tuple
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libmsegpu.so")
+HEADER = os.path.join(os.path.dirname(HERE), "include", "mse_b200.h")
+
+MSE_HOST, MSE_DEVICE = 0, 1
+MAX_TOPK = 4096
+EMB_DIM = 768
+KERNELS = {"bm25_score": 0, "topk_select": 1, "dense_scan": 2, "rerank": 3, "bm25_prepare": 4}
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC"]
+
+
+class NativeError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"mse_b200 error {code}: {msg}")
+        self.code = code
+
+
+def build(verbose: bool = False) -> str:
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    src = os.path.join(CSRC, "api.cu")
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))] + [HEADER]
+    if os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, src]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        sys.stderr.write(r.stderr)
+    return LIB_PATH
+
+
+_lib = None
+
+_i32p, _f32p, _i64p, _vp = C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(C.c_int64), C.c_void_p
+
+_SIGNATURES = {
+    "mse_last_error": (C.c_char_p, []),
+    "mse_abi_version": (C.c_int, []),
+    "mse_device_count": (C.c_int, [_i32p]),
+    "mse_index_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "mse_index_destroy": (C.c_int, [_vp]),
+    "mse_index_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int64]),
+    "mse_bm25_load": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, _vp,
+                                C.c_float, C.c_float, C.c_float, C.c_int]),
+    "mse_bm25_search_batch": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, C.c_int32, C.c_float, _vp, _vp, _vp, C.c_int, _vp]),
+    "mse_bm25_last_stats": (C.c_int, [_vp, _i64p]),
+    "mse_kernel_time": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), _i64p]),
+    "mse_dense_load": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp, C.c_int, _vp, C.c_int]),
+    "mse_dense_scan_batch": (C.c_int, [_vp, C.c_int32, _vp, C.c_int32, _vp, _vp, _vp, C.c_int, _vp]),
+    "mse_rerank_batch": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, C.c_float, C.c_int32, C.c_int32,
+                                   _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp]),
+    "mse_topk_merge": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, _vp, C.c_int32, _vp, _vp, _vp, C.c_int, _vp]),
+}
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def lib():
+    """Loads the shared library; raises if it has not been built (no silent fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError(-1, f"{LIB_PATH} is missing — run `python -c 'import __graft_entry__ as g; g.build()'`; "
+                                  "this package has no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise NativeError(rc, lib().mse_last_error().decode("utf-8", "replace"))
+
+
+def device_count() -> int:
+    n = C.c_int32(0)
+    rc = lib().mse_device_count(C.byref(n))
+    return 0 if rc else int(n.value)
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+def _ptr(x, dtype, where: int):
+    """Address of a contiguous numpy array (host) or torch tensor (host or device) of `dtype`."""
+    if x is None:
+        return None
+    if _is_torch(x):
+        import torch
+        want = {np.int32: torch.int32, np.int64: torch.int64, np.float32: torch.float32,
+                "bf16": torch.bfloat16}[dtype]
+        assert x.dtype == want, (x.dtype, want)
+        assert x.is_contiguous()
+        assert x.is_cuda == (where == MSE_DEVICE), "buffer location does not match `where`"
+        return C.c_void_p(x.data_ptr())
+    assert where == MSE_HOST, "numpy buffers are host memory"
+    assert x.dtype == np.dtype(dtype) and x.flags["C_CONTIGUOUS"], (x.dtype, dtype)
+    return C.c_void_p(x.ctypes.data)
+
+
+def _where_of(*xs) -> int:
+    for x in xs:
+        if x is not None and _is_torch(x) and x.is_cuda:
+            return MSE_DEVICE
+    return MSE_HOST
+
+
+def _stream_ptr(where: int):
+    if where == MSE_DEVICE:
+        import torch
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return None
+
+
+class NativeIndex:
+    """Owns one ``mse_index`` (all device memory of one shard on one GPU)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        _check(lib().mse_index_create(int(device), C.byref(self._h)))
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().mse_index_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, name: str, value: int):
+        _check(lib().mse_index_set_option(self._h, name.encode(), int(value)))
+
+    def kernel_time(self, kernel: str) -> Tuple[float, int]:
+        ms, n = C.c_double(0), C.c_int64(0)
+        _check(lib().mse_kernel_time(self._h, KERNELS[kernel], C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
+
+    def bm25_stats(self) -> dict:
+        arr = (C.c_int64 * 8)()
+        _check(lib().mse_bm25_last_stats(self._h, arr))
+        return {"postings": arr[0], "emitted": arr[1], "rerun_queries": arr[2], "ranges": arr[3], "ctas": arr[4]}
+
+    # ---- BM25 --------------------------------------------------------------------------------
+    def bm25_load(self, term_off, post_doc, post_tf, doc_len, idf, avgdl, k1=1.2, b=0.75, doc_base=0):
+        where = _where_of(term_off, post_doc, post_tf, doc_len, idf)
+        n_terms, n_docs = int(term_off.shape[0]) - 1, int(doc_len.shape[0])
+        _check(lib().mse_bm25_load(self._h, n_terms, n_docs, int(doc_base), _ptr(term_off, np.int64, where),
+                                   _ptr(post_doc, np.int32, where), _ptr(post_tf, np.int32, where),
+                                   _ptr(doc_len, np.int32, where), _ptr(idf, np.float32, where),
+                                   float(avgdl), float(k1), float(b), where))
+
+    def bm25_search(self, q_off, q_term, q_tf, top_k: int, min_score: float = 0.0, out=None):
+        where = _where_of(q_off, q_term, q_tf)
+        B = int(q_off.shape[0]) - 1
+        if out is None:
+            if where == MSE_DEVICE:
+                import torch
+                dev = q_off.device
+                out = (torch.empty((B, top_k), dtype=torch.int32, device=dev),
+                       torch.empty((B, top_k), dtype=torch.float32, device=dev),
+                       torch.empty((B,), dtype=torch.int32, device=dev))
+            else:
+                out = (np.empty((B, top_k), np.int32), np.empty((B, top_k), np.float32), np.empty((B,), np.int32))
+        o_doc, o_score, o_count = out
+        _check(lib().mse_bm25_search_batch(self._h, B, _ptr(q_off, np.int32, where), _ptr(q_term, np.int32, where),
+                                           _ptr(q_tf, np.int32, where), int(top_k), float(min_score),
+                                           _ptr(o_doc, np.int32, where), _ptr(o_score, np.float32, where),
+                                           _ptr(o_count, np.int32, where), where, _stream_ptr(where)))
+        return out
+
+    # ---- dense --------------------------------------------------------------------------------
+    def dense_load(self, emb, doc_chunk_off, doc_base=0, chunk_base=0):
+        where = _where_of(emb, doc_chunk_off)
+        is_bf16 = _is_torch(emb) and str(emb.dtype) == "torch.bfloat16"
+        n_chunks, n_docs = int(emb.shape[0]), int(doc_chunk_off.shape[0]) - 1
+        assert emb.shape[1] == EMB_DIM
+        _check(lib().mse_dense_load(self._h, n_chunks, n_docs, int(doc_base), int(chunk_base),
+                                    _ptr(emb, "bf16" if is_bf16 else np.float32, where), int(is_bf16),
+                                    _ptr(doc_chunk_off, np.int64, where), where))
+
+    def dense_scan(self, q, top_k: int, out=None):
+        where = _where_of(q)
+        B = int(q.shape[0])
+        if out is None:
+            if where == MSE_DEVICE:
+                import torch
+                out = (torch.empty((B, top_k), dtype=torch.int32, device=q.device),
+                       torch.empty((B, top_k), dtype=torch.float32, device=q.device),
+                       torch.empty((B,), dtype=torch.int32, device=q.device))
+            else:
+                out = (np.empty((B, top_k), np.int32), np.empty((B, top_k), np.float32), np.empty((B,), np.int32))
+        _check(lib().mse_dense_scan_batch(self._h, B, _ptr(q, np.float32, where), int(top_k),
+                                          _ptr(out[0], np.int32, where), _ptr(out[1], np.float32, where),
+                                          _ptr(out[2], np.int32, where), where, _stream_ptr(where)))
+        return out
+
+    def rerank(self, cand_off, cand_doc, cand_bm25, q, url_group=None, smoothing=0.15, max_chunks=10, max_out=1000):
+        where = _where_of(cand_off, cand_doc, cand_bm25, q)
+        B = int(cand_off.shape[0]) - 1
+        if where == MSE_DEVICE:
+            import torch
+            dev = q.device
+            mk = lambda dt: torch.empty((B, max_out), dtype=dt, device=dev)
+            out = (mk(torch.int32), mk(torch.float32), mk(torch.float32), mk(torch.int64),
+                   torch.empty((B,), dtype=torch.int32, device=dev), torch.empty((B,), dtype=torch.int32, device=dev))
+        else:
+            out = (np.empty((B, max_out), np.int32), np.empty((B, max_out), np.float32), np.empty((B, max_out), np.float32),
+                   np.empty((B, max_out), np.int64), np.empty((B,), np.int32), np.empty((B,), np.int32))
+        _check(lib().mse_rerank_batch(self._h, B, _ptr(cand_off, np.int32, where), _ptr(cand_doc, np.int32, where),
+                                      _ptr(cand_bm25, np.float32, where), _ptr(url_group, np.int32, where),
+                                      _ptr(q, np.float32, where), float(smoothing), int(max_chunks), int(max_out),
+                                      _ptr(out[0], np.int32, where), _ptr(out[1], np.float32, where),
+                                      _ptr(out[2], np.float32, where), _ptr(out[3], np.int64, where),
+                                      _ptr(out[4], np.int32, where), _ptr(out[5], np.int32, where),
+                                      where, _stream_ptr(where)))
+        return out
+
+    def topk_merge(self, in_doc, in_score, in_count, top_k: int):
+        """in_doc/in_score: [n_lists, B, list_k]; in_count: [n_lists, B]."""
+        where = _where_of(in_doc, in_score, in_count)
+        n_lists, B, list_k = (int(s) for s in in_doc.shape)
+        if where == MSE_DEVICE:
+            import torch
+            dev = in_doc.device
+            out = (torch.empty((B, top_k), dtype=torch.int32, device=dev), torch.empty((B, top_k), dtype=torch.float32, device=dev),
+                   torch.empty((B,), dtype=torch.int32, device=dev))
+        else:
+            out = (np.empty((B, top_k), np.int32), np.empty((B, top_k), np.float32), np.empty((B,), np.int32))
+        _check(lib().mse_topk_merge(self._h, B, n_lists, list_k, _ptr(in_doc, np.int32, where), _ptr(in_score, np.float32, where),
+                                    _ptr(in_count, np.int32, where), int(top_k), _ptr(out[0], np.int32, where),
+                                    _ptr(out[1], np.float32, where), _ptr(out[2], np.int32, where), where, _stream_ptr(where)))
+        return out

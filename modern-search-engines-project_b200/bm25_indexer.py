@@ -1,0 +1,259 @@
+"""Drop-in for ``indexer.bm25_indexer.BM25`` (``/root/reference/indexer/bm25_indexer.py:56-568``)
+whose query path runs on the GPU.
+
+Same constructor and method names, argument meaning, return shapes and empty-result behaviour as
+the reference class, so ``search_api.py:51,88,252`` work unchanged:
+
+    bm_25 = BM25(cfg.DB_PATH, read_only=True)
+    results = bm_25.search(query, top_k=1000)      # [{'doc_id', 'score', 'text_snippet'}, ...]
+
+What differs is where the work happens: the four ``bm25_*`` tables are read ONCE at construction
+into a CSR inverted index resident in HBM, and ``search`` / ``search_batch`` run the batched
+scoring + top-k kernels behind ``mse_bm25_search_batch``.  Host code keeps only what is string
+work in the reference: tokenisation (``:149-155``), the term dictionary lookup (``:412-432``) and
+the snippet fetch (``:491-514``).
+"""
+from __future__ import annotations
+
+import math
+from collections import defaultdict
+from typing import Callable, Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native
+from .store import ArrayStore, Bm25Tables, SqlStore, open_store
+
+
+def spacy_tokenizer():
+    """The reference's tokenizer (``:72-80,149-155``): spaCy ``en_core_web_sm`` lemmas that are alpha,
+    non-stop, non-punct.  Raises ImportError where spaCy is not installed."""
+    import spacy  # type: ignore
+    nlp = spacy.load("en_core_web_sm")
+
+    def tok(text: str) -> List[str]:
+        return [t.lemma_.lower() for t in nlp(text) if not t.is_stop and not t.is_punct and t.is_alpha]
+    return tok
+
+
+def whitespace_tokenizer(text: str) -> List[str]:
+    return text.split()
+
+
+def shard_bounds(term_weight_per_doc: np.ndarray, world: int) -> List[int]:
+    """Contiguous doc-index ranges balanced by per-doc weight (postings or chunks), SURVEY.md §8e."""
+    n = len(term_weight_per_doc)
+    cum = np.concatenate([[0], np.cumsum(term_weight_per_doc, dtype=np.int64)])
+    total = cum[-1]
+    bounds = [0]
+    for r in range(1, world):
+        bounds.append(int(np.searchsorted(cum, total * r // world)))
+    bounds.append(n)
+    for i in range(1, len(bounds)):
+        bounds[i] = max(bounds[i], bounds[i - 1])
+    return bounds
+
+
+def slice_bm25_tables(t: Bm25Tables, lo: int, hi: int) -> Bm25Tables:
+    """Postings of docs [lo, hi) re-based to local doc indices; idf / avgdl stay global."""
+    keep = (t.post_doc >= lo) & (t.post_doc < hi)
+    term_of = np.repeat(np.arange(len(t.term_off) - 1, dtype=np.int64), np.diff(t.term_off))
+    off = np.zeros(len(t.term_off), dtype=np.int64)
+    np.add.at(off, term_of[keep] + 1, 1)
+    return Bm25Tables(t.terms, np.cumsum(off), (t.post_doc[keep] - lo).astype(np.int32), t.post_tf[keep],
+                      t.doc_ids[lo:hi], t.doc_len[lo:hi], t.idf, t.total_freq, t.avgdl, t.total_docs)
+
+
+class BM25:
+    def __init__(self, db_path: Optional[str], k1: float = 1.2, b: float = 0.75, read_only: bool = True, *,
+                 store=None, tokenizer: Optional[Callable[[str], List[str]]] = None, device: int = 0,
+                 doc_range: Optional[Tuple[int, int]] = None, load: bool = True):
+        self.db_path = db_path
+        self.k1 = k1
+        self.b = b
+        self.read_only = read_only
+        self.store = store if store is not None else open_store(db_path, read_only=read_only)
+        self.conn = getattr(self.store, "conn", None)          # the reference exposes .conn (:69)
+        self._tokenizer = tokenizer
+        self.device = device
+        self.doc_range = doc_range
+        self.tables: Optional[Bm25Tables] = None
+        self.native: Optional[_native.NativeIndex] = None
+        self._term_index: Dict[str, int] = {}
+        self.doc_base = 0
+        if load and self.store.has_table("bm25_term_freq"):
+            self.reload()
+
+    # ------------------------------------------------------------------ loading
+    def reload(self):
+        """(Re)reads the bm25_* tables and uploads the CSR index to HBM."""
+        all_ids = self.store.all_doc_ids() if hasattr(self.store, "all_doc_ids") else None
+        full = self.store.load_bm25(all_ids)
+        self.global_doc_ids = full.doc_ids
+        self._df_global = np.diff(full.term_off)
+        t = full
+        if self.doc_range is not None:
+            lo, hi = self.doc_range
+            t = slice_bm25_tables(full, lo, hi)
+            self.doc_base = lo
+        self.tables = t
+        self._term_index = {s: i for i, s in enumerate(t.terms)} if t.terms is not None else {}
+        if self.native is None:
+            self.native = _native.NativeIndex(self.device)
+        self.native.bm25_load(np.ascontiguousarray(t.term_off, dtype=np.int64),
+                              np.ascontiguousarray(t.post_doc, dtype=np.int32),
+                              np.ascontiguousarray(t.post_tf, dtype=np.int32),
+                              np.ascontiguousarray(t.doc_len, dtype=np.int32),
+                              np.ascontiguousarray(t.idf, dtype=np.float32),
+                              t.avgdl, self.k1, self.b, doc_base=self.doc_base)
+
+    # ------------------------------------------------------------------ tokenisation (host)
+    def _tokenize(self, text: str) -> List[str]:
+        if self._tokenizer is None:
+            self._tokenizer = spacy_tokenizer()
+        return self._tokenizer(text)
+
+    def _query_slots(self, terms: Iterable) -> Tuple[List[int], List[int]]:
+        """``:405-432``: unique terms in first-occurrence order + query tf; unknown terms dropped."""
+        qtf: Dict[int, int] = {}
+        order: List[int] = []
+        n_terms = len(self._df_global)
+        for t in terms:
+            j = self._term_index.get(t, -1) if isinstance(t, str) else int(t)
+            if j < 0 or j >= n_terms or self._df_global[j] == 0:
+                continue
+            if j not in qtf:
+                qtf[j] = 0
+                order.append(j)
+            qtf[j] += 1
+        return order, [qtf[j] for j in order]
+
+    def encode_queries(self, queries: Sequence) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """List of query strings (tokenised here) or of term lists -> CSR batch."""
+        q_off, q_term, q_tf = [0], [], []
+        for q in queries:
+            terms = self._tokenize(q) if isinstance(q, str) else q
+            o, f = self._query_slots(terms)
+            q_term.extend(o); q_tf.extend(f); q_off.append(len(q_term))
+        return (np.asarray(q_off, dtype=np.int32), np.asarray(q_term, dtype=np.int32), np.asarray(q_tf, dtype=np.int32))
+
+    # ------------------------------------------------------------------ search
+    def search_batch_terms(self, q_off, q_term, q_tf, top_k: int = 1000, min_score: float = 0.0):
+        """CSR term-id batch -> (doc index [B,k] int32 (global dense index, -1 padded), score [B,k] fp32,
+        count [B]).  Accepts numpy (host) or torch CUDA tensors (device-resident, no copies)."""
+        self._require_loaded()
+        return self.native.bm25_search(q_off, q_term, q_tf, top_k, min_score)
+
+    def search_batch(self, queries: Sequence, top_k: int = 1000, min_score: float = 0.0):
+        """Batched ``search``: returns (doc_ids [B,k] int64 urlsDB ids, scores [B,k], counts [B])."""
+        q_off, q_term, q_tf = self.encode_queries(queries)
+        doc, score, count = self.search_batch_terms(q_off, q_term, q_tf, top_k, min_score)
+        ids = np.where(doc >= 0, self.global_doc_ids[np.maximum(doc, 0)], -1)
+        return ids, score, count
+
+    def search(self, query: str, top_k: int = 1000, min_score: float = 0.0) -> List[dict]:
+        """Same contract as the reference ``search`` (``:383-514``): ``[]`` when the query has no
+        tokens, no known terms or no surviving document; otherwise dicts in rank order."""
+        query_terms = self._tokenize(query)
+        if not query_terms:
+            return []
+        slots, _ = self._query_slots(query_terms)
+        if not slots:
+            return []
+        ids, score, count = self.search_batch([query_terms], top_k=top_k, min_score=min_score)
+        n = int(count[0])
+        if n == 0:
+            return []
+        top_ids = [int(x) for x in ids[0, :n]]
+        details = self.store.documents(top_ids)
+        out = []
+        for d, s in zip(top_ids, score[0, :n].tolist()):
+            if d in details:                                    # ids missing from urlsDB are dropped (:506)
+                title, text = details[d]
+                text = text or ""
+                snip = f"{title or 'N/A'}: {text[:200]}"
+                if len(text) > 200:
+                    snip += "..."
+                out.append({"doc_id": d, "score": s, "text_snippet": snip})
+        return out
+
+    # ------------------------------------------------------------------ introspection (:516-568)
+    def get_term_stats(self, term: str) -> Optional[Dict]:
+        self._require_loaded()
+        j = self._term_index.get(term.lower(), -1)
+        if j < 0:
+            return None
+        df = int(self._df_global[j])
+        n = self.tables.total_docs
+        return {"term": term, "document_frequency": df, "total_frequency": int(self.tables.total_freq[j]),
+                "inverse_document_frequency": math.log((n - df + 0.5) / (df + 0.5))}   # natural log, as :532
+
+    def get_document_terms(self, doc_id: int, limit: int = 20) -> List[Tuple[str, int]]:
+        self._require_loaded()
+        t = self.tables
+        pos = int(np.searchsorted(t.doc_ids, doc_id))
+        if pos >= len(t.doc_ids) or t.doc_ids[pos] != doc_id:
+            return []
+        hit = np.flatnonzero(t.post_doc == pos)
+        term_of = np.searchsorted(t.term_off, hit, side="right") - 1
+        order = np.argsort(-t.post_tf[hit], kind="stable")[:limit]
+        return [(t.terms[int(term_of[i])], int(t.post_tf[hit[i]])) for i in order]
+
+    def get_index_stats(self) -> Dict:
+        self._require_loaded()
+        t = self.tables
+        processed = int(np.count_nonzero(t.doc_len))
+        total = len(self.store.all_doc_ids()) if hasattr(self.store, "all_doc_ids") else processed
+        return {"total_documents_in_database": total, "processed_documents": processed,
+                "unique_terms": len(t.terms) if t.terms is not None else int(len(t.term_off) - 1),
+                "average_document_length": t.avgdl,
+                "index_coverage": f"{processed}/{total} ({100 * processed / max(total, 1):.1f}%)"}
+
+    # ------------------------------------------------------------------ index build (:252-369)
+    def build_index(self, batch_size: int = 5000):
+        """Host-side build of the four bm25_* tables from ``urlsDB`` (tokenise, per-doc tf, df /
+        total_freq, float32 corpus stats, float32 log10 IDF), then upload.  The text front-end
+        stays on the host as in the reference; see SURVEY.md §8f N4."""
+        if not isinstance(self.store, SqlStore):
+            raise RuntimeError("build_index needs an SQL store holding urlsDB")
+        doc_rows, tf_rows = [], []
+        df: Dict[str, int] = defaultdict(int)
+        tot: Dict[str, int] = defaultdict(int)
+        for doc_id, title, text in self.store.iter_documents():
+            s = f"{title or ''} {text or ''}".lower().replace("tuebingen", "tübingen").replace("tubingen", "tübingen")[:1_000_000]
+            toks = self._tokenize(s)
+            if not toks:
+                continue
+            counts: Dict[str, int] = defaultdict(int)
+            for w in toks:
+                counts[w] += 1
+            doc_rows.append((doc_id, len(toks)))
+            for w, c in counts.items():
+                tf_rows.append((doc_id, w, c)); df[w] += 1; tot[w] += c
+        n = len(doc_rows)
+        avg = float(np.float32(np.mean([r[1] for r in doc_rows]))) if n else 0.0
+        n32 = float(np.float32(n))
+        idf_of = lambda d: float(np.float32(math.log10((n32 - d + 0.5) / (d + 0.5))))
+        self.store.write_bm25(doc_rows, tf_rows, [(w, df[w], tot[w]) for w in df], avg, n, idf_of)
+        self.reload()
+
+    def _require_loaded(self):
+        if self.native is None or self.tables is None:
+            raise RuntimeError("BM25 index is not loaded (no bm25_* tables in the store; call build_index())")
+
+    def close(self):
+        if self.native is not None:
+            self.native.close()
+            self.native = None
+
+
+def bm25_from_arrays(term_off, post_doc, post_tf, doc_len, idf, avgdl, total_docs, doc_ids=None, terms=None,
+                     k1: float = 1.2, b: float = 0.75, device: int = 0, doc_range=None, tokenizer=None) -> BM25:
+    """BM25 façade over arrays already in memory (synthetic corpora: integer term ids)."""
+    n = len(doc_len)
+    ids = np.asarray(doc_ids if doc_ids is not None else np.arange(1, n + 1), dtype=np.int64)
+    t = Bm25Tables(terms, np.asarray(term_off, dtype=np.int64), np.asarray(post_doc, dtype=np.int32),
+                   np.asarray(post_tf, dtype=np.int32), ids, np.asarray(doc_len, dtype=np.int32),
+                   np.asarray(idf, dtype=np.float32), np.zeros(len(term_off) - 1, dtype=np.int64), float(avgdl), float(total_docs))
+    return BM25(None, k1, b, store=ArrayStore(bm25=t), tokenizer=tokenizer or whitespace_tokenizer,
+                device=device, doc_range=doc_range)

@@ -1,0 +1,727 @@
+// C-ABI of the B200-native retrieval hot path (see include/mse_b200.h for the contract).
+// Plain CUDA runtime only: no torch types cross this boundary.
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
+#include "bm25.cuh"
+#include "common.cuh"
+#include "dense.cuh"
+#include "rerank.cuh"
+#include "topk.cuh"
+
+namespace mse {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return MSE_OK;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            e = cudaMalloc(&p, bytes);
+            want = bytes;
+        }
+        if (e != cudaSuccess) {
+            p = nullptr;
+            set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+            (void)cudaGetLastError();
+            return MSE_ERR_NOMEM;
+        }
+        cap = want;
+        return MSE_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+constexpr int kNumTimers = 5;
+enum { T_SCORE = 0, T_SELECT = 1, T_SCAN = 2, T_RERANK = 3, T_PREPARE = 4 };
+
+}  // namespace mse
+
+using namespace mse;
+
+struct mse_index {
+    int device = 0;
+    int sm_count = 148;
+    std::mutex mu;
+
+    bool has_bm25 = false;
+    Bm25Dev bm{};
+    DevBuf term_off, post_doc, post_tf, doc_norm, idf;
+    std::vector<int64_t> h_term_off;
+
+    bool has_dense = false;
+    DenseDev dn{};
+    DevBuf emb, doc_chunk_off;
+
+    // workspace (guarded by mu)
+    DevBuf q_off, q_term, q_tf, slot_w, slot_base, seg, tau, hist, maxbin, cand, cand_count, overflow, misc;
+    DevBuf o_doc, o_score, o_count;          // device staging of results for MSE_HOST callers
+    DevBuf best, dq;                         // dense scan
+    DevBuf r_in[5], r_out[6];                // rerank staging
+    DevBuf m_in[3];                          // merge staging
+    DevBuf fb_q[3], fb_out[3];               // fallback sub-batches
+
+    int64_t opt_range_docs = 0, opt_qpi = 0, opt_cand_cap = 0, opt_use_tau = 1, opt_scan_ctas = 0;
+    int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+    cudaEvent_t ev[kNumTimers][2];
+    bool ev_ok = false;
+    double t_ms[kNumTimers] = {0, 0, 0, 0, 0};
+    int64_t t_n[kNumTimers] = {0, 0, 0, 0, 0};
+    bool t_pending[kNumTimers] = {false, false, false, false, false};
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+void timer_begin(mse_index* ix, int t, cudaStream_t s) {
+    if (ix->ev_ok) cudaEventRecord(ix->ev[t][0], s);
+}
+void timer_end(mse_index* ix, int t, cudaStream_t s) {
+    if (ix->ev_ok) { cudaEventRecord(ix->ev[t][1], s); ix->t_pending[t] = true; }
+}
+// call after the stream has been synchronised
+void timers_collect(mse_index* ix) {
+    for (int t = 0; t < kNumTimers; ++t) {
+        if (!ix->t_pending[t]) continue;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ix->ev[t][0], ix->ev[t][1]) == cudaSuccess) { ix->t_ms[t] += ms; ix->t_n[t] += 1; }
+        else (void)cudaGetLastError();
+        ix->t_pending[t] = false;
+    }
+}
+
+int copy_in(void* dst, const void* src, size_t bytes, int where, cudaStream_t s) {
+    if (bytes == 0) return MSE_OK;
+    MSE_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, where == MSE_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
+    return MSE_OK;
+}
+
+int round_up(int64_t v, int64_t m) { return int(((v + m - 1) / m) * m); }
+
+// ---- BM25 core: everything on device, outputs to device pointers ---------------------------------
+int bm25_run(mse_index* ix, int32_t B, const int32_t* d_q_off, const int32_t* d_q_term, const int32_t* d_q_tf,
+             int32_t S, int32_t top_k, float min_score, int32_t cap, int use_tau,
+             int32_t* d_out_doc, float* d_out_score, int32_t* d_out_count, bool mark_overflow, cudaStream_t st) {
+    const Bm25Dev& bm = ix->bm;
+    int R = ix->opt_range_docs > 0 ? round_up(ix->opt_range_docs, 256) : 6144;
+    if (R > 24576) R = 24576;
+    if (bm.n_docs < R) R = std::max(256, round_up(bm.n_docs, 256));
+    const int n_ranges = int((bm.n_docs + R - 1) / R);
+    int qpi = ix->opt_qpi > 0 ? int(ix->opt_qpi) : 8;
+    const int nb = n_ranges + 1;
+
+    int rc;
+    if ((rc = ix->slot_w.ensure(sizeof(float) * size_t(S + 1)))) return rc;
+    if ((rc = ix->slot_base.ensure(sizeof(int64_t) * size_t(S + 1)))) return rc;
+    if ((rc = ix->seg.ensure(sizeof(uint32_t) * size_t(S + 1) * nb))) return rc;
+    if ((rc = ix->tau.ensure(sizeof(uint32_t) * size_t(B)))) return rc;
+    if ((rc = ix->hist.ensure(sizeof(uint32_t) * size_t(B) * kHistBins))) return rc;
+    if ((rc = ix->maxbin.ensure(sizeof(uint32_t) * size_t(B)))) return rc;
+    if ((rc = ix->cand.ensure(sizeof(uint64_t) * size_t(B) * cap))) return rc;
+    if ((rc = ix->cand_count.ensure(sizeof(int32_t) * size_t(B)))) return rc;
+    if ((rc = ix->overflow.ensure(sizeof(int32_t) * size_t(B)))) return rc;
+    if ((rc = ix->misc.ensure(64))) return rc;
+
+    MSE_CUDA_TRY(cudaMemsetAsync(ix->cand_count.p, 0, sizeof(int32_t) * size_t(B), st));
+    MSE_CUDA_TRY(cudaMemsetAsync(ix->overflow.p, 0, sizeof(int32_t) * size_t(B), st));
+    MSE_CUDA_TRY(cudaMemsetAsync(ix->misc.p, 0, 64, st));
+    if (use_tau) {
+        MSE_CUDA_TRY(cudaMemsetAsync(ix->hist.p, 0, sizeof(uint32_t) * size_t(B) * kHistBins, st));
+        MSE_CUDA_TRY(cudaMemsetAsync(ix->maxbin.p, 0, sizeof(uint32_t) * size_t(B), st));
+    }
+
+    Bm25Work w{};
+    w.q_off = d_q_off; w.q_term = d_q_term; w.q_tf = d_q_tf;
+    w.slot_w = ix->slot_w.as<float>(); w.slot_base = ix->slot_base.as<int64_t>(); w.seg = ix->seg.as<uint32_t>();
+    w.tau = ix->tau.as<uint32_t>(); w.hist = ix->hist.as<uint32_t>(); w.maxbin = ix->maxbin.as<uint32_t>();
+    w.cand = ix->cand.as<uint64_t>(); w.cand_count = ix->cand_count.as<int32_t>(); w.overflow = ix->overflow.as<int32_t>();
+    w.item_counter = ix->misc.as<int32_t>();
+    w.stats = reinterpret_cast<unsigned long long*>(ix->misc.as<char>() + 16);
+    w.n_queries = B; w.n_slots = S; w.n_ranges = n_ranges; w.range_docs = R; w.queries_per_item = qpi;
+    w.cap = cap; w.top_k = top_k; w.min_key = float_to_key(min_score + 0.0f); w.use_tau = use_tau;
+
+    timer_begin(ix, T_PREPARE, st);
+    {
+        const int64_t n = std::max<int64_t>(int64_t(S) * nb, B);
+        const int threads = 256;
+        bm25_prepare_kernel<<<unsigned((n + threads - 1) / threads), threads, 0, st>>>(bm, w);
+        MSE_CUDA_TRY(cudaGetLastError());
+    }
+    timer_end(ix, T_PREPARE, st);
+
+    const size_t smem = sizeof(float) * 2 * size_t(R);
+    MSE_CUDA_TRY(cudaFuncSetAttribute(bm25_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    int per_sm = 0;
+    MSE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bm25_score_kernel, kBm25Threads, smem));
+    if (per_sm < 1) { set_error("bm25 score kernel does not fit (R=%d)", R); return MSE_ERR_INVALID; }
+    const int chunks = (B + qpi - 1) / qpi;
+    const int64_t n_items = int64_t(n_ranges) * chunks;
+    const int grid = int(std::min<int64_t>(n_items, int64_t(per_sm) * ix->sm_count));
+    timer_begin(ix, T_SCORE, st);
+    bm25_score_kernel<<<grid, kBm25Threads, smem, st>>>(bm, w);
+    MSE_CUDA_TRY(cudaGetLastError());
+    timer_end(ix, T_SCORE, st);
+
+    ListLoader ld{w.cand, w.cand_count, int64_t(cap), cap};
+    timer_begin(ix, T_SELECT, st);
+    topk_select_kernel<ListLoader><<<B, kSelectThreads, 0, st>>>(ld, top_k, d_out_doc, d_out_score, d_out_count,
+                                                                mark_overflow ? w.overflow : nullptr);
+    MSE_CUDA_TRY(cudaGetLastError());
+    timer_end(ix, T_SELECT, st);
+    ix->stats[3] = n_ranges;
+    ix->stats[4] = grid;
+    return MSE_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+const char* mse_last_error(void) { return g_err; }
+int mse_abi_version(void) { return MSE_ABI_VERSION; }
+
+int mse_device_count(int* n) {
+    if (!n) { set_error("null argument"); return MSE_ERR_INVALID; }
+    cudaError_t e = cudaGetDeviceCount(n);
+    if (e != cudaSuccess) {
+        *n = 0;
+        set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        return MSE_ERR_CUDA;
+    }
+    return MSE_OK;
+}
+
+int mse_index_create(int device, mse_index** out) {
+    if (!out) { set_error("null argument"); return MSE_ERR_INVALID; }
+    *out = nullptr;
+    int n = 0;
+    int rc = mse_device_count(&n);
+    if (rc) return rc;
+    if (n == 0) { set_error("no CUDA device: this library has no CPU fallback"); return MSE_ERR_CUDA; }
+    MSE_REQUIRE(device >= 0 && device < n, "device %d out of range (have %d)", device, n);
+    DeviceGuard g(device);
+    cudaDeviceProp prop;
+    MSE_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) { set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); return MSE_ERR_CUDA; }
+    mse_index* ix = new mse_index();
+    ix->device = device;
+    ix->sm_count = prop.multiProcessorCount;
+    ix->ev_ok = true;
+    for (int t = 0; t < kNumTimers; ++t)
+        for (int j = 0; j < 2; ++j)
+            if (cudaEventCreate(&ix->ev[t][j]) != cudaSuccess) ix->ev_ok = false;
+    *out = ix;
+    return MSE_OK;
+}
+
+int mse_index_destroy(mse_index* ix) {
+    if (!ix) return MSE_OK;
+    {
+        DeviceGuard g(ix->device);
+        cudaDeviceSynchronize();
+        DevBuf* all[] = {&ix->term_off, &ix->post_doc, &ix->post_tf, &ix->doc_norm, &ix->idf, &ix->emb, &ix->doc_chunk_off,
+                         &ix->q_off, &ix->q_term, &ix->q_tf, &ix->slot_w, &ix->slot_base, &ix->seg, &ix->tau, &ix->hist,
+                         &ix->maxbin, &ix->cand, &ix->cand_count, &ix->overflow, &ix->misc, &ix->o_doc, &ix->o_score,
+                         &ix->o_count, &ix->best, &ix->dq};
+        for (DevBuf* b : all) b->release();
+        for (auto& b : ix->r_in) b.release();
+        for (auto& b : ix->r_out) b.release();
+        for (auto& b : ix->m_in) b.release();
+        for (auto& b : ix->fb_q) b.release();
+        for (auto& b : ix->fb_out) b.release();
+        if (ix->ev_ok)
+            for (int t = 0; t < kNumTimers; ++t)
+                for (int j = 0; j < 2; ++j) cudaEventDestroy(ix->ev[t][j]);
+    }
+    delete ix;
+    return MSE_OK;
+}
+
+int mse_index_set_option(mse_index* ix, const char* name, int64_t value) {
+    if (!ix || !name) { set_error("null argument"); return MSE_ERR_INVALID; }
+    std::lock_guard<std::mutex> lk(ix->mu);
+    if (!strcmp(name, "bm25_range_docs")) ix->opt_range_docs = value;
+    else if (!strcmp(name, "bm25_queries_per_item")) ix->opt_qpi = value;
+    else if (!strcmp(name, "bm25_cand_cap")) ix->opt_cand_cap = value;
+    else if (!strcmp(name, "bm25_use_tau")) ix->opt_use_tau = value;
+    else if (!strcmp(name, "dense_scan_ctas_per_sm")) ix->opt_scan_ctas = value;
+    else if (!strcmp(name, "reset_timers")) {
+        for (int t = 0; t < kNumTimers; ++t) { ix->t_ms[t] = 0; ix->t_n[t] = 0; }
+    } else { set_error("unknown option '%s'", name); return MSE_ERR_INVALID; }
+    return MSE_OK;
+}
+
+int mse_kernel_time(mse_index* ix, int kernel, double* total_ms, int64_t* launches) {
+    if (!ix || kernel < 0 || kernel >= kNumTimers) { set_error("bad argument"); return MSE_ERR_INVALID; }
+    std::lock_guard<std::mutex> lk(ix->mu);
+    if (total_ms) *total_ms = ix->t_ms[kernel];
+    if (launches) *launches = ix->t_n[kernel];
+    return MSE_OK;
+}
+
+int mse_bm25_last_stats(mse_index* ix, int64_t stats[8]) {
+    if (!ix || !stats) { set_error("null argument"); return MSE_ERR_INVALID; }
+    std::lock_guard<std::mutex> lk(ix->mu);
+    memcpy(stats, ix->stats, sizeof(ix->stats));
+    return MSE_OK;
+}
+
+// ---- BM25 -------------------------------------------------------------------------------------------
+int mse_bm25_load(mse_index* ix, int64_t n_terms, int64_t n_docs, int64_t doc_base,
+                  const int64_t* term_off, const int32_t* post_doc, const int32_t* post_tf,
+                  const int32_t* doc_len, const float* idf, float avgdl, float k1, float b, int where) {
+    if (!ix) { set_error("null index"); return MSE_ERR_INVALID; }
+    MSE_REQUIRE(n_terms >= 0 && n_docs >= 0 && n_docs < (int64_t(1) << 31) && doc_base >= 0 &&
+                doc_base + n_docs < (int64_t(1) << 31), "n_terms/n_docs/doc_base out of range");
+    MSE_REQUIRE(term_off && doc_len && idf, "null array");
+    MSE_REQUIRE(avgdl > 0.f, "avgdl must be positive (got %g)", double(avgdl));
+    MSE_REQUIRE(where == MSE_HOST || where == MSE_DEVICE, "bad `where`");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = 0;
+    ix->has_bm25 = false;
+    ix->h_term_off.assign(size_t(n_terms) + 1, 0);
+    MSE_CUDA_TRY(cudaMemcpy(ix->h_term_off.data(), term_off, sizeof(int64_t) * (n_terms + 1),
+                            where == MSE_HOST ? cudaMemcpyHostToHost : cudaMemcpyDeviceToHost));
+    MSE_REQUIRE(ix->h_term_off[0] == 0, "term_off[0] must be 0");
+    const int64_t P = ix->h_term_off[n_terms];
+    MSE_REQUIRE(P >= 0 && P < (int64_t(1) << 32), "posting count out of range");
+    for (int64_t t = 0; t < n_terms; ++t)
+        MSE_REQUIRE(ix->h_term_off[t + 1] >= ix->h_term_off[t], "term_off not monotone at %lld", (long long)t);
+    MSE_REQUIRE(P == 0 || (post_doc && post_tf), "null posting arrays");
+    int rc;
+    if ((rc = ix->term_off.ensure(sizeof(int64_t) * (n_terms + 1)))) return rc;
+    if ((rc = ix->post_doc.ensure(sizeof(int32_t) * std::max<int64_t>(P, 1)))) return rc;
+    if ((rc = ix->post_tf.ensure(sizeof(int32_t) * std::max<int64_t>(P, 1)))) return rc;
+    if ((rc = ix->doc_norm.ensure(sizeof(float) * std::max<int64_t>(n_docs, 1)))) return rc;
+    if ((rc = ix->idf.ensure(sizeof(float) * std::max<int64_t>(n_terms, 1)))) return rc;
+    DevBuf d_len;
+    if ((rc = d_len.ensure(sizeof(int32_t) * std::max<int64_t>(n_docs, 1)))) return rc;
+    if ((rc = copy_in(ix->term_off.p, term_off, sizeof(int64_t) * (n_terms + 1), where, st))) return rc;
+    if ((rc = copy_in(ix->post_doc.p, post_doc, sizeof(int32_t) * P, where, st))) return rc;
+    if ((rc = copy_in(ix->post_tf.p, post_tf, sizeof(int32_t) * P, where, st))) return rc;
+    if ((rc = copy_in(d_len.p, doc_len, sizeof(int32_t) * n_docs, where, st))) return rc;
+    // idf: canonicalise -0.0 -> +0.0 (`idf_score or 0.0`, bm25_indexer.py:426)
+    std::vector<float> h_idf;
+    h_idf.resize(size_t(std::max<int64_t>(n_terms, 1)));
+    MSE_CUDA_TRY(cudaMemcpy(h_idf.data(), idf, sizeof(float) * n_terms, where == MSE_HOST ? cudaMemcpyHostToHost : cudaMemcpyDeviceToHost));
+    for (auto& v : h_idf) v = v + 0.0f;
+    MSE_CUDA_TRY(cudaMemcpyAsync(ix->idf.p, h_idf.data(), sizeof(float) * n_terms, cudaMemcpyHostToDevice, st));
+    if (n_docs > 0) {
+        bm25_norm_kernel<<<unsigned((n_docs + 255) / 256), 256, 0, st>>>(d_len.as<int32_t>(), ix->doc_norm.as<float>(), n_docs,
+                                                                        double(k1), double(b), double(avgdl));
+        MSE_CUDA_TRY(cudaGetLastError());
+    }
+    if ((rc = ix->misc.ensure(64))) return rc;
+    MSE_CUDA_TRY(cudaMemsetAsync(ix->misc.p, 0, 64, st));
+    if (n_terms > 0) {
+        bm25_validate_kernel<<<unsigned((n_terms + 7) / 8), 256, 0, st>>>(ix->term_off.as<int64_t>(), ix->post_doc.as<int32_t>(),
+                                                                         ix->post_tf.as<int32_t>(), n_terms, n_docs, ix->misc.as<int32_t>());
+        MSE_CUDA_TRY(cudaGetLastError());
+    }
+    int32_t bad = 0;
+    MSE_CUDA_TRY(cudaMemcpyAsync(&bad, ix->misc.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    MSE_CUDA_TRY(cudaStreamSynchronize(st));
+    d_len.release();
+    MSE_REQUIRE(bad == 0, "malformed postings (code %d): doc ids must be strictly ascending inside a term, within [0,n_docs), tf >= 1", bad);
+    ix->bm.term_off = ix->term_off.as<int64_t>();
+    ix->bm.post_doc = ix->post_doc.as<int32_t>();
+    ix->bm.post_tf = ix->post_tf.as<int32_t>();
+    ix->bm.doc_norm = ix->doc_norm.as<float>();
+    ix->bm.idf = ix->idf.as<float>();
+    ix->bm.n_terms = n_terms; ix->bm.n_docs = n_docs; ix->bm.n_postings = P;
+    ix->bm.doc_base = uint32_t(doc_base); ix->bm.k1 = k1;
+    ix->has_bm25 = true;
+    return MSE_OK;
+}
+
+int mse_bm25_search_batch(mse_index* ix, int32_t B, const int32_t* q_off, const int32_t* q_term, const int32_t* q_tf,
+                          int32_t top_k, float min_score, int32_t* out_doc, float* out_score, int32_t* out_count,
+                          int where, void* stream) {
+    if (!ix) { set_error("null index"); return MSE_ERR_INVALID; }
+    MSE_REQUIRE(where == MSE_HOST || where == MSE_DEVICE, "bad `where`");
+    MSE_REQUIRE(B >= 0 && q_off && out_count && (B == 0 || (out_doc && out_score)), "null/negative argument");
+    if (top_k < 1 || top_k > MSE_MAX_TOPK) { set_error("top_k %d outside [1, %d]", top_k, MSE_MAX_TOPK); return MSE_ERR_UNSUPPORTED; }
+    MSE_REQUIRE(min_score == min_score, "min_score is NaN");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    if (!ix->has_bm25) { set_error("mse_bm25_load has not been called"); return MSE_ERR_STATE; }
+    if (B == 0) return MSE_OK;
+    DeviceGuard g(ix->device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int rc;
+
+    // query CSR on the host (needed for the slot count and for the rare overflow re-run)
+    std::vector<int32_t> h_off;
+    h_off.resize(size_t(B) + 1);
+    if (where == MSE_HOST) memcpy(h_off.data(), q_off, sizeof(int32_t) * (B + 1));
+    else {
+        MSE_CUDA_TRY(cudaMemcpyAsync(h_off.data(), q_off, sizeof(int32_t) * (B + 1), cudaMemcpyDeviceToHost, st));
+        MSE_CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    MSE_REQUIRE(h_off[0] == 0, "q_off[0] must be 0");
+    for (int i = 0; i < B; ++i) MSE_REQUIRE(h_off[i + 1] >= h_off[i], "q_off not monotone at %d", i);
+    const int32_t S = h_off[B];
+    MSE_REQUIRE(S == 0 || (q_term && q_tf), "null query arrays");
+
+    const int32_t *d_off = q_off, *d_term = q_term, *d_tf = q_tf;
+    int32_t* d_doc = out_doc; float* d_score = out_score; int32_t* d_count = out_count;
+    if (where == MSE_HOST) {
+        if ((rc = ix->q_off.ensure(sizeof(int32_t) * (B + 1)))) return rc;
+        if ((rc = ix->q_term.ensure(sizeof(int32_t) * std::max(S, 1)))) return rc;
+        if ((rc = ix->q_tf.ensure(sizeof(int32_t) * std::max(S, 1)))) return rc;
+        if ((rc = ix->o_doc.ensure(sizeof(int32_t) * size_t(B) * top_k))) return rc;
+        if ((rc = ix->o_score.ensure(sizeof(float) * size_t(B) * top_k))) return rc;
+        if ((rc = ix->o_count.ensure(sizeof(int32_t) * size_t(B)))) return rc;
+        if ((rc = copy_in(ix->q_off.p, q_off, sizeof(int32_t) * (B + 1), where, st))) return rc;
+        if ((rc = copy_in(ix->q_term.p, q_term, sizeof(int32_t) * S, where, st))) return rc;
+        if ((rc = copy_in(ix->q_tf.p, q_tf, sizeof(int32_t) * S, where, st))) return rc;
+        d_off = ix->q_off.as<int32_t>(); d_term = ix->q_term.as<int32_t>(); d_tf = ix->q_tf.as<int32_t>();
+        d_doc = ix->o_doc.as<int32_t>(); d_score = ix->o_score.as<float>(); d_count = ix->o_count.as<int32_t>();
+    }
+
+    // candidate-list capacity: bounded workspace; overflowing queries are re-run below
+    int64_t cap = ix->opt_cand_cap > 0 ? ix->opt_cand_cap : std::max<int64_t>(16 * int64_t(top_k), 16384);
+    cap = std::min<int64_t>(cap, std::max<int64_t>(ix->bm.n_docs, 1));
+    const int64_t budget = int64_t(2) << 30;
+    cap = std::max<int64_t>(std::min<int64_t>(cap, budget / (8 * int64_t(B))), std::min<int64_t>(ix->bm.n_docs, int64_t(top_k)));
+    cap = std::max<int64_t>(cap, 1);
+    const int use_tau = ix->opt_use_tau ? 1 : 0;
+
+    if ((rc = bm25_run(ix, B, d_off, d_term, d_tf, S, top_k, min_score, int32_t(cap), use_tau, d_doc, d_score, d_count, true, st))) return rc;
+
+    std::vector<int32_t> h_cnt, h_ovf;
+    h_cnt.resize(size_t(B));
+    h_ovf.resize(size_t(B));
+    unsigned long long h_post = 0;
+    MSE_CUDA_TRY(cudaMemcpyAsync(h_cnt.data(), ix->cand_count.p, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
+    MSE_CUDA_TRY(cudaMemcpyAsync(h_ovf.data(), ix->overflow.p, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
+    MSE_CUDA_TRY(cudaMemcpyAsync(&h_post, ix->misc.as<char>() + 16, sizeof(h_post), cudaMemcpyDeviceToHost, st));
+    MSE_CUDA_TRY(cudaStreamSynchronize(st));
+    timers_collect(ix);
+    int64_t emitted = 0;
+    std::vector<int32_t> redo;
+    for (int i = 0; i < B; ++i) { emitted += h_cnt[i]; if (h_ovf[i]) redo.push_back(i); }
+    ix->stats[0] = int64_t(h_post);
+    ix->stats[1] = emitted;
+    ix->stats[2] = int64_t(redo.size());
+
+    if (!redo.empty()) {
+        // Unbounded path: capacity == n_docs cannot overflow.  Sub-batches sized to the budget.
+        std::vector<int32_t> h_term, h_tf;
+        h_term.resize(size_t(std::max(S, 1)));
+        h_tf.resize(size_t(std::max(S, 1)));
+        MSE_CUDA_TRY(cudaMemcpy(h_term.data(), d_term, sizeof(int32_t) * S, cudaMemcpyDeviceToHost));
+        MSE_CUDA_TRY(cudaMemcpy(h_tf.data(), d_tf, sizeof(int32_t) * S, cudaMemcpyDeviceToHost));
+        const int64_t fcap = std::max<int64_t>(ix->bm.n_docs, 1);
+        const int sub = int(std::max<int64_t>(1, std::min<int64_t>(int64_t(redo.size()), budget / (8 * fcap))));
+        for (size_t a = 0; a < redo.size(); a += sub) {
+            const int nb = int(std::min<size_t>(sub, redo.size() - a));
+            std::vector<int32_t> so(size_t(nb) + 1, 0), stm, stf;
+            for (int j = 0; j < nb; ++j) {
+                const int qq = redo[a + j];
+                for (int s = h_off[qq]; s < h_off[qq + 1]; ++s) { stm.push_back(h_term[s]); stf.push_back(h_tf[s]); }
+                so[j + 1] = int32_t(stm.size());
+            }
+            const int32_t SS = so[nb];
+            if ((rc = ix->fb_q[0].ensure(sizeof(int32_t) * (nb + 1)))) return rc;
+            if ((rc = ix->fb_q[1].ensure(sizeof(int32_t) * std::max(SS, 1)))) return rc;
+            if ((rc = ix->fb_q[2].ensure(sizeof(int32_t) * std::max(SS, 1)))) return rc;
+            if ((rc = ix->fb_out[0].ensure(sizeof(int32_t) * size_t(nb) * top_k))) return rc;
+            if ((rc = ix->fb_out[1].ensure(sizeof(float) * size_t(nb) * top_k))) return rc;
+            if ((rc = ix->fb_out[2].ensure(sizeof(int32_t) * size_t(nb)))) return rc;
+            MSE_CUDA_TRY(cudaMemcpyAsync(ix->fb_q[0].p, so.data(), sizeof(int32_t) * (nb + 1), cudaMemcpyHostToDevice, st));
+            MSE_CUDA_TRY(cudaMemcpyAsync(ix->fb_q[1].p, stm.data(), sizeof(int32_t) * SS, cudaMemcpyHostToDevice, st));
+            MSE_CUDA_TRY(cudaMemcpyAsync(ix->fb_q[2].p, stf.data(), sizeof(int32_t) * SS, cudaMemcpyHostToDevice, st));
+            if ((rc = bm25_run(ix, nb, ix->fb_q[0].as<int32_t>(), ix->fb_q[1].as<int32_t>(), ix->fb_q[2].as<int32_t>(), SS, top_k,
+                               min_score, int32_t(fcap), 0, ix->fb_out[0].as<int32_t>(), ix->fb_out[1].as<float>(),
+                               ix->fb_out[2].as<int32_t>(), false, st))) return rc;
+            for (int j = 0; j < nb; ++j) {
+                const int qq = redo[a + j];
+                MSE_CUDA_TRY(cudaMemcpyAsync(d_doc + size_t(qq) * top_k, ix->fb_out[0].as<int32_t>() + size_t(j) * top_k,
+                                             sizeof(int32_t) * top_k, cudaMemcpyDeviceToDevice, st));
+                MSE_CUDA_TRY(cudaMemcpyAsync(d_score + size_t(qq) * top_k, ix->fb_out[1].as<float>() + size_t(j) * top_k,
+                                             sizeof(float) * top_k, cudaMemcpyDeviceToDevice, st));
+                MSE_CUDA_TRY(cudaMemcpyAsync(d_count + qq, ix->fb_out[2].as<int32_t>() + j, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+            }
+            MSE_CUDA_TRY(cudaStreamSynchronize(st));     // staging buffers are reused by the next sub-batch
+            for (int t = 0; t < kNumTimers; ++t) ix->t_pending[t] = false;   // timers describe the main pass only
+        }
+    }
+
+    if (where == MSE_HOST) {
+        MSE_CUDA_TRY(cudaMemcpyAsync(out_doc, d_doc, sizeof(int32_t) * size_t(B) * top_k, cudaMemcpyDeviceToHost, st));
+        MSE_CUDA_TRY(cudaMemcpyAsync(out_score, d_score, sizeof(float) * size_t(B) * top_k, cudaMemcpyDeviceToHost, st));
+        MSE_CUDA_TRY(cudaMemcpyAsync(out_count, d_count, sizeof(int32_t) * size_t(B), cudaMemcpyDeviceToHost, st));
+        MSE_CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    return MSE_OK;
+}
+
+// ---- dense ------------------------------------------------------------------------------------------
+int mse_dense_load(mse_index* ix, int64_t n_chunks, int64_t n_docs, int64_t doc_base, int64_t chunk_base,
+                   const void* emb, int emb_is_bf16, const int64_t* doc_chunk_off, int where) {
+    if (!ix) { set_error("null index"); return MSE_ERR_INVALID; }
+    MSE_REQUIRE(n_chunks >= 0 && n_docs >= 0 && n_docs < (int64_t(1) << 31) && doc_base >= 0 && chunk_base >= 0 &&
+                doc_base + n_docs < (int64_t(1) << 31), "size arguments out of range");
+    MSE_REQUIRE(doc_chunk_off && (n_chunks == 0 || emb), "null array");
+    MSE_REQUIRE(where == MSE_HOST || where == MSE_DEVICE, "bad `where`");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = 0;
+    ix->has_dense = false;
+    std::vector<int64_t> h_off;
+    h_off.resize(size_t(n_docs) + 1);
+    MSE_CUDA_TRY(cudaMemcpy(h_off.data(), doc_chunk_off, sizeof(int64_t) * (n_docs + 1),
+                            where == MSE_HOST ? cudaMemcpyHostToHost : cudaMemcpyDeviceToHost));
+    MSE_REQUIRE(h_off[0] == 0 && h_off[n_docs] == n_chunks, "doc_chunk_off must start at 0 and end at n_chunks");
+    for (int64_t d = 0; d < n_docs; ++d) MSE_REQUIRE(h_off[d + 1] >= h_off[d], "doc_chunk_off not monotone at %lld", (long long)d);
+    int rc;
+    const size_t n_el = size_t(n_chunks) * kDim;
+    if ((rc = ix->emb.ensure(sizeof(__nv_bfloat16) * std::max<size_t>(n_el, 8)))) return rc;
+    if ((rc = ix->doc_chunk_off.ensure(sizeof(int64_t) * (n_docs + 1)))) return rc;
+    MSE_CUDA_TRY(cudaMemcpyAsync(ix->doc_chunk_off.p, h_off.data(), sizeof(int64_t) * (n_docs + 1), cudaMemcpyHostToDevice, st));
+    if (n_el) {
+        if (emb_is_bf16) {
+            if ((rc = copy_in(ix->emb.p, emb, sizeof(__nv_bfloat16) * n_el, where, st))) return rc;
+        } else {
+            // convert in slabs so a host fp32 table never needs a full device copy
+            const size_t slab = size_t(1) << 26;   // elements
+            DevBuf tmp;
+            const float* src = static_cast<const float*>(emb);
+            if (where == MSE_HOST && (rc = tmp.ensure(sizeof(float) * std::min(slab, n_el)))) return rc;
+            for (size_t a = 0; a < n_el; a += slab) {
+                const size_t n = std::min(slab, n_el - a);
+                const float* d_src = src + a;
+                if (where == MSE_HOST) {
+                    MSE_CUDA_TRY(cudaMemcpyAsync(tmp.p, src + a, sizeof(float) * n, cudaMemcpyHostToDevice, st));
+                    d_src = tmp.as<float>();
+                }
+                f32_to_bf16_kernel<<<unsigned((n / 4 + 256) / 256), 256, 0, st>>>(d_src, ix->emb.as<__nv_bfloat16>() + a, int64_t(n));
+                MSE_CUDA_TRY(cudaGetLastError());
+            }
+            MSE_CUDA_TRY(cudaStreamSynchronize(st));
+            tmp.release();
+        }
+    }
+    MSE_CUDA_TRY(cudaStreamSynchronize(st));
+    ix->dn.emb = ix->emb.as<__nv_bfloat16>();
+    ix->dn.doc_chunk_off = ix->doc_chunk_off.as<int64_t>();
+    ix->dn.n_chunks = n_chunks; ix->dn.n_docs = n_docs; ix->dn.doc_base = uint32_t(doc_base); ix->dn.chunk_base = chunk_base;
+    ix->has_dense = true;
+    return MSE_OK;
+}
+
+int mse_dense_scan_batch(mse_index* ix, int32_t B, const float* q, int32_t top_k, int32_t* out_doc, float* out_score,
+                         int32_t* out_count, int where, void* stream) {
+    if (!ix) { set_error("null index"); return MSE_ERR_INVALID; }
+    MSE_REQUIRE(where == MSE_HOST || where == MSE_DEVICE, "bad `where`");
+    MSE_REQUIRE(B >= 0 && out_count && (B == 0 || (q && out_doc && out_score)), "null/negative argument");
+    if (top_k < 1 || top_k > MSE_MAX_TOPK) { set_error("top_k %d outside [1, %d]", top_k, MSE_MAX_TOPK); return MSE_ERR_UNSUPPORTED; }
+    std::lock_guard<std::mutex> lk(ix->mu);
+    if (!ix->has_dense) { set_error("mse_dense_load has not been called"); return MSE_ERR_STATE; }
+    if (B == 0) return MSE_OK;
+    DeviceGuard g(ix->device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const DenseDev& dn = ix->dn;
+    int rc;
+    const float* d_q = q;
+    int32_t* d_doc = out_doc; float* d_score = out_score; int32_t* d_count = out_count;
+    if (where == MSE_HOST) {
+        if ((rc = ix->dq.ensure(sizeof(float) * size_t(B) * kDim))) return rc;
+        if ((rc = ix->o_doc.ensure(sizeof(int32_t) * size_t(B) * top_k))) return rc;
+        if ((rc = ix->o_score.ensure(sizeof(float) * size_t(B) * top_k))) return rc;
+        if ((rc = ix->o_count.ensure(sizeof(int32_t) * size_t(B)))) return rc;
+        if ((rc = copy_in(ix->dq.p, q, sizeof(float) * size_t(B) * kDim, where, st))) return rc;
+        d_q = ix->dq.as<float>(); d_doc = ix->o_doc.as<int32_t>(); d_score = ix->o_score.as<float>(); d_count = ix->o_count.as<int32_t>();
+    }
+    const int64_t D = std::max<int64_t>(dn.n_docs, 1);
+    const int group = int(std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(B, 32), (int64_t(1) << 30) / (4 * D))));
+    if ((rc = ix->best.ensure(sizeof(uint32_t) * size_t(group) * D))) return rc;
+    const int per_sm = ix->opt_scan_ctas > 0 ? int(ix->opt_scan_ctas) : 2;
+    const int grid = per_sm * ix->sm_count;
+    for (int g0 = 0; g0 < B; g0 += group) {
+        const int gn = std::min(group, B - g0);
+        MSE_CUDA_TRY(cudaMemsetAsync(ix->best.p, 0, sizeof(uint32_t) * size_t(gn) * D, st));
+        if (g0 == 0) timer_begin(ix, T_SCAN, st);
+        if (dn.n_chunks > 0) {
+            int b = 0;
+            while (b < gn) {
+                const float* qq = d_q + size_t(g0) * kDim;
+                if (gn - b >= 4) { dense_scan_kernel<4><<<grid, kScanThreads, 0, st>>>(dn, qq, b, ix->best.as<uint32_t>()); b += 4; }
+                else if (gn - b >= 2) { dense_scan_kernel<2><<<grid, kScanThreads, 0, st>>>(dn, qq, b, ix->best.as<uint32_t>()); b += 2; }
+                else { dense_scan_kernel<1><<<grid, kScanThreads, 0, st>>>(dn, qq, b, ix->best.as<uint32_t>()); b += 1; }
+                MSE_CUDA_TRY(cudaGetLastError());
+            }
+        }
+        if (g0 + gn >= B) timer_end(ix, T_SCAN, st);
+        DenseLoader ld{ix->best.as<uint32_t>(), dn.n_docs, dn.doc_base};
+        if (g0 == 0) timer_begin(ix, T_SELECT, st);
+        topk_select_kernel<DenseLoader><<<gn, kSelectThreads, 0, st>>>(ld, top_k, d_doc + size_t(g0) * top_k, d_score + size_t(g0) * top_k,
+                                                                      d_count + g0, nullptr);
+        MSE_CUDA_TRY(cudaGetLastError());
+        if (g0 + gn >= B) timer_end(ix, T_SELECT, st);
+    }
+    if (where == MSE_HOST) {
+        MSE_CUDA_TRY(cudaMemcpyAsync(out_doc, d_doc, sizeof(int32_t) * size_t(B) * top_k, cudaMemcpyDeviceToHost, st));
+        MSE_CUDA_TRY(cudaMemcpyAsync(out_score, d_score, sizeof(float) * size_t(B) * top_k, cudaMemcpyDeviceToHost, st));
+        MSE_CUDA_TRY(cudaMemcpyAsync(out_count, d_count, sizeof(int32_t) * size_t(B), cudaMemcpyDeviceToHost, st));
+    }
+    MSE_CUDA_TRY(cudaStreamSynchronize(st));
+    timers_collect(ix);
+    return MSE_OK;
+}
+
+int mse_rerank_batch(mse_index* ix, int32_t B, const int32_t* cand_off, const int32_t* cand_doc, const float* cand_bm25,
+                     const int32_t* url_group, const float* q, float smoothing, int32_t max_chunks, int32_t max_out,
+                     int32_t* out_doc, float* out_score, float* out_orig, int64_t* out_chunk, int32_t* out_count,
+                     int32_t* out_rows, int where, void* stream) {
+    if (!ix) { set_error("null index"); return MSE_ERR_INVALID; }
+    MSE_REQUIRE(where == MSE_HOST || where == MSE_DEVICE, "bad `where`");
+    MSE_REQUIRE(B >= 0 && cand_off && out_count && out_rows, "null/negative argument");
+    MSE_REQUIRE(B == 0 || (q && out_doc && out_score && out_orig && out_chunk), "null argument");
+    if (max_chunks < 1 || max_chunks > kRerankMaxChunks) { set_error("max_chunks %d outside [1, %d]", max_chunks, kRerankMaxChunks); return MSE_ERR_UNSUPPORTED; }
+    if (max_out < 1 || max_out > kRerankMaxCand) { set_error("max_out %d outside [1, %d]", max_out, kRerankMaxCand); return MSE_ERR_UNSUPPORTED; }
+    MSE_REQUIRE(smoothing >= 0.f && smoothing <= 1.f, "smoothing outside [0,1]");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    if (!ix->has_dense) { set_error("mse_dense_load has not been called"); return MSE_ERR_STATE; }
+    if (B == 0) return MSE_OK;
+    DeviceGuard g(ix->device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int rc;
+    std::vector<int32_t> h_off;
+    h_off.resize(size_t(B) + 1);
+    if (where == MSE_HOST) memcpy(h_off.data(), cand_off, sizeof(int32_t) * (B + 1));
+    else {
+        MSE_CUDA_TRY(cudaMemcpyAsync(h_off.data(), cand_off, sizeof(int32_t) * (B + 1), cudaMemcpyDeviceToHost, st));
+        MSE_CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    MSE_REQUIRE(h_off[0] == 0, "cand_off[0] must be 0");
+    for (int i = 0; i < B; ++i) {
+        MSE_REQUIRE(h_off[i + 1] >= h_off[i], "cand_off not monotone at %d", i);
+        if (h_off[i + 1] - h_off[i] > kRerankMaxCand) { set_error("query %d has %d candidates (max %d)", i, h_off[i + 1] - h_off[i], kRerankMaxCand); return MSE_ERR_UNSUPPORTED; }
+    }
+    const int32_t C = h_off[B];
+    MSE_REQUIRE(C == 0 || (cand_doc && cand_bm25), "null candidate arrays");
+
+    RerankArgs a{};
+    a.smoothing = smoothing; a.max_chunks = max_chunks; a.max_out = max_out;
+    if (where == MSE_HOST) {
+        if ((rc = ix->r_in[0].ensure(sizeof(int32_t) * (B + 1)))) return rc;
+        if ((rc = ix->r_in[1].ensure(sizeof(int32_t) * std::max(C, 1)))) return rc;
+        if ((rc = ix->r_in[2].ensure(sizeof(float) * std::max(C, 1)))) return rc;
+        if ((rc = ix->r_in[3].ensure(sizeof(float) * size_t(B) * kDim))) return rc;
+        if (url_group && (rc = ix->r_in[4].ensure(sizeof(int32_t) * std::max<int64_t>(ix->dn.n_docs, 1)))) return rc;
+        if ((rc = ix->r_out[0].ensure(sizeof(int32_t) * size_t(B) * max_out))) return rc;
+        if ((rc = ix->r_out[1].ensure(sizeof(float) * size_t(B) * max_out))) return rc;
+        if ((rc = ix->r_out[2].ensure(sizeof(float) * size_t(B) * max_out))) return rc;
+        if ((rc = ix->r_out[3].ensure(sizeof(int64_t) * size_t(B) * max_out))) return rc;
+        if ((rc = ix->r_out[4].ensure(sizeof(int32_t) * size_t(B)))) return rc;
+        if ((rc = ix->r_out[5].ensure(sizeof(int32_t) * size_t(B)))) return rc;
+        if ((rc = copy_in(ix->r_in[0].p, cand_off, sizeof(int32_t) * (B + 1), where, st))) return rc;
+        if ((rc = copy_in(ix->r_in[1].p, cand_doc, sizeof(int32_t) * C, where, st))) return rc;
+        if ((rc = copy_in(ix->r_in[2].p, cand_bm25, sizeof(float) * C, where, st))) return rc;
+        if ((rc = copy_in(ix->r_in[3].p, q, sizeof(float) * size_t(B) * kDim, where, st))) return rc;
+        if (url_group && (rc = copy_in(ix->r_in[4].p, url_group, sizeof(int32_t) * ix->dn.n_docs, where, st))) return rc;
+        a.cand_off = ix->r_in[0].as<int32_t>(); a.cand_doc = ix->r_in[1].as<int32_t>(); a.cand_bm25 = ix->r_in[2].as<float>();
+        a.q = ix->r_in[3].as<float>(); a.url_group = url_group ? ix->r_in[4].as<int32_t>() : nullptr;
+        a.out_doc = ix->r_out[0].as<int32_t>(); a.out_score = ix->r_out[1].as<float>(); a.out_orig = ix->r_out[2].as<float>();
+        a.out_chunk = ix->r_out[3].as<int64_t>(); a.out_count = ix->r_out[4].as<int32_t>(); a.out_rows = ix->r_out[5].as<int32_t>();
+    } else {
+        a.cand_off = cand_off; a.cand_doc = cand_doc; a.cand_bm25 = cand_bm25; a.q = q; a.url_group = url_group;
+        a.out_doc = out_doc; a.out_score = out_score; a.out_orig = out_orig; a.out_chunk = out_chunk;
+        a.out_count = out_count; a.out_rows = out_rows;
+    }
+    MSE_CUDA_TRY(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kRerankSmemBytes)));
+    timer_begin(ix, T_RERANK, st);
+    rerank_kernel<<<B, kRerankThreads, kRerankSmemBytes, st>>>(ix->dn, a);
+    MSE_CUDA_TRY(cudaGetLastError());
+    timer_end(ix, T_RERANK, st);
+    if (where == MSE_HOST) {
+        const size_t n = size_t(B) * max_out;
+        MSE_CUDA_TRY(cudaMemcpyAsync(out_doc, a.out_doc, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+        MSE_CUDA_TRY(cudaMemcpyAsync(out_score, a.out_score, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+        MSE_CUDA_TRY(cudaMemcpyAsync(out_orig, a.out_orig, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+        MSE_CUDA_TRY(cudaMemcpyAsync(out_chunk, a.out_chunk, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, st));
+        MSE_CUDA_TRY(cudaMemcpyAsync(out_count, a.out_count, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
+        MSE_CUDA_TRY(cudaMemcpyAsync(out_rows, a.out_rows, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
+    }
+    MSE_CUDA_TRY(cudaStreamSynchronize(st));
+    timers_collect(ix);
+    return MSE_OK;
+}
+
+int mse_topk_merge(mse_index* ix, int32_t B, int32_t n_lists, int32_t list_k, const int32_t* in_doc, const float* in_score,
+                   const int32_t* in_count, int32_t top_k, int32_t* out_doc, float* out_score, int32_t* out_count,
+                   int where, void* stream) {
+    if (!ix) { set_error("null index"); return MSE_ERR_INVALID; }
+    MSE_REQUIRE(where == MSE_HOST || where == MSE_DEVICE, "bad `where`");
+    MSE_REQUIRE(B >= 0 && n_lists >= 1 && list_k >= 1 && in_doc && in_score && in_count && out_doc && out_score && out_count,
+                "null/negative argument");
+    if (top_k < 1 || top_k > MSE_MAX_TOPK) { set_error("top_k %d outside [1, %d]", top_k, MSE_MAX_TOPK); return MSE_ERR_UNSUPPORTED; }
+    std::lock_guard<std::mutex> lk(ix->mu);
+    if (B == 0) return MSE_OK;
+    DeviceGuard g(ix->device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int rc;
+    const size_t n_in = size_t(n_lists) * B * list_k;
+    MergeLoader ld{in_doc, in_score, in_count, n_lists, B, list_k};
+    int32_t* d_doc = out_doc; float* d_score = out_score; int32_t* d_count = out_count;
+    if (where == MSE_HOST) {
+        if ((rc = ix->m_in[0].ensure(sizeof(int32_t) * n_in))) return rc;
+        if ((rc = ix->m_in[1].ensure(sizeof(float) * n_in))) return rc;
+        if ((rc = ix->m_in[2].ensure(sizeof(int32_t) * size_t(n_lists) * B))) return rc;
+        if ((rc = ix->o_doc.ensure(sizeof(int32_t) * size_t(B) * top_k))) return rc;
+        if ((rc = ix->o_score.ensure(sizeof(float) * size_t(B) * top_k))) return rc;
+        if ((rc = ix->o_count.ensure(sizeof(int32_t) * size_t(B)))) return rc;
+        if ((rc = copy_in(ix->m_in[0].p, in_doc, sizeof(int32_t) * n_in, where, st))) return rc;
+        if ((rc = copy_in(ix->m_in[1].p, in_score, sizeof(float) * n_in, where, st))) return rc;
+        if ((rc = copy_in(ix->m_in[2].p, in_count, sizeof(int32_t) * size_t(n_lists) * B, where, st))) return rc;
+        ld.doc = ix->m_in[0].as<int32_t>(); ld.score = ix->m_in[1].as<float>(); ld.count = ix->m_in[2].as<int32_t>();
+        d_doc = ix->o_doc.as<int32_t>(); d_score = ix->o_score.as<float>(); d_count = ix->o_count.as<int32_t>();
+    }
+    topk_select_kernel<MergeLoader><<<B, kSelectThreads, 0, st>>>(ld, top_k, d_doc, d_score, d_count, nullptr);
+    MSE_CUDA_TRY(cudaGetLastError());
+    if (where == MSE_HOST) {
+        MSE_CUDA_TRY(cudaMemcpyAsync(out_doc, d_doc, sizeof(int32_t) * size_t(B) * top_k, cudaMemcpyDeviceToHost, st));
+        MSE_CUDA_TRY(cudaMemcpyAsync(out_score, d_score, sizeof(float) * size_t(B) * top_k, cudaMemcpyDeviceToHost, st));
+        MSE_CUDA_TRY(cudaMemcpyAsync(out_count, d_count, sizeof(int32_t) * size_t(B), cudaMemcpyDeviceToHost, st));
+        MSE_CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    return MSE_OK;
+}
+
+}  // extern "C"

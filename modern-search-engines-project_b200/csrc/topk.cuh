@@ -1,0 +1,193 @@
+// K2 — batched exact top-k selection (one CTA per query).
+//
+// Replaces the full sort + slice of the reference (indexer/bm25_indexer.py:484-485) and the
+// sort_values of the reranker (reranker/reranker_api.py:372).  Elements are 64-bit keys
+// (order-preserving score bits << 32 | ~doc), all distinct, so "largest k keys, descending" is
+// exactly "score descending, ties by ascending doc id" — the order Python's stable sort yields
+// over rows that arrive in ascending doc id.
+//
+// Algorithm per query: (1) one pass computes the count and the common bit prefix of the keys,
+// (2) MSB-first radix select (<= 8-bit digits, shared-memory histogram) starting at the first
+// bit where the keys differ, with early exit as soon as a digit bucket is taken whole,
+// (3) the k survivors are compacted into shared memory and bitonic-sorted.  All traffic after
+// the first pass hits L2 (the candidate lists were just written by the scoring kernel).
+#pragma once
+#include "common.cuh"
+
+namespace mse {
+
+constexpr int kSelectThreads = 512;
+constexpr int kSortCap = MSE_MAX_TOPK;   // survivors sorted in shared memory
+
+struct ListLoader {          // candidate lists written by the scoring kernels
+    const uint64_t* keys;
+    const int32_t* count;
+    int64_t stride;
+    int32_t cap;
+    __device__ __forceinline__ int64_t n(int q) const { int c = count[q]; return c < cap ? c : cap; }
+    __device__ __forceinline__ uint64_t get(int q, int64_t i) const { return keys[int64_t(q) * stride + i]; }
+};
+
+struct DenseLoader {         // per-doc best score keys (0 == document has no chunk)
+    const uint32_t* best;
+    int64_t n_docs;
+    uint32_t doc_base;
+    __device__ __forceinline__ int64_t n(int) const { return n_docs; }
+    __device__ __forceinline__ uint64_t get(int q, int64_t i) const {
+        uint32_t k = best[int64_t(q) * n_docs + i];
+        return k ? make_key64(k, doc_base + uint32_t(i)) : 0ull;
+    }
+};
+
+struct MergeLoader {         // all-gathered per-rank top-k lists, [n_lists][n_queries][list_k]
+    const int32_t* doc;
+    const float* score;
+    const int32_t* count;
+    int32_t n_lists, n_queries, list_k;
+    __device__ __forceinline__ int64_t n(int) const { return int64_t(n_lists) * list_k; }
+    __device__ __forceinline__ uint64_t get(int q, int64_t i) const {
+        int l = int(i / list_k), j = int(i % list_k);
+        int64_t row = int64_t(l) * n_queries + q;
+        if (j >= count[row]) return 0ull;
+        float s = score[row * list_k + j] + 0.0f;
+        return make_key64(float_to_key(s), uint32_t(doc[row * list_k + j]));
+    }
+};
+
+template <class Loader>
+__global__ void __launch_bounds__(kSelectThreads, 2)
+topk_select_kernel(Loader ld, int32_t top_k, int32_t* __restrict__ out_doc, float* __restrict__ out_score,
+                   int32_t* __restrict__ out_count, const int32_t* __restrict__ skip_flag) {
+    constexpr int NT = kSelectThreads;
+    __shared__ uint64_t s_buf[kSortCap];
+    __shared__ int s_hist[256];
+    __shared__ uint64_t s_or[NT / 32], s_and[NT / 32];
+    __shared__ int s_cnt[NT / 32];
+    __shared__ int s_digit, s_above, s_cntd, s_n;
+
+    const int q = blockIdx.x;
+    const int tid = threadIdx.x;
+    if (skip_flag && skip_flag[q]) {            // query re-run elsewhere (capacity overflow)
+        if (tid == 0) out_count[q] = -1;
+        return;
+    }
+    const int64_t n = ld.n(q);
+
+    // ---- pass A: count valid keys, common prefix ------------------------------------------
+    uint64_t vor = 0, vand = ~0ull;
+    int cnt = 0;
+    for (int64_t i = tid; i < n; i += NT) {
+        uint64_t k = ld.get(q, i);
+        if (k) { vor |= k; vand &= k; ++cnt; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        vor |= __shfl_xor_sync(0xffffffffu, vor, o);
+        vand &= __shfl_xor_sync(0xffffffffu, vand, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if (lane_id() == 0) { s_or[warp_id()] = vor; s_and[warp_id()] = vand; s_cnt[warp_id()] = cnt; }
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    vor = 0; vand = ~0ull; int n_valid = 0;
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w) { vor |= s_or[w]; vand &= s_and[w]; n_valid += s_cnt[w]; }
+
+    const int kk = n_valid < top_k ? n_valid : top_k;
+    if (kk == 0) {
+        if (tid == 0) out_count[q] = 0;
+        for (int i = tid; i < top_k; i += NT) { out_doc[int64_t(q) * top_k + i] = -1; out_score[int64_t(q) * top_k + i] = 0.f; }
+        return;
+    }
+
+    // ---- radix select of the kk-th largest key ---------------------------------------------
+    int sel_shift = 0;            // selection criterion: (key >> sel_shift) >= (prefix >> sel_shift)
+    uint64_t prefix = 0;
+    bool select_all = (n_valid <= kk);
+    if (!select_all) {
+        const uint64_t diff = vor ^ vand;                 // != 0: at least two distinct keys
+        int rem = 64 - __clzll((long long)diff);          // number of low bits still undecided
+        prefix = (rem >= 64) ? 0ull : (vand >> rem) << rem;
+        int k_rem = kk;
+        while (true) {
+            const int width = rem < 8 ? rem : 8;
+            const int shift = rem - width;
+            const int hi = shift + width;                 // bits >= hi are decided (== prefix)
+            if (tid < 256) s_hist[tid] = 0;
+            __syncthreads();
+            for (int64_t i = tid; i < n; i += NT) {
+                uint64_t k = ld.get(q, i);
+                if (!k) continue;
+                bool match = (hi >= 64) ? true : (((k ^ prefix) >> hi) == 0);
+                if (match) atomicAdd(&s_hist[int(k >> shift) & ((1 << width) - 1)], 1);
+            }
+            __syncthreads();
+            if (tid < 32) {                               // descending suffix scan over 256 bins
+                int c[8], lane_sum = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { c[j] = s_hist[255 - (8 * tid + j)]; lane_sum += c[j]; }
+                int incl = warp_incl_scan(lane_sum);
+                int run = incl - lane_sum;
+                if (run < k_rem && k_rem <= incl) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (run < k_rem && k_rem <= run + c[j]) { s_digit = 255 - (8 * tid + j); s_above = run; s_cntd = c[j]; }
+                        run += c[j];
+                    }
+                }
+            }
+            __syncthreads();
+            const int d = s_digit, above = s_above, cntd = s_cntd;
+            __syncthreads();
+            k_rem -= above;
+            prefix |= uint64_t(d) << shift;
+            rem = shift;
+            if (cntd == k_rem || rem == 0) { sel_shift = shift; break; }
+        }
+    }
+
+    // ---- compaction of the survivors ---------------------------------------------------------
+    for (int64_t i = tid; i < n; i += NT) {
+        uint64_t k = ld.get(q, i);
+        if (!k) continue;
+        if (select_all || (k >> sel_shift) >= (prefix >> sel_shift)) {
+            int slot = atomicAdd(&s_n, 1);
+            if (slot < kSortCap) s_buf[slot] = k;
+        }
+    }
+    __syncthreads();
+    int m = s_n < kSortCap ? s_n : kSortCap;
+    int P = 1;
+    while (P < m) P <<= 1;
+    for (int i = m + tid; i < P; i += NT) s_buf[i] = 0ull;
+    __syncthreads();
+
+    // ---- bitonic sort, descending --------------------------------------------------------------
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (P >> 1); t += NT) {
+                int i = ((t / j) * 2 * j) + (t % j);
+                int p = i + j;
+                uint64_t a = s_buf[i], b = s_buf[p];
+                bool up = ((i & k) == 0);
+                if ((a < b) == up) { s_buf[i] = b; s_buf[p] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    const int out_n = m < kk ? m : kk;
+    for (int i = tid; i < top_k; i += NT) {
+        int64_t o = int64_t(q) * top_k + i;
+        if (i < out_n) {
+            uint64_t k = s_buf[i];
+            out_doc[o] = int32_t(key64_doc(k));
+            out_score[o] = key_to_float(key64_score_key(k));
+        } else {
+            out_doc[o] = -1;
+            out_score[o] = 0.f;
+        }
+    }
+    if (tid == 0) out_count[q] = out_n;
+}
+
+}  // namespace mse

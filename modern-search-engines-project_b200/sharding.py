@@ -1,0 +1,68 @@
+"""Document-range sharding across the GPUs of one box.
+
+Each rank owns a contiguous range of the dense doc index: all postings and all chunks of its
+documents, with GLOBAL ``idf`` / ``avgdl`` (per-shard statistics would change scores).  A batch is
+scored by every rank against its shard; the only exchange step is an all-gather of the per-rank
+top-k lists (``B*k*8`` bytes per rank, NCCL over NVLink when the tensors are CUDA, gloo on CPU
+tensors in the unit tests) followed by a device-side merge (``mse_topk_merge``) with the same
+ordering rule (score descending, ties to the lower doc id).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+
+
+def all_gather_topk(doc, score, count, group=None):
+    """doc/score [B,k], count [B] (torch tensors, CUDA for NCCL) -> stacked [W,B,k], [W,B,k], [W,B]."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    g_doc = torch.empty((world,) + tuple(doc.shape), dtype=doc.dtype, device=doc.device)
+    g_score = torch.empty((world,) + tuple(score.shape), dtype=score.dtype, device=score.device)
+    g_count = torch.empty((world,) + tuple(count.shape), dtype=count.dtype, device=count.device)
+    for out, t in ((g_doc, doc), (g_score, score), (g_count, count)):
+        if t.is_cuda:
+            dist.all_gather_into_tensor(out, t.contiguous(), group=group)      # one NCCL all-gather over NVLink
+        else:
+            dist.all_gather([out[w] for w in range(world)], t.contiguous(), group=group)   # gloo (CPU tests)
+    return g_doc, g_score, g_count
+
+
+def merge_topk_host(g_doc: np.ndarray, g_score: np.ndarray, g_count: np.ndarray, top_k: int):
+    """Host statement of the merge rule (used by the gloo tests to check the collective plumbing, and
+    as the specification of ``mse_topk_merge``): concatenate valid entries, order by (score desc,
+    doc asc), keep top_k."""
+    W, B, k = g_doc.shape
+    out_doc = np.full((B, top_k), -1, dtype=np.int32)
+    out_score = np.zeros((B, top_k), dtype=np.float32)
+    out_count = np.zeros(B, dtype=np.int32)
+    for q in range(B):
+        d = np.concatenate([g_doc[w, q, :g_count[w, q]] for w in range(W)])
+        s = np.concatenate([g_score[w, q, :g_count[w, q]] for w in range(W)])
+        order = np.lexsort((d, -s.astype(np.float64)))[:top_k]
+        n = len(order)
+        out_doc[q, :n], out_score[q, :n], out_count[q] = d[order], s[order], n
+    return out_doc, out_score, out_count
+
+
+class ShardedSearcher:
+    """Wraps a per-rank ``NativeIndex`` loaded with this rank's doc range."""
+
+    def __init__(self, native, rank: int, world: int, group=None):
+        self.native, self.rank, self.world, self.group = native, rank, world, group
+
+    def _merge(self, doc, score, count, top_k):
+        if self.world == 1:
+            return doc, score, count
+        g_doc, g_score, g_count = all_gather_topk(doc, score, count, self.group)
+        return self.native.topk_merge(g_doc, g_score, g_count, top_k)
+
+    def bm25_search(self, q_off, q_term, q_tf, top_k: int, min_score: float = 0.0):
+        doc, score, count = self.native.bm25_search(q_off, q_term, q_tf, top_k, min_score)
+        return self._merge(doc, score, count, top_k)
+
+    def dense_scan(self, q, top_k: int):
+        doc, score, count = self.native.dense_scan(q, top_k)
+        return self._merge(doc, score, count, top_k)

@@ -1,0 +1,239 @@
+"""Index store adapters: read the reference's table layout into arrays.
+
+The reference keeps everything in one DuckDB file (``config.py:3``): ``urlsDB``
+(``crawler/databaseManagement.py:18-51``), the four ``bm25_*`` tables
+(``indexer/bm25_indexer.py:82-128``) and ``chunks_optimized`` / ``embeddings``
+(``indexer/embedder.py:31-52``).  ``SqlStore`` runs the load queries against any connection
+that offers ``execute(sql, params).fetchall()`` — a real ``duckdb`` connection when that module is
+importable, or ``sqlite3`` (the SQL used here is portable).  ``ArrayStore`` wraps arrays that
+are already in memory (synthetic corpora).
+"""
+from __future__ import annotations
+
+import os
+import sqlite3
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+
+@dataclass
+class Bm25Tables:
+    """CSR-by-term view of bm25_term_freq + the per-doc / per-term / corpus statistics."""
+    terms: List[str]
+    term_off: np.ndarray        # int64 [V+1]
+    post_doc: np.ndarray        # int32 [P] dense doc index
+    post_tf: np.ndarray         # int32 [P]
+    doc_ids: np.ndarray         # int64 [N] ascending urlsDB ids
+    doc_len: np.ndarray         # int32 [N]
+    idf: np.ndarray             # float32 [V]  idf_score verbatim
+    total_freq: np.ndarray      # int64 [V]
+    avgdl: float
+    total_docs: float
+
+
+@dataclass
+class DenseTables:
+    emb: np.ndarray             # float32 (or torch bf16) [n_chunks, 768]
+    chunk_ids: np.ndarray       # int64 [n_chunks] ascending, doc-contiguous
+    doc_chunk_off: np.ndarray   # int64 [N+1] over the same dense doc index as Bm25Tables.doc_ids
+
+
+class SqlStore:
+    def __init__(self, conn, owns: bool = False):
+        self.conn = conn
+        self._owns = owns
+
+    # -- helpers
+    def _all(self, sql, params=()):
+        return self.conn.execute(sql, list(params)).fetchall()
+
+    def has_table(self, name: str) -> bool:
+        try:
+            self.conn.execute(f"SELECT 1 FROM {name} LIMIT 1").fetchall()
+            return True
+        except Exception:
+            return False
+
+    # -- BM25 tables
+    def load_bm25(self, doc_ids: Optional[np.ndarray] = None) -> Bm25Tables:
+        stats = dict(self._all("SELECT stat_name, stat_value FROM bm25_corpus_stats"))
+        trows = self._all("SELECT term, doc_freq, total_freq, idf_score FROM bm25_term_stats ORDER BY term")
+        drows = self._all("SELECT doc_id, doc_length FROM bm25_doc_stats ORDER BY doc_id")
+        terms = [r[0] for r in trows]
+        ids = np.asarray([r[0] for r in drows], dtype=np.int64)
+        if doc_ids is not None:          # unified dense index (docs without tokens get length 0)
+            all_ids = np.union1d(np.asarray(doc_ids, dtype=np.int64), ids)
+        else:
+            all_ids = ids
+        doc_len = np.zeros(len(all_ids), dtype=np.int32)
+        doc_len[np.searchsorted(all_ids, ids)] = np.asarray([r[1] for r in drows], dtype=np.int32)
+        # sort in numpy rather than ORDER BY term: python's str order == the order of `terms`
+        prows = self._all("SELECT term, doc_id, freq FROM bm25_term_freq")
+        tix = {t: i for i, t in enumerate(terms)}
+        pt = np.asarray([tix[r[0]] for r in prows], dtype=np.int64)
+        pd_ = np.searchsorted(all_ids, np.asarray([r[1] for r in prows], dtype=np.int64)).astype(np.int64)
+        pf = np.asarray([r[2] for r in prows], dtype=np.int32)
+        order = np.lexsort((pd_, pt))
+        term_off = np.zeros(len(terms) + 1, dtype=np.int64)
+        np.add.at(term_off, pt + 1, 1)
+        term_off = np.cumsum(term_off)
+        idf = np.asarray([(r[3] if r[3] is not None else 0.0) for r in trows], dtype=np.float32)
+        return Bm25Tables(terms, term_off, pd_[order].astype(np.int32), pf[order], all_ids, doc_len, idf,
+                          np.asarray([r[2] for r in trows], dtype=np.int64),
+                          float(np.float32(stats.get("avg_doc_length", 1.0))), float(np.float32(stats.get("total_docs", 1))))
+
+    # -- dense tables
+    def load_dense(self, doc_ids: np.ndarray) -> DenseTables:
+        rows = self._all("SELECT c.doc_id, c.chunk_id, e.embedding FROM chunks_optimized c "
+                         "JOIN embeddings e ON c.chunk_id = e.chunk_id ORDER BY c.doc_id, c.chunk_id")
+        doc_ids = np.asarray(doc_ids, dtype=np.int64)
+        cd = np.asarray([r[0] for r in rows], dtype=np.int64)
+        keep = np.isin(cd, doc_ids)
+        chunk_ids = np.asarray([r[1] for r in rows], dtype=np.int64)[keep]
+        emb = np.empty((int(keep.sum()), 768), dtype=np.float32)
+        j = 0
+        for r, k in zip(rows, keep):
+            if k:
+                v = r[2]
+                emb[j] = np.frombuffer(v, dtype=np.float32) if isinstance(v, (bytes, memoryview)) else np.asarray(v, dtype=np.float32)
+                j += 1
+        counts = np.bincount(np.searchsorted(doc_ids, cd[keep]), minlength=len(doc_ids))
+        off = np.zeros(len(doc_ids) + 1, dtype=np.int64)
+        off[1:] = np.cumsum(counts)
+        return DenseTables(emb, chunk_ids, off)
+
+    # -- urlsDB
+    def all_doc_ids(self) -> np.ndarray:
+        return np.asarray([r[0] for r in self._all("SELECT id FROM urlsDB ORDER BY id")], dtype=np.int64)
+
+    def urls(self, ids: Optional[Sequence[int]] = None) -> Dict[int, str]:
+        if ids is None:
+            return {int(r[0]): r[1] for r in self._all("SELECT id, url FROM urlsDB")}
+        return {int(k): v[0] for k, v in self._fetch_by_ids("url", ids).items()}
+
+    def _fetch_by_ids(self, cols: str, ids: Sequence[int], chunk: int = 900) -> Dict[int, tuple]:
+        out: Dict[int, tuple] = {}
+        ids = [int(i) for i in ids]
+        for a in range(0, len(ids), chunk):
+            part = ids[a:a + chunk]
+            ph = ",".join("?" for _ in part)
+            for r in self._all(f"SELECT id, {cols} FROM urlsDB WHERE id IN ({ph})", part):
+                out[int(r[0])] = tuple(r[1:])
+        return out
+
+    def documents(self, ids: Sequence[int]) -> Dict[int, Tuple[str, str]]:
+        """id -> (title, text) — the snippet query of bm25_indexer.py:494-501."""
+        return self._fetch_by_ids("title, text", ids)
+
+    def documents_full(self, ids: Sequence[int]) -> Dict[int, Tuple[str, str, str]]:
+        """id -> (title, url, text) — what reranker_api.py:38-41 selects."""
+        return self._fetch_by_ids("title, url, text", ids)
+
+    def iter_documents(self):
+        for r in self._all("SELECT id, title, text FROM urlsDB ORDER BY id"):
+            yield int(r[0]), r[1], r[2]
+
+    # -- writing the bm25_* tables (index build, bm25_indexer.py:82-128,283-367)
+    def write_bm25(self, doc_rows, tf_rows, term_rows, avgdl: float, total_docs: int, idf_of):
+        ex = self.conn.execute
+        ex("CREATE TABLE IF NOT EXISTS bm25_doc_stats (doc_id INTEGER PRIMARY KEY, doc_length INTEGER, processed_at TIMESTAMP DEFAULT CURRENT_TIMESTAMP)")
+        ex("CREATE TABLE IF NOT EXISTS bm25_term_freq (doc_id INTEGER, term TEXT, freq INTEGER, PRIMARY KEY (doc_id, term))")
+        ex("CREATE TABLE IF NOT EXISTS bm25_term_stats (term TEXT PRIMARY KEY, doc_freq INTEGER, total_freq INTEGER, idf_score REAL, last_updated TIMESTAMP DEFAULT CURRENT_TIMESTAMP)")
+        ex("CREATE TABLE IF NOT EXISTS bm25_corpus_stats (stat_name TEXT PRIMARY KEY, stat_value REAL, last_updated TIMESTAMP DEFAULT CURRENT_TIMESTAMP)")
+        self.conn.executemany("INSERT OR REPLACE INTO bm25_doc_stats (doc_id, doc_length) VALUES (?, ?)", list(doc_rows))
+        self.conn.executemany("INSERT OR REPLACE INTO bm25_term_freq (doc_id, term, freq) VALUES (?, ?, ?)", list(tf_rows))
+        self.conn.executemany("INSERT OR REPLACE INTO bm25_term_stats (term, doc_freq, total_freq, idf_score) VALUES (?, ?, ?, ?)",
+                              [(t, df, tot, idf_of(df)) for t, df, tot in term_rows])
+        for k, v in (("avg_doc_length", float(np.float32(avgdl))), ("total_docs", float(np.float32(total_docs)))):
+            ex("INSERT OR REPLACE INTO bm25_corpus_stats (stat_name, stat_value) VALUES (?, ?)", [k, v])
+        if hasattr(self.conn, "commit"):
+            self.conn.commit()
+
+    def close(self):
+        if self._owns:
+            try:
+                self.conn.close()
+            except Exception:
+                pass
+
+
+@dataclass
+class ArrayStore:
+    """In-memory store for synthetic corpora (integer-named terms, no text)."""
+    bm25: Optional[Bm25Tables] = None
+    dense: Optional[DenseTables] = None
+    url_list: Optional[List[str]] = None        # parallel to bm25.doc_ids / dense doc index
+    titles: Optional[List[str]] = None
+    texts: Optional[List[str]] = None
+    doc_id_array: Optional[np.ndarray] = None
+
+    def _ids(self) -> np.ndarray:
+        if self.doc_id_array is not None:
+            return self.doc_id_array
+        return self.bm25.doc_ids
+
+    def has_table(self, name: str) -> bool:
+        return {"bm25_term_freq": self.bm25 is not None, "chunks_optimized": self.dense is not None,
+                "urlsDB": True}.get(name, False)
+
+    def load_bm25(self, doc_ids=None) -> Bm25Tables:
+        return self.bm25
+
+    def load_dense(self, doc_ids) -> DenseTables:
+        return self.dense
+
+    def all_doc_ids(self) -> np.ndarray:
+        return self._ids()
+
+    def _index_of(self, ids):
+        all_ids = self._ids()
+        pos = np.searchsorted(all_ids, np.asarray(ids, dtype=np.int64))
+        ok = (pos < len(all_ids)) & (all_ids[np.minimum(pos, len(all_ids) - 1)] == np.asarray(ids, dtype=np.int64))
+        return pos, ok
+
+    def urls(self, ids=None) -> Dict[int, str]:
+        if self.url_list is None:
+            return {}
+        if ids is None:
+            return {int(d): u for d, u in zip(self._ids().tolist(), self.url_list)}
+        pos, ok = self._index_of(ids)
+        return {int(d): self.url_list[p] for d, p, k in zip(ids, pos, ok) if k}
+
+    def documents(self, ids) -> Dict[int, Tuple[str, str]]:
+        pos, ok = self._index_of(ids)
+        out = {}
+        for d, p, k in zip(ids, pos, ok):
+            if k:
+                out[int(d)] = (self.titles[p] if self.titles else "", self.texts[p] if self.texts else "")
+        return out
+
+    def documents_full(self, ids) -> Dict[int, Tuple[str, str, str]]:
+        pos, ok = self._index_of(ids)
+        out = {}
+        for d, p, k in zip(ids, pos, ok):
+            if k:
+                out[int(d)] = (self.titles[p] if self.titles else "", self.url_list[p] if self.url_list else "",
+                               self.texts[p] if self.texts else "")
+        return out
+
+    def close(self):
+        pass
+
+
+def open_store(db_path: str, read_only: bool = True):
+    """``duckdb.connect(db_path, read_only=...)`` as the reference does (bm25_indexer.py:69) when
+    duckdb is importable; an sqlite3 file otherwise (same SQL)."""
+    try:
+        import duckdb  # type: ignore
+        return SqlStore(duckdb.connect(db_path, read_only=read_only), owns=True)
+    except ImportError:
+        pass
+    if not os.path.exists(db_path) and read_only:
+        raise FileNotFoundError(db_path)
+    with open(db_path, "rb") as f:
+        head = f.read(16)
+    if not head.startswith(b"SQLite format 3"):
+        raise RuntimeError(f"{db_path} is not an sqlite file and the duckdb module is not installed")
+    return SqlStore(sqlite3.connect(db_path, check_same_thread=False), owns=True)

@@ -1,0 +1,145 @@
+"""GPU parity tests for Stage 2 (exhaustive dense scan, gathered rerank), through the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+import mse_b200
+import mse_testlib as helpers
+from mse_b200 import _native, synthetic
+from mse_b200.reranker import Reranker, hybrid_diversification
+from mse_b200.retriever import Retriever
+from mse_b200.store import ArrayStore, DenseTables
+from oracle import rerank_oracle as ro
+
+pytestmark = pytest.mark.gpu
+
+DENSE_RTOL = 2e-3   # north_star: dense scores within 2e-3 relative (bf16 storage, fp32 accumulate)
+
+
+def bf16_round(x: np.ndarray) -> np.ndarray:
+    return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(torch.bfloat16).float().numpy()
+
+
+@pytest.fixture(scope="module")
+def dense_small():
+    n_docs = 3000
+    d = synthetic.make_dense_corpus(n_docs, seed=5, device="cpu", dtype=torch.float32)
+    off = d.doc_chunk_off.numpy().copy()
+    emb = d.emb.numpy()
+    ids = np.arange(1, n_docs + 1, dtype=np.int64) * 3
+    urls = synthetic.make_urls(ids, n_domains=41, dup_frac=0.05)
+    oracle = ro.DenseArrays(bf16_round(emb), d.chunk_ids.numpy(), off, ids, urls)     # the STORED values
+    return emb, off, ids, urls, oracle
+
+
+@pytest.mark.parametrize("B,top_k", [(1, 1000), (3, 10), (7, 100)])
+def test_dense_scan_vs_oracle(dense_small, B, top_k):
+    emb, off, ids, urls, oracle = dense_small
+    rt = Retriever(store=ArrayStore(doc_id_array=ids), doc_ids=ids, dense_tables=DenseTables(emb, oracle.chunk_ids, off))
+    q = synthetic.make_query_vectors(B, seed=B, normalize=False)
+    doc, score, count = rt.scan_batch(q, top_k=top_k)
+    n_with_chunks = int(np.count_nonzero(np.diff(off)))
+    for i in range(B):
+        rd, rs = ro.dense_scan(oracle, q[i], top_k=top_k)
+        n = int(count[i])
+        assert n == min(top_k, n_with_chunks)
+        helpers.assert_topk_matches(doc[i, :n], score[i, :n], rd, rs, DENSE_RTOL, atol=1e-6)
+    res = rt.quick_search(q[0], top_k=5)
+    assert [r["doc_id"] for r in res] == ids[ro.dense_scan(oracle, q[0], top_k=5)[0]].tolist()
+    rt.native.close()
+
+
+def test_dense_scan_docs_without_chunks_and_straddling_tiles():
+    # doc sizes chosen so documents straddle the 64-row warp tiles, with empty docs in between
+    counts = np.asarray([0, 70, 0, 0, 1, 63, 130, 0, 5, 0], dtype=np.int64)
+    off = np.concatenate([[0], np.cumsum(counts)])
+    rng = np.random.default_rng(3)
+    emb = rng.standard_normal((int(off[-1]), 768)).astype(np.float32)
+    emb /= np.linalg.norm(emb, axis=1, keepdims=True)
+    nat = _native.NativeIndex(0)
+    nat.dense_load(emb, off)
+    q = synthetic.make_query_vectors(2, seed=9, normalize=True)
+    doc, score, count = nat.dense_scan(q, 10)
+    oracle = ro.DenseArrays(bf16_round(emb), np.arange(off[-1]), off, np.arange(len(counts)))
+    for i in range(2):
+        rd, rs = ro.dense_scan(oracle, q[i], top_k=10, normalize_query=False)
+        assert count[i] == 5
+        helpers.assert_topk_matches(doc[i, :5], score[i, :5], rd, rs, DENSE_RTOL, atol=1e-6)
+    nat.close()
+
+
+def _rerank_check(rr, oracle, cand, sims, q, tol=2e-3):
+    o_doc, o_score, o_orig, o_chunk, o_count, o_rows = rr.rerank_batch([cand], [sims], q[None, :])
+    ref = ro.rerank(oracle, cand, sims, q, faithful=False)
+    if ref is None:
+        assert o_rows[0] == 0 and o_count[0] == 0
+        return
+    n = int(o_count[0])
+    assert o_rows[0] == ref.total_rows and n == len(ref.doc)
+    helpers.assert_topk_matches(o_doc[0, :n], o_score[0, :n], ref.doc, ref.score, 0.0, atol=tol)
+    same = o_doc[0, :n] == ref.doc
+    np.testing.assert_allclose(o_orig[0, :n][same], ref.orig[same], atol=1e-6)
+    # the representative window may differ only when two chunks of a doc tie within tolerance
+    assert np.mean(o_chunk[0, :n][same] == ref.best_chunk[same]) > 0.98
+
+
+def test_rerank_golden_fixture():
+    """tests/golden/rerank_small: the unmodified reference rerank() (fp32 embeddings); the GPU stores
+    bf16, so scores agree within the dense tolerance and the order up to ties inside it."""
+    dense, j = helpers.load_rerank_small()
+    store = ArrayStore(doc_id_array=dense.doc_ids, url_list=j["urls"])
+    rr = Reranker(store, dense.doc_ids, dense_tables=DenseTables(dense.emb, dense.chunk_ids, dense.doc_chunk_off),
+                  diversification=False)
+    for case in j["cases"]:
+        cand = np.searchsorted(dense.doc_ids, np.asarray(case["cand_ids"]))
+        q = np.asarray(case["q"], dtype=np.float32)
+        o_doc, o_score, o_orig, o_chunk, o_count, o_rows = rr.rerank_batch([cand], [np.asarray(case["sims"])], q[None, :])
+        g = case["plain"]
+        n = int(o_count[0])
+        assert int(o_rows[0]) == g["total_documents"] and n == len(g["doc_id"])
+        helpers.assert_topk_matches(dense.doc_ids[o_doc[0, :n]], o_score[0, :n], g["doc_id"], g["score"], 0.0, atol=2e-3)
+    # reference-shaped call with diversification == fixture 'div'
+    rr.diversification = True
+    case = j["cases"][0]
+    resp = rr.rerank([str(x) for x in case["cand_ids"]], case["sims"], "q", query_vec=np.asarray(case["q"], np.float32))
+    g = case["div"]
+    assert resp.total_documents == g["total_documents"] and resp.total_windows == 100
+    got = [int(d.doc_id) for d in resp.document_scores]
+    assert len(got) == len(g["doc_id"]) and len(set(got) ^ set(g["doc_id"])) <= 2
+    np.testing.assert_allclose([d.similarity_score for d in resp.document_scores], g["score"], atol=3e-3)
+    rr.native.close()
+
+
+def test_rerank_synthetic_vs_oracle(dense_small):
+    emb, off, ids, urls, oracle = dense_small
+    store = ArrayStore(doc_id_array=ids, url_list=urls)
+    rr = Reranker(store, ids, dense_tables=DenseTables(emb, oracle.chunk_ids, off), diversification=False)
+    rng = np.random.default_rng(8)
+    for ci, k in enumerate([1000, 300, 17, 1]):
+        cand = rng.permutation(len(ids))[:k]
+        sims = np.sort(rng.gamma(2.0, 1.0, size=k))[::-1].astype(np.float32)
+        q = synthetic.make_query_vectors(1, seed=20 + ci)[0] * 2.5
+        _rerank_check(rr, oracle, cand, sims, q)
+    # all-equal BM25 scores and a single-chunk-only pool
+    single = np.flatnonzero(np.diff(off) == 1)[:40]
+    _rerank_check(rr, oracle, single, np.full(len(single), 2.0, np.float32), synthetic.make_query_vectors(1, seed=99)[0])
+    # candidates with no chunks at all -> "no documents" (HTTP 401 in the reference)
+    empty = np.flatnonzero(np.diff(off) == 0)
+    if len(empty):
+        _rerank_check(rr, oracle, empty[:3], np.ones(min(3, len(empty)), np.float32), synthetic.make_query_vectors(1, seed=1)[0])
+    rr.native.close()
+
+
+def test_rerank_batch_equals_single(dense_small):
+    emb, off, ids, urls, oracle = dense_small
+    rr = Reranker(ArrayStore(doc_id_array=ids, url_list=urls), ids, dense_tables=DenseTables(emb, oracle.chunk_ids, off))
+    rng = np.random.default_rng(2)
+    cands = [rng.permutation(len(ids))[:k] for k in (50, 1000, 0, 200)]
+    sims = [np.sort(rng.random(len(c)).astype(np.float32))[::-1] for c in cands]
+    q = synthetic.make_query_vectors(4, seed=4)
+    batch = rr.rerank_batch(cands, sims, q)
+    for i in range(4):
+        one = rr.rerank_batch([cands[i]], [sims[i]], q[i:i + 1])
+        for a, b in zip(batch, one):
+            np.testing.assert_array_equal(a[i], b[0])
+    rr.native.close()

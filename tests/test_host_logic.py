@@ -1,0 +1,127 @@
+"""CPU-only tests: the C-ABI library loads and exports every declared symbol, host-side logic
+(query encoding, sharding bounds, diversification, batch-file formatting, store adapters)."""
+import ctypes
+import os
+import re
+import sqlite3
+
+import numpy as np
+import pytest
+
+import mse_b200
+import mse_testlib as helpers
+from mse_b200 import _native, pipeline, reranker, sharding, store, synthetic
+from mse_b200.bm25_indexer import shard_bounds, slice_bm25_tables
+from oracle import bm25_oracle as bo
+from oracle import rerank_oracle as ro
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_symbol_declared_in_the_header():
+    import __graft_entry__ as ge
+    ge.build()
+    hdr = open(os.path.join(ROOT, "include", "mse_b200.h")).read()
+    declared = set(re.findall(r"\b(mse_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_native.exported_symbols())
+    L = ctypes.CDLL(_native.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+    L.mse_abi_version.restype = ctypes.c_int
+    assert L.mse_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_gpu():
+    if _native.device_count() > 0:
+        pytest.skip("GPU present")
+    with pytest.raises(_native.NativeError):
+        _native.NativeIndex(0)
+
+
+def test_preprocess_query_matches_reference_rules():
+    assert pipeline.preprocess_query("  Food and Drinks ") == "food and drinks tübingen"
+    assert pipeline.preprocess_query("university tuebingen research") == "university tübingen research"
+    assert pipeline.preprocess_query("castle hohentubingen history") == "castle hohentübingen history"
+    assert pipeline.preprocess_query("tübingen attractions") == "tübingen attractions"
+
+
+def test_url_groups_and_diversification_match_oracle():
+    urls = ["https://a.x/1", "https://a.x/1?q=2", "https://b.x/1", None, "https://a.x/1?z"]
+    g = reranker.url_groups(urls)
+    assert g[0] == g[1] == g[4] and g[2] != g[0] and g[3] not in (g[0], g[2])
+    dense, j = helpers.load_rerank_small()
+    for case in j["cases"]:
+        p, d = case["plain"], case["div"]
+        docs = [reranker.DocumentScore(doc_id=str(i), title="", url=u, similarity_score=s, original_similarity=0.0,
+                                       most_relevant_window=reranker.WindowScore(text="", similarity_score=s, doc_id=str(i),
+                                                                                 title="", window_index=0))
+                for i, u, s in zip(p["doc_id"], p["url"], p["score"])]
+        out = reranker.hybrid_diversification(docs, top_k=100)
+        assert [int(x.doc_id) for x in out] == d["doc_id"]                 # == the unmodified reference
+        np.testing.assert_allclose([x.similarity_score for x in out], d["score"], atol=1e-15)
+
+
+def test_shard_bounds_and_slices_cover_the_index():
+    ix, _, _ = helpers.load_bm25_small()
+    t = store.Bm25Tables(ix.terms, ix.term_off, ix.post_doc, ix.post_tf, ix.doc_ids, ix.doc_len, ix.idf,
+                         np.zeros(ix.n_terms, np.int64), ix.avgdl, ix.total_docs)
+    per_doc = np.bincount(ix.post_doc, minlength=ix.n_docs)
+    for world in (1, 2, 3, 8):
+        b = shard_bounds(per_doc, world)
+        assert b[0] == 0 and b[-1] == ix.n_docs and all(x <= y for x, y in zip(b, b[1:]))
+        total = 0
+        for r in range(world):
+            s = slice_bm25_tables(t, b[r], b[r + 1])
+            total += len(s.post_doc)
+            assert s.post_doc.min(initial=0) >= 0 and s.post_doc.max(initial=-1) < b[r + 1] - b[r]
+            assert s.avgdl == t.avgdl and np.array_equal(s.idf, t.idf)      # global statistics, never per shard
+        assert total == len(ix.post_doc)
+        if world > 1:
+            loads = [per_doc[b[r]:b[r + 1]].sum() for r in range(world)]
+            assert max(loads) <= 1.5 * (sum(loads) / world) + per_doc.max()
+
+
+def test_sql_store_roundtrip_on_sqlite():
+    ix, e = helpers.load_appendix_e()
+    conn = sqlite3.connect(":memory:")
+    conn.execute("CREATE TABLE urlsDB (id BIGINT PRIMARY KEY, url TEXT, title TEXT, text TEXT)")
+    conn.executemany("INSERT INTO urlsDB VALUES (?,?,?,?)", [(i, f"http://x/{i}?a", "", t) for i, t in e["docs"]])
+    st = store.SqlStore(conn)
+    st.write_bm25(e["doc_stats"], [(r[1], r[0], r[2]) for r in e["term_freq"]],
+                  [(r[0], r[1], r[2]) for r in e["term_stats"]], 3.5, 6,
+                  lambda df: float(np.float32(np.log10((6.0 - df + 0.5) / (df + 0.5)))))
+    t = st.load_bm25(st.all_doc_ids())
+    assert t.terms == ix.terms
+    for a, b in ((t.term_off, ix.term_off), (t.post_doc, ix.post_doc), (t.post_tf, ix.post_tf), (t.doc_len, ix.doc_len), (t.idf, ix.idf)):
+        np.testing.assert_array_equal(a, b)
+    assert t.avgdl == 3.5 and st.documents([2])[2] == ("", "beta gamma gamma gamma delta")
+    assert st.urls([1])[1] == "http://x/1?a"
+
+
+def test_synthetic_generator_is_consistent():
+    c = synthetic.make_bm25_corpus(2000, vocab=800, mean_len=40, seed=3, always_frac=0.9)
+    off, pd, tf = c.term_off.numpy(), c.post_doc.numpy(), c.post_tf.numpy()
+    assert off[-1] == len(pd) and np.all(tf >= 1)
+    for t in (0, 5, c.always_term):
+        seg = pd[off[t]:off[t + 1]]
+        assert np.all(np.diff(seg) > 0)
+    np.testing.assert_array_equal(np.bincount(pd, weights=tf, minlength=2000).astype(np.int64), c.doc_len.numpy())
+    q_off, q_term, q_tf = synthetic.make_bm25_queries(c, 50, min_rank=4, add_always=True)
+    assert q_off[-1] == len(q_term) and np.all(np.diff(off)[q_term] > 0)
+    for i in range(50):
+        seg = q_term[q_off[i]:q_off[i + 1]]
+        assert len(set(seg.tolist())) == len(seg)
+
+
+def test_merge_rule_on_host():
+    g_doc = np.asarray([[[5, 9, -1]], [[2, 7, 8]]], np.int32)
+    g_score = np.asarray([[[3.0, 1.0, 0]], [[3.0, 2.0, 1.0]]], np.float32)
+    g_count = np.asarray([[2], [3]], np.int32)
+    d, s, c = sharding.merge_topk_host(g_doc, g_score, g_count, 4)
+    assert d[0].tolist() == [2, 5, 7, 8] and s[0].tolist() == [3.0, 3.0, 2.0, 1.0] and c[0] == 4
+
+
+def test_batch_file_format(tmp_path):
+    p = tmp_path / "queries.txt"
+    p.write_text("1\ttübingen attractions\n\n2\tfood and drinks\nbroken line\n", encoding="utf-8")
+    assert pipeline.read_queries(str(p)) == [("1", "tübingen attractions"), ("2", "food and drinks")]
