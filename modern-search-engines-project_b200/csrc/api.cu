@@ -67,7 +67,8 @@ struct mse_index {
 
     bool has_bm25 = false;
     Bm25Dev bm{};
-    DevBuf term_off, post_doc, post_tf, doc_norm, idf;
+    DevBuf term_off, post_doc, post_tf, doc_norm, doc_len16, idf;
+    bool len16_ok = false;
     std::vector<int64_t> h_term_off;
 
     bool has_dense = false;
@@ -135,12 +136,13 @@ int bm25_run(mse_index* ix, int32_t B, const int32_t* d_q_off, const int32_t* d_
              int32_t S, int32_t top_k, float min_score, int32_t cap, int use_tau,
              int32_t* d_out_doc, float* d_out_score, int32_t* d_out_count, bool mark_overflow, cudaStream_t st) {
     const Bm25Dev& bm = ix->bm;
-    int R = ix->opt_range_docs > 0 ? round_up(ix->opt_range_docs, 256) : 6144;
-    if (R > 24576) R = 24576;
-    if (bm.n_docs < R) R = std::max(256, round_up(bm.n_docs, 256));
-    const int n_ranges = int((bm.n_docs + R - 1) / R);
-    int qpi = ix->opt_qpi > 0 ? int(ix->opt_qpi) : 8;
-    const int nb = n_ranges + 1;
+    const bool len16 = ix->len16_ok;
+    int RS = ix->opt_range_docs > 0 ? round_up(ix->opt_range_docs, 64) : 768;
+    RS = std::min(RS, 2048);
+    if (bm.n_docs < RS) RS = std::max(64, round_up(bm.n_docs, 64));
+    const int n_sub = int((bm.n_docs + RS - 1) / RS);
+    const int qpi = int(std::min<int64_t>(31, ix->opt_qpi > 0 ? ix->opt_qpi : 8));
+    const int nb = n_sub + 1;
 
     int rc;
     if ((rc = ix->slot_w.ensure(sizeof(float) * size_t(S + 1)))) return rc;
@@ -169,28 +171,30 @@ int bm25_run(mse_index* ix, int32_t B, const int32_t* d_q_off, const int32_t* d_
     w.cand = ix->cand.as<uint64_t>(); w.cand_count = ix->cand_count.as<int32_t>(); w.overflow = ix->overflow.as<int32_t>();
     w.item_counter = ix->misc.as<int32_t>();
     w.stats = reinterpret_cast<unsigned long long*>(ix->misc.as<char>() + 16);
-    w.n_queries = B; w.n_slots = S; w.n_ranges = n_ranges; w.range_docs = R; w.queries_per_item = qpi;
+    w.n_queries = B; w.n_slots = S; w.n_sub = n_sub; w.sub_docs = RS; w.queries_per_item = qpi;
     w.cap = cap; w.top_k = top_k; w.min_key = float_to_key(min_score + 0.0f); w.use_tau = use_tau;
 
     timer_begin(ix, T_PREPARE, st);
     {
-        const int64_t n = std::max<int64_t>(int64_t(S) * nb, B);
-        const int threads = 256;
-        bm25_prepare_kernel<<<unsigned((n + threads - 1) / threads), threads, 0, st>>>(bm, w);
+        const int tau_ctas = (B + kPrepThreads - 1) / kPrepThreads;
+        const size_t psm = sizeof(int64_t) * size_t((n_sub + kPrepCoarse - 1) / kPrepCoarse + 2);
+        bm25_prepare_kernel<<<unsigned(S + tau_ctas), kPrepThreads, psm, st>>>(bm, w);
         MSE_CUDA_TRY(cudaGetLastError());
     }
     timer_end(ix, T_PREPARE, st);
 
-    const size_t smem = sizeof(float) * 2 * size_t(R);
-    MSE_CUDA_TRY(cudaFuncSetAttribute(bm25_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    const size_t smem = size_t(kBm25Warps) * RS * (len16 ? 8 : 10);
+    const void* kfn = len16 ? (const void*)bm25_score_kernel<true> : (const void*)bm25_score_kernel<false>;
+    MSE_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     int per_sm = 0;
-    MSE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bm25_score_kernel, kBm25Threads, smem));
-    if (per_sm < 1) { set_error("bm25 score kernel does not fit (R=%d)", R); return MSE_ERR_INVALID; }
+    MSE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kBm25Threads, smem));
+    if (per_sm < 1) { set_error("bm25 score kernel does not fit (sub-range %d docs)", RS); return MSE_ERR_INVALID; }
     const int chunks = (B + qpi - 1) / qpi;
-    const int64_t n_items = int64_t(n_ranges) * chunks;
-    const int grid = int(std::min<int64_t>(n_items, int64_t(per_sm) * ix->sm_count));
+    const int64_t n_items = int64_t(n_sub) * chunks;
+    const int grid = int(std::min<int64_t>((n_items + kBm25Warps - 1) / kBm25Warps, int64_t(per_sm) * ix->sm_count));
     timer_begin(ix, T_SCORE, st);
-    bm25_score_kernel<<<grid, kBm25Threads, smem, st>>>(bm, w);
+    if (len16) bm25_score_kernel<true><<<grid, kBm25Threads, smem, st>>>(bm, w);
+    else bm25_score_kernel<false><<<grid, kBm25Threads, smem, st>>>(bm, w);
     MSE_CUDA_TRY(cudaGetLastError());
     timer_end(ix, T_SCORE, st);
 
@@ -200,8 +204,7 @@ int bm25_run(mse_index* ix, int32_t B, const int32_t* d_q_off, const int32_t* d_
                                                                 mark_overflow ? w.overflow : nullptr);
     MSE_CUDA_TRY(cudaGetLastError());
     timer_end(ix, T_SELECT, st);
-    ix->stats[3] = n_ranges;
-    ix->stats[4] = grid;
+    if (mark_overflow) { ix->stats[3] = n_sub; ix->stats[4] = grid; }
     return MSE_OK;
 }
 
@@ -253,7 +256,7 @@ int mse_index_destroy(mse_index* ix) {
     {
         DeviceGuard g(ix->device);
         cudaDeviceSynchronize();
-        DevBuf* all[] = {&ix->term_off, &ix->post_doc, &ix->post_tf, &ix->doc_norm, &ix->idf, &ix->emb, &ix->doc_chunk_off,
+        DevBuf* all[] = {&ix->term_off, &ix->post_doc, &ix->post_tf, &ix->doc_norm, &ix->doc_len16, &ix->idf, &ix->emb, &ix->doc_chunk_off,
                          &ix->q_off, &ix->q_term, &ix->q_tf, &ix->slot_w, &ix->slot_base, &ix->seg, &ix->tau, &ix->hist,
                          &ix->maxbin, &ix->cand, &ix->cand_count, &ix->overflow, &ix->misc, &ix->o_doc, &ix->o_score,
                          &ix->o_count, &ix->best, &ix->dq};
@@ -328,6 +331,9 @@ int mse_bm25_load(mse_index* ix, int64_t n_terms, int64_t n_docs, int64_t doc_ba
     if ((rc = ix->post_doc.ensure(sizeof(int32_t) * std::max<int64_t>(P, 1)))) return rc;
     if ((rc = ix->post_tf.ensure(sizeof(int32_t) * std::max<int64_t>(P, 1)))) return rc;
     if ((rc = ix->doc_norm.ensure(sizeof(float) * std::max<int64_t>(n_docs, 1)))) return rc;
+    if ((rc = ix->doc_len16.ensure(sizeof(uint16_t) * std::max<int64_t>(n_docs, 1)))) return rc;
+    if ((rc = ix->misc.ensure(64))) return rc;
+    MSE_CUDA_TRY(cudaMemsetAsync(ix->misc.p, 0, 64, st));
     if ((rc = ix->idf.ensure(sizeof(float) * std::max<int64_t>(n_terms, 1)))) return rc;
     DevBuf d_len;
     if ((rc = d_len.ensure(sizeof(int32_t) * std::max<int64_t>(n_docs, 1)))) return rc;
@@ -342,26 +348,30 @@ int mse_bm25_load(mse_index* ix, int64_t n_terms, int64_t n_docs, int64_t doc_ba
     for (auto& v : h_idf) v = v + 0.0f;
     MSE_CUDA_TRY(cudaMemcpyAsync(ix->idf.p, h_idf.data(), sizeof(float) * n_terms, cudaMemcpyHostToDevice, st));
     if (n_docs > 0) {
-        bm25_norm_kernel<<<unsigned((n_docs + 255) / 256), 256, 0, st>>>(d_len.as<int32_t>(), ix->doc_norm.as<float>(), n_docs,
-                                                                        double(k1), double(b), double(avgdl));
+        bm25_norm_kernel<<<unsigned((n_docs + 255) / 256), 256, 0, st>>>(d_len.as<int32_t>(), ix->doc_norm.as<float>(),
+                                                                        ix->doc_len16.as<uint16_t>(), n_docs, double(k1), double(b),
+                                                                        double(avgdl), ix->misc.as<int32_t>() + 1);
         MSE_CUDA_TRY(cudaGetLastError());
     }
-    if ((rc = ix->misc.ensure(64))) return rc;
-    MSE_CUDA_TRY(cudaMemsetAsync(ix->misc.p, 0, 64, st));
     if (n_terms > 0) {
         bm25_validate_kernel<<<unsigned((n_terms + 7) / 8), 256, 0, st>>>(ix->term_off.as<int64_t>(), ix->post_doc.as<int32_t>(),
                                                                          ix->post_tf.as<int32_t>(), n_terms, n_docs, ix->misc.as<int32_t>());
         MSE_CUDA_TRY(cudaGetLastError());
     }
-    int32_t bad = 0;
-    MSE_CUDA_TRY(cudaMemcpyAsync(&bad, ix->misc.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    int32_t flags[2] = {0, 0};
+    MSE_CUDA_TRY(cudaMemcpyAsync(flags, ix->misc.p, sizeof(flags), cudaMemcpyDeviceToHost, st));
     MSE_CUDA_TRY(cudaStreamSynchronize(st));
     d_len.release();
+    const int32_t bad = flags[0];
+    ix->len16_ok = flags[1] == 0;                 // every doc length fits 16 bits
     MSE_REQUIRE(bad == 0, "malformed postings (code %d): doc ids must be strictly ascending inside a term, within [0,n_docs), tf >= 1", bad);
     ix->bm.term_off = ix->term_off.as<int64_t>();
     ix->bm.post_doc = ix->post_doc.as<int32_t>();
     ix->bm.post_tf = ix->post_tf.as<int32_t>();
     ix->bm.doc_norm = ix->doc_norm.as<float>();
+    ix->bm.doc_len16 = ix->doc_len16.as<uint16_t>();
+    ix->bm.norm_c0 = float(double(k1) * (1.0 - double(b)));
+    ix->bm.norm_c1 = float(double(k1) * double(b) / double(avgdl));
     ix->bm.idf = ix->idf.as<float>();
     ix->bm.n_terms = n_terms; ix->bm.n_docs = n_docs; ix->bm.n_postings = P;
     ix->bm.doc_base = uint32_t(doc_base); ix->bm.k1 = k1;
@@ -393,7 +403,10 @@ int mse_bm25_search_batch(mse_index* ix, int32_t B, const int32_t* q_off, const 
         MSE_CUDA_TRY(cudaStreamSynchronize(st));
     }
     MSE_REQUIRE(h_off[0] == 0, "q_off[0] must be 0");
-    for (int i = 0; i < B; ++i) MSE_REQUIRE(h_off[i + 1] >= h_off[i], "q_off not monotone at %d", i);
+    for (int i = 0; i < B; ++i) {
+        MSE_REQUIRE(h_off[i + 1] >= h_off[i], "q_off not monotone at %d", i);
+        if (h_off[i + 1] - h_off[i] > 32) { set_error("query %d has %d distinct terms (max 32)", i, h_off[i + 1] - h_off[i]); return MSE_ERR_UNSUPPORTED; }
+    }
     const int32_t S = h_off[B];
     MSE_REQUIRE(S == 0 || (q_term && q_tf), "null query arrays");
 
@@ -414,7 +427,7 @@ int mse_bm25_search_batch(mse_index* ix, int32_t B, const int32_t* q_off, const 
     }
 
     // candidate-list capacity: bounded workspace; overflowing queries are re-run below
-    int64_t cap = ix->opt_cand_cap > 0 ? ix->opt_cand_cap : std::max<int64_t>(16 * int64_t(top_k), 16384);
+    int64_t cap = ix->opt_cand_cap > 0 ? ix->opt_cand_cap : std::max<int64_t>(32 * int64_t(top_k), 32768);
     cap = std::min<int64_t>(cap, std::max<int64_t>(ix->bm.n_docs, 1));
     const int64_t budget = int64_t(2) << 30;
     cap = std::max<int64_t>(std::min<int64_t>(cap, budget / (8 * int64_t(B))), std::min<int64_t>(ix->bm.n_docs, int64_t(top_k)));

@@ -7,35 +7,37 @@
 // score >= min_score.
 //
 // Layout in HBM: term_off int64[V+1]; postings as two int32 arrays (doc, tf), ascending doc
-// inside a term; doc_norm float32[N] = k1*(1-b+b*dl/avgdl) (computed in double from the
-// float32 avgdl); idf float32[V] verbatim from bm25_term_stats.
+// inside a term; per-doc length (uint16 when every length fits, else the fp32 norm
+// k1*(1-b+b*dl/avgdl)); idf float32[V] verbatim from bm25_term_stats.
 //
-// Execution model (doc-range tiling, no HBM accumulators):
-//   * the doc space is cut into ranges of R docs; a (range, query-chunk) pair is one work item;
-//     persistent CTAs pull items from an atomic counter in range-major order, so consecutive
-//     items reuse the range's doc_norm slice already staged in shared memory;
-//   * bm25_prepare_kernel binary-searches, once per (query term, range boundary), where each
-//     posting list crosses each range boundary; the scoring kernel then streams exactly the
-//     postings of its range with coalesced loads (no search on the critical path);
-//   * accumulators live in shared memory (fp32[R]); doc ids are unique inside a term, so a term
-//     is applied with plain read-modify-write and terms are separated by a CTA barrier —
-//     no atomics, deterministic summation order (= the reference's term order);
-//   * "touched" is tracked without a bitmap: accumulators start as -0.0f (x + -0.0 == x,
-//     +0.0 + -0.0 == +0.0), so a touched document whose score is exactly zero (idf == 0, kept by
-//     the reference) is distinguishable from an untouched one (never returned);
-//   * the scan that reads out a range re-arms the accumulators and emits only candidates whose
-//     score key is >= tau[q], a per-query lower bound of the final k-th best score.  tau is
-//     raised on the fly from a per-query histogram of the candidates emitted so far (any value
-//     tau ever took is a valid bound, so no inter-CTA synchronisation is needed); with
-//     range-major scheduling the ranges of one query are visited roughly in sequence and the
-//     emitted volume is ~k*ln(candidates/k) instead of every candidate.
+// Execution model ("warp tasks", no CTA barrier, no atomics on accumulators):
+//   * the doc space is cut into sub-ranges of RS docs (default 768); a (sub-range, query) pair
+//     is one task and a warp owns a task outright.  Persistent warps pull (sub-range,
+//     query-chunk) items from an atomic counter in sub-range-major order;
+//   * bm25_prepare_kernel finds, once per (query term, sub-range boundary), where each posting
+//     list crosses each boundary (two-level binary search); the scoring warp then streams exactly
+//     its task's postings with coalesced loads.  Loads are software-pipelined one query ahead
+//     (slot metadata two queries ahead), so HBM latency overlaps the previous query's work;
+//   * per-warp accumulators live in shared memory (fp32[RS]) next to the sub-range's doc lengths
+//     and a "touched list".  Doc ids are unique inside a term, so a term is applied with plain
+//     read-modify-write and terms are separated by __syncwarp: deterministic summation in the
+//     reference's term order;
+//   * accumulators rest at -0.0f (x + -0.0 == x, +0.0 + -0.0 == +0.0): a document whose score is
+//     exactly zero (idf == 0, kept by the reference) is distinguishable from an untouched one
+//     (never returned).  The first posting that finds -0.0 appends the doc to the touched list,
+//     and the read-out walks that list only (no scan over RS accumulators), re-arming as it goes;
+//   * read-out emits only candidates with score >= tau[q], a per-query lower bound of the final
+//     k-th best score, raised on the fly from a per-query histogram of emitted candidates (any
+//     value tau ever took is a valid bound, so no inter-warp synchronisation is needed).
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 
 namespace mse {
 
 constexpr int kBm25Threads = 256;
-constexpr int kBm25CtasPerSm = 4;
+constexpr int kBm25Warps = kBm25Threads / 32;
+constexpr int kBm25MaxPrefetchSlots = 8;         // terms per query whose postings are prefetched
 constexpr int kHistBits = 12;                    // sign + exponent + 3 mantissa bits
 constexpr int kHistBins = 1 << kHistBits;
 constexpr int kHistShift = 32 - kHistBits;
@@ -44,11 +46,13 @@ struct Bm25Dev {                                 // device-resident index of one
     const int64_t* term_off;
     const int32_t* post_doc;
     const int32_t* post_tf;
-    const float* doc_norm;
+    const float* doc_norm;       // fp32 norm per doc (always present)
+    const uint16_t* doc_len16;   // doc length per doc, or null when some length >= 65536
     const float* idf;
     int64_t n_terms, n_docs, n_postings;
     uint32_t doc_base;
     float k1;
+    float norm_c0, norm_c1;      // norm = c0 + c1 * len   (c0 = k1*(1-b), c1 = k1*b/avgdl)
 };
 
 struct Bm25Work {                                // per-call workspace
@@ -57,7 +61,7 @@ struct Bm25Work {                                // per-call workspace
     const int32_t* q_tf;
     float* slot_w;               // [S]  idf * qtf * (k1+1)
     int64_t* slot_base;          // [S]  term_off[term]
-    uint32_t* seg;               // [S * (n_ranges+1)] posting offset (relative to slot_base) of each range boundary
+    uint32_t* seg;               // [S * (n_sub+1)] posting offset (relative to slot_base) of each sub-range boundary
     uint32_t* tau;               // [B]  lower bound (score key) of the final k-th best
     uint32_t* hist;              // [B * kHistBins] emitted candidates per score bin
     uint32_t* maxbin;            // [B]
@@ -66,40 +70,64 @@ struct Bm25Work {                                // per-call workspace
     int32_t* overflow;           // [B] 1 when more than cap candidates were emitted
     int32_t* item_counter;       // [1]
     unsigned long long* stats;   // [0] postings traversed
-    int32_t n_queries, n_slots, n_ranges, range_docs, queries_per_item, cap, top_k;
+    int32_t n_queries, n_slots, n_sub, sub_docs, queries_per_item, cap, top_k;
     uint32_t min_key;
     int32_t use_tau;
 };
 
-// ---- prepare: slot weights, list bases, range boundaries, tau init ---------------------------
-__global__ void bm25_prepare_kernel(Bm25Dev ix, Bm25Work w) {
-    const int64_t gid = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    const int nb = w.n_ranges + 1;
-    if (gid < w.n_queries) w.tau[gid] = w.min_key;
-    if (gid >= int64_t(w.n_slots) * nb) return;
-    const int s = int(gid / nb), j = int(gid % nb);
+// ---- prepare: slot weights, list bases, sub-range boundaries, tau init --------------------------
+// One CTA per query-term slot.  Level 1: every 32nd boundary by binary search over the whole
+// list; level 2: the boundaries in between by binary search inside their bracket.
+constexpr int kPrepThreads = 256;
+constexpr int kPrepCoarse = 32;
+
+__device__ __forceinline__ int64_t lower_bound_doc(const int32_t* __restrict__ pd, int64_t lo, int64_t hi, int64_t target) {
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (int64_t(pd[mid]) < target) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(kPrepThreads)
+bm25_prepare_kernel(Bm25Dev ix, Bm25Work w) {
+    extern __shared__ int64_t s_coarse[];                      // [n_coarse + 1]
+    const int s = blockIdx.x;
+    const int tid = threadIdx.x;
+    if (s >= w.n_slots) {                                      // trailing CTAs initialise tau
+        for (int q = (s - w.n_slots) * kPrepThreads + tid; q < w.n_queries; q += (gridDim.x - w.n_slots) * kPrepThreads)
+            w.tau[q] = w.min_key;
+        return;
+    }
+    const int nb = w.n_sub + 1;
     const int t = w.q_term[s];
     int64_t a = 0, e = 0;
     if (t >= 0 && t < ix.n_terms) { a = ix.term_off[t]; e = ix.term_off[t + 1]; }
-    if (j == 0) {
-        float idf = (t >= 0 && t < ix.n_terms) ? ix.idf[t] : 0.f;
+    if (tid == 0) {
+        const float idf = (t >= 0 && t < ix.n_terms) ? ix.idf[t] : 0.f;
         // idf * qtf * (k1+1) formed in double, rounded once (reference: float64 throughout)
         w.slot_w[s] = float(double(idf) * double(w.q_tf[s]) * (double(ix.k1) + 1.0)) + 0.0f;
         w.slot_base[s] = a;
         if (e > a) atomicAdd(w.stats, (unsigned long long)(e - a));
     }
-    // first posting with doc >= j * R
-    const int64_t target = int64_t(j) * w.range_docs;
-    int64_t lo = a, hi = e;
-    if (j == w.n_ranges) lo = e;
-    while (lo < hi) {
-        int64_t mid = (lo + hi) >> 1;
-        if (int64_t(ix.post_doc[mid]) < target) lo = mid + 1; else hi = mid;
+    const int n_coarse = (w.n_sub + kPrepCoarse - 1) / kPrepCoarse;      // coarse brackets
+    const int32_t* __restrict__ pd = ix.post_doc;
+    for (int c = tid; c <= n_coarse; c += kPrepThreads) {
+        const int j = c * kPrepCoarse < w.n_sub ? c * kPrepCoarse : w.n_sub;
+        s_coarse[c] = (j == w.n_sub) ? e : lower_bound_doc(pd, a, e, int64_t(j) * w.sub_docs);
     }
-    w.seg[gid] = uint32_t(lo - a);
+    __syncthreads();
+    for (int j = tid; j < nb; j += kPrepThreads) {
+        const int c = j / kPrepCoarse;
+        int64_t pos;
+        if (j == w.n_sub) pos = e;
+        else if (j % kPrepCoarse == 0) pos = s_coarse[c];
+        else pos = lower_bound_doc(pd, s_coarse[c], s_coarse[c + 1 <= n_coarse ? c + 1 : n_coarse], int64_t(j) * w.sub_docs);
+        w.seg[int64_t(s) * nb + j] = uint32_t(pos - a);
+    }
 }
 
-// ---- tau update: largest bin edge with >= k emitted candidates at or above it ------------------
+// ---- tau update: largest bin edge with >= k emitted candidates at or above it (one warp) ------------
 __device__ __forceinline__ void bm25_raise_tau(const Bm25Work& w, int q) {
     const int lane = lane_id();
     const uint32_t cur = ld_relaxed_u32(&w.tau[q]);
@@ -109,12 +137,11 @@ __device__ __forceinline__ void bm25_raise_tau(const Bm25Work& w, int q) {
     const uint32_t* h = w.hist + int64_t(q) * kHistBins;
     while (b >= cur_bin) {
         const int bin = b - lane;
-        int c = (bin >= cur_bin && bin >= 0) ? int(ld_relaxed_u32(&h[bin])) : 0;
-        int incl = warp_incl_scan(c);
-        unsigned hit = __ballot_sync(0xffffffffu, acc + incl >= w.top_k);
+        const int c = (bin >= cur_bin && bin >= 0) ? int(ld_relaxed_u32(&h[bin])) : 0;
+        const int incl = warp_incl_scan(c);
+        const unsigned hit = __ballot_sync(0xffffffffu, acc + incl >= w.top_k);
         if (hit) {
-            const int first = __ffs(hit) - 1;
-            const int tb = b - first;
+            const int tb = b - (__ffs(hit) - 1);
             if (lane == 0 && tb > cur_bin) atomicMax(&w.tau[q], uint32_t(tb) << kHistShift);
             return;
         }
@@ -123,129 +150,205 @@ __device__ __forceinline__ void bm25_raise_tau(const Bm25Work& w, int q) {
     }
 }
 
-// ---- scoring ----------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBm25Threads, kBm25CtasPerSm)
+// ---- scoring ------------------------------------------------------------------------------------------
+struct SlotMeta {            // one query-term slot, held by the lane of the same index
+    uint32_t sb, se;         // posting range of this task, relative to base
+    int64_t base;
+    float wt;
+};
+
+template <bool LEN16>
+__global__ void __launch_bounds__(kBm25Threads, 4)
 bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
-    constexpr int NT = kBm25Threads;
-    extern __shared__ __align__(16) float smem[];
-    float* s_norm = smem;
-    float* s_acc = smem + w.range_docs;
-    __shared__ int s_item;
-    __shared__ int s_emit;
+    using LenT = typename std::conditional<LEN16, uint16_t, float>::type;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int RS = w.sub_docs;
+    const int lane = lane_id();
+    const int wid = warp_id();
+    const size_t per_warp = size_t(RS) * (4 + sizeof(LenT) + 2);
+    unsigned char* my = smem_raw + per_warp * wid;
+    float* s_acc = reinterpret_cast<float*>(my);
+    LenT* s_len = reinterpret_cast<LenT*>(my + size_t(RS) * 4);
+    uint16_t* s_list = reinterpret_cast<uint16_t*>(my + size_t(RS) * (4 + sizeof(LenT)));
 
-    const int tid = threadIdx.x;
-    const int R = w.range_docs;
-    const int nb = w.n_ranges + 1;
-    const int chunks = (w.n_queries + w.queries_per_item - 1) / w.queries_per_item;
-    const int n_items = w.n_ranges * chunks;
+    const int nb = w.n_sub + 1;
+    const int QC = w.queries_per_item;
+    const int chunks = (w.n_queries + QC - 1) / QC;
+    const int n_items = w.n_sub * chunks;
     const float neg0 = __uint_as_float(kUntouchedBits);
+    const unsigned lt_mask = (1u << lane) - 1u;
+    constexpr int MP = kBm25MaxPrefetchSlots;
 
-    for (int i = tid; i < R; i += NT) s_acc[i] = neg0;
-    int cur_r = -1;
+    for (int i = lane; i < RS; i += 32) s_acc[i] = neg0;
+    int cur_j = -1;
 
-    while (true) {
-        __syncthreads();                                   // previous item fully retired (s_item reuse)
-        if (tid == 0) s_item = atomicAdd(w.item_counter, 1);
-        __syncthreads();
-        const int item = s_item;
-        if (item >= n_items) break;
-        const int r = item / chunks, c = item % chunks;
-        const int lo = r * R;
-        const int nd = (ix.n_docs - lo) < R ? int(ix.n_docs - lo) : R;
-        if (r != cur_r) {                                  // stage this range's doc norms
-            for (int i = tid; i < nd; i += NT) s_norm[i] = ix.doc_norm[lo + i];
-            cur_r = r;
+    auto load_meta = [&](int q, int q1, int qo_reg, int q0, int j, SlotMeta& m, int& nt, uint32_t& tau) {
+        // lanes 0..nt-1 fetch the metadata of the query's slots; everything is uniform-predicated
+        nt = 0; m.sb = 0; m.se = 0; m.base = 0; m.wt = 0.f; tau = 0;
+        if (q < q1) {
+            const int s0 = __shfl_sync(0xffffffffu, qo_reg, q - q0);
+            const int s1 = __shfl_sync(0xffffffffu, qo_reg, q - q0 + 1);
+            nt = s1 - s0;
+            if (lane < nt) {
+                const int s = s0 + lane;
+                m.sb = w.seg[int64_t(s) * nb + j];
+                m.se = w.seg[int64_t(s) * nb + j + 1];
+                m.base = w.slot_base[s];
+                m.wt = w.slot_w[s];
+            }
+            tau = w.use_tau ? ld_relaxed_u32(&w.tau[q]) : w.min_key;
         }
-        const int q0 = c * w.queries_per_item;
-        const int q1 = (q0 + w.queries_per_item) < w.n_queries ? (q0 + w.queries_per_item) : w.n_queries;
-        for (int q = q0; q < q1; ++q) {
-            const int s0 = w.q_off[q], s1 = w.q_off[q + 1];
-            if (tid == 0) s_emit = 0;
-            __syncthreads();                               // norms staged / previous scan done
-            bool any = false;
-            for (int s = s0; s < s1; ++s) {
-                const uint32_t sb = w.seg[int64_t(s) * nb + r], se = w.seg[int64_t(s) * nb + r + 1];
-                if (se > sb) {
-                    any = true;
-                    const float wt = w.slot_w[s];
-                    const int64_t base = w.slot_base[s];
-                    const int32_t* __restrict__ pd = ix.post_doc + base;
-                    const int32_t* __restrict__ pt = ix.post_tf + base;
-                    for (uint32_t i = sb + tid; i < se; i += NT) {
-                        const int d = ldg_stream_i32(pd + i) - lo;
-                        const float tf = float(ldg_stream_i32(pt + i));
-                        // idf*qtf*(k1+1) * tf / (tf + k1*(1-b+b*dl/avgdl))
-                        const float contrib = (wt * tf) / (tf + s_norm[d]);
-                        s_acc[d] += contrib;               // docs are unique inside a term: no race
-                    }
-                    __syncthreads();                       // next term may touch the same docs
+    };
+    auto issue_posts = [&](const SlotMeta& m, int nt, int (&pd)[MP], int (&pt)[MP]) {
+#pragma unroll
+        for (int t = 0; t < MP; ++t) {
+            pd[t] = 0; pt[t] = 0;
+            if (t < nt) {                                           // uniform
+                const uint32_t sb = __shfl_sync(0xffffffffu, m.sb, t), se = __shfl_sync(0xffffffffu, m.se, t);
+                const int64_t base = __shfl_sync(0xffffffffu, m.base, t);
+                if (sb + lane < se) {
+                    pd[t] = ldg_stream_i32(ix.post_doc + base + sb + lane);
+                    pt[t] = ldg_stream_i32(ix.post_tf + base + sb + lane);
                 }
             }
-            if (!any) continue;                            // uniform: nothing touched in this range
-            // ---- read-out scan: emit candidates >= tau, re-arm accumulators --------------------
-            const uint32_t tau = w.use_tau ? ld_relaxed_u32(&w.tau[q]) : w.min_key;
-            float4* acc4 = reinterpret_cast<float4*>(s_acc);
-            const float4 rearm = make_float4(neg0, neg0, neg0, neg0);
-            const int n4 = (nd + 3) >> 2;
-            for (int j4 = tid; j4 < ((n4 + NT - 1) / NT) * NT; j4 += NT) {
-                uint32_t key[4];
-                int nem = 0;
-                if (j4 < n4) {
-                    float4 v = acc4[j4];
-                    acc4[j4] = rearm;
-                    const float vv[4] = {v.x, v.y, v.z, v.w};
+        }
+    };
+
+    while (true) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(w.item_counter, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= n_items) break;
+        const int j = item / chunks, c = item % chunks;
+        const int lo = j * RS;
+        const int nd = (ix.n_docs - lo) < RS ? int(ix.n_docs - lo) : RS;
+        const int q0 = c * QC;
+        const int q1 = (q0 + QC) < w.n_queries ? (q0 + QC) : w.n_queries;
+        // query CSR offsets of the chunk, one per lane (QC <= 31)
+        const int qo_reg = (q0 + lane <= q1) ? w.q_off[q0 + lane] : 0;
+        if (j != cur_j) {                                           // stage this sub-range's doc lengths
+            if (LEN16) { for (int i = lane; i < nd; i += 32) s_len[i] = LenT(ix.doc_len16[lo + i]); }
+            else { for (int i = lane; i < nd; i += 32) s_len[i] = LenT(ix.doc_norm[lo + i]); }
+            cur_j = j;
+        }
+        __syncwarp();
+
+        // software pipeline: metadata two queries ahead, postings one query ahead
+        SlotMeta m_cur, m_nxt, m_nn;
+        int nt_cur, nt_nxt, nt_nn;
+        uint32_t tau_cur, tau_nxt, tau_nn;
+        int pd_cur[MP], pt_cur[MP], pd_nxt[MP], pt_nxt[MP];
+        load_meta(q0, q1, qo_reg, q0, j, m_cur, nt_cur, tau_cur);
+        load_meta(q0 + 1, q1, qo_reg, q0, j, m_nxt, nt_nxt, tau_nxt);
+        issue_posts(m_cur, nt_cur, pd_cur, pt_cur);
+
+        for (int q = q0; q < q1; ++q) {
+            load_meta(q + 2, q1, qo_reg, q0, j, m_nn, nt_nn, tau_nn);
+            issue_posts(m_nxt, nt_nxt, pd_nxt, pt_nxt);
+
+            int nlist = 0;
+            // ---- apply the query's terms in order ----------------------------------------------
+            for (int t0 = 0; t0 < nt_cur; t0 += MP) {
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const bool touched = __float_as_uint(vv[u]) != kUntouchedBits;
-                        const uint32_t k = float_to_key(vv[u] + 0.0f);
-                        key[u] = (touched && k >= tau) ? k : 0u;
-                        nem += key[u] != 0u;
+                for (int tt = 0; tt < MP; ++tt) {
+                    const int t = t0 + tt;
+                    if (t < nt_cur) {                               // uniform
+                        const uint32_t sb = __shfl_sync(0xffffffffu, m_cur.sb, t), se = __shfl_sync(0xffffffffu, m_cur.se, t);
+                        if (se > sb) {
+                            const int64_t base = __shfl_sync(0xffffffffu, m_cur.base, t);
+                            const float wt = __shfl_sync(0xffffffffu, m_cur.wt, t);
+                            for (uint32_t i0 = sb; i0 < se; i0 += 32) {
+                                const bool valid = i0 + lane < se;
+                                int dd = 0, tfi = 0;
+                                if (t0 == 0 && i0 == sb) { dd = pd_cur[tt]; tfi = pt_cur[tt]; }     // prefetched
+                                else if (valid) {
+                                    dd = ldg_stream_i32(ix.post_doc + base + i0 + lane);
+                                    tfi = ldg_stream_i32(ix.post_tf + base + i0 + lane);
+                                }
+                                bool fresh = false;
+                                int d = 0;
+                                if (valid) {
+                                    d = dd - lo;
+                                    const float tf = float(tfi);
+                                    const float norm = LEN16 ? fmaf(float(s_len[d]), ix.norm_c1, ix.norm_c0) : float(s_len[d]);
+                                    // idf*qtf*(k1+1) * tf / (tf + k1*(1-b+b*dl/avgdl))
+                                    const float contrib = (wt * tf) / (tf + norm);
+                                    const float old = s_acc[d];
+                                    fresh = __float_as_uint(old) == kUntouchedBits;
+                                    s_acc[d] = old + contrib;       // docs are unique inside a term: no race
+                                }
+                                const unsigned fm = __ballot_sync(0xffffffffu, fresh);
+                                if (fresh) s_list[nlist + __popc(fm & lt_mask)] = uint16_t(d);
+                                nlist += __popc(fm);
+                            }
+                            __syncwarp();                           // next term may touch the same docs
+                        }
                     }
                 }
-                if (__ballot_sync(0xffffffffu, nem > 0) == 0u) continue;
-                const int incl = warp_incl_scan(nem);
-                const int total = __shfl_sync(0xffffffffu, incl, 31);
-                int base_slot = 0;
-                if (lane_id() == 31) {
-                    base_slot = atomicAdd(&w.cand_count[q], total);
-                    atomicAdd(&s_emit, total);
-                }
-                base_slot = __shfl_sync(0xffffffffu, base_slot, 31);
-                int slot = base_slot + incl - nem;
-                if (nem) {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        if (key[u]) {
+            }
+            // ---- read-out: walk the touched list, emit candidates >= tau, re-arm ------------------
+            if (nlist > 0) {
+                const float tau_f = key_to_float(tau_cur);
+                int emitted = 0;
+                for (int i0 = 0; i0 < nlist; i0 += 32) {
+                    const bool valid = i0 + lane < nlist;
+                    int d = 0;
+                    float v = 0.f;
+                    bool pass = false;
+                    if (valid) {
+                        d = s_list[i0 + lane];
+                        v = s_acc[d] + 0.0f;
+                        s_acc[d] = neg0;
+                        pass = v >= tau_f;
+                    }
+                    const unsigned pm = __ballot_sync(0xffffffffu, pass);
+                    if (pm) {
+                        const int total = __popc(pm);
+                        int base_slot = 0;
+                        if (lane == 0) base_slot = atomicAdd(&w.cand_count[q], total);
+                        base_slot = __shfl_sync(0xffffffffu, base_slot, 0);
+                        if (pass) {
+                            const int slot = base_slot + __popc(pm & lt_mask);
                             if (slot < w.cap) {
-                                w.cand[int64_t(q) * w.cap + slot] =
-                                    make_key64(key[u], ix.doc_base + uint32_t(lo + 4 * j4 + u));
+                                const uint32_t key = float_to_key(v);
+                                w.cand[int64_t(q) * w.cap + slot] = make_key64(key, ix.doc_base + uint32_t(lo + d));
                                 if (w.use_tau) {
-                                    const uint32_t bin = key[u] >> kHistShift;
+                                    const uint32_t bin = key >> kHistShift;
                                     atomicAdd(&w.hist[int64_t(q) * kHistBins + bin], 1u);
                                     atomicMax(&w.maxbin[q], bin);
                                 }
                             } else {
                                 w.overflow[q] = 1;
                             }
-                            ++slot;
                         }
+                        emitted += total;
                     }
                 }
+                __syncwarp();
+                if (w.use_tau && emitted > 0) {
+                    __threadfence();                                // this warp's histogram updates are visible
+                    bm25_raise_tau(w, q);
+                }
             }
-            __syncthreads();                               // accumulators re-armed; s_emit final
-            if (w.use_tau && warp_id() == 0 && s_emit > 0) {
-                __threadfence();                           // histogram updates of this CTA are visible
-                bm25_raise_tau(w, q);
-            }
+            // ---- rotate the pipeline -------------------------------------------------------------------
+            m_cur = m_nxt; nt_cur = nt_nxt; tau_cur = tau_nxt;
+            m_nxt = m_nn; nt_nxt = nt_nn; tau_nxt = tau_nn;
+#pragma unroll
+            for (int t = 0; t < MP; ++t) { pd_cur[t] = pd_nxt[t]; pt_cur[t] = pt_nxt[t]; }
         }
     }
 }
 
-// ---- load-time kernels --------------------------------------------------------------------------
-__global__ void bm25_norm_kernel(const int32_t* __restrict__ doc_len, float* __restrict__ norm, int64_t n,
-                                 double k1, double b, double avgdl) {
+// ---- load-time kernels ----------------------------------------------------------------------------------
+__global__ void bm25_norm_kernel(const int32_t* __restrict__ doc_len, float* __restrict__ norm, uint16_t* __restrict__ len16,
+                                 int64_t n, double k1, double b, double avgdl, int32_t* __restrict__ max_len) {
     int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i < n) norm[i] = float(k1 * (1.0 - b + b * double(doc_len[i]) / avgdl));
+    if (i < n) {
+        const int32_t l = doc_len[i];
+        norm[i] = float(k1 * (1.0 - b + b * double(l) / avgdl));
+        len16[i] = uint16_t(l < 0 ? 0 : (l > 65535 ? 65535 : l));
+        if (l > 65535 || l < 0) atomicMax(max_len, 65536);
+    }
 }
 
 // postings must be strictly ascending inside a term and inside [0, n_docs); tf >= 1

@@ -168,6 +168,10 @@ rerank_kernel(DenseDev dx, RerankArgs a) {
     const int T = s_rows;
     if (T == 0) {                                          // reference: HTTP 401 "No documents found"
         if (tid == 0) { a.out_count[qi] = 0; a.out_rows[qi] = 0; }
+        for (int o = tid; o < a.max_out; o += NT) {
+            const int64_t dst = int64_t(qi) * a.max_out + o;
+            a.out_doc[dst] = -1; a.out_score[dst] = 0.f; a.out_orig[dst] = 0.f; a.out_chunk[dst] = -1;
+        }
         return;
     }
     for (int i = tid; i < ns; i += NT)
