@@ -76,7 +76,7 @@ struct mse_index {
     DevBuf emb, doc_chunk_off;
 
     // workspace (guarded by mu)
-    DevBuf q_off, q_term, q_tf, slot_w, slot_base, seg, tau, hist, maxbin, cand, cand_count, overflow, misc;
+    DevBuf q_off, q_term, q_tf, slot_w, rec, tau, hist, maxbin, cand, cand_count, overflow, misc;
     DevBuf o_doc, o_score, o_count;          // device staging of results for MSE_HOST callers
     DevBuf best, dq;                         // dense scan
     DevBuf r_in[5], r_out[6];                // rerank staging
@@ -137,17 +137,14 @@ int bm25_run(mse_index* ix, int32_t B, const int32_t* d_q_off, const int32_t* d_
              int32_t* d_out_doc, float* d_out_score, int32_t* d_out_count, bool mark_overflow, cudaStream_t st) {
     const Bm25Dev& bm = ix->bm;
     const bool len16 = ix->len16_ok;
-    int RS = ix->opt_range_docs > 0 ? round_up(ix->opt_range_docs, 64) : 768;
+    int RS = ix->opt_range_docs > 0 ? round_up(ix->opt_range_docs, 64) : 640;
     RS = std::min(RS, 2048);
     if (bm.n_docs < RS) RS = std::max(64, round_up(bm.n_docs, 64));
     const int n_sub = int((bm.n_docs + RS - 1) / RS);
     const int qpi = int(std::min<int64_t>(31, ix->opt_qpi > 0 ? ix->opt_qpi : 8));
-    const int nb = n_sub + 1;
-
     int rc;
     if ((rc = ix->slot_w.ensure(sizeof(float) * size_t(S + 1)))) return rc;
-    if ((rc = ix->slot_base.ensure(sizeof(int64_t) * size_t(S + 1)))) return rc;
-    if ((rc = ix->seg.ensure(sizeof(uint32_t) * size_t(S + 1) * nb))) return rc;
+    if ((rc = ix->rec.ensure(sizeof(uint2) * (size_t(S) * n_sub + 1)))) return rc;
     if ((rc = ix->tau.ensure(sizeof(uint32_t) * size_t(B)))) return rc;
     if ((rc = ix->hist.ensure(sizeof(uint32_t) * size_t(B) * kHistBins))) return rc;
     if ((rc = ix->maxbin.ensure(sizeof(uint32_t) * size_t(B)))) return rc;
@@ -166,7 +163,7 @@ int bm25_run(mse_index* ix, int32_t B, const int32_t* d_q_off, const int32_t* d_
 
     Bm25Work w{};
     w.q_off = d_q_off; w.q_term = d_q_term; w.q_tf = d_q_tf;
-    w.slot_w = ix->slot_w.as<float>(); w.slot_base = ix->slot_base.as<int64_t>(); w.seg = ix->seg.as<uint32_t>();
+    w.slot_w = ix->slot_w.as<float>(); w.rec = ix->rec.as<uint2>();
     w.tau = ix->tau.as<uint32_t>(); w.hist = ix->hist.as<uint32_t>(); w.maxbin = ix->maxbin.as<uint32_t>();
     w.cand = ix->cand.as<uint64_t>(); w.cand_count = ix->cand_count.as<int32_t>(); w.overflow = ix->overflow.as<int32_t>();
     w.item_counter = ix->misc.as<int32_t>();
@@ -177,13 +174,14 @@ int bm25_run(mse_index* ix, int32_t B, const int32_t* d_q_off, const int32_t* d_
     timer_begin(ix, T_PREPARE, st);
     {
         const int tau_ctas = (B + kPrepThreads - 1) / kPrepThreads;
-        const size_t psm = sizeof(int64_t) * size_t((n_sub + kPrepCoarse - 1) / kPrepCoarse + 2);
+        const size_t psm = sizeof(int64_t) * size_t((n_sub + kPrepCoarse - 1) / kPrepCoarse + 2) + sizeof(uint32_t) * size_t(n_sub + 2);
+        MSE_CUDA_TRY(cudaFuncSetAttribute(bm25_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(std::max<size_t>(psm, 1024))));
         bm25_prepare_kernel<<<unsigned(S + tau_ctas), kPrepThreads, psm, st>>>(bm, w);
         MSE_CUDA_TRY(cudaGetLastError());
     }
     timer_end(ix, T_PREPARE, st);
 
-    const size_t smem = size_t(kBm25Warps) * RS * (len16 ? 8 : 10);
+    const size_t smem = size_t(kBm25Warps) * (size_t(kMetaSlots) * 16 + size_t(RS) * (len16 ? 8 : 10));
     const void* kfn = len16 ? (const void*)bm25_score_kernel<true> : (const void*)bm25_score_kernel<false>;
     MSE_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     int per_sm = 0;
@@ -257,7 +255,7 @@ int mse_index_destroy(mse_index* ix) {
         DeviceGuard g(ix->device);
         cudaDeviceSynchronize();
         DevBuf* all[] = {&ix->term_off, &ix->post_doc, &ix->post_tf, &ix->doc_norm, &ix->doc_len16, &ix->idf, &ix->emb, &ix->doc_chunk_off,
-                         &ix->q_off, &ix->q_term, &ix->q_tf, &ix->slot_w, &ix->slot_base, &ix->seg, &ix->tau, &ix->hist,
+                         &ix->q_off, &ix->q_term, &ix->q_tf, &ix->slot_w, &ix->rec, &ix->tau, &ix->hist,
                          &ix->maxbin, &ix->cand, &ix->cand_count, &ix->overflow, &ix->misc, &ix->o_doc, &ix->o_score,
                          &ix->o_count, &ix->best, &ix->dq};
         for (DevBuf* b : all) b->release();

@@ -15,9 +15,10 @@
 //     is one task and a warp owns a task outright.  Persistent warps pull (sub-range,
 //     query-chunk) items from an atomic counter in sub-range-major order;
 //   * bm25_prepare_kernel finds, once per (query term, sub-range boundary), where each posting
-//     list crosses each boundary (two-level binary search); the scoring warp then streams exactly
-//     its task's postings with coalesced loads.  Loads are software-pipelined one query ahead
-//     (slot metadata two queries ahead), so HBM latency overlaps the previous query's work;
+//     list crosses each boundary (two-level binary search) and writes {first posting, count}
+//     records sub-range-major; a warp stages the records of its item with one coalesced load and
+//     then streams exactly its task's postings.  Posting loads are software-pipelined one query
+//     ahead, so HBM latency overlaps the previous query's work;
 //   * per-warp accumulators live in shared memory (fp32[RS]) next to the sub-range's doc lengths
 //     and a "touched list".  Doc ids are unique inside a term, so a term is applied with plain
 //     read-modify-write and terms are separated by __syncwarp: deterministic summation in the
@@ -60,8 +61,7 @@ struct Bm25Work {                                // per-call workspace
     const int32_t* q_term;
     const int32_t* q_tf;
     float* slot_w;               // [S]  idf * qtf * (k1+1)
-    int64_t* slot_base;          // [S]  term_off[term]
-    uint32_t* seg;               // [S * (n_sub+1)] posting offset (relative to slot_base) of each sub-range boundary
+    uint2* rec;                  // [n_sub * S] {first posting (absolute), count} of slot s in sub-range j
     uint32_t* tau;               // [B]  lower bound (score key) of the final k-th best
     uint32_t* hist;              // [B * kHistBins] emitted candidates per score bin
     uint32_t* maxbin;            // [B]
@@ -75,9 +75,12 @@ struct Bm25Work {                                // per-call workspace
     int32_t use_tau;
 };
 
-// ---- prepare: slot weights, list bases, sub-range boundaries, tau init --------------------------
+// ---- prepare: slot weights, per-(sub-range, slot) task records, tau init ---------------------------
 // One CTA per query-term slot.  Level 1: every 32nd boundary by binary search over the whole
-// list; level 2: the boundaries in between by binary search inside their bracket.
+// list; level 2: the boundaries in between by binary search inside their bracket.  The result is
+// written sub-range-major: rec[j * S + s] = {absolute index of the first posting of slot s in
+// sub-range j, number of postings}, so that the records a scoring warp needs for one work item
+// (consecutive slots of one sub-range) are contiguous.
 constexpr int kPrepThreads = 256;
 constexpr int kPrepCoarse = 32;
 
@@ -91,7 +94,10 @@ __device__ __forceinline__ int64_t lower_bound_doc(const int32_t* __restrict__ p
 
 __global__ void __launch_bounds__(kPrepThreads)
 bm25_prepare_kernel(Bm25Dev ix, Bm25Work w) {
-    extern __shared__ int64_t s_coarse[];                      // [n_coarse + 1]
+    extern __shared__ __align__(16) unsigned char prep_smem[];
+    const int n_coarse = (w.n_sub + kPrepCoarse - 1) / kPrepCoarse;      // coarse brackets
+    int64_t* s_coarse = reinterpret_cast<int64_t*>(prep_smem);           // [n_coarse + 1]
+    uint32_t* s_pos = reinterpret_cast<uint32_t*>(s_coarse + n_coarse + 1);   // [n_sub + 1]
     const int s = blockIdx.x;
     const int tid = threadIdx.x;
     if (s >= w.n_slots) {                                      // trailing CTAs initialise tau
@@ -99,7 +105,6 @@ bm25_prepare_kernel(Bm25Dev ix, Bm25Work w) {
             w.tau[q] = w.min_key;
         return;
     }
-    const int nb = w.n_sub + 1;
     const int t = w.q_term[s];
     int64_t a = 0, e = 0;
     if (t >= 0 && t < ix.n_terms) { a = ix.term_off[t]; e = ix.term_off[t + 1]; }
@@ -107,24 +112,26 @@ bm25_prepare_kernel(Bm25Dev ix, Bm25Work w) {
         const float idf = (t >= 0 && t < ix.n_terms) ? ix.idf[t] : 0.f;
         // idf * qtf * (k1+1) formed in double, rounded once (reference: float64 throughout)
         w.slot_w[s] = float(double(idf) * double(w.q_tf[s]) * (double(ix.k1) + 1.0)) + 0.0f;
-        w.slot_base[s] = a;
         if (e > a) atomicAdd(w.stats, (unsigned long long)(e - a));
     }
-    const int n_coarse = (w.n_sub + kPrepCoarse - 1) / kPrepCoarse;      // coarse brackets
     const int32_t* __restrict__ pd = ix.post_doc;
     for (int c = tid; c <= n_coarse; c += kPrepThreads) {
         const int j = c * kPrepCoarse < w.n_sub ? c * kPrepCoarse : w.n_sub;
         s_coarse[c] = (j == w.n_sub) ? e : lower_bound_doc(pd, a, e, int64_t(j) * w.sub_docs);
     }
     __syncthreads();
-    for (int j = tid; j < nb; j += kPrepThreads) {
+    for (int j = tid; j <= w.n_sub; j += kPrepThreads) {
         const int c = j / kPrepCoarse;
         int64_t pos;
         if (j == w.n_sub) pos = e;
         else if (j % kPrepCoarse == 0) pos = s_coarse[c];
-        else pos = lower_bound_doc(pd, s_coarse[c], s_coarse[c + 1 <= n_coarse ? c + 1 : n_coarse], int64_t(j) * w.sub_docs);
-        w.seg[int64_t(s) * nb + j] = uint32_t(pos - a);
+        else pos = lower_bound_doc(pd, s_coarse[c], s_coarse[c + 1], int64_t(j) * w.sub_docs);
+        s_pos[j] = uint32_t(pos - a);
     }
+    __syncthreads();
+    const uint32_t a32 = uint32_t(a);                          // n_postings < 2^32 (checked at load)
+    for (int j = tid; j < w.n_sub; j += kPrepThreads)
+        w.rec[int64_t(j) * w.n_slots + s] = make_uint2(a32 + s_pos[j], s_pos[j + 1] - s_pos[j]);
 }
 
 // ---- tau update: largest bin edge with >= k emitted candidates at or above it (one warp) ------------
@@ -151,67 +158,55 @@ __device__ __forceinline__ void bm25_raise_tau(const Bm25Work& w, int q) {
 }
 
 // ---- scoring ------------------------------------------------------------------------------------------
-struct SlotMeta {            // one query-term slot, held by the lane of the same index
-    uint32_t sb, se;         // posting range of this task, relative to base
-    int64_t base;
-    float wt;
-};
+constexpr int kMetaSlots = 64;                   // slot records staged per warp at a time (16 B each)
+constexpr int kPrefetchSlots = 4;                // terms per query whose first 32 postings are prefetched
 
 template <bool LEN16>
 __global__ void __launch_bounds__(kBm25Threads, 4)
 bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
     using LenT = typename std::conditional<LEN16, uint16_t, float>::type;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(16) unsigned char bm25_smem[];
     const int RS = w.sub_docs;
     const int lane = lane_id();
-    const int wid = warp_id();
-    const size_t per_warp = size_t(RS) * (4 + sizeof(LenT) + 2);
-    unsigned char* my = smem_raw + per_warp * wid;
-    float* s_acc = reinterpret_cast<float*>(my);
-    LenT* s_len = reinterpret_cast<LenT*>(my + size_t(RS) * 4);
-    uint16_t* s_list = reinterpret_cast<uint16_t*>(my + size_t(RS) * (4 + sizeof(LenT)));
+    const size_t per_warp = size_t(kMetaSlots) * 16 + size_t(RS) * (4 + sizeof(LenT) + 2);
+    unsigned char* my = bm25_smem + per_warp * warp_id();
+    uint4* s_meta = reinterpret_cast<uint4*>(my);                                  // {begin, count, weight bits, -}
+    float* s_acc = reinterpret_cast<float*>(my + kMetaSlots * 16);
+    LenT* s_len = reinterpret_cast<LenT*>(my + kMetaSlots * 16 + size_t(RS) * 4);
+    uint16_t* s_list = reinterpret_cast<uint16_t*>(my + kMetaSlots * 16 + size_t(RS) * (4 + sizeof(LenT)));
 
-    const int nb = w.n_sub + 1;
     const int QC = w.queries_per_item;
     const int chunks = (w.n_queries + QC - 1) / QC;
     const int n_items = w.n_sub * chunks;
     const float neg0 = __uint_as_float(kUntouchedBits);
     const unsigned lt_mask = (1u << lane) - 1u;
-    constexpr int MP = kBm25MaxPrefetchSlots;
+    const float c0 = ix.norm_c0, c1 = ix.norm_c1;
+    const int32_t* __restrict__ g_doc = ix.post_doc;
+    const int32_t* __restrict__ g_tf = ix.post_tf;
+    constexpr int MP = kPrefetchSlots;
 
     for (int i = lane; i < RS; i += 32) s_acc[i] = neg0;
     int cur_j = -1;
+    int lo = 0;
+    int nlist = 0;
 
-    auto load_meta = [&](int q, int q1, int qo_reg, int q0, int j, SlotMeta& m, int& nt, uint32_t& tau) {
-        // lanes 0..nt-1 fetch the metadata of the query's slots; everything is uniform-predicated
-        nt = 0; m.sb = 0; m.se = 0; m.base = 0; m.wt = 0.f; tau = 0;
-        if (q < q1) {
-            const int s0 = __shfl_sync(0xffffffffu, qo_reg, q - q0);
-            const int s1 = __shfl_sync(0xffffffffu, qo_reg, q - q0 + 1);
-            nt = s1 - s0;
-            if (lane < nt) {
-                const int s = s0 + lane;
-                m.sb = w.seg[int64_t(s) * nb + j];
-                m.se = w.seg[int64_t(s) * nb + j + 1];
-                m.base = w.slot_base[s];
-                m.wt = w.slot_w[s];
-            }
-            tau = w.use_tau ? ld_relaxed_u32(&w.tau[q]) : w.min_key;
+    // one warp-round: up to 32 postings of one term; docs are unique inside a term (no race)
+    auto apply = [&](int dd, int tfi, bool valid, float wt) {
+        bool fresh = false;
+        int d = 0;
+        if (valid) {
+            d = dd - lo;
+            const float tf = float(tfi);
+            const float norm = LEN16 ? fmaf(float(s_len[d]), c1, c0) : float(s_len[d]);
+            // idf*qtf*(k1+1) * tf / (tf + k1*(1-b+b*dl/avgdl)); __fdividef: <= 2 ulp
+            const float contrib = __fdividef(wt * tf, tf + norm);
+            const float old = s_acc[d];
+            fresh = __float_as_uint(old) == kUntouchedBits;
+            s_acc[d] = old + contrib;
         }
-    };
-    auto issue_posts = [&](const SlotMeta& m, int nt, int (&pd)[MP], int (&pt)[MP]) {
-#pragma unroll
-        for (int t = 0; t < MP; ++t) {
-            pd[t] = 0; pt[t] = 0;
-            if (t < nt) {                                           // uniform
-                const uint32_t sb = __shfl_sync(0xffffffffu, m.sb, t), se = __shfl_sync(0xffffffffu, m.se, t);
-                const int64_t base = __shfl_sync(0xffffffffu, m.base, t);
-                if (sb + lane < se) {
-                    pd[t] = ldg_stream_i32(ix.post_doc + base + sb + lane);
-                    pt[t] = ldg_stream_i32(ix.post_tf + base + sb + lane);
-                }
-            }
-        }
+        const unsigned fm = __ballot_sync(0xffffffffu, fresh);
+        if (fresh) s_list[nlist + __popc(fm & lt_mask)] = uint16_t(d);
+        nlist += __popc(fm);
     };
 
     while (true) {
@@ -219,122 +214,144 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
         if (lane == 0) item = atomicAdd(w.item_counter, 1);
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= n_items) break;
-        const int j = item / chunks, c = item % chunks;
-        const int lo = j * RS;
+        const int j = item / chunks, c = item - j * chunks;
+        lo = j * RS;
         const int nd = (ix.n_docs - lo) < RS ? int(ix.n_docs - lo) : RS;
         const int q0 = c * QC;
         const int q1 = (q0 + QC) < w.n_queries ? (q0 + QC) : w.n_queries;
-        // query CSR offsets of the chunk, one per lane (QC <= 31)
-        const int qo_reg = (q0 + lane <= q1) ? w.q_off[q0 + lane] : 0;
-        if (j != cur_j) {                                           // stage this sub-range's doc lengths
+        const int nq = q1 - q0;
+        const int qo_reg = (lane <= nq) ? w.q_off[q0 + lane] : 0;          // CSR offsets of the chunk (QC <= 31)
+        if (j != cur_j) {                                                   // stage this sub-range's doc lengths
             if (LEN16) { for (int i = lane; i < nd; i += 32) s_len[i] = LenT(ix.doc_len16[lo + i]); }
             else { for (int i = lane; i < nd; i += 32) s_len[i] = LenT(ix.doc_norm[lo + i]); }
             cur_j = j;
         }
-        __syncwarp();
+        const uint2* __restrict__ rec = w.rec + int64_t(j) * w.n_slots;
 
-        // software pipeline: metadata two queries ahead, postings one query ahead
-        SlotMeta m_cur, m_nxt, m_nn;
-        int nt_cur, nt_nxt, nt_nn;
-        uint32_t tau_cur, tau_nxt, tau_nn;
-        int pd_cur[MP], pt_cur[MP], pd_nxt[MP], pt_nxt[MP];
-        load_meta(q0, q1, qo_reg, q0, j, m_cur, nt_cur, tau_cur);
-        load_meta(q0 + 1, q1, qo_reg, q0, j, m_nxt, nt_nxt, tau_nxt);
-        issue_posts(m_cur, nt_cur, pd_cur, pt_cur);
+        int qa = 0;                                                         // queries are indexed relative to q0 below
+        while (qa < nq) {
+            // largest qb in (qa, nq] whose slots still fit the staging area (a query has <= 32 slots)
+            const int sa = __shfl_sync(0xffffffffu, qo_reg, qa);
+            const unsigned okm = __ballot_sync(0xffffffffu, lane > qa && lane <= nq && (qo_reg - sa) <= kMetaSlots);
+            const int qb = 31 - __clz(okm);
+            const int ns = __shfl_sync(0xffffffffu, qo_reg, qb) - sa;
+            __syncwarp();
+            for (int i = lane; i < ns; i += 32) {
+                const uint2 r = rec[sa + i];
+                s_meta[i] = make_uint4(r.x, r.y, __float_as_uint(w.slot_w[sa + i]), 0u);
+            }
+            __syncwarp();
 
-        for (int q = q0; q < q1; ++q) {
-            load_meta(q + 2, q1, qo_reg, q0, j, m_nn, nt_nn, tau_nn);
-            issue_posts(m_nxt, nt_nxt, pd_nxt, pt_nxt);
-
-            int nlist = 0;
-            // ---- apply the query's terms in order ----------------------------------------------
-            for (int t0 = 0; t0 < nt_cur; t0 += MP) {
+            int pd_cur[MP], pt_cur[MP], pd_nxt[MP], pt_nxt[MP];
+            int o_nxt = 0;                                                  // first staged slot of the next query
+            int e_nxt = __shfl_sync(0xffffffffu, qo_reg, qa + 1) - sa;
+            // prefetch of the first query of the group
 #pragma unroll
-                for (int tt = 0; tt < MP; ++tt) {
-                    const int t = t0 + tt;
-                    if (t < nt_cur) {                               // uniform
-                        const uint32_t sb = __shfl_sync(0xffffffffu, m_cur.sb, t), se = __shfl_sync(0xffffffffu, m_cur.se, t);
-                        if (se > sb) {
-                            const int64_t base = __shfl_sync(0xffffffffu, m_cur.base, t);
-                            const float wt = __shfl_sync(0xffffffffu, m_cur.wt, t);
-                            for (uint32_t i0 = sb; i0 < se; i0 += 32) {
-                                const bool valid = i0 + lane < se;
+            for (int t = 0; t < MP; ++t) {
+                pd_nxt[t] = 0; pt_nxt[t] = 0;
+                if (o_nxt + t < e_nxt) {
+                    const uint4 m = s_meta[o_nxt + t];
+                    if (lane < int(m.y)) { pd_nxt[t] = ldg_stream_i32(g_doc + m.x + lane); pt_nxt[t] = ldg_stream_i32(g_tf + m.x + lane); }
+                }
+            }
+#pragma unroll 1
+            for (int qr = qa; qr < qb; ++qr) {
+                const int o_cur = o_nxt, e_cur = e_nxt;
+#pragma unroll
+                for (int t = 0; t < MP; ++t) { pd_cur[t] = pd_nxt[t]; pt_cur[t] = pt_nxt[t]; }
+                const int q = q0 + qr;
+                const uint32_t tau_key = w.use_tau ? ld_relaxed_u32(&w.tau[q]) : w.min_key;
+                // ---- prefetch the next query of the group ---------------------------------------------
+                o_nxt = e_cur;
+                if (qr + 1 < qb) {
+                    e_nxt = __shfl_sync(0xffffffffu, qo_reg, qr + 2) - sa;
+#pragma unroll
+                    for (int t = 0; t < MP; ++t) {
+                        if (o_nxt + t < e_nxt) {
+                            const uint4 m = s_meta[o_nxt + t];
+                            if (lane < int(m.y)) { pd_nxt[t] = ldg_stream_i32(g_doc + m.x + lane); pt_nxt[t] = ldg_stream_i32(g_tf + m.x + lane); }
+                        }
+                    }
+                }
+                // ---- apply the query's terms in order ---------------------------------------------------
+                nlist = 0;
+#pragma unroll
+                for (int t = 0; t < MP; ++t) {
+                    if (o_cur + t < e_cur) {
+                        const uint4 m = s_meta[o_cur + t];
+                        const int n = int(m.y);
+                        if (n > 0) {
+                            const float wt = __uint_as_float(m.z);
+                            apply(pd_cur[t], pt_cur[t], lane < n, wt);
+#pragma unroll 1
+                            for (int i0 = 32; i0 < n; i0 += 32) {
+                                const bool valid = i0 + lane < n;
                                 int dd = 0, tfi = 0;
-                                if (t0 == 0 && i0 == sb) { dd = pd_cur[tt]; tfi = pt_cur[tt]; }     // prefetched
-                                else if (valid) {
-                                    dd = ldg_stream_i32(ix.post_doc + base + i0 + lane);
-                                    tfi = ldg_stream_i32(ix.post_tf + base + i0 + lane);
-                                }
-                                bool fresh = false;
-                                int d = 0;
-                                if (valid) {
-                                    d = dd - lo;
-                                    const float tf = float(tfi);
-                                    const float norm = LEN16 ? fmaf(float(s_len[d]), ix.norm_c1, ix.norm_c0) : float(s_len[d]);
-                                    // idf*qtf*(k1+1) * tf / (tf + k1*(1-b+b*dl/avgdl))
-                                    const float contrib = (wt * tf) / (tf + norm);
-                                    const float old = s_acc[d];
-                                    fresh = __float_as_uint(old) == kUntouchedBits;
-                                    s_acc[d] = old + contrib;       // docs are unique inside a term: no race
-                                }
-                                const unsigned fm = __ballot_sync(0xffffffffu, fresh);
-                                if (fresh) s_list[nlist + __popc(fm & lt_mask)] = uint16_t(d);
-                                nlist += __popc(fm);
+                                if (valid) { dd = ldg_stream_i32(g_doc + m.x + i0 + lane); tfi = ldg_stream_i32(g_tf + m.x + i0 + lane); }
+                                apply(dd, tfi, valid, wt);
                             }
-                            __syncwarp();                           // next term may touch the same docs
+                            __syncwarp();                                   // next term may touch the same docs
                         }
                     }
                 }
-            }
-            // ---- read-out: walk the touched list, emit candidates >= tau, re-arm ------------------
-            if (nlist > 0) {
-                const float tau_f = key_to_float(tau_cur);
-                int emitted = 0;
-                for (int i0 = 0; i0 < nlist; i0 += 32) {
-                    const bool valid = i0 + lane < nlist;
-                    int d = 0;
-                    float v = 0.f;
-                    bool pass = false;
-                    if (valid) {
-                        d = s_list[i0 + lane];
-                        v = s_acc[d] + 0.0f;
-                        s_acc[d] = neg0;
-                        pass = v >= tau_f;
+#pragma unroll 1
+                for (int sl = o_cur + MP; sl < e_cur; ++sl) {               // queries with more than MP terms
+                    const uint4 m = s_meta[sl];
+                    const int n = int(m.y);
+                    const float wt = __uint_as_float(m.z);
+#pragma unroll 1
+                    for (int i0 = 0; i0 < n; i0 += 32) {
+                        const bool valid = i0 + lane < n;
+                        int dd = 0, tfi = 0;
+                        if (valid) { dd = ldg_stream_i32(g_doc + m.x + i0 + lane); tfi = ldg_stream_i32(g_tf + m.x + i0 + lane); }
+                        apply(dd, tfi, valid, wt);
                     }
-                    const unsigned pm = __ballot_sync(0xffffffffu, pass);
-                    if (pm) {
-                        const int total = __popc(pm);
-                        int base_slot = 0;
-                        if (lane == 0) base_slot = atomicAdd(&w.cand_count[q], total);
-                        base_slot = __shfl_sync(0xffffffffu, base_slot, 0);
-                        if (pass) {
-                            const int slot = base_slot + __popc(pm & lt_mask);
-                            if (slot < w.cap) {
-                                const uint32_t key = float_to_key(v);
-                                w.cand[int64_t(q) * w.cap + slot] = make_key64(key, ix.doc_base + uint32_t(lo + d));
-                                if (w.use_tau) {
-                                    const uint32_t bin = key >> kHistShift;
-                                    atomicAdd(&w.hist[int64_t(q) * kHistBins + bin], 1u);
-                                    atomicMax(&w.maxbin[q], bin);
-                                }
-                            } else {
-                                w.overflow[q] = 1;
-                            }
+                    __syncwarp();
+                }
+                // ---- read-out: walk the touched list, emit candidates >= tau, re-arm ------------------
+                if (nlist > 0) {
+                    const float tau_f = key_to_float(tau_key);
+                    int emitted = 0;
+#pragma unroll 1
+                    for (int i0 = 0; i0 < nlist; i0 += 32) {
+                        int d = 0;
+                        float v = 0.f;
+                        bool pass = false;
+                        if (i0 + lane < nlist) {
+                            d = s_list[i0 + lane];
+                            v = s_acc[d] + 0.0f;
+                            s_acc[d] = neg0;
+                            pass = v >= tau_f;
                         }
-                        emitted += total;
+                        const unsigned pm = __ballot_sync(0xffffffffu, pass);
+                        if (pm) {
+                            const int total = __popc(pm);
+                            int base_slot = 0;
+                            if (lane == 0) base_slot = atomicAdd(&w.cand_count[q], total);
+                            base_slot = __shfl_sync(0xffffffffu, base_slot, 0);
+                            if (pass) {
+                                const int slot = base_slot + __popc(pm & lt_mask);
+                                if (slot < w.cap) {
+                                    const uint32_t key = float_to_key(v);
+                                    w.cand[int64_t(q) * w.cap + slot] = make_key64(key, ix.doc_base + uint32_t(lo + d));
+                                    if (w.use_tau) {
+                                        const uint32_t bin = key >> kHistShift;
+                                        atomicAdd(&w.hist[int64_t(q) * kHistBins + bin], 1u);
+                                        atomicMax(&w.maxbin[q], bin);
+                                    }
+                                } else {
+                                    w.overflow[q] = 1;
+                                }
+                            }
+                            emitted += total;
+                        }
                     }
-                }
-                __syncwarp();
-                if (w.use_tau && emitted > 0) {
-                    __threadfence();                                // this warp's histogram updates are visible
-                    bm25_raise_tau(w, q);
+                    __syncwarp();
+                    // a stale histogram only gives a weaker (still valid) bound: no fence needed
+                    if (w.use_tau && emitted > 0 && (emitted >= 4 || ((q ^ j) & 3) == 0)) bm25_raise_tau(w, q);
                 }
             }
-            // ---- rotate the pipeline -------------------------------------------------------------------
-            m_cur = m_nxt; nt_cur = nt_nxt; tau_cur = tau_nxt;
-            m_nxt = m_nn; nt_nxt = nt_nn; tau_nxt = tau_nn;
-#pragma unroll
-            for (int t = 0; t < MP; ++t) { pd_cur[t] = pd_nxt[t]; pt_cur[t] = pt_nxt[t]; }
+            qa = qb;
         }
     }
 }
