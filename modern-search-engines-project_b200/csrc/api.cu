@@ -73,7 +73,7 @@ struct mse_index {
 
     bool has_dense = false;
     DenseDev dn{};
-    DevBuf emb, doc_chunk_off;
+    DevBuf emb, doc_chunk_off, row_doc, tile_row;
 
     // workspace (guarded by mu)
     DevBuf q_off, q_term, q_tf, slot_w, rec, tau, hist, maxbin, cand, cand_count, overflow, misc;
@@ -164,12 +164,12 @@ int bm25_run(mse_index* ix, int32_t B, const int32_t* d_q_off, const int32_t* d_
     Bm25Work w{};
     w.q_off = d_q_off; w.q_term = d_q_term; w.q_tf = d_q_tf;
     w.slot_w = ix->slot_w.as<float>(); w.rec = ix->rec.as<uint2>();
-    w.tau = ix->tau.as<uint32_t>(); w.hist = ix->hist.as<uint32_t>(); w.maxbin = ix->maxbin.as<uint32_t>();
+    w.ts = TauState{ix->tau.as<uint32_t>(), ix->hist.as<uint32_t>(), ix->maxbin.as<uint32_t>(), top_k};
     w.cand = ix->cand.as<uint64_t>(); w.cand_count = ix->cand_count.as<int32_t>(); w.overflow = ix->overflow.as<int32_t>();
     w.item_counter = ix->misc.as<int32_t>();
     w.stats = reinterpret_cast<unsigned long long*>(ix->misc.as<char>() + 16);
     w.n_queries = B; w.n_slots = S; w.n_sub = n_sub; w.sub_docs = RS; w.queries_per_item = qpi;
-    w.cap = cap; w.top_k = top_k; w.min_key = float_to_key(min_score + 0.0f); w.use_tau = use_tau;
+    w.cap = cap; w.min_key = float_to_key(min_score + 0.0f); w.use_tau = use_tau;
 
     timer_begin(ix, T_PREPARE, st);
     {
@@ -254,7 +254,7 @@ int mse_index_destroy(mse_index* ix) {
     {
         DeviceGuard g(ix->device);
         cudaDeviceSynchronize();
-        DevBuf* all[] = {&ix->term_off, &ix->post_doc, &ix->post_tf, &ix->doc_norm, &ix->doc_len16, &ix->idf, &ix->emb, &ix->doc_chunk_off,
+        DevBuf* all[] = {&ix->term_off, &ix->post_doc, &ix->post_tf, &ix->doc_norm, &ix->doc_len16, &ix->idf, &ix->emb, &ix->doc_chunk_off, &ix->row_doc, &ix->tile_row,
                          &ix->q_off, &ix->q_term, &ix->q_tf, &ix->slot_w, &ix->rec, &ix->tau, &ix->hist,
                          &ix->maxbin, &ix->cand, &ix->cand_count, &ix->overflow, &ix->misc, &ix->o_doc, &ix->o_score,
                          &ix->o_count, &ix->best, &ix->dq};
@@ -548,9 +548,26 @@ int mse_dense_load(mse_index* ix, int64_t n_chunks, int64_t n_docs, int64_t doc_
             tmp.release();
         }
     }
+    // doc-aligned scan tiles of ~kScanTileRows rows, and the row -> doc map
+    std::vector<int64_t> tiles;
+    tiles.push_back(0);
+    for (int64_t d = 0; d < n_docs; ++d)
+        if (h_off[d + 1] - tiles.back() >= kScanTileRows) tiles.push_back(h_off[d + 1]);
+    if (tiles.back() != n_chunks) tiles.push_back(n_chunks);
+    const int64_t n_tiles = int64_t(tiles.size()) - 1;
+    if ((rc = ix->tile_row.ensure(sizeof(int64_t) * tiles.size()))) return rc;
+    if ((rc = ix->row_doc.ensure(sizeof(int32_t) * std::max<int64_t>(n_chunks, 1)))) return rc;
+    MSE_CUDA_TRY(cudaMemcpyAsync(ix->tile_row.p, tiles.data(), sizeof(int64_t) * tiles.size(), cudaMemcpyHostToDevice, st));
+    if (n_docs > 0) {
+        dense_row_doc_kernel<<<unsigned((n_docs + 255) / 256), 256, 0, st>>>(ix->doc_chunk_off.as<int64_t>(), ix->row_doc.as<int32_t>(), n_docs);
+        MSE_CUDA_TRY(cudaGetLastError());
+    }
     MSE_CUDA_TRY(cudaStreamSynchronize(st));
     ix->dn.emb = ix->emb.as<__nv_bfloat16>();
     ix->dn.doc_chunk_off = ix->doc_chunk_off.as<int64_t>();
+    ix->dn.row_doc = ix->row_doc.as<int32_t>();
+    ix->dn.tile_row = ix->tile_row.as<int64_t>();
+    ix->dn.n_tiles = n_tiles;
     ix->dn.n_chunks = n_chunks; ix->dn.n_docs = n_docs; ix->dn.doc_base = uint32_t(doc_base); ix->dn.chunk_base = chunk_base;
     ix->has_dense = true;
     return MSE_OK;
@@ -580,31 +597,62 @@ int mse_dense_scan_batch(mse_index* ix, int32_t B, const float* q, int32_t top_k
         d_q = ix->dq.as<float>(); d_doc = ix->o_doc.as<int32_t>(); d_score = ix->o_score.as<float>(); d_count = ix->o_count.as<int32_t>();
     }
     const int64_t D = std::max<int64_t>(dn.n_docs, 1);
-    const int group = int(std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(B, 32), (int64_t(1) << 30) / (4 * D))));
-    if ((rc = ix->best.ensure(sizeof(uint32_t) * size_t(group) * D))) return rc;
+    int64_t cap = ix->opt_cand_cap > 0 ? ix->opt_cand_cap : std::max<int64_t>(64 * int64_t(top_k), 262144);
+    cap = std::max<int64_t>(1, std::min<int64_t>(cap, D));
+    const int group = int(std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(B, 64), (int64_t(1) << 30) / (8 * cap))));
+    const int use_tau = ix->opt_use_tau ? 1 : 0;
     const int per_sm = ix->opt_scan_ctas > 0 ? int(ix->opt_scan_ctas) : 2;
-    const int grid = per_sm * ix->sm_count;
-    for (int g0 = 0; g0 < B; g0 += group) {
-        const int gn = std::min(group, B - g0);
-        MSE_CUDA_TRY(cudaMemsetAsync(ix->best.p, 0, sizeof(uint32_t) * size_t(gn) * D, st));
-        if (g0 == 0) timer_begin(ix, T_SCAN, st);
+    const int grid = int(std::min<int64_t>((dn.n_tiles + kScanThreads / 32 - 1) / (kScanThreads / 32) + 1, int64_t(per_sm) * ix->sm_count));
+    std::vector<int32_t> h_ovf;
+    h_ovf.resize(size_t(B));
+    if ((rc = ix->overflow.ensure(sizeof(int32_t) * size_t(B)))) return rc;
+    MSE_CUDA_TRY(cudaMemsetAsync(ix->overflow.p, 0, sizeof(int32_t) * size_t(B), st));
+    auto run = [&](int g0, int gn, int64_t rcap, int rtau, int32_t* o_doc, float* o_score, int32_t* o_count, bool mark, bool timed) -> int {
+        int r;
+        if ((r = ix->tau.ensure(sizeof(uint32_t) * size_t(gn)))) return r;
+        if ((r = ix->hist.ensure(sizeof(uint32_t) * size_t(gn) * kHistBins))) return r;
+        if ((r = ix->maxbin.ensure(sizeof(uint32_t) * size_t(gn)))) return r;
+        if ((r = ix->cand.ensure(sizeof(uint64_t) * size_t(gn) * rcap))) return r;
+        if ((r = ix->cand_count.ensure(sizeof(int32_t) * size_t(gn)))) return r;
+        MSE_CUDA_TRY(cudaMemsetAsync(ix->cand_count.p, 0, sizeof(int32_t) * size_t(gn), st));
+        MSE_CUDA_TRY(cudaMemsetAsync(ix->tau.p, 0, sizeof(uint32_t) * size_t(gn), st));
+        if (rtau) {
+            MSE_CUDA_TRY(cudaMemsetAsync(ix->hist.p, 0, sizeof(uint32_t) * size_t(gn) * kHistBins, st));
+            MSE_CUDA_TRY(cudaMemsetAsync(ix->maxbin.p, 0, sizeof(uint32_t) * size_t(gn), st));
+        }
+        DenseWork w{};
+        w.q = d_q + size_t(g0) * kDim;
+        w.cand = ix->cand.as<uint64_t>(); w.cand_count = ix->cand_count.as<int32_t>();
+        w.overflow = ix->overflow.as<int32_t>() + g0;
+        w.ts = TauState{ix->tau.as<uint32_t>(), ix->hist.as<uint32_t>(), ix->maxbin.as<uint32_t>(), top_k};
+        w.cap = int32_t(rcap); w.use_tau = rtau;
+        if (timed) timer_begin(ix, T_SCAN, st);
         if (dn.n_chunks > 0) {
             int b = 0;
-            while (b < gn) {
-                const float* qq = d_q + size_t(g0) * kDim;
-                if (gn - b >= 4) { dense_scan_kernel<4><<<grid, kScanThreads, 0, st>>>(dn, qq, b, ix->best.as<uint32_t>()); b += 4; }
-                else if (gn - b >= 2) { dense_scan_kernel<2><<<grid, kScanThreads, 0, st>>>(dn, qq, b, ix->best.as<uint32_t>()); b += 2; }
-                else { dense_scan_kernel<1><<<grid, kScanThreads, 0, st>>>(dn, qq, b, ix->best.as<uint32_t>()); b += 1; }
+            while (b < gn) {                                   // every pass streams the whole matrix once
+                if (gn - b >= 2) { dense_scan_kernel<2><<<grid, kScanThreads, 0, st>>>(dn, w, b); b += 2; }
+                else { dense_scan_kernel<1><<<grid, kScanThreads, 0, st>>>(dn, w, b); b += 1; }
                 MSE_CUDA_TRY(cudaGetLastError());
             }
         }
-        if (g0 + gn >= B) timer_end(ix, T_SCAN, st);
-        DenseLoader ld{ix->best.as<uint32_t>(), dn.n_docs, dn.doc_base};
-        if (g0 == 0) timer_begin(ix, T_SELECT, st);
-        topk_select_kernel<DenseLoader><<<gn, kSelectThreads, 0, st>>>(ld, top_k, d_doc + size_t(g0) * top_k, d_score + size_t(g0) * top_k,
-                                                                      d_count + g0, nullptr);
+        if (timed) timer_end(ix, T_SCAN, st);
+        ListLoader ld{w.cand, w.cand_count, rcap, int32_t(rcap)};
+        if (timed) timer_begin(ix, T_SELECT, st);
+        topk_select_kernel<ListLoader><<<gn, kSelectThreads, 0, st>>>(ld, top_k, o_doc, o_score, o_count, mark ? w.overflow : nullptr);
         MSE_CUDA_TRY(cudaGetLastError());
-        if (g0 + gn >= B) timer_end(ix, T_SELECT, st);
+        if (timed) timer_end(ix, T_SELECT, st);
+        return MSE_OK;
+    };
+    for (int g0 = 0; g0 < B; g0 += group) {
+        const int gn = std::min(group, B - g0);
+        if ((rc = run(g0, gn, cap, use_tau, d_doc + size_t(g0) * top_k, d_score + size_t(g0) * top_k, d_count + g0, true, g0 == 0))) return rc;
+    }
+    MSE_CUDA_TRY(cudaMemcpyAsync(h_ovf.data(), ix->overflow.p, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
+    MSE_CUDA_TRY(cudaStreamSynchronize(st));
+    timers_collect(ix);
+    for (int i = 0; i < B; ++i) {
+        if (!h_ovf[i]) continue;                               // candidate list overflowed: unbounded re-run of this query
+        if ((rc = run(i, 1, D, 0, d_doc + size_t(i) * top_k, d_score + size_t(i) * top_k, d_count + i, false, false))) return rc;
     }
     if (where == MSE_HOST) {
         MSE_CUDA_TRY(cudaMemcpyAsync(out_doc, d_doc, sizeof(int32_t) * size_t(B) * top_k, cudaMemcpyDeviceToHost, st));

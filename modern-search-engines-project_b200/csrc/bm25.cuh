@@ -33,15 +33,13 @@
 #pragma once
 #include <type_traits>
 #include "common.cuh"
+#include "topk.cuh"
 
 namespace mse {
 
 constexpr int kBm25Threads = 256;
 constexpr int kBm25Warps = kBm25Threads / 32;
 constexpr int kBm25MaxPrefetchSlots = 8;         // terms per query whose postings are prefetched
-constexpr int kHistBits = 12;                    // sign + exponent + 3 mantissa bits
-constexpr int kHistBins = 1 << kHistBits;
-constexpr int kHistShift = 32 - kHistBits;
 
 struct Bm25Dev {                                 // device-resident index of one shard
     const int64_t* term_off;
@@ -62,15 +60,13 @@ struct Bm25Work {                                // per-call workspace
     const int32_t* q_tf;
     float* slot_w;               // [S]  idf * qtf * (k1+1)
     uint2* rec;                  // [n_sub * S] {first posting (absolute), count} of slot s in sub-range j
-    uint32_t* tau;               // [B]  lower bound (score key) of the final k-th best
-    uint32_t* hist;              // [B * kHistBins] emitted candidates per score bin
-    uint32_t* maxbin;            // [B]
+    TauState ts;                 // running per-query lower bound of the final k-th best score
     uint64_t* cand;              // [B * cap]
     int32_t* cand_count;         // [B]
     int32_t* overflow;           // [B] 1 when more than cap candidates were emitted
     int32_t* item_counter;       // [1]
     unsigned long long* stats;   // [0] postings traversed
-    int32_t n_queries, n_slots, n_sub, sub_docs, queries_per_item, cap, top_k;
+    int32_t n_queries, n_slots, n_sub, sub_docs, queries_per_item, cap;
     uint32_t min_key;
     int32_t use_tau;
 };
@@ -102,7 +98,7 @@ bm25_prepare_kernel(Bm25Dev ix, Bm25Work w) {
     const int tid = threadIdx.x;
     if (s >= w.n_slots) {                                      // trailing CTAs initialise tau
         for (int q = (s - w.n_slots) * kPrepThreads + tid; q < w.n_queries; q += (gridDim.x - w.n_slots) * kPrepThreads)
-            w.tau[q] = w.min_key;
+            w.ts.tau[q] = w.min_key;
         return;
     }
     const int t = w.q_term[s];
@@ -132,29 +128,6 @@ bm25_prepare_kernel(Bm25Dev ix, Bm25Work w) {
     const uint32_t a32 = uint32_t(a);                          // n_postings < 2^32 (checked at load)
     for (int j = tid; j < w.n_sub; j += kPrepThreads)
         w.rec[int64_t(j) * w.n_slots + s] = make_uint2(a32 + s_pos[j], s_pos[j + 1] - s_pos[j]);
-}
-
-// ---- tau update: largest bin edge with >= k emitted candidates at or above it (one warp) ------------
-__device__ __forceinline__ void bm25_raise_tau(const Bm25Work& w, int q) {
-    const int lane = lane_id();
-    const uint32_t cur = ld_relaxed_u32(&w.tau[q]);
-    const int cur_bin = int(cur >> kHistShift);
-    int b = int(ld_relaxed_u32(&w.maxbin[q]));
-    int acc = 0;
-    const uint32_t* h = w.hist + int64_t(q) * kHistBins;
-    while (b >= cur_bin) {
-        const int bin = b - lane;
-        const int c = (bin >= cur_bin && bin >= 0) ? int(ld_relaxed_u32(&h[bin])) : 0;
-        const int incl = warp_incl_scan(c);
-        const unsigned hit = __ballot_sync(0xffffffffu, acc + incl >= w.top_k);
-        if (hit) {
-            const int tb = b - (__ffs(hit) - 1);
-            if (lane == 0 && tb > cur_bin) atomicMax(&w.tau[q], uint32_t(tb) << kHistShift);
-            return;
-        }
-        acc += __shfl_sync(0xffffffffu, incl, 31);
-        b -= 32;
-    }
 }
 
 // ---- scoring ------------------------------------------------------------------------------------------
@@ -260,7 +233,7 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
 #pragma unroll
                 for (int t = 0; t < MP; ++t) { pd_cur[t] = pd_nxt[t]; pt_cur[t] = pt_nxt[t]; }
                 const int q = q0 + qr;
-                const uint32_t tau_key = w.use_tau ? ld_relaxed_u32(&w.tau[q]) : w.min_key;
+                const uint32_t tau_key = w.use_tau ? ld_relaxed_u32(&w.ts.tau[q]) : w.min_key;
                 // ---- prefetch the next query of the group ---------------------------------------------
                 o_nxt = e_cur;
                 if (qr + 1 < qb) {
@@ -334,11 +307,7 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
                                 if (slot < w.cap) {
                                     const uint32_t key = float_to_key(v);
                                     w.cand[int64_t(q) * w.cap + slot] = make_key64(key, ix.doc_base + uint32_t(lo + d));
-                                    if (w.use_tau) {
-                                        const uint32_t bin = key >> kHistShift;
-                                        atomicAdd(&w.hist[int64_t(q) * kHistBins + bin], 1u);
-                                        atomicMax(&w.maxbin[q], bin);
-                                    }
+                                    if (w.use_tau) tau_count(w.ts, q, key);
                                 } else {
                                     w.overflow[q] = 1;
                                 }
@@ -348,7 +317,7 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
                     }
                     __syncwarp();
                     // a stale histogram only gives a weaker (still valid) bound: no fence needed
-                    if (w.use_tau && emitted > 0 && (emitted >= 4 || ((q ^ j) & 3) == 0)) bm25_raise_tau(w, q);
+                    if (w.use_tau && emitted > 0 && (emitted >= 4 || ((q ^ j) & 3) == 0)) tau_raise(w.ts, q);
                 }
             }
             qa = qb;

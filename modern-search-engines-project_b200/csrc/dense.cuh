@@ -4,32 +4,48 @@
 // vectors are L2-normalised, indexer/indexer.py:165): score(chunk) = <q, e_chunk>, document
 // score = max over its chunks, then top-k documents (selection: topk.cuh).
 //
-// Layout in HBM: emb bf16 [n_chunks][768] row-major (1536 B per row), doc_chunk_off int64[D+1];
-// chunks of a document are contiguous rows.  Per query a uint32 array best[D] of
-// order-preserving score keys (0 == no chunk) receives the per-document maxima.
+// Layout in HBM: emb bf16 [n_chunks][768] row-major (1536 B per row); doc_chunk_off int64[D+1];
+// row_doc int32[n_chunks] (document of every row, 0.26 % extra traffic); tile_row int64[T+1]
+// (doc-aligned tiles of ~128 rows, so a document never spans two warps).
 //
-// Each warp owns a contiguous tile of rows.  A row is read as 3 x 128-bit loads per lane
-// (coalesced 512 B per warp instruction, L1::no_allocate: every byte is used once), multiplied
-// against query fragments held in registers (fp32), reduced with shuffles; lane 0 walks the
-// document boundaries of its tile and issues one atomicMax per (document, query) — documents
-// straddling two tiles are merged by that atomic.
+// Each warp owns a tile.  A row is read as 3 x 128-bit loads per lane (coalesced 512 B per warp
+// instruction, L1::no_allocate: every byte is used once), multiplied against query fragments
+// held in registers (fp32 accumulate), reduced with shuffles, and lane (row % 32) keeps the row's
+// score.  Every 32 rows the warp does a segmented max over the lanes (rows of a document are
+// adjacent), carries a document that continues into the next 32 rows, and the lane holding the
+// last row of a finished document emits (score, doc) — but only when the score reaches tau[q],
+// the running lower bound of the final k-th best (same scheme as the BM25 kernel).  There is no
+// per-document array in HBM and no atomic per row: the selection stage reads a short candidate
+// list instead of every document.
 #pragma once
 #include "common.cuh"
+#include "topk.cuh"
 
 namespace mse {
 
 constexpr int kDim = MSE_EMB_DIM;
 constexpr int kRowBytes = kDim * 2;
 constexpr int kScanThreads = 256;
-constexpr int kScanTileRows = 64;       // rows per warp tile
+constexpr int kScanTileRows = 128;      // target rows per warp tile (tiles are doc-aligned)
 constexpr int kScanRowsInFlight = 4;
 
 struct DenseDev {
     const __nv_bfloat16* emb;
     const int64_t* doc_chunk_off;
-    int64_t n_chunks, n_docs;
+    const int32_t* row_doc;
+    const int64_t* tile_row;
+    int64_t n_chunks, n_docs, n_tiles;
     uint32_t doc_base;
     int64_t chunk_base;
+};
+
+struct DenseWork {
+    const float* q;              // [B][768]
+    uint64_t* cand;              // [B * cap]
+    int32_t* cand_count;         // [B]
+    int32_t* overflow;           // [B]
+    TauState ts;
+    int32_t cap, use_tau;
 };
 
 __device__ __forceinline__ void bf16x8_to_float(const uint4& v, float* f) {
@@ -41,23 +57,13 @@ __device__ __forceinline__ void bf16x8_to_float(const uint4& v, float* f) {
     }
 }
 
-// first doc whose chunk range ends after `row` (docs without chunks are skipped naturally)
-__device__ __forceinline__ int64_t doc_of_row(const int64_t* __restrict__ off, int64_t n_docs, int64_t row) {
-    int64_t lo = 0, hi = n_docs;          // find smallest d with off[d+1] > row
-    while (lo < hi) {
-        int64_t mid = (lo + hi) >> 1;
-        if (off[mid + 1] > row) hi = mid; else lo = mid + 1;
-    }
-    return lo;
-}
-
 template <int QB>
 __global__ void __launch_bounds__(kScanThreads)
-dense_scan_kernel(DenseDev dx, const float* __restrict__ q, int q0, uint32_t* __restrict__ best) {
+dense_scan_kernel(DenseDev dx, DenseWork w, int q0) {
     const int lane = lane_id();
     const int64_t warp_global = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
-    const int64_t n_tiles = (dx.n_chunks + kScanTileRows - 1) / kScanTileRows;
+    const unsigned lt_mask = (1u << lane) - 1u;
 
     float qf[QB][24];                     // lane's 3 x 8 query elements per query
 #pragma unroll
@@ -65,65 +71,116 @@ dense_scan_kernel(DenseDev dx, const float* __restrict__ q, int q0, uint32_t* __
 #pragma unroll
         for (int j = 0; j < 3; ++j)
 #pragma unroll
-            for (int e = 0; e < 8; ++e) qf[b][j * 8 + e] = q[int64_t(q0 + b) * kDim + j * 256 + lane * 8 + e];
+            for (int e = 0; e < 8; ++e) qf[b][j * 8 + e] = w.q[int64_t(q0 + b) * kDim + j * 256 + lane * 8 + e];
 
-    for (int64_t tile = warp_global; tile < n_tiles; tile += n_warps) {
-        const int64_t r0 = tile * kScanTileRows;
-        const int64_t r1 = (r0 + kScanTileRows) < dx.n_chunks ? (r0 + kScanTileRows) : dx.n_chunks;
-        int64_t doc = 0, doc_end = 0;     // lane 0 only
-        float run[QB];
-        if (lane == 0) {
-            doc = doc_of_row(dx.doc_chunk_off, dx.n_docs, r0);
-            doc_end = dx.doc_chunk_off[doc + 1];
+    for (int64_t tile = warp_global; tile < dx.n_tiles; tile += n_warps) {
+        const int64_t r0 = dx.tile_row[tile], r1 = dx.tile_row[tile + 1];
+        float tau_f[QB];
 #pragma unroll
-            for (int b = 0; b < QB; ++b) run[b] = -INFINITY;
+        for (int b = 0; b < QB; ++b) {
+            const uint32_t tk = w.use_tau ? ld_relaxed_u32(&w.ts.tau[q0 + b]) : 0u;      // key 0 == no bound yet
+            tau_f[b] = tk ? key_to_float(tk) : -INFINITY;
         }
-        for (int64_t r = r0; r < r1; r += kScanRowsInFlight) {
-            uint4 v[kScanRowsInFlight][3];
+        int carry_doc = -1;
+        float carry_val[QB];
 #pragma unroll
-            for (int i = 0; i < kScanRowsInFlight; ++i) {
-                const int64_t row = (r + i) < r1 ? (r + i) : (r1 - 1);
-                const uint4* p = reinterpret_cast<const uint4*>(dx.emb + row * kDim) + lane;
+        for (int b = 0; b < QB; ++b) carry_val[b] = -INFINITY;
+        int emitted = 0;
+
+        for (int64_t g = r0; g < r1; g += 32) {
+            const int nrow = (r1 - g) < 32 ? int(r1 - g) : 32;
+            const int my_doc = lane < nrow ? dx.row_doc[g + lane] : (-2 - lane);
+            const int next_doc = (g + 32 < r1) ? dx.row_doc[g + 32] : -1;        // uniform
+            float my_score[QB];
 #pragma unroll
-                for (int j = 0; j < 3; ++j) v[i][j] = ldg_stream(p + j * 32);
-            }
+            for (int b = 0; b < QB; ++b) my_score[b] = -INFINITY;
+#pragma unroll 1
+            for (int i = 0; i < nrow; i += kScanRowsInFlight) {
+                uint4 v[kScanRowsInFlight][3];
 #pragma unroll
-            for (int i = 0; i < kScanRowsInFlight; ++i) {
-                float acc[QB];
+                for (int k = 0; k < kScanRowsInFlight; ++k) {
+                    const int64_t row = (g + i + k) < r1 ? (g + i + k) : (r1 - 1);
+                    const uint4* p = reinterpret_cast<const uint4*>(dx.emb + row * kDim) + lane;
 #pragma unroll
-                for (int b = 0; b < QB; ++b) acc[b] = 0.f;
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    float f[8];
-                    bf16x8_to_float(v[i][j], f);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e)
-#pragma unroll
-                        for (int b = 0; b < QB; ++b) acc[b] = fmaf(f[e], qf[b][j * 8 + e], acc[b]);
+                    for (int j = 0; j < 3; ++j) v[k][j] = ldg_stream(p + j * 32);
                 }
 #pragma unroll
-                for (int b = 0; b < QB; ++b) acc[b] = warp_sum(acc[b]);
-                if (lane == 0 && (r + i) < r1) {
-                    const int64_t row = r + i;
-                    if (row >= doc_end) {                 // document finished: publish its maximum
+                for (int k = 0; k < kScanRowsInFlight; ++k) {
+                    float acc[QB];
 #pragma unroll
-                        for (int b = 0; b < QB; ++b) {
-                            atomicMax(&best[int64_t(q0 + b) * dx.n_docs + doc], float_to_key(run[b] + 0.0f));
-                            run[b] = -INFINITY;
-                        }
-                        do { ++doc; doc_end = dx.doc_chunk_off[doc + 1]; } while (row >= doc_end);
+                    for (int b = 0; b < QB; ++b) acc[b] = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        float f[8];
+                        bf16x8_to_float(v[k][j], f);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e)
+#pragma unroll
+                            for (int b = 0; b < QB; ++b) acc[b] = fmaf(f[e], qf[b][j * 8 + e], acc[b]);
                     }
 #pragma unroll
-                    for (int b = 0; b < QB; ++b) run[b] = fmaxf(run[b], acc[b]);
+                    for (int b = 0; b < QB; ++b) {
+                        const float s = warp_sum(acc[b]);
+                        if (lane == i + k) my_score[b] = s;          // rows beyond nrow land in lanes >= nrow (ignored)
+                    }
+                }
+            }
+            // ---- per-document max over adjacent lanes (segmented inclusive max-scan) --------------
+#pragma unroll
+            for (int b = 0; b < QB; ++b)
+                if (my_doc == carry_doc) my_score[b] = fmaxf(my_score[b], carry_val[b]);
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int od = __shfl_up_sync(0xffffffffu, my_doc, o);
+#pragma unroll
+                for (int b = 0; b < QB; ++b) {
+                    const float ov = __shfl_up_sync(0xffffffffu, my_score[b], o);
+                    if (lane >= o && od == my_doc) my_score[b] = fmaxf(my_score[b], ov);
+                }
+            }
+            const int nd = __shfl_down_sync(0xffffffffu, my_doc, 1);
+            const bool is_tail = lane < nrow && (lane == nrow - 1 ? (my_doc != next_doc) : (nd != my_doc));
+            carry_doc = __shfl_sync(0xffffffffu, my_doc, nrow - 1);
+#pragma unroll
+            for (int b = 0; b < QB; ++b) carry_val[b] = __shfl_sync(0xffffffffu, my_score[b], nrow - 1);
+            // ---- emit finished documents whose score reaches the running bound -----------------------
+#pragma unroll
+            for (int b = 0; b < QB; ++b) {
+                const float v = my_score[b] + 0.0f;
+                const bool pass = is_tail && v >= tau_f[b];
+                const unsigned pm = __ballot_sync(0xffffffffu, pass);
+                if (pm) {
+                    const int q = q0 + b;
+                    const int total = __popc(pm);
+                    int slot0 = 0;
+                    if (lane == 0) slot0 = atomicAdd(&w.cand_count[q], total);
+                    slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+                    if (pass) {
+                        const int slot = slot0 + __popc(pm & lt_mask);
+                        if (slot < w.cap) {
+                            const uint32_t key = float_to_key(v);
+                            w.cand[int64_t(q) * w.cap + slot] = make_key64(key, dx.doc_base + uint32_t(my_doc));
+                            if (w.use_tau) tau_count(w.ts, q, key);
+                        } else {
+                            w.overflow[q] = 1;
+                        }
+                    }
+                    emitted += total;
                 }
             }
         }
-        if (lane == 0 && r1 > r0) {
+        if (w.use_tau && emitted > 0) {
 #pragma unroll
-            for (int b = 0; b < QB; ++b)
-                atomicMax(&best[int64_t(q0 + b) * dx.n_docs + doc], float_to_key(run[b] + 0.0f));
+            for (int b = 0; b < QB; ++b) tau_raise(w.ts, q0 + b);
         }
     }
+}
+
+// row -> document map, built once at load
+__global__ void dense_row_doc_kernel(const int64_t* __restrict__ off, int32_t* __restrict__ row_doc, int64_t n_docs) {
+    const int64_t d = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (d >= n_docs) return;
+    for (int64_t r = off[d]; r < off[d + 1]; ++r) row_doc[r] = int32_t(d);
 }
 
 // fp32 -> bf16 conversion of the embedding table at load time

@@ -16,6 +16,49 @@
 
 namespace mse {
 
+constexpr int kHistBits = 12;                    // sign + exponent + 3 mantissa bits of the score key
+constexpr int kHistBins = 1 << kHistBits;
+constexpr int kHistShift = 32 - kHistBits;
+
+// Running lower bound of the final k-th best score of every query (see bm25.cuh / dense.cuh):
+// producers count each emitted candidate in hist[q][score bin]; tau[q] is the largest bin edge with
+// >= top_k emitted candidates at or above it.  Any value tau ever took is a valid bound.
+struct TauState {
+    uint32_t* tau;      // [B] score key
+    uint32_t* hist;     // [B * kHistBins]
+    uint32_t* maxbin;   // [B]
+    int32_t top_k;
+};
+
+__device__ __forceinline__ void tau_count(const TauState& ts, int q, uint32_t key) {
+    const uint32_t bin = key >> kHistShift;
+    atomicAdd(&ts.hist[int64_t(q) * kHistBins + bin], 1u);
+    atomicMax(&ts.maxbin[q], bin);
+}
+
+// one full warp
+__device__ __forceinline__ void tau_raise(const TauState& ts, int q) {
+    const int lane = lane_id();
+    const uint32_t cur = ld_relaxed_u32(&ts.tau[q]);
+    const int cur_bin = int(cur >> kHistShift);
+    int b = int(ld_relaxed_u32(&ts.maxbin[q]));
+    int acc = 0;
+    const uint32_t* h = ts.hist + int64_t(q) * kHistBins;
+    while (b >= cur_bin) {
+        const int bin = b - lane;
+        const int c = (bin >= cur_bin && bin >= 0) ? int(ld_relaxed_u32(&h[bin])) : 0;
+        const int incl = warp_incl_scan(c);
+        const unsigned hit = __ballot_sync(0xffffffffu, acc + incl >= ts.top_k);
+        if (hit) {
+            const int tb = b - (__ffs(hit) - 1);
+            if (lane == 0 && tb > cur_bin) atomicMax(&ts.tau[q], uint32_t(tb) << kHistShift);
+            return;
+        }
+        acc += __shfl_sync(0xffffffffu, incl, 31);
+        b -= 32;
+    }
+}
+
 constexpr int kSelectThreads = 512;
 constexpr int kSortCap = MSE_MAX_TOPK;   // survivors sorted in shared memory
 
