@@ -10,6 +10,7 @@
 #include "bm25.cuh"
 #include "common.cuh"
 #include "dense.cuh"
+#include "gemm.cuh"
 #include "rerank.cuh"
 #include "topk.cuh"
 
@@ -73,7 +74,10 @@ struct mse_index {
 
     bool has_dense = false;
     DenseDev dn{};
-    DevBuf emb, doc_chunk_off, row_doc, tile_row;
+    DevBuf emb, doc_chunk_off, row_doc, tile_row, group_row, qb16;
+    bool gemm_ok = false;
+    int64_t n_groups = 0;
+    CUtensorMap map_e;
 
     // workspace (guarded by mu)
     DevBuf q_off, q_term, q_tf, slot_w, rec, tau, hist, maxbin, cand, cand_count, overflow, misc;
@@ -83,7 +87,7 @@ struct mse_index {
     DevBuf m_in[3];                          // merge staging
     DevBuf fb_q[3], fb_out[3];               // fallback sub-batches
 
-    int64_t opt_range_docs = 0, opt_qpi = 0, opt_cand_cap = 0, opt_use_tau = 1, opt_scan_ctas = 0;
+    int64_t opt_range_docs = 0, opt_qpi = 0, opt_cand_cap = 0, opt_use_tau = 1, opt_scan_ctas = 0, opt_gemm_min_batch = 0;
     int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
     cudaEvent_t ev[kNumTimers][2];
@@ -130,6 +134,34 @@ int copy_in(void* dst, const void* src, size_t bytes, int where, cudaStream_t s)
 }
 
 int round_up(int64_t v, int64_t m) { return int(((v + m - 1) / m) * m); }
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int make_bf16_rowmajor_map(CUtensorMap* map, const void* base, uint64_t rows, uint32_t box_rows) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) {
+            set_error("cuTensorMapEncodeTiled is not available: %s", cudaGetErrorString(e));
+            (void)cudaGetLastError();
+            return MSE_ERR_CUDA;
+        }
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    const cuuint64_t dims[2] = {cuuint64_t(kDim), cuuint64_t(rows)};
+    const cuuint64_t strides[1] = {cuuint64_t(kDim) * 2};
+    const cuuint32_t box[2] = {cuuint32_t(kGemmBlockK), box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", int(r)); return MSE_ERR_CUDA; }
+    return MSE_OK;
+}
 
 // ---- BM25 core: everything on device, outputs to device pointers ---------------------------------
 int bm25_run(mse_index* ix, int32_t B, const int32_t* d_q_off, const int32_t* d_q_term, const int32_t* d_q_tf,
@@ -254,7 +286,7 @@ int mse_index_destroy(mse_index* ix) {
     {
         DeviceGuard g(ix->device);
         cudaDeviceSynchronize();
-        DevBuf* all[] = {&ix->term_off, &ix->post_doc, &ix->post_tf, &ix->doc_norm, &ix->doc_len16, &ix->idf, &ix->emb, &ix->doc_chunk_off, &ix->row_doc, &ix->tile_row,
+        DevBuf* all[] = {&ix->term_off, &ix->post_doc, &ix->post_tf, &ix->doc_norm, &ix->doc_len16, &ix->idf, &ix->emb, &ix->doc_chunk_off, &ix->row_doc, &ix->tile_row, &ix->group_row, &ix->qb16,
                          &ix->q_off, &ix->q_term, &ix->q_tf, &ix->slot_w, &ix->rec, &ix->tau, &ix->hist,
                          &ix->maxbin, &ix->cand, &ix->cand_count, &ix->overflow, &ix->misc, &ix->o_doc, &ix->o_score,
                          &ix->o_count, &ix->best, &ix->dq};
@@ -280,6 +312,7 @@ int mse_index_set_option(mse_index* ix, const char* name, int64_t value) {
     else if (!strcmp(name, "bm25_cand_cap")) ix->opt_cand_cap = value;
     else if (!strcmp(name, "bm25_use_tau")) ix->opt_use_tau = value;
     else if (!strcmp(name, "dense_scan_ctas_per_sm")) ix->opt_scan_ctas = value;
+    else if (!strcmp(name, "dense_gemm_min_batch")) ix->opt_gemm_min_batch = value;
     else if (!strcmp(name, "reset_timers")) {
         for (int t = 0; t < kNumTimers; ++t) { ix->t_ms[t] = 0; ix->t_n[t] = 0; }
     } else { set_error("unknown option '%s'", name); return MSE_ERR_INVALID; }
@@ -562,6 +595,26 @@ int mse_dense_load(mse_index* ix, int64_t n_chunks, int64_t n_docs, int64_t doc_
         dense_row_doc_kernel<<<unsigned((n_docs + 255) / 256), 256, 0, st>>>(ix->doc_chunk_off.as<int64_t>(), ix->row_doc.as<int32_t>(), n_docs);
         MSE_CUDA_TRY(cudaGetLastError());
     }
+    // doc-aligned groups of <= 32 rows for the tensor-core scan (a longer document disables that path)
+    {
+        std::vector<int64_t> groups;
+        groups.push_back(0);
+        bool ok = n_chunks > 0;
+        for (int64_t d = 0; d < n_docs && ok; ++d) {
+            const int64_t len = h_off[d + 1] - h_off[d];
+            if (len > kGemmGroupRows) { ok = false; break; }
+            if (h_off[d + 1] - groups.back() > kGemmGroupRows) groups.push_back(h_off[d]);
+        }
+        if (ok && groups.back() != n_chunks) groups.push_back(n_chunks);
+        ix->gemm_ok = false;
+        if (ok) {
+            ix->n_groups = int64_t(groups.size()) - 1;
+            if ((rc = ix->group_row.ensure(sizeof(int64_t) * groups.size()))) return rc;
+            MSE_CUDA_TRY(cudaMemcpyAsync(ix->group_row.p, groups.data(), sizeof(int64_t) * groups.size(), cudaMemcpyHostToDevice, st));
+            MSE_CUDA_TRY(cudaStreamSynchronize(st));
+            if (make_bf16_rowmajor_map(&ix->map_e, ix->emb.p, uint64_t(n_chunks), kGemmGroupRows) == MSE_OK) ix->gemm_ok = true;
+        }
+    }
     MSE_CUDA_TRY(cudaStreamSynchronize(st));
     ix->dn.emb = ix->emb.as<__nv_bfloat16>();
     ix->dn.doc_chunk_off = ix->doc_chunk_off.as<int64_t>();
@@ -599,7 +652,9 @@ int mse_dense_scan_batch(mse_index* ix, int32_t B, const float* q, int32_t top_k
     const int64_t D = std::max<int64_t>(dn.n_docs, 1);
     int64_t cap = ix->opt_cand_cap > 0 ? ix->opt_cand_cap : std::max<int64_t>(64 * int64_t(top_k), 262144);
     cap = std::max<int64_t>(1, std::min<int64_t>(cap, D));
-    const int group = int(std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(B, 64), (int64_t(1) << 30) / (8 * cap))));
+    const int64_t gemm_min = ix->opt_gemm_min_batch > 0 ? ix->opt_gemm_min_batch : 8;
+    const bool use_gemm = ix->gemm_ok && B >= gemm_min;
+    const int group = int(std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(B, 256), (int64_t(2) << 30) / (8 * cap))));
     const int use_tau = ix->opt_use_tau ? 1 : 0;
     const int per_sm = ix->opt_scan_ctas > 0 ? int(ix->opt_scan_ctas) : 2;
     const int grid = int(std::min<int64_t>((dn.n_tiles + kScanThreads / 32 - 1) / (kScanThreads / 32) + 1, int64_t(per_sm) * ix->sm_count));
@@ -627,7 +682,25 @@ int mse_dense_scan_batch(mse_index* ix, int32_t B, const float* q, int32_t top_k
         w.ts = TauState{ix->tau.as<uint32_t>(), ix->hist.as<uint32_t>(), ix->maxbin.as<uint32_t>(), top_k};
         w.cap = int32_t(rcap); w.use_tau = rtau;
         if (timed) timer_begin(ix, T_SCAN, st);
-        if (dn.n_chunks > 0) {
+        if (dn.n_chunks > 0 && use_gemm && rtau) {
+            // ---- tensor-core path: S = E * Q^T with the per-doc max / emit epilogue on TMEM ----
+            const int n_pad = round_up(gn, 32);
+            if ((r = ix->qb16.ensure(sizeof(__nv_bfloat16) * size_t(n_pad) * kDim))) return r;
+            gemm_pack_q_kernel<<<unsigned((int64_t(n_pad) * kDim + 255) / 256), 256, 0, st>>>(w.q, ix->qb16.as<__nv_bfloat16>(), gn, n_pad);
+            MSE_CUDA_TRY(cudaGetLastError());
+            CUtensorMap map_q;
+            if ((r = make_bf16_rowmajor_map(&map_q, ix->qb16.p, uint64_t(n_pad), uint32_t(n_pad)))) return r;
+            GemmWork gw{};
+            gw.group_row = ix->group_row.as<int64_t>(); gw.n_groups = ix->n_groups; gw.n_tiles = (ix->n_groups + 3) / 4;
+            gw.n_pad = n_pad; gw.n_real = gn; gw.q0 = 0;
+            const size_t stage_bytes = size_t(kGemmATileBytes) + size_t(n_pad) * 128;
+            gw.stages = int(std::min<size_t>(8, (size_t(200) * 1024) / stage_bytes));
+            const size_t gsmem = stage_bytes * gw.stages + 1024;
+            MSE_CUDA_TRY(cudaFuncSetAttribute(dense_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gsmem)));
+            const int ggrid = int(std::min<int64_t>(gw.n_tiles, ix->sm_count));
+            dense_gemm_kernel<<<ggrid, kGemmThreads, gsmem, st>>>(ix->map_e, map_q, dn, w, gw);
+            MSE_CUDA_TRY(cudaGetLastError());
+        } else if (dn.n_chunks > 0) {
             int b = 0;
             while (b < gn) {                                   // every pass streams the whole matrix once
                 if (gn - b >= 2) { dense_scan_kernel<2><<<grid, kScanThreads, 0, st>>>(dn, w, b); b += 2; }

@@ -49,6 +49,31 @@ def test_dense_scan_vs_oracle(dense_small, B, top_k):
     rt.native.close()
 
 
+@pytest.mark.parametrize("B,top_k", [(8, 100), (40, 1000), (256, 10), (33, 4096)])
+def test_dense_gemm_path_vs_oracle(dense_small, B, top_k):
+    """Batches >= 8 take the tcgen05 GEMM kernel (queries rounded to bf16 there): same documents and
+    scores within the dense tolerance."""
+    emb, off, ids, urls, oracle = dense_small
+    nat = _native.NativeIndex(0)
+    nat.dense_load(emb, off)
+    q = synthetic.make_query_vectors(B, seed=100 + B, normalize=True)
+    doc, score, count = nat.dense_scan(q, top_k)
+    n_with_chunks = int(np.count_nonzero(np.diff(off)))
+    for i in range(B):
+        rd, rs = ro.dense_scan(oracle, q[i], top_k=top_k, normalize_query=False)
+        n = int(count[i])
+        assert n == min(top_k, n_with_chunks)
+        helpers.assert_topk_matches(doc[i, :n], score[i, :n], rd, rs, DENSE_RTOL, atol=2e-4)
+    # the GEMV kernel on the same batch agrees with the tensor-core kernel within the same tolerance
+    nat.set_option("dense_gemm_min_batch", 1 << 20)
+    d2, s2, c2 = nat.dense_scan(q[:6], min(top_k, 100))
+    nat.set_option("dense_gemm_min_batch", 1)
+    d3, s3, c3 = nat.dense_scan(q[:6], min(top_k, 100))
+    for i in range(6):
+        helpers.assert_topk_matches(d3[i, :c3[i]], s3[i, :c3[i]], d2[i, :c2[i]], s2[i, :c2[i]], DENSE_RTOL, atol=2e-4)
+    nat.close()
+
+
 def test_dense_scan_docs_without_chunks_and_straddling_tiles():
     # doc sizes chosen so documents straddle the 64-row warp tiles, with empty docs in between
     counts = np.asarray([0, 70, 0, 0, 1, 63, 130, 0, 5, 0], dtype=np.int64)
@@ -64,6 +89,12 @@ def test_dense_scan_docs_without_chunks_and_straddling_tiles():
     for i in range(2):
         rd, rs = ro.dense_scan(oracle, q[i], top_k=10, normalize_query=False)
         assert count[i] == 5
+        helpers.assert_topk_matches(doc[i, :5], score[i, :5], rd, rs, DENSE_RTOL, atol=1e-6)
+    # documents longer than 32 chunks cannot use the tensor-core tiling: a large batch silently takes the GEMV kernel
+    q9 = synthetic.make_query_vectors(9, seed=10, normalize=True)
+    doc, score, count = nat.dense_scan(q9, 10)
+    for i in range(9):
+        rd, rs = ro.dense_scan(oracle, q9[i], top_k=10, normalize_query=False)
         helpers.assert_topk_matches(doc[i, :5], score[i, :5], rd, rs, DENSE_RTOL, atol=1e-6)
     nat.close()
 
