@@ -120,6 +120,41 @@ def shard_corpus(c, rank, world):
     return term_off, (c.post_doc[keep] - lo).contiguous(), c.post_tf[keep].contiguous(), c.doc_len[lo:hi].contiguous(), lo
 
 
+def dense_scan_supplement(nat, dev, peak, n_chunks=10_000_000, chunks_per_doc=5, top_k=1000, steps=5):
+    """C3: 10M x 768 bf16 chunks, 2M docs, per-doc max-pool + top-1000.  B=1/2 use the GEMV kernel, B>=8 the
+    tcgen05 GEMM kernel.  Reports the scan kernel's algorithmic HBM GB/s and, for the GEMM, bf16 TFLOP/s."""
+    import torch
+    from mse_b200 import synthetic
+    n_docs = n_chunks // chunks_per_doc
+    d = synthetic.make_dense_corpus(n_docs, seed=SEED, device=dev, dtype=torch.bfloat16, chunks_per_doc=chunks_per_doc)
+    nat.dense_load(d.emb, d.doc_chunk_off)
+    del d
+    torch.cuda.empty_cache()
+    out = []
+    for B in (1, 8, 64, 256):
+        q = torch.from_numpy(synthetic.make_query_vectors(B, seed=77, normalize=True)).to(dev)
+        for _ in range(3):
+            nat.dense_scan(q, top_k)
+        torch.cuda.synchronize()
+        nat.set_option("reset_timers", 1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            nat.dense_scan(q, top_k)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        scan_ms, n = nat.kernel_time("dense_scan")
+        scan_ms /= max(n, 1)
+        alg = 2.0 * 768 * n_chunks + 8.0 * (n_docs + 1) + 4.0 * 768 * B + 8.0 * top_k * B
+        out.append({"batch": B, "kernel": "dense_gemm_kernel (tcgen05)" if B >= 8 else "dense_scan_kernel (GEMV)",
+                    "ms_per_batch": ms, "queries_per_s": B / (ms / 1e3), "scan_kernel_ms": scan_ms,
+                    "hbm_GBps_algorithmic": alg / (scan_ms * 1e-3) / 1e9, "frac_of_hbm_peak": alg / (scan_ms * 1e-3) / 1e9 / peak,
+                    "bf16_TFLOPs": 2.0 * 768 * n_chunks * B / (scan_ms * 1e-3) / 1e12})
+    return {"workload": f"C3 dense exhaustive scan: {n_chunks} x 768 bf16 chunks, {n_docs} docs, per-doc max-pool, top-{top_k}",
+            "results": out}
+
+
 def run_reference_arm(args, rank, world):
     """The reference's CPU path for this workload: the oracle port of BM25.search's Python loop
     (the reference is pure Python; nothing compiles to oracle/_ref), one process per host core."""
@@ -181,6 +216,7 @@ def main():
     ap.add_argument("--queries-per-item", type=int, default=0)
     ap.add_argument("--cand-cap", type=int, default=0)
     ap.add_argument("--no-tau", action="store_true")
+    ap.add_argument("--no-dense", action="store_true", help="skip the supplementary dense-scan (C3) measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -356,6 +392,14 @@ def main():
                                   f"bm25_indexer.py:435-485 (no SQL cost)",
                         "vectorised_numpy_value": n_s / fast_s}
 
+    # ---- supplementary: dense exhaustive scan (BASELINE.json configs[2]) on rank 0 at N=1 ------------------
+    dense = None
+    if rank == 0 and world == 1 and not args.no_dense:
+        try:
+            dense = dense_scan_supplement(nat, dev, peak)
+        except Exception as e:  # noqa: BLE001 - the headline number must not depend on the supplement
+            dense = {"error": repr(e)}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -376,6 +420,7 @@ def main():
                           "candidates_emitted_per_query": stats["emitted"] / BATCH, "rerun_queries": stats["rerun_queries"],
                           "ranges": stats["ranges"], "score_ctas": stats["ctas"], "setup_s": setup_s},
             "parity": parity,
+            "dense_scan": dense,
         }
         print(json.dumps(line))
     if world > 1:

@@ -74,7 +74,7 @@ struct mse_index {
 
     bool has_dense = false;
     DenseDev dn{};
-    DevBuf emb, doc_chunk_off, row_doc, tile_row, group_row, qb16;
+    DevBuf emb, doc_chunk_off, row_doc, tile_row, group_row, qb16, log_key, log_q;
     bool gemm_ok = false;
     int64_t n_groups = 0;
     CUtensorMap map_e;
@@ -87,7 +87,7 @@ struct mse_index {
     DevBuf m_in[3];                          // merge staging
     DevBuf fb_q[3], fb_out[3];               // fallback sub-batches
 
-    int64_t opt_range_docs = 0, opt_qpi = 0, opt_cand_cap = 0, opt_use_tau = 1, opt_scan_ctas = 0, opt_gemm_min_batch = 0;
+    int64_t opt_range_docs = 0, opt_qpi = 0, opt_cand_cap = 0, opt_use_tau = 1, opt_scan_ctas = 0, opt_gemm_min_batch = 0, opt_gemm_debug = 0;
     int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
     cudaEvent_t ev[kNumTimers][2];
@@ -286,7 +286,7 @@ int mse_index_destroy(mse_index* ix) {
     {
         DeviceGuard g(ix->device);
         cudaDeviceSynchronize();
-        DevBuf* all[] = {&ix->term_off, &ix->post_doc, &ix->post_tf, &ix->doc_norm, &ix->doc_len16, &ix->idf, &ix->emb, &ix->doc_chunk_off, &ix->row_doc, &ix->tile_row, &ix->group_row, &ix->qb16,
+        DevBuf* all[] = {&ix->term_off, &ix->post_doc, &ix->post_tf, &ix->doc_norm, &ix->doc_len16, &ix->idf, &ix->emb, &ix->doc_chunk_off, &ix->row_doc, &ix->tile_row, &ix->group_row, &ix->qb16, &ix->log_key, &ix->log_q,
                          &ix->q_off, &ix->q_term, &ix->q_tf, &ix->slot_w, &ix->rec, &ix->tau, &ix->hist,
                          &ix->maxbin, &ix->cand, &ix->cand_count, &ix->overflow, &ix->misc, &ix->o_doc, &ix->o_score,
                          &ix->o_count, &ix->best, &ix->dq};
@@ -313,6 +313,7 @@ int mse_index_set_option(mse_index* ix, const char* name, int64_t value) {
     else if (!strcmp(name, "bm25_use_tau")) ix->opt_use_tau = value;
     else if (!strcmp(name, "dense_scan_ctas_per_sm")) ix->opt_scan_ctas = value;
     else if (!strcmp(name, "dense_gemm_min_batch")) ix->opt_gemm_min_batch = value;
+    else if (!strcmp(name, "dense_gemm_debug")) ix->opt_gemm_debug = value;
     else if (!strcmp(name, "reset_timers")) {
         for (int t = 0; t < kNumTimers; ++t) { ix->t_ms[t] = 0; ix->t_n[t] = 0; }
     } else { set_error("unknown option '%s'", name); return MSE_ERR_INVALID; }
@@ -692,13 +693,23 @@ int mse_dense_scan_batch(mse_index* ix, int32_t B, const float* q, int32_t top_k
             if ((r = make_bf16_rowmajor_map(&map_q, ix->qb16.p, uint64_t(n_pad), uint32_t(n_pad)))) return r;
             GemmWork gw{};
             gw.group_row = ix->group_row.as<int64_t>(); gw.n_groups = ix->n_groups; gw.n_tiles = (ix->n_groups + 3) / 4;
-            gw.n_pad = n_pad; gw.n_real = gn; gw.q0 = 0;
+            gw.n_pad = n_pad; gw.n_real = gn; gw.q0 = 0; gw.debug = int(ix->opt_gemm_debug);
             const size_t stage_bytes = size_t(kGemmATileBytes) + size_t(n_pad) * 128;
-            gw.stages = int(std::min<size_t>(8, (size_t(200) * 1024) / stage_bytes));
+            gw.stages = int(std::min<size_t>(8, (size_t(196) * 1024) / stage_bytes));
             const size_t gsmem = stage_bytes * gw.stages + 1024;
             MSE_CUDA_TRY(cudaFuncSetAttribute(dense_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gsmem)));
             const int ggrid = int(std::min<int64_t>(gw.n_tiles, ix->sm_count));
+            const int64_t log_cap = std::min<int64_t>(int64_t(gn) * 65536, int64_t(64) << 20);
+            if ((r = ix->log_key.ensure(sizeof(uint64_t) * size_t(log_cap)))) return r;
+            if ((r = ix->log_q.ensure(sizeof(uint16_t) * size_t(log_cap)))) return r;
+            if ((r = ix->misc.ensure(64))) return r;
+            MSE_CUDA_TRY(cudaMemsetAsync(ix->misc.p, 0, 64, st));
+            w.log_key = ix->log_key.as<uint64_t>(); w.log_q = ix->log_q.as<uint16_t>();
+            w.log_count = reinterpret_cast<unsigned long long*>(ix->misc.as<char>() + 32);
+            w.log_cap = log_cap; w.n_log_queries = gn;
             dense_gemm_kernel<<<ggrid, kGemmThreads, gsmem, st>>>(ix->map_e, map_q, dn, w, gw);
+            MSE_CUDA_TRY(cudaGetLastError());
+            gemm_bucket_kernel<<<ix->sm_count * 4, 256, 0, st>>>(w);
             MSE_CUDA_TRY(cudaGetLastError());
         } else if (dn.n_chunks > 0) {
             int b = 0;

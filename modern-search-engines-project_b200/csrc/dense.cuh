@@ -46,6 +46,13 @@ struct DenseWork {
     int32_t* overflow;           // [B]
     TauState ts;
     int32_t cap, use_tau;
+    // batch-wide emission log of the tensor-core kernel (gemm.cuh): entries (query, key) appended with one
+    // atomic per flush, split into the per-query lists above by gemm_bucket_kernel
+    uint64_t* log_key;
+    uint16_t* log_q;
+    unsigned long long* log_count;
+    int64_t log_cap;
+    int32_t n_log_queries;
 };
 
 __device__ __forceinline__ void bf16x8_to_float(const uint4& v, float* f) {

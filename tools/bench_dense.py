@@ -16,6 +16,7 @@ ap.add_argument("--batches", default="1,2,4,8")
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--top-k", type=int, default=1000)
 ap.add_argument("--ctas-per-sm", type=int, default=0)
+ap.add_argument("--gemm-debug", type=int, default=0)
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 n_docs = a.chunks // a.chunks_per_doc
@@ -25,6 +26,8 @@ nat = _native.NativeIndex(0)
 nat.dense_load(d.emb, d.doc_chunk_off)
 del d.emb
 torch.cuda.empty_cache()
+if a.gemm_debug:
+    nat.set_option("dense_gemm_debug", a.gemm_debug)
 if a.ctas_per_sm:
     nat.set_option("dense_scan_ctas_per_sm", a.ctas_per_sm)
 print(f"# corpus ready in {time.time()-t0:.1f}s", file=sys.stderr)
