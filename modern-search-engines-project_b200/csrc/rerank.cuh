@@ -191,24 +191,32 @@ rerank_kernel(DenseDev dx, RerankArgs a) {
     qq = warp_sum(qq);
     const float qn = sqrtf(qq);
     __syncthreads();
-    for (int r = warp_id(); r < T; r += NT / 32) {
-        const int i = s_rowcand[r];
-        const int64_t row = dx.doc_chunk_off[s_doc[i]] + (r - s_row0[i]);
-        const uint4* p = reinterpret_cast<const uint4*>(dx.emb + row * kDim) + lane_id();
-        uint4 v[3];
+    constexpr int RIF = 4;                                 // rows in flight per warp (12 x 128-bit loads per lane)
+    for (int r0 = warp_id() * RIF; r0 < T; r0 += (NT / 32) * RIF) {
+        uint4 v[RIF][3];
 #pragma unroll
-        for (int j = 0; j < 3; ++j) v[j] = ldg_stream(p + j * 32);
-        float dot = 0.f, ee = 0.f;
+        for (int k = 0; k < RIF; ++k) {
+            const int r = (r0 + k) < T ? (r0 + k) : (T - 1);
+            const int i = s_rowcand[r];
+            const int64_t row = dx.doc_chunk_off[s_doc[i]] + (r - s_row0[i]);
+            const uint4* p = reinterpret_cast<const uint4*>(dx.emb + row * kDim) + lane_id();
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            float f[8];
-            bf16x8_to_float(v[j], f);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) { dot = fmaf(f[e], qf[j * 8 + e], dot); ee = fmaf(f[e], f[e], ee); }
+            for (int j = 0; j < 3; ++j) v[k][j] = ldg_stream(p + j * 32);
         }
-        dot = warp_sum(dot);
-        ee = warp_sum(ee);
-        if (lane_id() == 0) s_cos[r] = dot / (sqrtf(ee) * qn);
+#pragma unroll
+        for (int k = 0; k < RIF; ++k) {
+            float dot = 0.f, ee = 0.f;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                float f[8];
+                bf16x8_to_float(v[k][j], f);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { dot = fmaf(f[e], qf[j * 8 + e], dot); ee = fmaf(f[e], f[e], ee); }
+            }
+            dot = warp_sum(dot);
+            ee = warp_sum(ee);
+            if (lane_id() == 0 && (r0 + k) < T) s_cos[r0 + k] = dot / (sqrtf(ee) * qn);
+        }
     }
     __syncthreads();
 
