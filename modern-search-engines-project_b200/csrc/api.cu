@@ -213,7 +213,7 @@ int bm25_run(mse_index* ix, int32_t B, const int32_t* d_q_off, const int32_t* d_
     }
     timer_end(ix, T_PREPARE, st);
 
-    const size_t smem = size_t(kBm25Warps) * (size_t(kMetaSlots) * 16 + size_t(RS) * (len16 ? 8 : 10));
+    const size_t smem = size_t(kBm25Warps) * (size_t(kMetaSlots) * 16 + size_t(2 * kEmitStage) * 8 + size_t(RS) * (len16 ? 8 : 10));
     const void* kfn = len16 ? (const void*)bm25_score_kernel<true> : (const void*)bm25_score_kernel<false>;
     MSE_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     int per_sm = 0;

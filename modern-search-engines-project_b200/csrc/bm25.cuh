@@ -133,6 +133,7 @@ bm25_prepare_kernel(Bm25Dev ix, Bm25Work w) {
 // ---- scoring ------------------------------------------------------------------------------------------
 constexpr int kMetaSlots = 64;                   // slot records staged per warp at a time (16 B each)
 constexpr int kPrefetchSlots = 4;                // terms per query whose first 32 postings are prefetched
+constexpr int kEmitStage = 32;                   // candidates of one task staged in shared memory (deferred write-out)
 
 template <bool LEN16>
 __global__ void __launch_bounds__(kBm25Threads, 4)
@@ -141,12 +142,14 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
     extern __shared__ __align__(16) unsigned char bm25_smem[];
     const int RS = w.sub_docs;
     const int lane = lane_id();
-    const size_t per_warp = size_t(kMetaSlots) * 16 + size_t(RS) * (4 + sizeof(LenT) + 2);
+    const size_t per_warp = size_t(kMetaSlots) * 16 + size_t(2 * kEmitStage) * 8 + size_t(RS) * (4 + sizeof(LenT) + 2);
     unsigned char* my = bm25_smem + per_warp * warp_id();
     uint4* s_meta = reinterpret_cast<uint4*>(my);                                  // {begin, count, weight bits, -}
-    float* s_acc = reinterpret_cast<float*>(my + kMetaSlots * 16);
-    LenT* s_len = reinterpret_cast<LenT*>(my + kMetaSlots * 16 + size_t(RS) * 4);
-    uint16_t* s_list = reinterpret_cast<uint16_t*>(my + kMetaSlots * 16 + size_t(RS) * (4 + sizeof(LenT)));
+    uint64_t* s_emit = reinterpret_cast<uint64_t*>(my + kMetaSlots * 16);          // [2][kEmitStage] staged candidates
+    unsigned char* body = my + kMetaSlots * 16 + size_t(2 * kEmitStage) * 8;
+    float* s_acc = reinterpret_cast<float*>(body);
+    LenT* s_len = reinterpret_cast<LenT*>(body + size_t(RS) * 4);
+    uint16_t* s_list = reinterpret_cast<uint16_t*>(body + size_t(RS) * (4 + sizeof(LenT)));
 
     const int QC = w.queries_per_item;
     const int chunks = (w.n_queries + QC - 1) / QC;
@@ -162,6 +165,23 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
     int cur_j = -1;
     int lo = 0;
     int nlist = 0;
+    // Deferred emission: the slot-reserving atomicAdd of task t is issued without waiting for its
+    // result; the staged candidates are written out at the end of task t+1, when it has long returned.
+    int pend_n = 0, pend_q = 0, pend_base = 0, stage_sel = 0;
+    auto complete_pending = [&]() {
+        if (pend_n == 0) return;
+        const int base = __shfl_sync(0xffffffffu, pend_base, 0);
+        const uint64_t* st = s_emit + (stage_sel ^ 1) * kEmitStage;
+        if (lane < pend_n) {
+            const int slot = base + lane;
+            if (slot < w.cap) w.cand[int64_t(pend_q) * w.cap + slot] = st[lane];
+            else w.overflow[pend_q] = 1;
+        }
+        // refresh the bound when the query's candidate count crosses a multiple of 64 (a stale histogram
+        // only gives a weaker, still valid bound: no fence needed)
+        if (w.use_tau && (((base + pend_n) ^ base) >> 6)) tau_raise(w.ts, pend_q);
+        pend_n = 0;
+    };
 
     // one warp-round: up to 32 postings of one term; docs are unique inside a term (no race)
     auto apply = [&](int dd, int tfi, bool valid, float wt) {
@@ -281,10 +301,11 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
                     }
                     __syncwarp();
                 }
-                // ---- read-out: walk the touched list, emit candidates >= tau, re-arm ------------------
+                // ---- read-out: walk the touched list, stage candidates >= tau, re-arm -------------------
                 if (nlist > 0) {
                     const float tau_f = key_to_float(tau_key);
-                    int emitted = 0;
+                    uint64_t* st = s_emit + stage_sel * kEmitStage;
+                    int staged = 0;
 #pragma unroll 1
                     for (int i0 = 0; i0 < nlist; i0 += 32) {
                         int d = 0;
@@ -299,30 +320,43 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
                         const unsigned pm = __ballot_sync(0xffffffffu, pass);
                         if (pm) {
                             const int total = __popc(pm);
-                            int base_slot = 0;
-                            if (lane == 0) base_slot = atomicAdd(&w.cand_count[q], total);
-                            base_slot = __shfl_sync(0xffffffffu, base_slot, 0);
-                            if (pass) {
-                                const int slot = base_slot + __popc(pm & lt_mask);
-                                if (slot < w.cap) {
-                                    const uint32_t key = float_to_key(v);
-                                    w.cand[int64_t(q) * w.cap + slot] = make_key64(key, ix.doc_base + uint32_t(lo + d));
+                            const uint32_t key = float_to_key(v);
+                            const uint64_t k64 = make_key64(key, ix.doc_base + uint32_t(lo + d));
+                            if (staged + total <= kEmitStage) {              // common case: stage, write out one task later
+                                if (pass) {
+                                    st[staged + __popc(pm & lt_mask)] = k64;
                                     if (w.use_tau) tau_count(w.ts, q, key);
-                                } else {
-                                    w.overflow[q] = 1;
                                 }
+                                staged += total;
+                            } else {                                         // ramp-up / dense ranges: write through
+                                int base_slot = 0;
+                                if (lane == 0) base_slot = atomicAdd(&w.cand_count[q], total);
+                                base_slot = __shfl_sync(0xffffffffu, base_slot, 0);
+                                if (pass) {
+                                    const int slot = base_slot + __popc(pm & lt_mask);
+                                    if (slot < w.cap) {
+                                        w.cand[int64_t(q) * w.cap + slot] = k64;
+                                        if (w.use_tau) tau_count(w.ts, q, key);
+                                    } else {
+                                        w.overflow[q] = 1;
+                                    }
+                                }
+                                if (w.use_tau && (((base_slot + total) ^ base_slot) >> 6)) tau_raise(w.ts, q);
                             }
-                            emitted += total;
                         }
                     }
                     __syncwarp();
-                    // a stale histogram only gives a weaker (still valid) bound: no fence needed
-                    if (w.use_tau && emitted > 0 && (emitted >= 4 || ((q ^ j) & 3) == 0)) tau_raise(w.ts, q);
+                    complete_pending();                                      // previous task's atomic has returned by now
+                    if (staged > 0) {
+                        if (lane == 0) pend_base = atomicAdd(&w.cand_count[q], staged);   // result consumed one task later
+                        pend_n = staged; pend_q = q; stage_sel ^= 1;
+                    }
                 }
             }
             qa = qb;
         }
     }
+    complete_pending();
 }
 
 // ---- load-time kernels ----------------------------------------------------------------------------------
