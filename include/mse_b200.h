@@ -48,6 +48,8 @@ extern "C" {
 
 #define MSE_HOST 0             /* buffers are host memory; the call copies and synchronises */
 #define MSE_DEVICE 1           /* buffers are device memory; work is ordered on `stream` */
+#define MSE_DEVICE_BORROW 2    /* mse_dense_load only: `emb` is bf16 device memory that the index uses IN PLACE
+                                  (no copy; the caller keeps it alive and unchanged until the next load/destroy) */
 
 typedef struct mse_index mse_index;
 

@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libmsegpu.so")
 HEADER = os.path.join(os.path.dirname(HERE), "include", "mse_b200.h")
 
-MSE_HOST, MSE_DEVICE = 0, 1
+MSE_HOST, MSE_DEVICE, MSE_DEVICE_BORROW = 0, 1, 2
 MAX_TOPK = 4096
 EMB_DIM = 768
 KERNELS = {"bm25_score": 0, "topk_select": 1, "dense_scan": 2, "rerank": 3, "bm25_prepare": 4}
@@ -199,14 +199,21 @@ class NativeIndex:
         return out
 
     # ---- dense --------------------------------------------------------------------------------
-    def dense_load(self, emb, doc_chunk_off, doc_base=0, chunk_base=0):
+    def dense_load(self, emb, doc_chunk_off, doc_base=0, chunk_base=0, borrow=False):
+        """``borrow=True`` (bf16 CUDA tensor only): the index scans the tensor in place instead of copying it
+        (a 77-154 GB shard cannot be resident twice); the tensor is kept alive by this object."""
         where = _where_of(emb, doc_chunk_off)
         is_bf16 = _is_torch(emb) and str(emb.dtype) == "torch.bfloat16"
         n_chunks, n_docs = int(emb.shape[0]), int(doc_chunk_off.shape[0]) - 1
         assert emb.shape[1] == EMB_DIM
+        flag = where
+        if borrow:
+            assert where == MSE_DEVICE and is_bf16, "borrow needs a bf16 CUDA tensor"
+            flag = MSE_DEVICE_BORROW
         _check(lib().mse_dense_load(self._h, n_chunks, n_docs, int(doc_base), int(chunk_base),
                                     _ptr(emb, "bf16" if is_bf16 else np.float32, where), int(is_bf16),
-                                    _ptr(doc_chunk_off, np.int64, where), where))
+                                    _ptr(doc_chunk_off, np.int64, where), flag))
+        self._borrowed = emb if borrow else None
 
     def dense_scan(self, q, top_k: int, out=None):
         where = _where_of(q)

@@ -543,7 +543,10 @@ int mse_dense_load(mse_index* ix, int64_t n_chunks, int64_t n_docs, int64_t doc_
     MSE_REQUIRE(n_chunks >= 0 && n_docs >= 0 && n_docs < (int64_t(1) << 31) && doc_base >= 0 && chunk_base >= 0 &&
                 doc_base + n_docs < (int64_t(1) << 31), "size arguments out of range");
     MSE_REQUIRE(doc_chunk_off && (n_chunks == 0 || emb), "null array");
-    MSE_REQUIRE(where == MSE_HOST || where == MSE_DEVICE, "bad `where`");
+    MSE_REQUIRE(where == MSE_HOST || where == MSE_DEVICE || where == MSE_DEVICE_BORROW, "bad `where`");
+    const bool borrow = where == MSE_DEVICE_BORROW;
+    MSE_REQUIRE(!borrow || (emb_is_bf16 && (reinterpret_cast<uintptr_t>(emb) & 15) == 0), "borrowed embeddings must be bf16 and 16-byte aligned");
+    if (borrow) where = MSE_DEVICE;
     std::lock_guard<std::mutex> lk(ix->mu);
     DeviceGuard g(ix->device);
     cudaStream_t st = 0;
@@ -556,10 +559,12 @@ int mse_dense_load(mse_index* ix, int64_t n_chunks, int64_t n_docs, int64_t doc_
     for (int64_t d = 0; d < n_docs; ++d) MSE_REQUIRE(h_off[d + 1] >= h_off[d], "doc_chunk_off not monotone at %lld", (long long)d);
     int rc;
     const size_t n_el = size_t(n_chunks) * kDim;
-    if ((rc = ix->emb.ensure(sizeof(__nv_bfloat16) * std::max<size_t>(n_el, 8)))) return rc;
+    if (borrow) ix->emb.release();
+    else if ((rc = ix->emb.ensure(sizeof(__nv_bfloat16) * std::max<size_t>(n_el, 8)))) return rc;
+    const __nv_bfloat16* emb_dev = borrow ? static_cast<const __nv_bfloat16*>(emb) : ix->emb.as<__nv_bfloat16>();
     if ((rc = ix->doc_chunk_off.ensure(sizeof(int64_t) * (n_docs + 1)))) return rc;
     MSE_CUDA_TRY(cudaMemcpyAsync(ix->doc_chunk_off.p, h_off.data(), sizeof(int64_t) * (n_docs + 1), cudaMemcpyHostToDevice, st));
-    if (n_el) {
+    if (n_el && !borrow) {
         if (emb_is_bf16) {
             if ((rc = copy_in(ix->emb.p, emb, sizeof(__nv_bfloat16) * n_el, where, st))) return rc;
         } else {
@@ -613,11 +618,11 @@ int mse_dense_load(mse_index* ix, int64_t n_chunks, int64_t n_docs, int64_t doc_
             if ((rc = ix->group_row.ensure(sizeof(int64_t) * groups.size()))) return rc;
             MSE_CUDA_TRY(cudaMemcpyAsync(ix->group_row.p, groups.data(), sizeof(int64_t) * groups.size(), cudaMemcpyHostToDevice, st));
             MSE_CUDA_TRY(cudaStreamSynchronize(st));
-            if (make_bf16_rowmajor_map(&ix->map_e, ix->emb.p, uint64_t(n_chunks), kGemmGroupRows) == MSE_OK) ix->gemm_ok = true;
+            if (make_bf16_rowmajor_map(&ix->map_e, emb_dev, uint64_t(n_chunks), kGemmGroupRows) == MSE_OK) ix->gemm_ok = true;
         }
     }
     MSE_CUDA_TRY(cudaStreamSynchronize(st));
-    ix->dn.emb = ix->emb.as<__nv_bfloat16>();
+    ix->dn.emb = emb_dev;
     ix->dn.doc_chunk_off = ix->doc_chunk_off.as<int64_t>();
     ix->dn.row_doc = ix->row_doc.as<int32_t>();
     ix->dn.tile_row = ix->tile_row.as<int64_t>();

@@ -85,3 +85,51 @@ def test_batch_search_file_matches_oracle_pipeline(tmp_path):
         same = sum(a == b for (_, a, _), b in zip(g, want_urls))
         assert same >= 0.9 * len(want_urls)          # order may differ only inside the dense tolerance
     bm.close()
+
+
+def test_c1_config_against_oracle():
+    """BASELINE.json configs[0] shape: 10k synthetic docs (with the always-present 'tübingen' term), 50k
+    768-d chunks, the five queries.txt queries mapped to term ids + the always-term, BM25 top-100 -> rerank ->
+    top-100.  GPU pipeline (array store) vs the oracle pipeline on the same arrays."""
+    from mse_b200.bm25_indexer import bm25_from_arrays
+    from mse_b200.store import ArrayStore, DenseTables
+    c = synthetic.make_bm25_corpus(10_000, vocab=200_000, seed=1234, always_frac=0.95)
+    ix = bo.Bm25Arrays(c.term_off.numpy(), c.post_doc.numpy(), c.post_tf.numpy(), c.doc_len.numpy(), c.idf.numpy(),
+                       c.avgdl, c.total_docs, c.doc_ids.numpy())
+    d = synthetic.make_dense_corpus(10_000, seed=1234, device="cpu", dtype=torch.float32, total_chunks=50_000)
+    emb, off = d.emb.numpy(), d.doc_chunk_off.numpy()
+    assert emb.shape[0] == 50_000
+    urls = synthetic.make_urls(ix.doc_ids, n_domains=997, dup_frac=0.02)
+    bm = bm25_from_arrays(ix.term_off, ix.post_doc, ix.post_tf, ix.doc_len, ix.idf, ix.avgdl, ix.total_docs, doc_ids=ix.doc_ids)
+    store = ArrayStore(bm25=bm.tables, doc_id_array=ix.doc_ids, url_list=urls)
+    rr = Reranker(store, ix.doc_ids, native=bm.native, dense_tables=DenseTables(emb, d.chunk_ids.numpy(), off), diversification=False)
+    stored = torch.from_numpy(emb).to(torch.bfloat16).float().numpy()
+    dense = ro.DenseArrays(stored, d.chunk_ids.numpy(), off, ix.doc_ids, urls)
+    # queries.txt lines -> 2-4 hashed term ranks (>= 64, with postings) + the always-present term
+    df = np.diff(ix.term_off)
+    lines = ["tübingen attractions", "food and drinks", "university tuebingen research programs",
+             "castle hohentubingen history", "botanical garden opening hours"]
+    known = np.flatnonzero(df[:c.always_term] > 0)
+    known = known[known >= 64]
+    qv = synthetic.make_query_vectors(len(lines), seed=8) * 1.7
+    for li, line in enumerate(lines):
+        words = [w for w in pipeline.preprocess_query(line).split() if w != "tübingen"]
+        import zlib
+        terms = [int(known[zlib.crc32(w.encode()) % len(known)]) for w in words] + [c.always_term]
+        q_off, q_term, q_tf = bm.encode_queries([terms])
+        doc, score, count = bm.search_batch_terms(q_off, q_term, q_tf, 100, 0.0)
+        ref = bo.search_fast(ix, terms, top_k=100, min_score=0.0)
+        n = int(count[0])
+        assert n == len(ref)
+        if n == 0:
+            continue
+        import mse_testlib as helpers
+        scale = bo.abs_contrib_sum(ix, terms)
+        rd = [x for x, _ in ref]
+        helpers.assert_topk_matches(doc[0, :n], score[0, :n], rd, [s for _, s in ref], 1e-5, scale=scale[rd])
+        out = rr.rerank_batch([doc[0, :n]], [score[0, :n]], qv[li:li + 1])
+        res = ro.rerank(dense, rd, [s for _, s in ref], qv[li], faithful=False)
+        m = int(out[4][0])
+        assert m == len(res.doc) and int(out[5][0]) == res.total_rows
+        helpers.assert_topk_matches(out[0][0, :m], out[1][0, :m], res.doc, res.score, 0.0, atol=2e-3)
+    bm.close()
