@@ -67,7 +67,7 @@ def slice_bm25_tables(t: Bm25Tables, lo: int, hi: int) -> Bm25Tables:
 class BM25:
     def __init__(self, db_path: Optional[str], k1: float = 1.2, b: float = 0.75, read_only: bool = True, *,
                  store=None, tokenizer: Optional[Callable[[str], List[str]]] = None, device: int = 0,
-                 doc_range: Optional[Tuple[int, int]] = None, load: bool = True):
+                 doc_range: Optional[Tuple[int, int]] = None, load: bool = True, cache_path: Optional[str] = None):
         self.db_path = db_path
         self.k1 = k1
         self.b = b
@@ -77,6 +77,7 @@ class BM25:
         self._tokenizer = tokenizer
         self.device = device
         self.doc_range = doc_range
+        self.cache_path = cache_path                      # optional .npz of the CSR arrays (skips the SQL scan)
         self.tables: Optional[Bm25Tables] = None
         self.native: Optional[_native.NativeIndex] = None
         self._term_index: Dict[str, int] = {}
@@ -88,7 +89,14 @@ class BM25:
     def reload(self):
         """(Re)reads the bm25_* tables and uploads the CSR index to HBM."""
         all_ids = self.store.all_doc_ids() if hasattr(self.store, "all_doc_ids") else None
-        full = self.store.load_bm25(all_ids)
+        full = None
+        if self.cache_path:
+            from .store import load_bm25_cache, save_bm25_cache
+            full = load_bm25_cache(self.cache_path, expect_docs=None if all_ids is None else len(all_ids))
+        if full is None:
+            full = self.store.load_bm25(all_ids)
+            if self.cache_path:
+                save_bm25_cache(self.cache_path, full)
         self.global_doc_ids = full.doc_ids
         self._df_global = np.diff(full.term_off)
         t = full

@@ -222,6 +222,28 @@ class ArrayStore:
         pass
 
 
+# ---- on-disk cache of the loaded arrays ---------------------------------------------
+def save_bm25_cache(path: str, t: Bm25Tables) -> None:
+    """Persist the CSR arrays beside the database so the next start-up skips the SQL scan.  The cache is
+    keyed by (n_docs, n_postings, n_terms, avgdl, total_docs): `load_bm25_cache` returns None on mismatch."""
+    np.savez(path, term_off=t.term_off, post_doc=t.post_doc, post_tf=t.post_tf, doc_ids=t.doc_ids, doc_len=t.doc_len,
+             idf=t.idf, total_freq=t.total_freq, scalars=np.asarray([t.avgdl, t.total_docs], dtype=np.float64),
+             terms=np.asarray(t.terms if t.terms is not None else [], dtype=object))
+
+
+def load_bm25_cache(path: str, expect_docs: Optional[int] = None, expect_terms: Optional[int] = None) -> Optional[Bm25Tables]:
+    if not os.path.exists(path):
+        return None
+    z = np.load(path, allow_pickle=True)
+    t = Bm25Tables(list(z["terms"]) or None, z["term_off"], z["post_doc"], z["post_tf"], z["doc_ids"], z["doc_len"], z["idf"],
+                   z["total_freq"], float(z["scalars"][0]), float(z["scalars"][1]))
+    if expect_docs is not None and len(t.doc_ids) != expect_docs:
+        return None
+    if expect_terms is not None and len(t.term_off) - 1 != expect_terms:
+        return None
+    return t
+
+
 def open_store(db_path: str, read_only: bool = True):
     """``duckdb.connect(db_path, read_only=...)`` as the reference does (bm25_indexer.py:69) when
     duckdb is importable; an sqlite3 file otherwise (same SQL)."""

@@ -125,3 +125,27 @@ def test_batch_file_format(tmp_path):
     p = tmp_path / "queries.txt"
     p.write_text("1\ttübingen attractions\n\n2\tfood and drinks\nbroken line\n", encoding="utf-8")
     assert pipeline.read_queries(str(p)) == [("1", "tübingen attractions"), ("2", "food and drinks")]
+
+
+def test_bm25_cache_roundtrip(tmp_path):
+    ix, _, _ = helpers.load_bm25_small()
+    t = store.Bm25Tables(ix.terms, ix.term_off, ix.post_doc, ix.post_tf, ix.doc_ids, ix.doc_len, ix.idf,
+                         np.zeros(ix.n_terms, np.int64), ix.avgdl, ix.total_docs)
+    p = str(tmp_path / "bm25_cache.npz")
+    store.save_bm25_cache(p, t)
+    u = store.load_bm25_cache(p, expect_docs=len(ix.doc_ids))
+    assert u.terms == t.terms and u.avgdl == t.avgdl and u.total_docs == t.total_docs
+    for a, b in ((u.term_off, t.term_off), (u.post_doc, t.post_doc), (u.post_tf, t.post_tf), (u.doc_len, t.doc_len), (u.idf, t.idf)):
+        np.testing.assert_array_equal(a, b)
+    assert store.load_bm25_cache(p, expect_docs=len(ix.doc_ids) + 1) is None        # stale cache is rejected
+    assert store.load_bm25_cache(str(tmp_path / "missing.npz")) is None
+
+
+def test_reference_arm_of_bench_runs_on_cpu():
+    import json, subprocess, sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "3"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["metric"] == "bm25_queries_per_sec"
