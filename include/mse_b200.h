@@ -135,6 +135,22 @@ int mse_rerank_batch(mse_index* idx, int32_t n_queries, const int32_t* cand_off,
                      int32_t* out_doc, float* out_score, float* out_orig, int64_t* out_chunk,
                      int32_t* out_count, int32_t* out_rows, int where, void* stream);
 
+/* Sharded form of mse_rerank_batch (chunk table sharded by doc range over several GPUs); device buffers only.
+ * Step 1, every rank: same replicated candidates; dedupes, then fills the cosines of the candidates whose
+ * documents THIS shard owns into cos[B][1024][10] / rows[B][1024] / chunk0[B][1024] (zeroed here first) and the
+ * replicated survivor description surv_*.  url_group is indexed by the GLOBAL dense doc index.
+ * The caller then sums cos / rows / chunk0 over the ranks (NCCL all-reduce) and calls step 2 on any rank. */
+int mse_rerank_shard_cos(mse_index* idx, int32_t n_queries, const int32_t* cand_off, const int32_t* cand_doc,
+                         const float* cand_bm25, const int32_t* url_group, int64_t n_docs_global, const float* q,
+                         int32_t max_chunks, float* cos, int32_t* rows, int64_t* chunk0,
+                         int32_t* surv_doc, float* surv_bm25, int32_t* surv_count, void* stream);
+/* Step 2: pool-wide min-max, fusion, positional weighting, per-doc max, sort (reranker_api.py:289-372) from the
+ * gathered arrays; outputs as mse_rerank_batch. */
+int mse_rerank_shard_fuse(mse_index* idx, int32_t n_queries, const float* cos, const int32_t* rows, const int64_t* chunk0,
+                          const int32_t* surv_doc, const float* surv_bm25, const int32_t* surv_count,
+                          float smoothing, int32_t max_out, int32_t* out_doc, float* out_score, float* out_orig,
+                          int64_t* out_chunk, int32_t* out_count, int32_t* out_rows, void* stream);
+
 /* ---- shard merge (multi-GPU) ------------------------------------------------------------ */
 
 /* Merges n_lists sorted top-k lists per query (the all-gathered per-rank results, laid out

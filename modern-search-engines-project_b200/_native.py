@@ -69,6 +69,10 @@ _SIGNATURES = {
     "mse_dense_scan_batch": (C.c_int, [_vp, C.c_int32, _vp, C.c_int32, _vp, _vp, _vp, C.c_int, _vp]),
     "mse_rerank_batch": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, C.c_float, C.c_int32, C.c_int32,
                                    _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp]),
+    "mse_rerank_shard_cos": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, _vp, C.c_int64, _vp, C.c_int32,
+                                       _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mse_rerank_shard_fuse": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, C.c_float, C.c_int32,
+                                        _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mse_topk_merge": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, _vp, C.c_int32, _vp, _vp, _vp, C.c_int, _vp]),
 }
 
@@ -250,6 +254,44 @@ class NativeIndex:
                                       _ptr(out[2], np.float32, where), _ptr(out[3], np.int64, where),
                                       _ptr(out[4], np.int32, where), _ptr(out[5], np.int32, where),
                                       where, _stream_ptr(where)))
+        return out
+
+    MAX_CAND, MAX_CHUNKS = 1024, 10
+
+    def rerank_shard_cos(self, cand_off, cand_doc, cand_bm25, q, n_docs_global: int, url_group=None, max_chunks=10):
+        """Sharded rerank, step 1 (CUDA tensors only).  Returns the exchange arrays (cos, rows, chunk0) — to be
+        summed over the ranks — and the replicated survivor description (surv_doc, surv_bm25, surv_count)."""
+        import torch
+        B, dev = int(cand_off.shape[0]) - 1, q.device
+        cos = torch.empty((B, self.MAX_CAND, self.MAX_CHUNKS), dtype=torch.float32, device=dev)
+        rows = torch.empty((B, self.MAX_CAND), dtype=torch.int32, device=dev)
+        chunk0 = torch.empty((B, self.MAX_CAND), dtype=torch.int64, device=dev)
+        surv_doc = torch.empty((B, self.MAX_CAND), dtype=torch.int32, device=dev)
+        surv_bm25 = torch.empty((B, self.MAX_CAND), dtype=torch.float32, device=dev)
+        surv_count = torch.empty((B,), dtype=torch.int32, device=dev)
+        D = MSE_DEVICE
+        _check(lib().mse_rerank_shard_cos(self._h, B, _ptr(cand_off, np.int32, D), _ptr(cand_doc, np.int32, D),
+                                          _ptr(cand_bm25, np.float32, D), _ptr(url_group, np.int32, D), int(n_docs_global),
+                                          _ptr(q, np.float32, D), int(max_chunks), _ptr(cos, np.float32, D), _ptr(rows, np.int32, D),
+                                          _ptr(chunk0, np.int64, D), _ptr(surv_doc, np.int32, D), _ptr(surv_bm25, np.float32, D),
+                                          _ptr(surv_count, np.int32, D), _stream_ptr(D)))
+        return (cos, rows, chunk0), (surv_doc, surv_bm25, surv_count)
+
+    def rerank_shard_fuse(self, exchange, survivors, smoothing=0.15, max_out=1000):
+        """Sharded rerank, step 2: outputs as ``rerank``."""
+        import torch
+        cos, rows, chunk0 = exchange
+        surv_doc, surv_bm25, surv_count = survivors
+        B, dev = int(cos.shape[0]), cos.device
+        mk = lambda dt: torch.empty((B, max_out), dtype=dt, device=dev)
+        out = (mk(torch.int32), mk(torch.float32), mk(torch.float32), mk(torch.int64),
+               torch.empty((B,), dtype=torch.int32, device=dev), torch.empty((B,), dtype=torch.int32, device=dev))
+        D = MSE_DEVICE
+        _check(lib().mse_rerank_shard_fuse(self._h, B, _ptr(cos, np.float32, D), _ptr(rows, np.int32, D), _ptr(chunk0, np.int64, D),
+                                           _ptr(surv_doc, np.int32, D), _ptr(surv_bm25, np.float32, D), _ptr(surv_count, np.int32, D),
+                                           float(smoothing), int(max_out), _ptr(out[0], np.int32, D), _ptr(out[1], np.float32, D),
+                                           _ptr(out[2], np.float32, D), _ptr(out[3], np.int64, D), _ptr(out[4], np.int32, D),
+                                           _ptr(out[5], np.int32, D), _stream_ptr(D)))
         return out
 
     def topk_merge(self, in_doc, in_score, in_count, top_k: int):

@@ -12,6 +12,7 @@
 #include "dense.cuh"
 #include "gemm.cuh"
 #include "rerank.cuh"
+#include "rerank_shard.cuh"
 #include "topk.cuh"
 
 namespace mse {
@@ -829,6 +830,50 @@ int mse_rerank_batch(mse_index* ix, int32_t B, const int32_t* cand_off, const in
     }
     MSE_CUDA_TRY(cudaStreamSynchronize(st));
     timers_collect(ix);
+    return MSE_OK;
+}
+
+int mse_rerank_shard_cos(mse_index* ix, int32_t B, const int32_t* cand_off, const int32_t* cand_doc, const float* cand_bm25,
+                         const int32_t* url_group, int64_t n_docs_global, const float* q, int32_t max_chunks,
+                         float* cos, int32_t* rows, int64_t* chunk0, int32_t* surv_doc, float* surv_bm25,
+                         int32_t* surv_count, void* stream) {
+    if (!ix) { set_error("null index"); return MSE_ERR_INVALID; }
+    MSE_REQUIRE(B >= 0 && cand_off && cos && rows && chunk0 && surv_doc && surv_bm25 && surv_count, "null/negative argument");
+    MSE_REQUIRE(B == 0 || (q && cand_doc && cand_bm25), "null argument");
+    if (max_chunks < 1 || max_chunks > kRerankMaxChunks) { set_error("max_chunks %d outside [1, %d]", max_chunks, kRerankMaxChunks); return MSE_ERR_UNSUPPORTED; }
+    std::lock_guard<std::mutex> lk(ix->mu);
+    if (!ix->has_dense) { set_error("mse_dense_load has not been called"); return MSE_ERR_STATE; }
+    if (B == 0) return MSE_OK;
+    DeviceGuard g(ix->device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t slots = size_t(B) * kRerankMaxCand;
+    MSE_CUDA_TRY(cudaMemsetAsync(cos, 0, sizeof(float) * slots * kRerankMaxChunks, st));
+    MSE_CUDA_TRY(cudaMemsetAsync(rows, 0, sizeof(int32_t) * slots, st));
+    MSE_CUDA_TRY(cudaMemsetAsync(chunk0, 0, sizeof(int64_t) * slots, st));
+    MSE_CUDA_TRY(cudaMemsetAsync(surv_doc, 0xff, sizeof(int32_t) * slots, st));
+    MSE_CUDA_TRY(cudaMemsetAsync(surv_bm25, 0, sizeof(float) * slots, st));
+    RerankShardArgs a{cand_off, cand_doc, cand_bm25, url_group, q, max_chunks, n_docs_global, cos, rows, chunk0, surv_doc, surv_bm25, surv_count};
+    rerank_shard_cos_kernel<<<B, kRerankThreads, 0, st>>>(ix->dn, a);
+    MSE_CUDA_TRY(cudaGetLastError());
+    return MSE_OK;
+}
+
+int mse_rerank_shard_fuse(mse_index* ix, int32_t B, const float* cos, const int32_t* rows, const int64_t* chunk0,
+                          const int32_t* surv_doc, const float* surv_bm25, const int32_t* surv_count, float smoothing,
+                          int32_t max_out, int32_t* out_doc, float* out_score, float* out_orig, int64_t* out_chunk,
+                          int32_t* out_count, int32_t* out_rows, void* stream) {
+    if (!ix) { set_error("null index"); return MSE_ERR_INVALID; }
+    MSE_REQUIRE(B >= 0 && cos && rows && chunk0 && surv_doc && surv_bm25 && surv_count && out_doc && out_score && out_orig &&
+                out_chunk && out_count && out_rows, "null/negative argument");
+    if (max_out < 1 || max_out > kRerankMaxCand) { set_error("max_out %d outside [1, %d]", max_out, kRerankMaxCand); return MSE_ERR_UNSUPPORTED; }
+    MSE_REQUIRE(smoothing >= 0.f && smoothing <= 1.f, "smoothing outside [0,1]");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    if (B == 0) return MSE_OK;
+    DeviceGuard g(ix->device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    RerankFuseArgs a{cos, rows, chunk0, surv_doc, surv_bm25, surv_count, smoothing, max_out, out_doc, out_score, out_orig, out_chunk, out_count, out_rows};
+    rerank_shard_fuse_kernel<<<B, kRerankThreads, 0, st>>>(a);
+    MSE_CUDA_TRY(cudaGetLastError());
     return MSE_OK;
 }
 

@@ -63,6 +63,17 @@ class ShardedSearcher:
         doc, score, count = self.native.bm25_search(q_off, q_term, q_tf, top_k, min_score)
         return self._merge(doc, score, count, top_k)
 
+    def hybrid_rerank(self, cand_off, cand_doc, cand_bm25, q, n_docs_global: int, url_group=None,
+                      smoothing: float = 0.15, max_chunks: int = 10, max_out: int = 1000):
+        """Rerank of replicated (already merged) BM25 candidates against a doc-range-sharded chunk table:
+        per-rank cosines -> all-reduce(sum) of the (query, candidate, row) arrays -> fuse on every rank."""
+        exchange, survivors = self.native.rerank_shard_cos(cand_off, cand_doc, cand_bm25, q, n_docs_global, url_group, max_chunks)
+        if self.world > 1:
+            import torch.distributed as dist
+            for t in exchange:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return self.native.rerank_shard_fuse(exchange, survivors, smoothing, max_out)
+
     def dense_scan(self, q, top_k: int):
         doc, score, count = self.native.dense_scan(q, top_k)
         return self._merge(doc, score, count, top_k)

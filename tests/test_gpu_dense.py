@@ -174,3 +174,39 @@ def test_rerank_batch_equals_single(dense_small):
         for a, b in zip(batch, one):
             np.testing.assert_array_equal(a[i], b[0])
     rr.native.close()
+
+
+def test_sharded_rerank_equals_fused(dense_small):
+    """Doc-range shards: per-shard cosine kernel, sum of the exchange arrays (what the NCCL all-reduce does),
+    fuse kernel == the fused single-GPU rerank kernel, bit for bit."""
+    emb, off, ids, urls, oracle = dense_small
+    dev = torch.device("cuda:0")
+    from mse_b200.reranker import url_groups
+    ug = url_groups(urls)
+    whole = _native.NativeIndex(0)
+    whole.dense_load(emb, off)
+    rng = np.random.default_rng(12)
+    cands = [rng.permutation(len(ids))[:k].astype(np.int32) for k in (1000, 37, 0, 400)]
+    sims = [np.sort(rng.gamma(2.0, 1.0, size=len(c)).astype(np.float32))[::-1].copy() for c in cands]
+    q = synthetic.make_query_vectors(4, seed=21) * 2.0
+    cand_off = np.concatenate([[0], np.cumsum([len(c) for c in cands])]).astype(np.int32)
+    cd, cs = np.concatenate(cands), np.concatenate(sims)
+    ref = whole.rerank(cand_off, cd, cs, q, ug, 0.15, 10, 1000)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    bounds = [0, 900, 901, 2100, len(ids)]
+    exch, surv = None, None
+    for r in range(4):
+        lo, hi = bounds[r], bounds[r + 1]
+        sh = _native.NativeIndex(0)
+        sh.dense_load(np.ascontiguousarray(emb[off[lo]:off[hi]]), np.ascontiguousarray(off[lo:hi + 1] - off[lo]),
+                      doc_base=lo, chunk_base=int(off[lo]))
+        e, s = sh.rerank_shard_cos(t(cand_off), t(cd), t(cs), t(q), len(ids), t(ug), 10)
+        torch.cuda.synchronize()
+        exch = e if exch is None else tuple(a + b for a, b in zip(exch, e))
+        surv = s
+        sh.close()
+    out = whole.rerank_shard_fuse(exch, surv, 0.15, 1000)
+    torch.cuda.synchronize()
+    for a, b in zip(ref, out):
+        np.testing.assert_array_equal(a, b.cpu().numpy())
+    whole.close()
