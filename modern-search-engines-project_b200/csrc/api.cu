@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "bm25.cuh"
+#include "bm25_staged.cuh"
 #include "common.cuh"
 #include "dense.cuh"
 #include "gemm.cuh"
@@ -69,7 +70,7 @@ struct mse_index {
 
     bool has_bm25 = false;
     Bm25Dev bm{};
-    DevBuf term_off, post_doc, post_tf, doc_norm, doc_len16, idf;
+    DevBuf term_off, post_doc, post_tf, post2, imp_levels, doc_norm, doc_len16, idf;
     bool len16_ok = false;
     std::vector<int64_t> h_term_off;
 
@@ -88,6 +89,7 @@ struct mse_index {
     DevBuf m_in[3];                          // merge staging
     DevBuf fb_q[3], fb_out[3];               // fallback sub-batches
 
+    int64_t opt_bm25_kernel = 1, opt_stage_cap = 0, opt_nbuf = 0, opt_bm25_warps = 0, opt_readout = 1, opt_debug_skip = 0, opt_tau_init = 1;
     int64_t opt_range_docs = 0, opt_qpi = 0, opt_cand_cap = 0, opt_use_tau = 1, opt_scan_ctas = 0, opt_gemm_min_batch = 0, opt_gemm_debug = 0;
     int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
@@ -166,15 +168,22 @@ int make_bf16_rowmajor_map(CUtensorMap* map, const void* base, uint64_t rows, ui
 
 // ---- BM25 core: everything on device, outputs to device pointers ---------------------------------
 int bm25_run(mse_index* ix, int32_t B, const int32_t* d_q_off, const int32_t* d_q_term, const int32_t* d_q_tf,
-             int32_t S, int32_t top_k, float min_score, int32_t cap, int use_tau,
+             int32_t S, int32_t max_terms, int32_t top_k, float min_score, int32_t cap, int use_tau,
              int32_t* d_out_doc, float* d_out_score, int32_t* d_out_count, bool mark_overflow, cudaStream_t st) {
     const Bm25Dev& bm = ix->bm;
     const bool len16 = ix->len16_ok;
-    int RS = ix->opt_range_docs > 0 ? round_up(ix->opt_range_docs, 64) : 640;
-    RS = std::min(RS, 2048);
-    if (bm.n_docs < RS) RS = std::max(64, round_up(bm.n_docs, 64));
+    const bool staged = ix->opt_bm25_kernel != 1;
+    int RS;
+    if (staged) {                                      // sub-ranges of whole 128-doc scan rows, at most 32 of them
+        RS = ix->opt_range_docs > 0 ? round_up(std::min<int64_t>(ix->opt_range_docs, 4096), 128) : 1024;
+        if (bm.n_docs < RS) RS = std::max(128, round_up(bm.n_docs, 128));
+    } else {
+        RS = ix->opt_range_docs > 0 ? round_up(ix->opt_range_docs, 64) : 640;
+        RS = std::min(RS, 2048);
+        if (bm.n_docs < RS) RS = std::max(64, round_up(bm.n_docs, 64));
+    }
     const int n_sub = int((bm.n_docs + RS - 1) / RS);
-    const int qpi = int(std::min<int64_t>(31, ix->opt_qpi > 0 ? ix->opt_qpi : 8));
+    const int qpi = int(std::min<int64_t>(31, ix->opt_qpi > 0 ? ix->opt_qpi : (staged ? 31 : 8)));
     int rc;
     if ((rc = ix->slot_w.ensure(sizeof(float) * size_t(S + 1)))) return rc;
     if ((rc = ix->rec.ensure(sizeof(uint2) * (size_t(S) * n_sub + 1)))) return rc;
@@ -189,10 +198,13 @@ int bm25_run(mse_index* ix, int32_t B, const int32_t* d_q_off, const int32_t* d_
     MSE_CUDA_TRY(cudaMemsetAsync(ix->cand_count.p, 0, sizeof(int32_t) * size_t(B), st));
     MSE_CUDA_TRY(cudaMemsetAsync(ix->overflow.p, 0, sizeof(int32_t) * size_t(B), st));
     MSE_CUDA_TRY(cudaMemsetAsync(ix->misc.p, 0, 64, st));
-    if (use_tau) {
+    if (use_tau && !staged) {
         MSE_CUDA_TRY(cudaMemsetAsync(ix->hist.p, 0, sizeof(uint32_t) * size_t(B) * kHistBins, st));
         MSE_CUDA_TRY(cudaMemsetAsync(ix->maxbin.p, 0, sizeof(uint32_t) * size_t(B), st));
     }
+    // staged kernel: the bound is refreshed by reading the candidate lists while they grow; a slot that has been
+    // reserved but not written yet must read as "no candidate"
+    if (use_tau && staged) MSE_CUDA_TRY(cudaMemsetAsync(ix->cand.p, 0, sizeof(uint64_t) * size_t(B) * cap, st));
 
     Bm25Work w{};
     w.q_off = d_q_off; w.q_term = d_q_term; w.q_tf = d_q_tf;
@@ -214,20 +226,52 @@ int bm25_run(mse_index* ix, int32_t B, const int32_t* d_q_off, const int32_t* d_
     }
     timer_end(ix, T_PREPARE, st);
 
-    const size_t smem = size_t(kBm25Warps) * (size_t(kMetaSlots) * 16 + size_t(2 * kEmitStage) * 8 + size_t(RS) * (len16 ? 8 : 10));
-    const void* kfn = len16 ? (const void*)bm25_score_kernel<true> : (const void*)bm25_score_kernel<false>;
-    MSE_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    int per_sm = 0;
-    MSE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kBm25Threads, smem));
-    if (per_sm < 1) { set_error("bm25 score kernel does not fit (sub-range %d docs)", RS); return MSE_ERR_INVALID; }
     const int chunks = (B + qpi - 1) / qpi;
     const int64_t n_items = int64_t(n_sub) * chunks;
-    const int grid = int(std::min<int64_t>((n_items + kBm25Warps - 1) / kBm25Warps, int64_t(per_sm) * ix->sm_count));
-    timer_begin(ix, T_SCORE, st);
-    if (len16) bm25_score_kernel<true><<<grid, kBm25Threads, smem, st>>>(bm, w);
-    else bm25_score_kernel<false><<<grid, kBm25Threads, smem, st>>>(bm, w);
-    MSE_CUDA_TRY(cudaGetLastError());
-    timer_end(ix, T_SCORE, st);
+    int grid = 0;
+    if (staged) {
+        const int nbuf = ix->opt_nbuf == 3 ? 3 : 2;
+        int cap_st = ix->opt_stage_cap > 0 ? round_up(std::min<int64_t>(ix->opt_stage_cap, 16384), 32) : std::max(128, round_up(RS / 4, 32));
+        const int slots = std::max(1, std::min(32, max_terms));
+        w.stage_cap = cap_st;
+        w.stage_slots = slots;
+        w.readout_mode = ix->opt_readout ? 1 : 0;
+        w.debug_skip = int32_t(ix->opt_debug_skip);
+        const size_t per_warp = bm25_staged_warp_bytes(RS, cap_st, slots, nbuf, len16);
+        const size_t smem_max = 227 * 1024 - kStTailSlack;
+        int warps = int(std::min<size_t>(32, smem_max / per_warp));
+        if (ix->opt_bm25_warps > 0) warps = int(std::min<int64_t>(warps, ix->opt_bm25_warps));
+        if (warps < 1) { set_error("bm25 staged kernel does not fit (sub-range %d docs, staging %d postings)", RS, cap_st); return MSE_ERR_INVALID; }
+        const size_t smem = per_warp * size_t(warps) + kStTailSlack;
+        const bool big = warps > 16;                   // more than 16 warps per CTA: the 64-register build
+        const void* kfn;
+        if (len16) kfn = nbuf == 3 ? (big ? (const void*)bm25_score_staged_kernel<true, 3, 32> : (const void*)bm25_score_staged_kernel<true, 3, 16>)
+                                   : (big ? (const void*)bm25_score_staged_kernel<true, 2, 32> : (const void*)bm25_score_staged_kernel<true, 2, 16>);
+        else kfn = nbuf == 3 ? (big ? (const void*)bm25_score_staged_kernel<false, 3, 32> : (const void*)bm25_score_staged_kernel<false, 3, 16>)
+                             : (big ? (const void*)bm25_score_staged_kernel<false, 2, 32> : (const void*)bm25_score_staged_kernel<false, 2, 16>);
+        MSE_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        int per_sm = 0;
+        MSE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, warps * 32, smem));
+        if (per_sm < 1) { set_error("bm25 staged kernel does not fit (%zu bytes of shared memory)", smem); return MSE_ERR_INVALID; }
+        grid = int(std::min<int64_t>((n_items + warps - 1) / warps, int64_t(per_sm) * ix->sm_count));
+        timer_begin(ix, T_SCORE, st);
+        void* args[] = {(void*)&bm, (void*)&w};
+        MSE_CUDA_TRY(cudaLaunchKernel(kfn, dim3(unsigned(grid)), dim3(unsigned(warps * 32)), args, smem, st));
+        timer_end(ix, T_SCORE, st);
+    } else {
+        const size_t smem = size_t(kBm25Warps) * (size_t(kMetaSlots) * 16 + size_t(2 * kEmitStage) * 8 + size_t(RS) * (len16 ? 8 : 10));
+        const void* kfn = len16 ? (const void*)bm25_score_kernel<true> : (const void*)bm25_score_kernel<false>;
+        MSE_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        int per_sm = 0;
+        MSE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kBm25Threads, smem));
+        if (per_sm < 1) { set_error("bm25 score kernel does not fit (sub-range %d docs)", RS); return MSE_ERR_INVALID; }
+        grid = int(std::min<int64_t>((n_items + kBm25Warps - 1) / kBm25Warps, int64_t(per_sm) * ix->sm_count));
+        timer_begin(ix, T_SCORE, st);
+        if (len16) bm25_score_kernel<true><<<grid, kBm25Threads, smem, st>>>(bm, w);
+        else bm25_score_kernel<false><<<grid, kBm25Threads, smem, st>>>(bm, w);
+        MSE_CUDA_TRY(cudaGetLastError());
+        timer_end(ix, T_SCORE, st);
+    }
 
     ListLoader ld{w.cand, w.cand_count, int64_t(cap), cap};
     timer_begin(ix, T_SELECT, st);
@@ -287,7 +331,7 @@ int mse_index_destroy(mse_index* ix) {
     {
         DeviceGuard g(ix->device);
         cudaDeviceSynchronize();
-        DevBuf* all[] = {&ix->term_off, &ix->post_doc, &ix->post_tf, &ix->doc_norm, &ix->doc_len16, &ix->idf, &ix->emb, &ix->doc_chunk_off, &ix->row_doc, &ix->tile_row, &ix->group_row, &ix->qb16, &ix->log_key, &ix->log_q,
+        DevBuf* all[] = {&ix->term_off, &ix->post_doc, &ix->post_tf, &ix->post2, &ix->imp_levels, &ix->doc_norm, &ix->doc_len16, &ix->idf, &ix->emb, &ix->doc_chunk_off, &ix->row_doc, &ix->tile_row, &ix->group_row, &ix->qb16, &ix->log_key, &ix->log_q,
                          &ix->q_off, &ix->q_term, &ix->q_tf, &ix->slot_w, &ix->rec, &ix->tau, &ix->hist,
                          &ix->maxbin, &ix->cand, &ix->cand_count, &ix->overflow, &ix->misc, &ix->o_doc, &ix->o_score,
                          &ix->o_count, &ix->best, &ix->dq};
@@ -309,6 +353,13 @@ int mse_index_set_option(mse_index* ix, const char* name, int64_t value) {
     if (!ix || !name) { set_error("null argument"); return MSE_ERR_INVALID; }
     std::lock_guard<std::mutex> lk(ix->mu);
     if (!strcmp(name, "bm25_range_docs")) ix->opt_range_docs = value;
+    else if (!strcmp(name, "bm25_kernel")) ix->opt_bm25_kernel = value;
+    else if (!strcmp(name, "bm25_stage_cap")) ix->opt_stage_cap = value;
+    else if (!strcmp(name, "bm25_stage_buffers")) ix->opt_nbuf = value;
+    else if (!strcmp(name, "bm25_warps_per_cta")) ix->opt_bm25_warps = value;
+    else if (!strcmp(name, "bm25_readout")) ix->opt_readout = value;
+    else if (!strcmp(name, "bm25_debug_skip")) ix->opt_debug_skip = value;
+    else if (!strcmp(name, "bm25_tau_init")) { ix->opt_tau_init = value; ix->bm.imp_levels = (value && ix->has_bm25) ? ix->imp_levels.as<float>() : nullptr; }
     else if (!strcmp(name, "bm25_queries_per_item")) ix->opt_qpi = value;
     else if (!strcmp(name, "bm25_cand_cap")) ix->opt_cand_cap = value;
     else if (!strcmp(name, "bm25_use_tau")) ix->opt_use_tau = value;
@@ -361,10 +412,11 @@ int mse_bm25_load(mse_index* ix, int64_t n_terms, int64_t n_docs, int64_t doc_ba
     MSE_REQUIRE(P == 0 || (post_doc && post_tf), "null posting arrays");
     int rc;
     if ((rc = ix->term_off.ensure(sizeof(int64_t) * (n_terms + 1)))) return rc;
-    if ((rc = ix->post_doc.ensure(sizeof(int32_t) * std::max<int64_t>(P, 1)))) return rc;
-    if ((rc = ix->post_tf.ensure(sizeof(int32_t) * std::max<int64_t>(P, 1)))) return rc;
-    if ((rc = ix->doc_norm.ensure(sizeof(float) * std::max<int64_t>(n_docs, 1)))) return rc;
-    if ((rc = ix->doc_len16.ensure(sizeof(uint16_t) * std::max<int64_t>(n_docs, 1)))) return rc;
+    if ((rc = ix->post_doc.ensure(sizeof(int32_t) * (std::max<int64_t>(P, 1) + 8)))) return rc;
+    if ((rc = ix->post_tf.ensure(sizeof(int32_t) * (std::max<int64_t>(P, 1) + 8)))) return rc;
+    if ((rc = ix->post2.ensure(sizeof(int2) * (std::max<int64_t>(P, 1) + 8)))) return rc;
+    if ((rc = ix->doc_norm.ensure(sizeof(float) * (std::max<int64_t>(n_docs, 1) + 8)))) return rc;
+    if ((rc = ix->doc_len16.ensure(sizeof(uint16_t) * (std::max<int64_t>(n_docs, 1) + 16)))) return rc;
     if ((rc = ix->misc.ensure(64))) return rc;
     MSE_CUDA_TRY(cudaMemsetAsync(ix->misc.p, 0, 64, st));
     if ((rc = ix->idf.ensure(sizeof(float) * std::max<int64_t>(n_terms, 1)))) return rc;
@@ -386,6 +438,12 @@ int mse_bm25_load(mse_index* ix, int64_t n_terms, int64_t n_docs, int64_t doc_ba
                                                                         double(avgdl), ix->misc.as<int32_t>() + 1);
         MSE_CUDA_TRY(cudaGetLastError());
     }
+    {
+        const int64_t np = P + 8;
+        bm25_interleave_kernel<<<unsigned((np + 255) / 256), 256, 0, st>>>(ix->post_doc.as<int32_t>(), ix->post_tf.as<int32_t>(),
+                                                                          ix->post2.as<int2>(), P, np);
+        MSE_CUDA_TRY(cudaGetLastError());
+    }
     if (n_terms > 0) {
         bm25_validate_kernel<<<unsigned((n_terms + 7) / 8), 256, 0, st>>>(ix->term_off.as<int64_t>(), ix->post_doc.as<int32_t>(),
                                                                          ix->post_tf.as<int32_t>(), n_terms, n_docs, ix->misc.as<int32_t>());
@@ -398,14 +456,24 @@ int mse_bm25_load(mse_index* ix, int64_t n_terms, int64_t n_docs, int64_t doc_ba
     const int32_t bad = flags[0];
     ix->len16_ok = flags[1] == 0;                 // every doc length fits 16 bits
     MSE_REQUIRE(bad == 0, "malformed postings (code %d): doc ids must be strictly ascending inside a term, within [0,n_docs), tf >= 1", bad);
+    if ((rc = ix->imp_levels.ensure(sizeof(float) * kImpLevels * size_t(std::max<int64_t>(n_terms, 1))))) return rc;
+    if (n_terms > 0 && n_docs > 0) {                     // needs doc_norm (bm25_norm_kernel above, same stream)
+        bm25_impact_levels_kernel<<<unsigned(n_terms), kImpThreads, 0, st>>>(ix->term_off.as<int64_t>(), ix->post_doc.as<int32_t>(),
+                                                                            ix->post_tf.as<int32_t>(), ix->doc_norm.as<float>(),
+                                                                            ix->imp_levels.as<float>(), n_terms);
+        MSE_CUDA_TRY(cudaGetLastError());
+    }
+    MSE_CUDA_TRY(cudaStreamSynchronize(st));
     ix->bm.term_off = ix->term_off.as<int64_t>();
     ix->bm.post_doc = ix->post_doc.as<int32_t>();
     ix->bm.post_tf = ix->post_tf.as<int32_t>();
+    ix->bm.post2 = ix->post2.as<int2>();
     ix->bm.doc_norm = ix->doc_norm.as<float>();
     ix->bm.doc_len16 = ix->doc_len16.as<uint16_t>();
     ix->bm.norm_c0 = float(double(k1) * (1.0 - double(b)));
     ix->bm.norm_c1 = float(double(k1) * double(b) / double(avgdl));
     ix->bm.idf = ix->idf.as<float>();
+    ix->bm.imp_levels = (ix->opt_tau_init && n_terms > 0 && n_docs > 0) ? ix->imp_levels.as<float>() : nullptr;
     ix->bm.n_terms = n_terms; ix->bm.n_docs = n_docs; ix->bm.n_postings = P;
     ix->bm.doc_base = uint32_t(doc_base); ix->bm.k1 = k1;
     ix->has_bm25 = true;
@@ -436,8 +504,10 @@ int mse_bm25_search_batch(mse_index* ix, int32_t B, const int32_t* q_off, const 
         MSE_CUDA_TRY(cudaStreamSynchronize(st));
     }
     MSE_REQUIRE(h_off[0] == 0, "q_off[0] must be 0");
+    int32_t max_terms = 0;
     for (int i = 0; i < B; ++i) {
         MSE_REQUIRE(h_off[i + 1] >= h_off[i], "q_off not monotone at %d", i);
+        max_terms = std::max(max_terms, h_off[i + 1] - h_off[i]);
         if (h_off[i + 1] - h_off[i] > 32) { set_error("query %d has %d distinct terms (max 32)", i, h_off[i + 1] - h_off[i]); return MSE_ERR_UNSUPPORTED; }
     }
     const int32_t S = h_off[B];
@@ -467,7 +537,7 @@ int mse_bm25_search_batch(mse_index* ix, int32_t B, const int32_t* q_off, const 
     cap = std::max<int64_t>(cap, 1);
     const int use_tau = ix->opt_use_tau ? 1 : 0;
 
-    if ((rc = bm25_run(ix, B, d_off, d_term, d_tf, S, top_k, min_score, int32_t(cap), use_tau, d_doc, d_score, d_count, true, st))) return rc;
+    if ((rc = bm25_run(ix, B, d_off, d_term, d_tf, S, max_terms, top_k, min_score, int32_t(cap), use_tau, d_doc, d_score, d_count, true, st))) return rc;
 
     std::vector<int32_t> h_cnt, h_ovf;
     h_cnt.resize(size_t(B));
@@ -512,7 +582,7 @@ int mse_bm25_search_batch(mse_index* ix, int32_t B, const int32_t* q_off, const 
             MSE_CUDA_TRY(cudaMemcpyAsync(ix->fb_q[0].p, so.data(), sizeof(int32_t) * (nb + 1), cudaMemcpyHostToDevice, st));
             MSE_CUDA_TRY(cudaMemcpyAsync(ix->fb_q[1].p, stm.data(), sizeof(int32_t) * SS, cudaMemcpyHostToDevice, st));
             MSE_CUDA_TRY(cudaMemcpyAsync(ix->fb_q[2].p, stf.data(), sizeof(int32_t) * SS, cudaMemcpyHostToDevice, st));
-            if ((rc = bm25_run(ix, nb, ix->fb_q[0].as<int32_t>(), ix->fb_q[1].as<int32_t>(), ix->fb_q[2].as<int32_t>(), SS, top_k,
+            if ((rc = bm25_run(ix, nb, ix->fb_q[0].as<int32_t>(), ix->fb_q[1].as<int32_t>(), ix->fb_q[2].as<int32_t>(), SS, max_terms, top_k,
                                min_score, int32_t(fcap), 0, ix->fb_out[0].as<int32_t>(), ix->fb_out[1].as<float>(),
                                ix->fb_out[2].as<int32_t>(), false, st))) return rc;
             for (int j = 0; j < nb; ++j) {

@@ -40,14 +40,17 @@ namespace mse {
 constexpr int kBm25Threads = 256;
 constexpr int kBm25Warps = kBm25Threads / 32;
 constexpr int kBm25MaxPrefetchSlots = 8;         // terms per query whose postings are prefetched
+constexpr int kImpLevels = 8;                    // ranks 64, 128, ..., 4096 (7 used) of the per-term impact table
 
 struct Bm25Dev {                                 // device-resident index of one shard
     const int64_t* term_off;
     const int32_t* post_doc;
     const int32_t* post_tf;
+    const int2* post2;           // the same postings interleaved {doc, tf} (staged kernel: one bulk copy per slice)
     const float* doc_norm;       // fp32 norm per doc (always present)
     const uint16_t* doc_len16;   // doc length per doc, or null when some length >= 65536
     const float* idf;
+    const float* imp_levels;     // [n_terms * kImpLevels] lower bound of the (64 << l)-th largest tf/(tf+norm) of a term, 0 = unknown
     int64_t n_terms, n_docs, n_postings;
     uint32_t doc_base;
     float k1;
@@ -69,6 +72,10 @@ struct Bm25Work {                                // per-call workspace
     int32_t n_queries, n_slots, n_sub, sub_docs, queries_per_item, cap;
     uint32_t min_key;
     int32_t use_tau;
+    int32_t stage_cap;           // staged kernel: postings per staging buffer
+    int32_t stage_slots;         // staged kernel: slice-table entries per staging buffer
+    int32_t debug_skip;          // staged kernel, timing experiments only: 1 = no scoring, 2 = no read-out, 4 = no copies, 8 = no emission
+    int32_t readout_mode;        // staged kernel: 0 = always scan the accumulators, 1 = walk staged postings when possible
 };
 
 // ---- prepare: slot weights, per-(sub-range, slot) task records, tau init ---------------------------
@@ -88,6 +95,34 @@ __device__ __forceinline__ int64_t lower_bound_doc(const int32_t* __restrict__ p
     return lo;
 }
 
+// Initial lower bound of a query's final k-th best score, from the per-term impact table built at load time:
+// a term t with positive weight w_t and at least r >= top_k postings has r documents whose contribution from t
+// alone is >= w_t * imp_r(t); the other terms of the query add at least the (negative) sum of the negative
+// weights (0 < tf/(tf+norm) < 1).  So r >= top_k candidates score >= max_t w_t * imp_r(t) + sum of negative
+// weights, and nothing below that value can reach the top-k.  (The bound only filters candidates; results stay exact.)
+__device__ __forceinline__ uint32_t bm25_initial_bound(const Bm25Dev& ix, const Bm25Work& w, int q) {
+    if (!w.use_tau || ix.imp_levels == nullptr) return w.min_key;
+    int lv = 0;
+    while (lv < 7 && (64 << lv) < w.ts.top_k) ++lv;
+    if ((64 << lv) < w.ts.top_k) return w.min_key;
+    const int64_t need = int64_t(64) << lv;
+    float best = 0.f, neg = 0.f, mag = 0.f;
+    for (int s = w.q_off[q]; s < w.q_off[q + 1]; ++s) {
+        const int t = w.q_term[s];
+        if (t < 0 || t >= ix.n_terms) continue;
+        const int64_t df = ix.term_off[t + 1] - ix.term_off[t];
+        if (df == 0) continue;
+        const float wt = float(double(ix.idf[t]) * double(w.q_tf[s]) * (double(ix.k1) + 1.0));
+        mag += fabsf(wt);
+        if (wt < 0.f) neg += wt;
+        else if (df >= need) best = fmaxf(best, wt * ix.imp_levels[int64_t(t) * kImpLevels + lv]);
+    }
+    const float bound = best * (1.0f - 1e-5f) + neg - 4e-6f * mag;     // slack for the fp32 summation of the score kernel
+    if (!(bound > 0.f)) return w.min_key;
+    const uint32_t key = float_to_key(bound);
+    return key > w.min_key ? key : w.min_key;
+}
+
 __global__ void __launch_bounds__(kPrepThreads)
 bm25_prepare_kernel(Bm25Dev ix, Bm25Work w) {
     extern __shared__ __align__(16) unsigned char prep_smem[];
@@ -98,7 +133,7 @@ bm25_prepare_kernel(Bm25Dev ix, Bm25Work w) {
     const int tid = threadIdx.x;
     if (s >= w.n_slots) {                                      // trailing CTAs initialise tau
         for (int q = (s - w.n_slots) * kPrepThreads + tid; q < w.n_queries; q += (gridDim.x - w.n_slots) * kPrepThreads)
-            w.ts.tau[q] = w.min_key;
+            w.ts.tau[q] = bm25_initial_bound(ix, w, q);
         return;
     }
     const int t = w.q_term[s];
@@ -369,6 +404,77 @@ __global__ void bm25_norm_kernel(const int32_t* __restrict__ doc_len, float* __r
         len16[i] = uint16_t(l < 0 ? 0 : (l > 65535 ? 65535 : l));
         if (l > 65535 || l < 0) atomicMax(max_len, 65536);
     }
+}
+
+// Per-term impact table (load time): for l = 0..6 a LOWER bound of the (64 << l)-th largest tf/(tf+norm) among the
+// postings of the term, found with a two-level 256-bin histogram of the 16-bit fixed-point impact; 0 when the
+// term has fewer postings.  One CTA per term.
+constexpr int kImpThreads = 256;
+__global__ void __launch_bounds__(kImpThreads)
+bm25_impact_levels_kernel(const int64_t* __restrict__ term_off, const int32_t* __restrict__ post_doc,
+                          const int32_t* __restrict__ post_tf, const float* __restrict__ doc_norm,
+                          float* __restrict__ imp_levels, int64_t n_terms) {
+    __shared__ int h1[256];
+    __shared__ int h2[7][256];
+    __shared__ int s_bin[7], s_above[7], s_low[7];
+    const int64_t t = blockIdx.x;
+    if (t >= n_terms) return;
+    const int tid = threadIdx.x;
+    const int64_t a = term_off[t], e = term_off[t + 1];
+    const int64_t df = e - a;
+    if (df < 64) {
+        if (tid < kImpLevels) imp_levels[t * kImpLevels + tid] = 0.f;
+        return;
+    }
+    auto fixed16 = [&](int64_t i) {
+        const float tf = float(post_tf[i]);
+        const float imp = tf / (tf + doc_norm[post_doc[i]]);
+        const int u = int(imp * 65536.0f);
+        return u < 0 ? 0 : (u > 65535 ? 65535 : u);
+    };
+    h1[tid] = 0;
+    for (int l = 0; l < 7; ++l) h2[l][tid] = 0;
+    if (tid < 7) { s_bin[tid] = -1; s_above[tid] = 0; s_low[tid] = -1; }
+    __syncthreads();
+    for (int64_t i = a + tid; i < e; i += kImpThreads) atomicAdd(&h1[fixed16(i) >> 8], 1);
+    __syncthreads();
+    if (tid < 7 && (int64_t(64) << tid) <= df) {                 // descending scan of the coarse histogram
+        const int r = 64 << tid;
+        int run = 0;
+        for (int b = 255; b >= 0; --b) {
+            if (run + h1[b] >= r) { s_bin[tid] = b; s_above[tid] = run; break; }
+            run += h1[b];
+        }
+    }
+    __syncthreads();
+    for (int64_t i = a + tid; i < e; i += kImpThreads) {
+        const int u = fixed16(i);
+#pragma unroll
+        for (int l = 0; l < 7; ++l)
+            if ((u >> 8) == s_bin[l]) atomicAdd(&h2[l][u & 255], 1);
+    }
+    __syncthreads();
+    if (tid < 7 && s_bin[tid] >= 0) {
+        const int r = (64 << tid) - s_above[tid];
+        int run = 0;
+        for (int b = 255; b >= 0; --b) {
+            if (run + h2[tid][b] >= r) { s_low[tid] = b; break; }
+            run += h2[tid][b];
+        }
+    }
+    __syncthreads();
+    if (tid < kImpLevels) {
+        float v = 0.f;
+        if (tid < 7 && s_bin[tid] >= 0 && s_low[tid] >= 0) v = float((s_bin[tid] << 8) | s_low[tid]) / 65536.0f;
+        imp_levels[t * kImpLevels + tid] = v;
+    }
+}
+
+__global__ void bm25_interleave_kernel(const int32_t* __restrict__ post_doc, const int32_t* __restrict__ post_tf,
+                                       int2* __restrict__ post2, int64_t n, int64_t n_padded) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) post2[i] = make_int2(post_doc[i], post_tf[i]);
+    else if (i < n_padded) post2[i] = make_int2(0, 1);
 }
 
 // postings must be strictly ascending inside a term and inside [0, n_docs); tf >= 1
