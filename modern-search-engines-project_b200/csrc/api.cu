@@ -178,9 +178,8 @@ int bm25_run(mse_index* ix, int32_t B, const int32_t* d_q_off, const int32_t* d_
         RS = ix->opt_range_docs > 0 ? round_up(std::min<int64_t>(ix->opt_range_docs, 4096), 128) : 1024;
         if (bm.n_docs < RS) RS = std::max(128, round_up(bm.n_docs, 128));
     } else {
-        RS = ix->opt_range_docs > 0 ? round_up(ix->opt_range_docs, 64) : 640;
-        RS = std::min(RS, 2048);
-        if (bm.n_docs < RS) RS = std::max(64, round_up(bm.n_docs, 64));
+        RS = ix->opt_range_docs > 0 ? round_up(std::min<int64_t>(ix->opt_range_docs, 4096), 128) : 896;
+        if (bm.n_docs < RS) RS = std::max(128, round_up(bm.n_docs, 128));
     }
     const int n_sub = int((bm.n_docs + RS - 1) / RS);
     const int qpi = int(std::min<int64_t>(31, ix->opt_qpi > 0 ? ix->opt_qpi : (staged ? 31 : 8)));
@@ -259,7 +258,7 @@ int bm25_run(mse_index* ix, int32_t B, const int32_t* d_q_off, const int32_t* d_
         MSE_CUDA_TRY(cudaLaunchKernel(kfn, dim3(unsigned(grid)), dim3(unsigned(warps * 32)), args, smem, st));
         timer_end(ix, T_SCORE, st);
     } else {
-        const size_t smem = size_t(kBm25Warps) * (size_t(kMetaSlots) * 16 + size_t(2 * kEmitStage) * 8 + size_t(RS) * (len16 ? 8 : 10));
+        const size_t smem = size_t(kBm25Warps) * bm25_score_warp_bytes(RS, len16);
         const void* kfn = len16 ? (const void*)bm25_score_kernel<true> : (const void*)bm25_score_kernel<false>;
         MSE_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         int per_sm = 0;

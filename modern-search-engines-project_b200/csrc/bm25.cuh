@@ -170,21 +170,23 @@ constexpr int kMetaSlots = 64;                   // slot records staged per warp
 constexpr int kPrefetchSlots = 4;                // terms per query whose first 32 postings are prefetched
 constexpr int kEmitStage = 32;                   // candidates of one task staged in shared memory (deferred write-out)
 
+__host__ __device__ inline size_t bm25_score_warp_bytes(int rs, bool len16) {
+    return size_t(kMetaSlots) * 16 + size_t(2 * kEmitStage) * 8 + size_t(rs) * (len16 ? 6 : 8);
+}
+
 template <bool LEN16>
 __global__ void __launch_bounds__(kBm25Threads, 4)
 bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
     using LenT = typename std::conditional<LEN16, uint16_t, float>::type;
     extern __shared__ __align__(16) unsigned char bm25_smem[];
-    const int RS = w.sub_docs;
+    const int RS = w.sub_docs;                   // multiple of 128
     const int lane = lane_id();
-    const size_t per_warp = size_t(kMetaSlots) * 16 + size_t(2 * kEmitStage) * 8 + size_t(RS) * (4 + sizeof(LenT) + 2);
-    unsigned char* my = bm25_smem + per_warp * warp_id();
+    unsigned char* my = bm25_smem + bm25_score_warp_bytes(RS, LEN16) * warp_id();
     uint4* s_meta = reinterpret_cast<uint4*>(my);                                  // {begin, count, weight bits, -}
     uint64_t* s_emit = reinterpret_cast<uint64_t*>(my + kMetaSlots * 16);          // [2][kEmitStage] staged candidates
     unsigned char* body = my + kMetaSlots * 16 + size_t(2 * kEmitStage) * 8;
     float* s_acc = reinterpret_cast<float*>(body);
     LenT* s_len = reinterpret_cast<LenT*>(body + size_t(RS) * 4);
-    uint16_t* s_list = reinterpret_cast<uint16_t*>(body + size_t(RS) * (4 + sizeof(LenT)));
 
     const int QC = w.queries_per_item;
     const int chunks = (w.n_queries + QC - 1) / QC;
@@ -195,11 +197,11 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
     const int32_t* __restrict__ g_doc = ix.post_doc;
     const int32_t* __restrict__ g_tf = ix.post_tf;
     constexpr int MP = kPrefetchSlots;
+    const int scan_iters = RS >> 7;
 
     for (int i = lane; i < RS; i += 32) s_acc[i] = neg0;
     int cur_j = -1;
     int lo = 0;
-    int nlist = 0;
     // Deferred emission: the slot-reserving atomicAdd of task t is issued without waiting for its
     // result; the staged candidates are written out at the end of task t+1, when it has long returned.
     int pend_n = 0, pend_q = 0, pend_base = 0, stage_sel = 0;
@@ -217,24 +219,61 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
         if (w.use_tau && (((base + pend_n) ^ base) >> 6)) tau_raise(w.ts, pend_q);
         pend_n = 0;
     };
+    int staged = 0;
+    // all lanes call; `pass` lanes hold a candidate (score bits vb of local doc d)
+    auto emit_round = [&](int q, bool pass, int vb, int d) {
+        const unsigned pm = __ballot_sync(0xffffffffu, pass);
+        if (pm == 0u) return;
+        const int total = __popc(pm);
+        uint64_t* st = s_emit + stage_sel * kEmitStage;
+        if (staged + total > kEmitStage) {                            // stage full (before the bound bites): write it through
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&w.cand_count[q], staged);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (lane < staged) {
+                if (base + lane < w.cap) w.cand[int64_t(q) * w.cap + base + lane] = st[lane];
+                else w.overflow[q] = 1;
+            }
+            if (w.use_tau && (((base + staged) ^ base) >> 6)) tau_raise(w.ts, q);
+            staged = 0;
+            __syncwarp();
+        }
+        if (pass) {
+            const uint32_t key = float_to_key(__int_as_float(vb) + 0.0f);
+            st[staged + __popc(pm & lt_mask)] = make_key64(key, ix.doc_base + uint32_t(lo + d));
+            if (w.use_tau) tau_count(w.ts, q, key);
+        }
+        staged += total;
+    };
 
     // one warp-round: up to 32 postings of one term; docs are unique inside a term (no race)
     auto apply = [&](int dd, int tfi, bool valid, float wt) {
-        bool fresh = false;
-        int d = 0;
         if (valid) {
-            d = dd - lo;
+            const int d = dd - lo;
             const float tf = float(tfi);
             const float norm = LEN16 ? fmaf(float(s_len[d]), c1, c0) : float(s_len[d]);
-            // idf*qtf*(k1+1) * tf / (tf + k1*(1-b+b*dl/avgdl)); __fdividef: <= 2 ulp
-            const float contrib = __fdividef(wt * tf, tf + norm);
-            const float old = s_acc[d];
-            fresh = __float_as_uint(old) == kUntouchedBits;
-            s_acc[d] = old + contrib;
+            // idf*qtf*(k1+1) * tf / (tf + k1*(1-b+b*dl/avgdl)); tf + norm >= 1, rcp.approx: <= 1 ulp
+            float r;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(tf + norm));
+            s_acc[d] = fmaf(wt * tf, r, s_acc[d]);
         }
-        const unsigned fm = __ballot_sync(0xffffffffu, fresh);
-        if (fresh) s_list[nlist + __popc(fm & lt_mask)] = uint16_t(d);
-        nlist += __popc(fm);
+    };
+    // postings 32.. of a slice: the loads of up to four rounds are issued before the first is applied
+    auto apply_rest = [&](uint32_t begin, int n, float wt) {
+#pragma unroll 1
+        for (int i0 = 32; i0 < n; i0 += 128) {
+            int dd[4], tt[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                dd[u] = 0; tt[u] = 0;
+                if (i0 + 32 * u + lane < n) {
+                    dd[u] = ldg_stream_i32(g_doc + begin + i0 + 32 * u + lane);
+                    tt[u] = ldg_stream_i32(g_tf + begin + i0 + 32 * u + lane);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) apply(dd[u], tt[u], i0 + 32 * u + lane < n, wt);
+        }
     };
 
     while (true) {
@@ -249,9 +288,12 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
         const int q1 = (q0 + QC) < w.n_queries ? (q0 + QC) : w.n_queries;
         const int nq = q1 - q0;
         const int qo_reg = (lane <= nq) ? w.q_off[q0 + lane] : 0;          // CSR offsets of the chunk (QC <= 31)
-        if (j != cur_j) {                                                   // stage this sub-range's doc lengths
-            if (LEN16) { for (int i = lane; i < nd; i += 32) s_len[i] = LenT(ix.doc_len16[lo + i]); }
-            else { for (int i = lane; i < nd; i += 32) s_len[i] = LenT(ix.doc_norm[lo + i]); }
+        const uint32_t tau_reg = (lane < nq && w.use_tau) ? ld_relaxed_u32(&w.ts.tau[q0 + lane]) : w.min_key;
+        if (j != cur_j) {                                                   // stage this sub-range's doc lengths (16-byte loads;
+            const uint4* src = LEN16 ? reinterpret_cast<const uint4*>(ix.doc_len16 + lo)   // lo % 128 == 0, arrays padded)
+                                     : reinterpret_cast<const uint4*>(ix.doc_norm + lo);
+            const int n16 = (nd * int(sizeof(LenT)) + 15) >> 4;
+            for (int i = lane; i < n16; i += 32) reinterpret_cast<uint4*>(s_len)[i] = __ldg(src + i);
             cur_j = j;
         }
         const uint2* __restrict__ rec = w.rec + int64_t(j) * w.n_slots;
@@ -288,7 +330,9 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
 #pragma unroll
                 for (int t = 0; t < MP; ++t) { pd_cur[t] = pd_nxt[t]; pt_cur[t] = pt_nxt[t]; }
                 const int q = q0 + qr;
-                const uint32_t tau_key = w.use_tau ? ld_relaxed_u32(&w.ts.tau[q]) : w.min_key;
+                // the bound read at the start of the item; refreshed from memory once per item only (any older
+                // value is a valid, merely weaker bound)
+                const uint32_t tau_key = __shfl_sync(0xffffffffu, tau_reg, qr);
                 // ---- prefetch the next query of the group ---------------------------------------------
                 o_nxt = e_cur;
                 if (qr + 1 < qb) {
@@ -302,7 +346,7 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
                     }
                 }
                 // ---- apply the query's terms in order ---------------------------------------------------
-                nlist = 0;
+                int touched = 0;
 #pragma unroll
                 for (int t = 0; t < MP; ++t) {
                     if (o_cur + t < e_cur) {
@@ -310,14 +354,9 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
                         const int n = int(m.y);
                         if (n > 0) {
                             const float wt = __uint_as_float(m.z);
+                            touched = 1;
                             apply(pd_cur[t], pt_cur[t], lane < n, wt);
-#pragma unroll 1
-                            for (int i0 = 32; i0 < n; i0 += 32) {
-                                const bool valid = i0 + lane < n;
-                                int dd = 0, tfi = 0;
-                                if (valid) { dd = ldg_stream_i32(g_doc + m.x + i0 + lane); tfi = ldg_stream_i32(g_tf + m.x + i0 + lane); }
-                                apply(dd, tfi, valid, wt);
-                            }
+                            if (n > 32) apply_rest(m.x, n, wt);
                             __syncwarp();                                   // next term may touch the same docs
                         }
                     }
@@ -326,63 +365,65 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
                 for (int sl = o_cur + MP; sl < e_cur; ++sl) {               // queries with more than MP terms
                     const uint4 m = s_meta[sl];
                     const int n = int(m.y);
+                    if (n == 0) continue;
                     const float wt = __uint_as_float(m.z);
-#pragma unroll 1
-                    for (int i0 = 0; i0 < n; i0 += 32) {
-                        const bool valid = i0 + lane < n;
-                        int dd = 0, tfi = 0;
-                        if (valid) { dd = ldg_stream_i32(g_doc + m.x + i0 + lane); tfi = ldg_stream_i32(g_tf + m.x + i0 + lane); }
-                        apply(dd, tfi, valid, wt);
-                    }
+                    touched = 1;
+                    int dd = 0, tfi = 0;
+                    if (lane < n) { dd = ldg_stream_i32(g_doc + m.x + lane); tfi = ldg_stream_i32(g_tf + m.x + lane); }
+                    apply(dd, tfi, lane < n, wt);
+                    if (n > 32) apply_rest(m.x, n, wt);
                     __syncwarp();
                 }
-                // ---- read-out: walk the touched list, stage candidates >= tau, re-arm -------------------
-                if (nlist > 0) {
+                // ---- read-out: scan the accumulators 128 per round, stage candidates >= tau, re-arm -------
+                if (touched) {
                     const float tau_f = key_to_float(tau_key);
-                    uint64_t* st = s_emit + stage_sel * kEmitStage;
-                    int staged = 0;
-#pragma unroll 1
-                    for (int i0 = 0; i0 < nlist; i0 += 32) {
-                        int d = 0;
-                        float v = 0.f;
-                        bool pass = false;
-                        if (i0 + lane < nlist) {
-                            d = s_list[i0 + lane];
-                            v = s_acc[d] + 0.0f;
-                            s_acc[d] = neg0;
-                            pass = v >= tau_f;
+                    const int tau_i = __float_as_int(tau_f);
+                    const bool fast = tau_i >= 0;        // tau is +0.0 or positive: one signed compare also rejects
+                                                         // -0.0 (untouched) and every negative score
+                    const int4* a4 = reinterpret_cast<const int4*>(s_acc);
+                    uint32_t flag = 0;
+                    if (fast) {
+#pragma unroll 4
+                        for (int it = 0; it < scan_iters; ++it) {
+                            const int4 v = a4[it * 32 + lane];
+                            flag |= uint32_t(max(max(v.x, v.y), max(v.z, v.w)) >= tau_i) << it;
                         }
-                        const unsigned pm = __ballot_sync(0xffffffffu, pass);
-                        if (pm) {
-                            const int total = __popc(pm);
-                            const uint32_t key = float_to_key(v);
-                            const uint64_t k64 = make_key64(key, ix.doc_base + uint32_t(lo + d));
-                            if (staged + total <= kEmitStage) {              // common case: stage, write out one task later
-                                if (pass) {
-                                    st[staged + __popc(pm & lt_mask)] = k64;
-                                    if (w.use_tau) tau_count(w.ts, q, key);
-                                }
-                                staged += total;
-                            } else {                                         // ramp-up / dense ranges: write through
-                                int base_slot = 0;
-                                if (lane == 0) base_slot = atomicAdd(&w.cand_count[q], total);
-                                base_slot = __shfl_sync(0xffffffffu, base_slot, 0);
-                                if (pass) {
-                                    const int slot = base_slot + __popc(pm & lt_mask);
-                                    if (slot < w.cap) {
-                                        w.cand[int64_t(q) * w.cap + slot] = k64;
-                                        if (w.use_tau) tau_count(w.ts, q, key);
-                                    } else {
-                                        w.overflow[q] = 1;
-                                    }
-                                }
-                                if (w.use_tau && (((base_slot + total) ^ base_slot) >> 6)) tau_raise(w.ts, q);
-                            }
+                    } else {
+#pragma unroll 2
+                        for (int it = 0; it < scan_iters; ++it) {
+                            const int4 v = a4[it * 32 + lane];
+                            const bool p = (uint32_t(v.x) != kUntouchedBits && __int_as_float(v.x) >= tau_f) ||
+                                           (uint32_t(v.y) != kUntouchedBits && __int_as_float(v.y) >= tau_f) ||
+                                           (uint32_t(v.z) != kUntouchedBits && __int_as_float(v.z) >= tau_f) ||
+                                           (uint32_t(v.w) != kUntouchedBits && __int_as_float(v.w) >= tau_f);
+                            flag |= uint32_t(p) << it;
                         }
                     }
+                    staged = 0;
+                    while (__any_sync(0xffffffffu, flag != 0u)) {           // rare once the bound bites
+                        int4 v = make_int4(0, 0, 0, 0);
+                        int d0 = 0;
+                        const bool have = flag != 0u;
+                        if (have) {
+                            const int it = __ffs(int(flag)) - 1;
+                            flag &= flag - 1u;
+                            v = a4[it * 32 + lane];
+                            d0 = (it * 32 + lane) * 4;
+                        }
+                        const int vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const bool pass = have && (fast ? (vv[u] >= tau_i)
+                                                            : (uint32_t(vv[u]) != kUntouchedBits && __int_as_float(vv[u]) >= tau_f));
+                            emit_round(q, pass, vv[u], d0 + u);
+                        }
+                    }
+                    const float4 z4 = make_float4(neg0, neg0, neg0, neg0);
+#pragma unroll 4
+                    for (int it = 0; it < scan_iters; ++it) reinterpret_cast<float4*>(s_acc)[it * 32 + lane] = z4;
                     __syncwarp();
-                    complete_pending();                                      // previous task's atomic has returned by now
                     if (staged > 0) {
+                        complete_pending();                                  // previous task's atomic has returned by now
                         if (lane == 0) pend_base = atomicAdd(&w.cand_count[q], staged);   // result consumed one task later
                         pend_n = staged; pend_q = q; stage_sel ^= 1;
                     }
