@@ -15,7 +15,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libmsegpu.so")
+LIB_PATH = os.environ.get("MSE_B200_LIB") or os.path.join(CSRC, "libmsegpu.so")   # override: experiments only
 HEADER = os.path.join(os.path.dirname(HERE), "include", "mse_b200.h")
 
 MSE_HOST, MSE_DEVICE, MSE_DEVICE_BORROW = 0, 1, 2

@@ -7,6 +7,7 @@
 #include <mutex>
 #include <vector>
 
+#include <cstdlib>
 #include "bm25.cuh"
 #include "bm25_staged.cuh"
 #include "common.cuh"
@@ -138,6 +139,15 @@ int copy_in(void* dst, const void* src, size_t bytes, int where, cudaStream_t s)
 
 int round_up(int64_t v, int64_t m) { return int(((v + m - 1) / m) * m); }
 
+// MSE_DEBUG_SYNC=1: synchronise after every kernel of the BM25 path so that a device fault names its kernel
+int debug_sync(cudaStream_t st, const char* what) {
+    static const bool on = getenv("MSE_DEBUG_SYNC") != nullptr;
+    if (!on) return MSE_OK;
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return MSE_ERR_CUDA; }
+    return MSE_OK;
+}
+
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -214,6 +224,7 @@ int bm25_run(mse_index* ix, int32_t B, const int32_t* d_q_off, const int32_t* d_
     w.stats = reinterpret_cast<unsigned long long*>(ix->misc.as<char>() + 16);
     w.n_queries = B; w.n_slots = S; w.n_sub = n_sub; w.sub_docs = RS; w.queries_per_item = qpi;
     w.cap = cap; w.min_key = float_to_key(min_score + 0.0f); w.use_tau = use_tau;
+    w.debug_skip = int32_t(ix->opt_debug_skip);
 
     timer_begin(ix, T_PREPARE, st);
     {
@@ -224,6 +235,7 @@ int bm25_run(mse_index* ix, int32_t B, const int32_t* d_q_off, const int32_t* d_
         MSE_CUDA_TRY(cudaGetLastError());
     }
     timer_end(ix, T_PREPARE, st);
+    if ((rc = debug_sync(st, "bm25_prepare_kernel"))) return rc;
 
     const int chunks = (B + qpi - 1) / qpi;
     const int64_t n_items = int64_t(n_sub) * chunks;
@@ -259,25 +271,27 @@ int bm25_run(mse_index* ix, int32_t B, const int32_t* d_q_off, const int32_t* d_
         timer_end(ix, T_SCORE, st);
     } else {
         const size_t smem = size_t(kBm25Warps) * bm25_score_warp_bytes(RS, len16);
-        const void* kfn = len16 ? (const void*)bm25_score_kernel<true> : (const void*)bm25_score_kernel<false>;
+        const void* kfn = len16 ? (RS == 896 ? (const void*)bm25_score_kernel<true, 896> : (const void*)bm25_score_kernel<true, 0>)
+                                : (const void*)bm25_score_kernel<false, 0>;
         MSE_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         int per_sm = 0;
         MSE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kBm25Threads, smem));
         if (per_sm < 1) { set_error("bm25 score kernel does not fit (sub-range %d docs)", RS); return MSE_ERR_INVALID; }
         grid = int(std::min<int64_t>((n_items + kBm25Warps - 1) / kBm25Warps, int64_t(per_sm) * ix->sm_count));
         timer_begin(ix, T_SCORE, st);
-        if (len16) bm25_score_kernel<true><<<grid, kBm25Threads, smem, st>>>(bm, w);
-        else bm25_score_kernel<false><<<grid, kBm25Threads, smem, st>>>(bm, w);
-        MSE_CUDA_TRY(cudaGetLastError());
+        void* args[] = {(void*)&bm, (void*)&w};
+        MSE_CUDA_TRY(cudaLaunchKernel(kfn, dim3(unsigned(grid)), dim3(kBm25Threads), args, smem, st));
         timer_end(ix, T_SCORE, st);
     }
 
+    if ((rc = debug_sync(st, staged ? "bm25_score_staged_kernel" : "bm25_score_kernel"))) return rc;
     ListLoader ld{w.cand, w.cand_count, int64_t(cap), cap};
     timer_begin(ix, T_SELECT, st);
     topk_select_kernel<ListLoader><<<B, kSelectThreads, 0, st>>>(ld, top_k, d_out_doc, d_out_score, d_out_count,
                                                                 mark_overflow ? w.overflow : nullptr);
     MSE_CUDA_TRY(cudaGetLastError());
     timer_end(ix, T_SELECT, st);
+    if ((rc = debug_sync(st, "topk_select_kernel"))) return rc;
     if (mark_overflow) { ix->stats[3] = n_sub; ix->stats[4] = grid; }
     return MSE_OK;
 }

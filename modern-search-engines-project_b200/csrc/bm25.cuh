@@ -171,20 +171,21 @@ constexpr int kPrefetchSlots = 4;                // terms per query whose first 
 constexpr int kEmitStage = 32;                   // candidates of one task staged in shared memory (deferred write-out)
 
 __host__ __device__ inline size_t bm25_score_warp_bytes(int rs, bool len16) {
-    return size_t(kMetaSlots) * 16 + size_t(2 * kEmitStage) * 8 + size_t(rs) * (len16 ? 6 : 8);
+    return size_t(kMetaSlots) * 16 + size_t(2 * kEmitStage) * 8 + 16 + size_t(rs) * (len16 ? 6 : 8);
 }
 
-template <bool LEN16>
+template <bool LEN16, int RS_T>                  // RS_T: sub-range size known at compile time (0 = take it from the workspace)
 __global__ void __launch_bounds__(kBm25Threads, 4)
 bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
     using LenT = typename std::conditional<LEN16, uint16_t, float>::type;
     extern __shared__ __align__(16) unsigned char bm25_smem[];
-    const int RS = w.sub_docs;                   // multiple of 128
+    const int RS = RS_T ? RS_T : w.sub_docs;     // multiple of 128
     const int lane = lane_id();
     unsigned char* my = bm25_smem + bm25_score_warp_bytes(RS, LEN16) * warp_id();
     uint4* s_meta = reinterpret_cast<uint4*>(my);                                  // {begin, count, weight bits, -}
     uint64_t* s_emit = reinterpret_cast<uint64_t*>(my + kMetaSlots * 16);          // [2][kEmitStage] staged candidates
-    unsigned char* body = my + kMetaSlots * 16 + size_t(2 * kEmitStage) * 8;
+    int* s_cnt = reinterpret_cast<int*>(my + kMetaSlots * 16 + size_t(2 * kEmitStage) * 8);   // candidates staged by the current task
+    unsigned char* body = my + kMetaSlots * 16 + size_t(2 * kEmitStage) * 8 + 16;
     float* s_acc = reinterpret_cast<float*>(body);
     LenT* s_len = reinterpret_cast<LenT*>(body + size_t(RS) * 4);
 
@@ -200,6 +201,8 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
     const int scan_iters = RS >> 7;
 
     for (int i = lane; i < RS; i += 32) s_acc[i] = neg0;
+    if (lane == 0) *s_cnt = 0;
+    __syncwarp();
     int cur_j = -1;
     int lo = 0;
     // Deferred emission: the slot-reserving atomicAdd of task t is issued without waiting for its
@@ -219,31 +222,22 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
         if (w.use_tau && (((base + pend_n) ^ base) >> 6)) tau_raise(w.ts, pend_q);
         pend_n = 0;
     };
-    int staged = 0;
-    // all lanes call; `pass` lanes hold a candidate (score bits vb of local doc d)
-    auto emit_round = [&](int q, bool pass, int vb, int d) {
-        const unsigned pm = __ballot_sync(0xffffffffu, pass);
-        if (pm == 0u) return;
-        const int total = __popc(pm);
-        uint64_t* st = s_emit + stage_sel * kEmitStage;
-        if (staged + total > kEmitStage) {                            // stage full (before the bound bites): write it through
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&w.cand_count[q], staged);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (lane < staged) {
-                if (base + lane < w.cap) w.cand[int64_t(q) * w.cap + base + lane] = st[lane];
-                else w.overflow[q] = 1;
-            }
-            if (w.use_tau && (((base + staged) ^ base) >> 6)) tau_raise(w.ts, q);
-            staged = 0;
-            __syncwarp();
+    // one candidate (the calling lanes are a subset of the warp inside a warp-uniform loop): the slot in the task's
+    // stage comes from a shared-memory counter; what does not fit goes straight to the list.  Do NOT call this from
+    // a loop whose trip count differs between lanes: that variant faulted sporadically ("illegal instruction") on
+    // sm_100a under heavy emission (shared + global atomics with results inside a divergent loop).
+    auto emit_one = [&](int q, int vb, int d) {
+        const uint32_t key = float_to_key(__int_as_float(vb) + 0.0f);
+        const uint64_t k64 = make_key64(key, ix.doc_base + uint32_t(lo + d));
+        const int slot = atomicAdd(s_cnt, 1);
+        if (slot < kEmitStage) {
+            s_emit[stage_sel * kEmitStage + slot] = k64;
+        } else {
+            const int g = atomicAdd(&w.cand_count[q], 1);
+            if (g < w.cap) w.cand[int64_t(q) * w.cap + g] = k64;
+            else w.overflow[q] = 1;
         }
-        if (pass) {
-            const uint32_t key = float_to_key(__int_as_float(vb) + 0.0f);
-            st[staged + __popc(pm & lt_mask)] = make_key64(key, ix.doc_base + uint32_t(lo + d));
-            if (w.use_tau) tau_count(w.ts, q, key);
-        }
-        staged += total;
+        if (w.use_tau) tau_count(w.ts, q, key);
     };
 
     // one warp-round: up to 32 postings of one term; docs are unique inside a term (no race)
@@ -374,58 +368,64 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
                     if (n > 32) apply_rest(m.x, n, wt);
                     __syncwarp();
                 }
-                // ---- read-out: scan the accumulators 128 per round, stage candidates >= tau, re-arm -------
+                // ---- read-out: scan the accumulators 128 per round, re-arm them, stage candidates >= tau ----
                 if (touched) {
                     const float tau_f = key_to_float(tau_key);
                     const int tau_i = __float_as_int(tau_f);
                     const bool fast = tau_i >= 0;        // tau is +0.0 or positive: one signed compare also rejects
                                                          // -0.0 (untouched) and every negative score
-                    const int4* a4 = reinterpret_cast<const int4*>(s_acc);
+                    int4* a4 = reinterpret_cast<int4*>(s_acc) + lane;
+                    const int4 z4 = make_int4(int(kUntouchedBits), int(kUntouchedBits), int(kUntouchedBits), int(kUntouchedBits));
+                    // pass 1: re-arm every 4-doc group that holds no candidate, flag the (rare) others
                     uint32_t flag = 0;
                     if (fast) {
-#pragma unroll 4
+#pragma unroll 7
                         for (int it = 0; it < scan_iters; ++it) {
-                            const int4 v = a4[it * 32 + lane];
-                            flag |= uint32_t(max(max(v.x, v.y), max(v.z, v.w)) >= tau_i) << it;
+                            const int4 v = a4[it * 32];
+                            const bool p = max(max(v.x, v.y), max(v.z, v.w)) >= tau_i;
+                            if (!p) a4[it * 32] = z4;
+                            flag |= uint32_t(p) << it;
                         }
                     } else {
-#pragma unroll 2
+#pragma unroll 1
                         for (int it = 0; it < scan_iters; ++it) {
-                            const int4 v = a4[it * 32 + lane];
+                            const int4 v = a4[it * 32];
                             const bool p = (uint32_t(v.x) != kUntouchedBits && __int_as_float(v.x) >= tau_f) ||
                                            (uint32_t(v.y) != kUntouchedBits && __int_as_float(v.y) >= tau_f) ||
                                            (uint32_t(v.z) != kUntouchedBits && __int_as_float(v.z) >= tau_f) ||
                                            (uint32_t(v.w) != kUntouchedBits && __int_as_float(v.w) >= tau_f);
+                            if (!p) a4[it * 32] = z4;
                             flag |= uint32_t(p) << it;
                         }
                     }
-                    staged = 0;
-                    while (__any_sync(0xffffffffu, flag != 0u)) {           // rare once the bound bites
-                        int4 v = make_int4(0, 0, 0, 0);
-                        int d0 = 0;
-                        const bool have = flag != 0u;
-                        if (have) {
-                            const int it = __ffs(int(flag)) - 1;
-                            flag &= flag - 1u;
-                            v = a4[it * 32 + lane];
-                            d0 = (it * 32 + lane) * 4;
-                        }
+                    // pass 2 (lanes that hold flagged groups only)
+                    while (__any_sync(0xffffffffu, flag != 0u)) {
+                        if (flag == 0u) continue;
+                        const int it = __ffs(int(flag)) - 1;
+                        flag &= flag - 1u;
+                        const int4 v = a4[it * 32];
+                        a4[it * 32] = z4;
+                        const int d0 = (it * 32 + lane) * 4;
                         const int vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-                            const bool pass = have && (fast ? (vv[u] >= tau_i)
-                                                            : (uint32_t(vv[u]) != kUntouchedBits && __int_as_float(vv[u]) >= tau_f));
-                            emit_round(q, pass, vv[u], d0 + u);
+                            const bool pass = fast ? (vv[u] >= tau_i)
+                                                   : (uint32_t(vv[u]) != kUntouchedBits && __int_as_float(vv[u]) >= tau_f);
+                            if (pass) emit_one(q, vv[u], d0 + u);
                         }
                     }
-                    const float4 z4 = make_float4(neg0, neg0, neg0, neg0);
-#pragma unroll 4
-                    for (int it = 0; it < scan_iters; ++it) reinterpret_cast<float4*>(s_acc)[it * 32 + lane] = z4;
                     __syncwarp();
-                    if (staged > 0) {
+                    const int emitted = *s_cnt;
+                    __syncwarp();
+                    if (emitted > 0) {
+                        const int staged = emitted < kEmitStage ? emitted : kEmitStage;
                         complete_pending();                                  // previous task's atomic has returned by now
-                        if (lane == 0) pend_base = atomicAdd(&w.cand_count[q], staged);   // result consumed one task later
+                        if (lane == 0) {
+                            pend_base = atomicAdd(&w.cand_count[q], staged);   // result consumed one task later
+                            *s_cnt = 0;
+                        }
                         pend_n = staged; pend_q = q; stage_sel ^= 1;
+                        __syncwarp();
                     }
                 }
             }
