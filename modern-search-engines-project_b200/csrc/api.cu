@@ -188,7 +188,7 @@ int bm25_run(mse_index* ix, int32_t B, const int32_t* d_q_off, const int32_t* d_
         RS = ix->opt_range_docs > 0 ? round_up(std::min<int64_t>(ix->opt_range_docs, 4096), 128) : 1024;
         if (bm.n_docs < RS) RS = std::max(128, round_up(bm.n_docs, 128));
     } else {
-        RS = ix->opt_range_docs > 0 ? round_up(std::min<int64_t>(ix->opt_range_docs, 4096), 128) : 896;
+        RS = ix->opt_range_docs > 0 ? round_up(std::min<int64_t>(ix->opt_range_docs, 4096), 128) : 1024;
         if (bm.n_docs < RS) RS = std::max(128, round_up(bm.n_docs, 128));
     }
     const int n_sub = int((bm.n_docs + RS - 1) / RS);
@@ -271,7 +271,7 @@ int bm25_run(mse_index* ix, int32_t B, const int32_t* d_q_off, const int32_t* d_
         timer_end(ix, T_SCORE, st);
     } else {
         const size_t smem = size_t(kBm25Warps) * bm25_score_warp_bytes(RS, len16);
-        const void* kfn = len16 ? (RS == 896 ? (const void*)bm25_score_kernel<true, 896> : (const void*)bm25_score_kernel<true, 0>)
+        const void* kfn = len16 ? (RS == 1024 ? (const void*)bm25_score_kernel<true, 1024> : (const void*)bm25_score_kernel<true, 0>)
                                 : (const void*)bm25_score_kernel<false, 0>;
         MSE_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         int per_sm = 0;
@@ -478,8 +478,11 @@ int mse_bm25_load(mse_index* ix, int64_t n_terms, int64_t n_docs, int64_t doc_ba
     }
     MSE_CUDA_TRY(cudaStreamSynchronize(st));
     ix->bm.term_off = ix->term_off.as<int64_t>();
-    ix->bm.post_doc = ix->post_doc.as<int32_t>();
-    ix->bm.post_tf = ix->post_tf.as<int32_t>();
+    // the kernels read the interleaved {doc, tf} array only; the separate copies were needed by the load-time kernels
+    ix->post_doc.release();
+    ix->post_tf.release();
+    ix->bm.post_doc = nullptr;
+    ix->bm.post_tf = nullptr;
     ix->bm.post2 = ix->post2.as<int2>();
     ix->bm.doc_norm = ix->doc_norm.as<float>();
     ix->bm.doc_len16 = ix->doc_len16.as<uint16_t>();

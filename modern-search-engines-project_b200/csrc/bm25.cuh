@@ -87,10 +87,10 @@ struct Bm25Work {                                // per-call workspace
 constexpr int kPrepThreads = 256;
 constexpr int kPrepCoarse = 32;
 
-__device__ __forceinline__ int64_t lower_bound_doc(const int32_t* __restrict__ pd, int64_t lo, int64_t hi, int64_t target) {
+__device__ __forceinline__ int64_t lower_bound_doc(const int2* __restrict__ pd, int64_t lo, int64_t hi, int64_t target) {
     while (lo < hi) {
         const int64_t mid = (lo + hi) >> 1;
-        if (int64_t(pd[mid]) < target) lo = mid + 1; else hi = mid;
+        if (int64_t(pd[mid].x) < target) lo = mid + 1; else hi = mid;
     }
     return lo;
 }
@@ -145,7 +145,7 @@ bm25_prepare_kernel(Bm25Dev ix, Bm25Work w) {
         w.slot_w[s] = float(double(idf) * double(w.q_tf[s]) * (double(ix.k1) + 1.0)) + 0.0f;
         if (e > a) atomicAdd(w.stats, (unsigned long long)(e - a));
     }
-    const int32_t* __restrict__ pd = ix.post_doc;
+    const int2* __restrict__ pd = ix.post2;
     for (int c = tid; c <= n_coarse; c += kPrepThreads) {
         const int j = c * kPrepCoarse < w.n_sub ? c * kPrepCoarse : w.n_sub;
         s_coarse[c] = (j == w.n_sub) ? e : lower_bound_doc(pd, a, e, int64_t(j) * w.sub_docs);
@@ -166,9 +166,9 @@ bm25_prepare_kernel(Bm25Dev ix, Bm25Work w) {
 }
 
 // ---- scoring ------------------------------------------------------------------------------------------
-constexpr int kMetaSlots = 64;                   // slot records staged per warp at a time (16 B each)
+constexpr int kMetaSlots = 32;                   // slot records staged per warp at a time (16 B each)
 constexpr int kPrefetchSlots = 4;                // terms per query whose first 32 postings are prefetched
-constexpr int kEmitStage = 32;                   // candidates of one task staged in shared memory (deferred write-out)
+constexpr int kEmitStage = 24;                   // candidates of one task staged in shared memory (deferred write-out)
 
 __host__ __device__ inline size_t bm25_score_warp_bytes(int rs, bool len16) {
     return size_t(kMetaSlots) * 16 + size_t(2 * kEmitStage) * 8 + 16 + size_t(rs) * (len16 ? 6 : 8);
@@ -195,11 +195,15 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
     const float neg0 = __uint_as_float(kUntouchedBits);
     const unsigned lt_mask = (1u << lane) - 1u;
     const float c0 = ix.norm_c0, c1 = ix.norm_c1;
-    const int32_t* __restrict__ g_doc = ix.post_doc;
-    const int32_t* __restrict__ g_tf = ix.post_tf;
+    const int2* __restrict__ g_post = ix.post2;          // {doc, tf}: one 8-byte load per posting
     constexpr int MP = kPrefetchSlots;
     const int scan_iters = RS >> 7;
 
+    // the re-arm pattern lives in four registers for the whole kernel (opaque to the compiler, which would
+    // otherwise rebuild it with four moves in front of every 16-byte store of the read-out pass)
+    int4 zq;
+    asm volatile("mov.b32 %0, 0x80000000;\n\tmov.b32 %1, 0x80000000;\n\tmov.b32 %2, 0x80000000;\n\tmov.b32 %3, 0x80000000;"
+                 : "=r"(zq.x), "=r"(zq.y), "=r"(zq.z), "=r"(zq.w));
     for (int i = lane; i < RS; i += 32) s_acc[i] = neg0;
     if (lane == 0) *s_cnt = 0;
     __syncwarp();
@@ -261,8 +265,8 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
             for (int u = 0; u < 4; ++u) {
                 dd[u] = 0; tt[u] = 0;
                 if (i0 + 32 * u + lane < n) {
-                    dd[u] = ldg_stream_i32(g_doc + begin + i0 + 32 * u + lane);
-                    tt[u] = ldg_stream_i32(g_tf + begin + i0 + 32 * u + lane);
+                    const int2 p = ldg_stream_i2(g_post + begin + i0 + 32 * u + lane);
+                    dd[u] = p.x; tt[u] = p.y;
                 }
             }
 #pragma unroll
@@ -315,7 +319,7 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
                 pd_nxt[t] = 0; pt_nxt[t] = 0;
                 if (o_nxt + t < e_nxt) {
                     const uint4 m = s_meta[o_nxt + t];
-                    if (lane < int(m.y)) { pd_nxt[t] = ldg_stream_i32(g_doc + m.x + lane); pt_nxt[t] = ldg_stream_i32(g_tf + m.x + lane); }
+                    if (lane < int(m.y)) { const int2 p = ldg_stream_i2(g_post + m.x + lane); pd_nxt[t] = p.x; pt_nxt[t] = p.y; }
                 }
             }
 #pragma unroll 1
@@ -335,7 +339,7 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
                     for (int t = 0; t < MP; ++t) {
                         if (o_nxt + t < e_nxt) {
                             const uint4 m = s_meta[o_nxt + t];
-                            if (lane < int(m.y)) { pd_nxt[t] = ldg_stream_i32(g_doc + m.x + lane); pt_nxt[t] = ldg_stream_i32(g_tf + m.x + lane); }
+                            if (lane < int(m.y)) { const int2 p = ldg_stream_i2(g_post + m.x + lane); pd_nxt[t] = p.x; pt_nxt[t] = p.y; }
                         }
                     }
                 }
@@ -363,7 +367,7 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
                     const float wt = __uint_as_float(m.z);
                     touched = 1;
                     int dd = 0, tfi = 0;
-                    if (lane < n) { dd = ldg_stream_i32(g_doc + m.x + lane); tfi = ldg_stream_i32(g_tf + m.x + lane); }
+                    if (lane < n) { const int2 p = ldg_stream_i2(g_post + m.x + lane); dd = p.x; tfi = p.y; }
                     apply(dd, tfi, lane < n, wt);
                     if (n > 32) apply_rest(m.x, n, wt);
                     __syncwarp();
@@ -375,11 +379,11 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
                     const bool fast = tau_i >= 0;        // tau is +0.0 or positive: one signed compare also rejects
                                                          // -0.0 (untouched) and every negative score
                     int4* a4 = reinterpret_cast<int4*>(s_acc) + lane;
-                    const int4 z4 = make_int4(int(kUntouchedBits), int(kUntouchedBits), int(kUntouchedBits), int(kUntouchedBits));
+                    const int4 z4 = make_int4(zq.x, zq.y, zq.z, zq.w);
                     // pass 1: re-arm every 4-doc group that holds no candidate, flag the (rare) others
                     uint32_t flag = 0;
                     if (fast) {
-#pragma unroll 7
+#pragma unroll 8
                         for (int it = 0; it < scan_iters; ++it) {
                             const int4 v = a4[it * 32];
                             const bool p = max(max(v.x, v.y), max(v.z, v.w)) >= tau_i;

@@ -99,6 +99,11 @@ __device__ __forceinline__ int ldg_stream_i32(const int* p) {
     asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
     return r;
 }
+__device__ __forceinline__ int2 ldg_stream_i2(const int2* p) {
+    int2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
 __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
     uint32_t r;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(r) : "l"(p));
