@@ -71,7 +71,7 @@ struct mse_index {
 
     bool has_bm25 = false;
     Bm25Dev bm{};
-    DevBuf term_off, post_doc, post_tf, post2, imp_levels, doc_norm, doc_len16, idf;
+    DevBuf term_off, post_doc, post_tf, post2, skip, skip_row, imp_levels, doc_norm, doc_len16, idf;
     bool len16_ok = false;
     std::vector<int64_t> h_term_off;
 
@@ -229,7 +229,8 @@ int bm25_run(mse_index* ix, int32_t B, const int32_t* d_q_off, const int32_t* d_
     timer_begin(ix, T_PREPARE, st);
     {
         const int tau_ctas = (B + kPrepThreads - 1) / kPrepThreads;
-        const size_t psm = sizeof(int64_t) * size_t((n_sub + kPrepCoarse - 1) / kPrepCoarse + 2) + sizeof(uint32_t) * size_t(n_sub + 2);
+        const size_t psm = std::max(sizeof(int64_t) * size_t((n_sub + kPrepCoarse - 1) / kPrepCoarse + 2) + sizeof(uint32_t) * size_t(n_sub + 2),
+                                    n_sub <= kPrepCountMaxSub ? sizeof(int) * size_t(n_sub + 2) : size_t(0));
         MSE_CUDA_TRY(cudaFuncSetAttribute(bm25_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(std::max<size_t>(psm, 1024))));
         bm25_prepare_kernel<<<unsigned(S + tau_ctas), kPrepThreads, psm, st>>>(bm, w);
         MSE_CUDA_TRY(cudaGetLastError());
@@ -344,7 +345,7 @@ int mse_index_destroy(mse_index* ix) {
     {
         DeviceGuard g(ix->device);
         cudaDeviceSynchronize();
-        DevBuf* all[] = {&ix->term_off, &ix->post_doc, &ix->post_tf, &ix->post2, &ix->imp_levels, &ix->doc_norm, &ix->doc_len16, &ix->idf, &ix->emb, &ix->doc_chunk_off, &ix->row_doc, &ix->tile_row, &ix->group_row, &ix->qb16, &ix->log_key, &ix->log_q,
+        DevBuf* all[] = {&ix->term_off, &ix->post_doc, &ix->post_tf, &ix->post2, &ix->skip, &ix->skip_row, &ix->imp_levels, &ix->doc_norm, &ix->doc_len16, &ix->idf, &ix->emb, &ix->doc_chunk_off, &ix->row_doc, &ix->tile_row, &ix->group_row, &ix->qb16, &ix->log_key, &ix->log_q,
                          &ix->q_off, &ix->q_term, &ix->q_tf, &ix->slot_w, &ix->rec, &ix->tau, &ix->hist,
                          &ix->maxbin, &ix->cand, &ix->cand_count, &ix->overflow, &ix->misc, &ix->o_doc, &ix->o_score,
                          &ix->o_count, &ix->best, &ix->dq};
@@ -478,6 +479,27 @@ int mse_bm25_load(mse_index* ix, int64_t n_terms, int64_t n_docs, int64_t doc_ba
     }
     MSE_CUDA_TRY(cudaStreamSynchronize(st));
     ix->bm.term_off = ix->term_off.as<int64_t>();
+    {   // skip table of the heavy terms
+        ix->bm.skip = nullptr; ix->bm.skip_row = nullptr; ix->bm.skip_docs = 0; ix->bm.n_skip = 0;
+        const int32_t n_skip = int32_t((n_docs + kSkipDocs - 1) / kSkipDocs);
+        const int64_t min_df = std::max<int64_t>(kSkipMinDf, n_skip);
+        std::vector<int64_t> h_row(size_t(std::max<int64_t>(n_terms, 1)), -1);
+        int64_t entries = 0;
+        for (int64_t t = 0; t < n_terms; ++t)
+            if (ix->h_term_off[t + 1] - ix->h_term_off[t] >= min_df) { h_row[t] = entries; entries += n_skip + 1; }
+        if (entries > 0 && n_docs > 0) {
+            if ((rc = ix->skip.ensure(sizeof(uint32_t) * size_t(entries)))) return rc;
+            if ((rc = ix->skip_row.ensure(sizeof(int64_t) * size_t(n_terms)))) return rc;
+            MSE_CUDA_TRY(cudaMemcpyAsync(ix->skip_row.p, h_row.data(), sizeof(int64_t) * n_terms, cudaMemcpyHostToDevice, st));
+            bm25_skip_build_kernel<<<unsigned(n_terms), kPrepThreads, 0, st>>>(ix->term_off.as<int64_t>(), ix->post2.as<int2>(),
+                                                                              ix->skip_row.as<int64_t>(), ix->skip.as<uint32_t>(),
+                                                                              n_terms, kSkipDocs, n_skip);
+            MSE_CUDA_TRY(cudaGetLastError());
+            MSE_CUDA_TRY(cudaStreamSynchronize(st));
+            ix->bm.skip = ix->skip.as<uint32_t>(); ix->bm.skip_row = ix->skip_row.as<int64_t>();
+            ix->bm.skip_docs = kSkipDocs; ix->bm.n_skip = n_skip;
+        }
+    }
     // the kernels read the interleaved {doc, tf} array only; the separate copies were needed by the load-time kernels
     ix->post_doc.release();
     ix->post_tf.release();

@@ -50,6 +50,9 @@ struct Bm25Dev {                                 // device-resident index of one
     const float* doc_norm;       // fp32 norm per doc (always present)
     const uint16_t* doc_len16;   // doc length per doc, or null when some length >= 65536
     const float* idf;
+    const uint32_t* skip;        // skip table: for every "heavy" term, the offset (relative to the term's first posting) of the
+    const int64_t* skip_row;     //   first posting with doc >= g * skip_docs, g = 0..n_skip; skip_row[t] = first entry of term t, -1 = none
+    int32_t skip_docs, n_skip;   //   granularity in docs (0 = no table) and ceil(n_docs / skip_docs)
     const float* imp_levels;     // [n_terms * kImpLevels] lower bound of the (64 << l)-th largest tf/(tf+norm) of a term, 0 = unknown
     int64_t n_terms, n_docs, n_postings;
     uint32_t doc_base;
@@ -86,6 +89,9 @@ struct Bm25Work {                                // per-call workspace
 // (consecutive slots of one sub-range) are contiguous.
 constexpr int kPrepThreads = 256;
 constexpr int kPrepCoarse = 32;
+constexpr int kSkipDocs = 1024;                  // granularity of the skip table == default sub-range size
+constexpr int kSkipMinDf = 4096;                 // terms with fewer postings are bucketed on the fly (one pass over the list)
+constexpr int kPrepCountMaxSub = 12000;          // the on-the-fly path keeps one counter per sub-range in shared memory
 
 __device__ __forceinline__ int64_t lower_bound_doc(const int2* __restrict__ pd, int64_t lo, int64_t hi, int64_t target) {
     while (lo < hi) {
@@ -146,6 +152,50 @@ bm25_prepare_kernel(Bm25Dev ix, Bm25Work w) {
         if (e > a) atomicAdd(w.stats, (unsigned long long)(e - a));
     }
     const int2* __restrict__ pd = ix.post2;
+    const uint32_t a32f = uint32_t(a);
+    // (1) heavy term, sub-range size a multiple of the skip granularity: the boundaries are in the skip table
+    if (ix.skip_docs > 0 && t >= 0 && t < ix.n_terms && w.sub_docs % ix.skip_docs == 0 && ix.skip_row[t] >= 0) {
+        const uint32_t* __restrict__ row = ix.skip + ix.skip_row[t];
+        const int m = w.sub_docs / ix.skip_docs;
+        for (int j = tid; j < w.n_sub; j += kPrepThreads) {
+            const int g0 = j * m, g1 = (j + 1) * m < ix.n_skip ? (j + 1) * m : ix.n_skip;
+            const uint32_t o0 = row[g0], o1 = row[g1];
+            w.rec[int64_t(j) * w.n_slots + s] = make_uint2(a32f + o0, o1 - o0);
+        }
+        return;
+    }
+    // (2) short list: count the postings of every sub-range in one pass over the list, then an exclusive scan
+    if (e - a < int64_t(4) * kSkipMinDf && w.n_sub <= kPrepCountMaxSub) {
+        int* s_cnt = reinterpret_cast<int*>(prep_smem);                   // [n_sub]
+        __shared__ int s_part[kPrepThreads];
+        for (int j = tid; j < w.n_sub; j += kPrepThreads) s_cnt[j] = 0;
+        __syncthreads();
+        for (int64_t i = a + tid; i < e; i += kPrepThreads) atomicAdd(&s_cnt[pd[i].x / w.sub_docs], 1);
+        __syncthreads();
+        const int per = (w.n_sub + kPrepThreads - 1) / kPrepThreads;     // contiguous sub-ranges per thread
+        const int j0 = tid * per, j1 = (j0 + per) < w.n_sub ? (j0 + per) : w.n_sub;
+        int sum = 0;
+        for (int j = j0; j < j1; ++j) sum += s_cnt[j];
+        s_part[tid] = sum;
+        __syncthreads();
+        if (tid < 32) {                                                  // exclusive scan of the 256 partial sums
+            int v[kPrepThreads / 32], tot = 0;
+#pragma unroll
+            for (int k = 0; k < kPrepThreads / 32; ++k) { v[k] = s_part[tid * (kPrepThreads / 32) + k]; tot += v[k]; }
+            int run = warp_incl_scan(tot) - tot;
+#pragma unroll
+            for (int k = 0; k < kPrepThreads / 32; ++k) { s_part[tid * (kPrepThreads / 32) + k] = run; run += v[k]; }
+        }
+        __syncthreads();
+        uint32_t run = a32f + uint32_t(s_part[tid]);
+        for (int j = j0; j < j1; ++j) {
+            const int c = s_cnt[j];
+            w.rec[int64_t(j) * w.n_slots + s] = make_uint2(run, uint32_t(c));
+            run += uint32_t(c);
+        }
+        return;
+    }
+    // (3) general case: two-level binary search
     for (int c = tid; c <= n_coarse; c += kPrepThreads) {
         const int j = c * kPrepCoarse < w.n_sub ? c * kPrepCoarse : w.n_sub;
         s_coarse[c] = (j == w.n_sub) ? e : lower_bound_doc(pd, a, e, int64_t(j) * w.sub_docs);
@@ -449,6 +499,18 @@ __global__ void bm25_norm_kernel(const int32_t* __restrict__ doc_len, float* __r
         len16[i] = uint16_t(l < 0 ? 0 : (l > 65535 ? 65535 : l));
         if (l > 65535 || l < 0) atomicMax(max_len, 65536);
     }
+}
+
+// Skip table (load time): one CTA per heavy term; entry g = number of postings of the term with doc < g * skip_docs.
+__global__ void __launch_bounds__(kPrepThreads)
+bm25_skip_build_kernel(const int64_t* __restrict__ term_off, const int2* __restrict__ post2, const int64_t* __restrict__ skip_row,
+                       uint32_t* __restrict__ skip, int64_t n_terms, int32_t skip_docs, int32_t n_skip) {
+    const int64_t t = blockIdx.x;
+    if (t >= n_terms || skip_row[t] < 0) return;
+    const int64_t a = term_off[t], e = term_off[t + 1];
+    uint32_t* row = skip + skip_row[t];
+    for (int g = threadIdx.x; g <= n_skip; g += kPrepThreads)
+        row[g] = (g == n_skip) ? uint32_t(e - a) : uint32_t(lower_bound_doc(post2, a, e, int64_t(g) * skip_docs) - a);
 }
 
 // Per-term impact table (load time): for l = 0..6 a LOWER bound of the (64 << l)-th largest tf/(tf+norm) among the
