@@ -113,6 +113,46 @@ def test_synthetic_batch_vs_oracle(corpus20k, opts, top_k, min_score):
     bm.close()
 
 
+@pytest.mark.parametrize("opts", [
+    dict(bm25_tau_init=0),                                    # no impact-table seed: the running bound alone
+    dict(bm25_kernel=2),                                      # experimental bulk-copy staged score kernel
+    dict(bm25_kernel=2, bm25_range_docs=512, bm25_readout=0, bm25_stage_buffers=3),
+    dict(bm25_kernel=2, bm25_range_docs=2048, bm25_stage_cap=64),   # slices larger than the staging buffer
+    dict(bm25_range_docs=2048),                               # skip table with two entries per sub-range
+])
+def test_kernel_variants_agree(corpus20k, opts):
+    """Every variant returns exactly what the default configuration returns (same summation order)."""
+    c, ix = corpus20k
+    q_off, q_term, q_tf = synthetic.make_bm25_queries(c, 64, terms_per_query=4, min_rank=8, seed=21,
+                                                       repeat_frac=0.2, add_always=True)
+    bm = _facade(ix)
+    ref = bm.search_batch_terms(q_off, q_term, q_tf, 200, 0.0)
+    for k, v in opts.items():
+        bm.native.set_option(k, v)
+    got = bm.search_batch_terms(q_off, q_term, q_tf, 200, 0.0)
+    assert np.array_equal(ref[2], got[2])
+    np.testing.assert_allclose(got[1], ref[1], rtol=2e-6, atol=1e-7)
+    assert np.mean(ref[0] == got[0]) > 0.995
+    _check_batch(ix, q_off, q_term, q_tf, got[0], got[1], got[2], 200, 0.0)
+    bm.close()
+
+
+def test_impact_table_matches_checker(corpus20k):
+    """The seed of the candidate filter: GPU results with and without it are identical, and the bound the oracle-side
+    restatement derives for these queries is below the k-th returned score."""
+    c, ix = corpus20k
+    levels = bo.impact_levels(ix)
+    q_off, q_term, q_tf = synthetic.make_bm25_queries(c, 32, terms_per_query=3, min_rank=8, seed=31, add_always=False)
+    bm = _facade(ix)
+    doc, score, count = bm.search_batch_terms(q_off, q_term, q_tf, 100, 0.0)
+    for i in range(32):
+        terms = [int(t) for s in range(q_off[i], q_off[i + 1]) for t in [q_term[s]] * int(q_tf[s])]
+        bound = bo.initial_bound(ix, levels, terms, 100)
+        if bound > 0:
+            assert count[i] == 100 and score[i, 99] >= bound * (1 - 1e-6)
+    bm.close()
+
+
 def test_edge_cases(corpus20k):
     c, ix = corpus20k
     bm = _facade(ix)

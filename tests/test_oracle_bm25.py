@@ -98,3 +98,30 @@ def test_live_reference_agrees_with_oracle_on_fresh_corpus():
             ref = bm.search(" ".join(q), top_k=20, min_score=-5.0)
             got = bo.search_faithful(ix, q, top_k=20, min_score=-5.0)
             assert [(r["doc_id"], r["score"]) for r in ref] == [(int(ix.doc_ids[d]), s) for d, s in got]
+
+
+def test_initial_bound_never_exceeds_the_kth_score():
+    """The candidate-filter seed of the GPU path (oracle.initial_bound restates csrc/bm25.cuh::bm25_initial_bound) must be
+    a lower bound of the k-th best score, otherwise results would be lost."""
+    import torch  # noqa: F401  (synthetic generators are torch based)
+    from mse_b200 import synthetic
+    c = synthetic.make_bm25_corpus(6000, vocab=800, mean_len=48, seed=5, always_frac=0.9)
+    ix = bo.Bm25Arrays(c.term_off.numpy(), c.post_doc.numpy(), c.post_tf.numpy(), c.doc_len.numpy(), c.idf.numpy(),
+                       c.avgdl, c.total_docs, c.doc_ids.numpy())
+    levels = bo.impact_levels(ix)
+    assert (levels[:, 0] > 0).sum() > 50
+    qa = synthetic.make_bm25_queries(c, 20, terms_per_query=3, min_rank=2, seed=9, repeat_frac=0.3, add_always=True)
+    qb = synthetic.make_bm25_queries(c, 20, terms_per_query=3, min_rank=2, seed=10, repeat_frac=0.3, add_always=False)
+    useful = 0
+    for k in (64, 100, 500):
+      for (q_off, q_term, q_tf) in (qa, qb):
+        for i in range(20):
+            terms = [int(t) for s in range(q_off[i], q_off[i + 1]) for t in [q_term[s]] * int(q_tf[s])]
+            bound = bo.initial_bound(ix, levels, terms, k)
+            if bound <= 0:
+                continue
+            score, touched = bo.score_all_fast(ix, terms)
+            cand = np.sort(score[touched])[::-1]
+            assert cand.size >= k and cand[k - 1] >= bound, (k, i, bound, cand[k - 1] if cand.size >= k else None)
+            useful += 1
+    assert useful > 20
