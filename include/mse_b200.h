@@ -60,13 +60,18 @@ int mse_device_count(int* n_devices);
 int mse_index_create(int device, mse_index** out);
 int mse_index_destroy(mse_index* idx);
 
-/* Tuning knobs (all optional; 0 restores the automatic choice):
- *   "bm25_range_docs"        docs per shared-memory accumulator range (multiple of 256)
- *   "bm25_queries_per_item"  queries a CTA scores per scheduled work item
+/* Tuning knobs (all optional; 0 restores the automatic choice unless stated):
+ *   "bm25_range_docs"        docs per shared-memory accumulator range (rounded up to a multiple of 128, default 1024)
+ *   "bm25_queries_per_item"  queries a warp scores per scheduled work item (<= 31, default 8)
  *   "bm25_cand_cap"          per-query capacity of the candidate list between scoring and selection
  *   "bm25_use_tau"           1 (default) = running k-th-score bound filters candidates, 0 = emit all
+ *   "bm25_tau_init"          1 (default) = seed the bound from the per-term impact table built at load time, 0 = off
+ *   "bm25_kernel"            1 (default) = warp-task score kernel, 2 = experimental bulk-copy staged kernel
+ *   "bm25_stage_cap", "bm25_stage_buffers", "bm25_warps_per_cta", "bm25_readout"   knobs of kernel 2 only
  *   "dense_scan_ctas_per_sm" persistent CTAs per SM of the scan kernel
- *   "reset_timers"           any value: zero the accumulated kernel timers */
+ *   "dense_gemm_min_batch"   smallest batch routed to the tcgen05 GEMM kernel
+ *   "reset_timers"           any value: zero the accumulated kernel timers
+ * Environment: MSE_DEBUG_SYNC=1 synchronises after every BM25 kernel so that a device fault names its kernel. */
 int mse_index_set_option(mse_index* idx, const char* name, int64_t value);
 
 /* ---- BM25 (Stage 1) -------------------------------------------------------------------- */
