@@ -200,17 +200,12 @@ int bm25_run(mse_index* ix, int32_t B, const int32_t* d_q_off, const int32_t* d_
     if ((rc = ix->hist.ensure(sizeof(uint32_t) * size_t(B) * kHistBins))) return rc;
     if ((rc = ix->maxbin.ensure(sizeof(uint32_t) * size_t(B)))) return rc;
     if ((rc = ix->cand.ensure(sizeof(uint64_t) * size_t(B) * cap))) return rc;
-    if ((rc = ix->cand_count.ensure(sizeof(int32_t) * size_t(B)))) return rc;
-    if ((rc = ix->overflow.ensure(sizeof(int32_t) * size_t(B)))) return rc;
+    if ((rc = ix->cand_count.ensure(sizeof(int32_t) * 2 * size_t(B)))) return rc;     // [B] counts, then [B] overflow flags
     if ((rc = ix->misc.ensure(64))) return rc;
 
-    MSE_CUDA_TRY(cudaMemsetAsync(ix->cand_count.p, 0, sizeof(int32_t) * size_t(B), st));
-    MSE_CUDA_TRY(cudaMemsetAsync(ix->overflow.p, 0, sizeof(int32_t) * size_t(B), st));
+    MSE_CUDA_TRY(cudaMemsetAsync(ix->cand_count.p, 0, sizeof(int32_t) * 2 * size_t(B), st));
     MSE_CUDA_TRY(cudaMemsetAsync(ix->misc.p, 0, 64, st));
-    if (use_tau && !staged) {
-        MSE_CUDA_TRY(cudaMemsetAsync(ix->hist.p, 0, sizeof(uint32_t) * size_t(B) * kHistBins, st));
-        MSE_CUDA_TRY(cudaMemsetAsync(ix->maxbin.p, 0, sizeof(uint32_t) * size_t(B), st));
-    }
+    if (use_tau && !staged) MSE_CUDA_TRY(cudaMemsetAsync(ix->hist.p, 0, sizeof(uint32_t) * size_t(B) * kHistBins, st));   // maxbin: prepare kernel
     // staged kernel: the bound is refreshed by reading the candidate lists while they grow; a slot that has been
     // reserved but not written yet must read as "no candidate"
     if (use_tau && staged) MSE_CUDA_TRY(cudaMemsetAsync(ix->cand.p, 0, sizeof(uint64_t) * size_t(B) * cap, st));
@@ -219,7 +214,7 @@ int bm25_run(mse_index* ix, int32_t B, const int32_t* d_q_off, const int32_t* d_
     w.q_off = d_q_off; w.q_term = d_q_term; w.q_tf = d_q_tf;
     w.slot_w = ix->slot_w.as<float>(); w.rec = ix->rec.as<uint2>();
     w.ts = TauState{ix->tau.as<uint32_t>(), ix->hist.as<uint32_t>(), ix->maxbin.as<uint32_t>(), top_k};
-    w.cand = ix->cand.as<uint64_t>(); w.cand_count = ix->cand_count.as<int32_t>(); w.overflow = ix->overflow.as<int32_t>();
+    w.cand = ix->cand.as<uint64_t>(); w.cand_count = ix->cand_count.as<int32_t>(); w.overflow = ix->cand_count.as<int32_t>() + B;
     w.item_counter = ix->misc.as<int32_t>();
     w.stats = reinterpret_cast<unsigned long long*>(ix->misc.as<char>() + 16);
     w.n_queries = B; w.n_slots = S; w.n_sub = n_sub; w.sub_docs = RS; w.queries_per_item = qpi;
@@ -289,7 +284,8 @@ int bm25_run(mse_index* ix, int32_t B, const int32_t* d_q_off, const int32_t* d_
     ListLoader ld{w.cand, w.cand_count, int64_t(cap), cap};
     timer_begin(ix, T_SELECT, st);
     topk_select_kernel<ListLoader><<<B, kSelectThreads, 0, st>>>(ld, top_k, d_out_doc, d_out_score, d_out_count,
-                                                                mark_overflow ? w.overflow : nullptr);
+                                                                mark_overflow ? w.overflow : nullptr,
+                                                                reinterpret_cast<unsigned long long*>(ix->misc.as<char>() + 32));
     MSE_CUDA_TRY(cudaGetLastError());
     timer_end(ix, T_SELECT, st);
     if ((rc = debug_sync(st, "topk_select_kernel"))) return rc;
@@ -577,20 +573,20 @@ int mse_bm25_search_batch(mse_index* ix, int32_t B, const int32_t* q_off, const 
 
     if ((rc = bm25_run(ix, B, d_off, d_term, d_tf, S, max_terms, top_k, min_score, int32_t(cap), use_tau, d_doc, d_score, d_count, true, st))) return rc;
 
-    std::vector<int32_t> h_cnt, h_ovf;
-    h_cnt.resize(size_t(B));
-    h_ovf.resize(size_t(B));
-    unsigned long long h_post = 0;
-    MSE_CUDA_TRY(cudaMemcpyAsync(h_cnt.data(), ix->cand_count.p, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
-    MSE_CUDA_TRY(cudaMemcpyAsync(h_ovf.data(), ix->overflow.p, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
-    MSE_CUDA_TRY(cudaMemcpyAsync(&h_post, ix->misc.as<char>() + 16, sizeof(h_post), cudaMemcpyDeviceToHost, st));
+    // one 32-byte status read: {postings traversed, -, candidates handed to the selection, overflowed queries}
+    unsigned long long h_status[4] = {0, 0, 0, 0};
+    MSE_CUDA_TRY(cudaMemcpyAsync(h_status, ix->misc.as<char>() + 16, sizeof(h_status), cudaMemcpyDeviceToHost, st));
     MSE_CUDA_TRY(cudaStreamSynchronize(st));
     timers_collect(ix);
-    int64_t emitted = 0;
     std::vector<int32_t> redo;
-    for (int i = 0; i < B; ++i) { emitted += h_cnt[i]; if (h_ovf[i]) redo.push_back(i); }
-    ix->stats[0] = int64_t(h_post);
-    ix->stats[1] = emitted;
+    if (h_status[3] > 0) {
+        std::vector<int32_t> h_ovf;
+        h_ovf.resize(size_t(B));
+        MSE_CUDA_TRY(cudaMemcpy(h_ovf.data(), ix->cand_count.as<int32_t>() + B, sizeof(int32_t) * B, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < B; ++i) if (h_ovf[i]) redo.push_back(i);
+    }
+    ix->stats[0] = int64_t(h_status[0]);
+    ix->stats[1] = int64_t(h_status[2]);
     ix->stats[2] = int64_t(redo.size());
 
     if (!redo.empty()) {

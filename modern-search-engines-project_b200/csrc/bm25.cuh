@@ -106,13 +106,15 @@ __device__ __forceinline__ int64_t lower_bound_doc(const int2* __restrict__ pd, 
 // alone is >= w_t * imp_r(t); the other terms of the query add at least the (negative) sum of the negative
 // weights (0 < tf/(tf+norm) < 1).  So r >= top_k candidates score >= max_t w_t * imp_r(t) + sum of negative
 // weights, and nothing below that value can reach the top-k.  (The bound only filters candidates; results stay exact.)
+// Also sets maxbin[q], the top histogram bin the bound refresh starts from, to the bin of the query's score ceiling
+// (sum of the positive weights), so that the score kernel needs no atomicMax per candidate.
 __device__ __forceinline__ uint32_t bm25_initial_bound(const Bm25Dev& ix, const Bm25Work& w, int q) {
-    if (!w.use_tau || ix.imp_levels == nullptr) return w.min_key;
+    if (!w.use_tau) return w.min_key;
     int lv = 0;
     while (lv < 7 && (64 << lv) < w.ts.top_k) ++lv;
-    if ((64 << lv) < w.ts.top_k) return w.min_key;
+    const bool have_level = ix.imp_levels != nullptr && (64 << lv) >= w.ts.top_k;
     const int64_t need = int64_t(64) << lv;
-    float best = 0.f, neg = 0.f, mag = 0.f;
+    float best = 0.f, neg = 0.f, mag = 0.f, pos = 0.f;
     for (int s = w.q_off[q]; s < w.q_off[q + 1]; ++s) {
         const int t = w.q_term[s];
         if (t < 0 || t >= ix.n_terms) continue;
@@ -121,8 +123,12 @@ __device__ __forceinline__ uint32_t bm25_initial_bound(const Bm25Dev& ix, const 
         const float wt = float(double(ix.idf[t]) * double(w.q_tf[s]) * (double(ix.k1) + 1.0));
         mag += fabsf(wt);
         if (wt < 0.f) neg += wt;
-        else if (df >= need) best = fmaxf(best, wt * ix.imp_levels[int64_t(t) * kImpLevels + lv]);
+        else {
+            pos += wt;
+            if (have_level && df >= need) best = fmaxf(best, wt * ix.imp_levels[int64_t(t) * kImpLevels + lv]);
+        }
     }
+    w.ts.maxbin[q] = float_to_key(pos * 1.001f + 1e-30f) >> kHistShift;
     const float bound = best * (1.0f - 1e-5f) + neg - 4e-6f * mag;     // slack for the fp32 summation of the score kernel
     if (!(bound > 0.f)) return w.min_key;
     const uint32_t key = float_to_key(bound);
@@ -291,7 +297,7 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
             if (g < w.cap) w.cand[int64_t(q) * w.cap + g] = k64;
             else w.overflow[q] = 1;
         }
-        if (w.use_tau) tau_count(w.ts, q, key);
+        if (w.use_tau) atomicAdd(&w.ts.hist[int64_t(q) * kHistBins + (key >> kHistShift)], 1u);   // maxbin[q] is preset
     };
 
     // one warp-round: up to 32 postings of one term; docs are unique inside a term (no race)

@@ -100,7 +100,8 @@ struct MergeLoader {         // all-gathered per-rank top-k lists, [n_lists][n_q
 template <class Loader>
 __global__ void __launch_bounds__(kSelectThreads, 2)
 topk_select_kernel(Loader ld, int32_t top_k, int32_t* __restrict__ out_doc, float* __restrict__ out_score,
-                   int32_t* __restrict__ out_count, const int32_t* __restrict__ skip_flag) {
+                   int32_t* __restrict__ out_count, const int32_t* __restrict__ skip_flag,
+                   unsigned long long* __restrict__ summary = nullptr) {   // [0] += elements selected from, [1] += skipped queries
     constexpr int NT = kSelectThreads;
     __shared__ uint64_t s_buf[kSortCap];
     __shared__ int s_hist[256];
@@ -111,10 +112,14 @@ topk_select_kernel(Loader ld, int32_t top_k, int32_t* __restrict__ out_doc, floa
     const int q = blockIdx.x;
     const int tid = threadIdx.x;
     if (skip_flag && skip_flag[q]) {            // query re-run elsewhere (capacity overflow)
-        if (tid == 0) out_count[q] = -1;
+        if (tid == 0) {
+            out_count[q] = -1;
+            if (summary) atomicAdd(summary + 1, 1ull);
+        }
         return;
     }
     const int64_t n = ld.n(q);
+    if (summary && tid == 0) atomicAdd(summary, (unsigned long long)n);
 
     // ---- pass A: count valid keys, common prefix ------------------------------------------
     uint64_t vor = 0, vand = ~0ull;
