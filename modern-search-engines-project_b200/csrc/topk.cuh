@@ -120,12 +120,17 @@ topk_select_kernel(Loader ld, int32_t top_k, int32_t* __restrict__ out_doc, floa
     }
     const int64_t n = ld.n(q);
     if (summary && tid == 0) atomicAdd(summary, (unsigned long long)n);
+    // Lists that fit the sort buffer (the common case once the scoring kernels filter by a running bound) are
+    // copied to shared memory once; every later pass reads them from there instead of from L2.
+    const bool in_smem = n <= kSortCap;
+    auto key_at = [&](int64_t i) -> uint64_t { return in_smem ? s_buf[i] : ld.get(q, i); };
 
     // ---- pass A: count valid keys, common prefix ------------------------------------------
     uint64_t vor = 0, vand = ~0ull;
     int cnt = 0;
     for (int64_t i = tid; i < n; i += NT) {
         uint64_t k = ld.get(q, i);
+        if (in_smem) s_buf[i] = k;
         if (k) { vor |= k; vand &= k; ++cnt; }
     }
 #pragma unroll
@@ -164,7 +169,7 @@ topk_select_kernel(Loader ld, int32_t top_k, int32_t* __restrict__ out_doc, floa
             if (tid < 256) s_hist[tid] = 0;
             __syncthreads();
             for (int64_t i = tid; i < n; i += NT) {
-                uint64_t k = ld.get(q, i);
+                uint64_t k = key_at(i);
                 if (!k) continue;
                 bool match = (hi >= 64) ? true : (((k ^ prefix) >> hi) == 0);
                 if (match) atomicAdd(&s_hist[int(k >> shift) & ((1 << width) - 1)], 1);
@@ -195,12 +200,38 @@ topk_select_kernel(Loader ld, int32_t top_k, int32_t* __restrict__ out_doc, floa
     }
 
     // ---- compaction of the survivors ---------------------------------------------------------
-    for (int64_t i = tid; i < n; i += NT) {
-        uint64_t k = ld.get(q, i);
-        if (!k) continue;
-        if (select_all || (k >> sel_shift) >= (prefix >> sel_shift)) {
-            int slot = atomicAdd(&s_n, 1);
-            if (slot < kSortCap) s_buf[slot] = k;
+    if (in_smem) {
+        // in place: every thread keeps the survivors of its contiguous slice in registers, a block-wide scan of
+        // the counts gives their destination, and the writes start only after everybody has read
+        constexpr int C = (kSortCap + NT - 1) / NT;
+        uint64_t keep[C];
+        int mine = 0;
+        const int per = int((n + NT - 1) / NT);
+#pragma unroll
+        for (int j = 0; j < C; ++j) {
+            const int i = tid * per + j;
+            uint64_t k = (j < per && i < n) ? s_buf[i] : 0ull;
+            const bool sel = k != 0ull && (select_all || (k >> sel_shift) >= (prefix >> sel_shift));
+            keep[j] = sel ? k : 0ull;
+            mine += sel ? 1 : 0;
+        }
+        const int incl = warp_incl_scan(mine);
+        if (lane_id() == 31) s_cnt[warp_id()] = incl;
+        __syncthreads();
+        int base = incl - mine;
+#pragma unroll
+        for (int w = 0; w < NT / 32; ++w) if (w < warp_id()) base += s_cnt[w];
+        if (tid == NT - 1) s_n = base + mine;
+#pragma unroll
+        for (int j = 0; j < C; ++j) if (keep[j] != 0ull) { if (base < kSortCap) s_buf[base] = keep[j]; ++base; }
+    } else {
+        for (int64_t i = tid; i < n; i += NT) {
+            uint64_t k = ld.get(q, i);
+            if (!k) continue;
+            if (select_all || (k >> sel_shift) >= (prefix >> sel_shift)) {
+                int slot = atomicAdd(&s_n, 1);
+                if (slot < kSortCap) s_buf[slot] = k;
+            }
         }
     }
     __syncthreads();
@@ -211,17 +242,22 @@ topk_select_kernel(Loader ld, int32_t top_k, int32_t* __restrict__ out_doc, floa
     __syncthreads();
 
     // ---- bitonic sort, descending --------------------------------------------------------------
+    // With compare distance j <= 32 the pairs a warp handles stay inside that warp's own 64-key segments
+    // (pair index t -> positions in [64 * (t / 32), 64 * (t / 32) + 63]), so those steps only need __syncwarp;
+    // a block barrier is needed after the steps with j >= 64 and between merges.
     for (int k = 2; k <= P; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
+            const int lj = 31 - __clz(j);                                  // j is a power of two
             for (int t = tid; t < (P >> 1); t += NT) {
-                int i = ((t / j) * 2 * j) + (t % j);
-                int p = i + j;
-                uint64_t a = s_buf[i], b = s_buf[p];
-                bool up = ((i & k) == 0);
+                const int i = ((t >> lj) << (lj + 1)) | (t & (j - 1));
+                const int p = i + j;
+                const uint64_t a = s_buf[i], b = s_buf[p];
+                const bool up = ((i & k) == 0);
                 if ((a < b) == up) { s_buf[i] = b; s_buf[p] = a; }
             }
-            __syncthreads();
+            if (j > 32) __syncthreads(); else __syncwarp();
         }
+        __syncthreads();
     }
     const int out_n = m < kk ? m : kk;
     for (int i = tid; i < top_k; i += NT) {
