@@ -804,8 +804,8 @@ int mse_dense_scan_batch(mse_index* ix, int32_t B, const float* q, int32_t top_k
             GemmWork gw{};
             gw.group_row = ix->group_row.as<int64_t>(); gw.n_groups = ix->n_groups; gw.n_tiles = (ix->n_groups + 3) / 4;
             gw.n_pad = n_pad; gw.n_real = gn; gw.q0 = 0; gw.debug = int(ix->opt_gemm_debug);
-            const size_t stage_bytes = size_t(kGemmATileBytes) + size_t(n_pad) * 128;
-            gw.stages = int(std::min<size_t>(8, (size_t(196) * 1024) / stage_bytes));
+            const size_t stage_bytes = gemm_stage_bytes(n_pad);
+            gw.stages = int(std::min<size_t>(8, (size_t(208) * 1024) / stage_bytes));
             const size_t gsmem = stage_bytes * gw.stages + 1024;
             MSE_CUDA_TRY(cudaFuncSetAttribute(dense_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gsmem)));
             const int ggrid = int(std::min<int64_t>(gw.n_tiles, ix->sm_count));

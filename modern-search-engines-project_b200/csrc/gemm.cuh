@@ -1,21 +1,26 @@
 // K4 — exhaustive dense scan for large query batches on the 5th-gen tensor cores (tcgen05).
 //
-// S[rows x B] = E[rows x 768] * Q^T, bf16 operands, fp32 accumulators in TMEM; the epilogue is the
+// S^T[B x rows] = Q[B x 768] * E^T, bf16 operands, fp32 accumulators in TMEM; the epilogue is the
 // same per-document max + running-bound candidate emission as the GEMV kernel (dense.cuh), so the
 // score matrix never exists in HBM.
 //
-// Tiling: UMMA M=128 (cta_group::1) x N=B padded to a multiple of 32 (<= 256) x K=16, 12 k-blocks
-// of 64 elements (one 128-byte SWIZZLE_128B row per k-block).  A 128-row MMA tile is assembled from
-// FOUR doc-aligned groups of <= 32 rows (four {64 x 32} TMA boxes per k-block, each starting at the
-// first row of a document): TMEM lane quarter w then holds whole documents only, and epilogue warp
-// w — the only warp allowed to read that quarter — needs no cross-warp exchange for the per-doc max.
-// (Rows past the end of a group belong to the next group; they are computed twice and masked, ~8 %
-// redundant L2 reads.)  Documents with more than 32 chunks do not fit a group: the caller falls back
-// to the GEMV kernel for such corpora.
+// Roles of the operands: the QUERIES are the M dimension (TMEM lanes), the chunk rows the N dimension (TMEM
+// columns).  A tcgen05.ld (32x32b) therefore hands every epilogue thread 32 consecutive chunk scores of ITS
+// query: the per-document max is a running max over registers with warp-uniform document boundaries — no
+// shuffles — and the query's running bound is one register.  (The first version of this kernel had the chunk
+// rows on the lanes and spent 20k warp-instructions per tile on segmented max-scans across lanes.)
+//
+// Tiling: UMMA M=128 queries (one or two M tiles for B <= 128 / <= 256) x N=128 chunk rows x K=16, 12 k-blocks
+// of 64 elements (one 128-byte SWIZZLE_128B row per k-block).  A 128-row tile is assembled from FOUR
+// doc-aligned groups of <= 32 rows (four {64 x 32} TMA boxes per k-block, each starting at the first row of a
+// document), so a 32-column tcgen05.ld covers whole documents only.  (Rows past the end of a group belong to
+// the next group; they are computed twice and masked, ~8 % redundant L2 reads.)  Documents with more than 32
+// chunks do not fit a group: the caller falls back to the GEMV kernel for such corpora.
 //
 // Warp roles (320 threads, 1 CTA/SM, persistent over tiles): warp 0 = TMA producer (one lane),
-// warp 1 = TMEM allocator + MMA issuer (one lane), warps 2-9 = epilogue (tcgen05.ld 32x32b; warp w reads
-// TMEM lane quarter w%4, the two warps of a quarter take alternate 32-column chunks).
+// warp 1 = TMEM allocator + MMA issuer (one lane), warps 2-9 = epilogue (warp w reads TMEM lane quarter w%4 =
+// queries 32*(w%4).. of an M tile; the two warps of a quarter take one M tile each, or two groups each when
+// there is a single M tile).
 // Pipelines: smem ring full/empty mbarriers (TMA <-> MMA, freed by tcgen05.commit) and a
 // double-buffered TMEM accumulator full/empty pair (MMA <-> epilogue), so the epilogue of tile i
 // overlaps the MMAs of tile i+1.
@@ -36,6 +41,12 @@ constexpr int kGemmTileRows = 128;
 constexpr int kGemmGroupRows = 32;
 constexpr int kGemmATileBytes = kGemmTileRows * 128;   // 16 KB per stage
 constexpr int kGemmStage = 96;                         // emissions staged per epilogue warp between flushes
+
+// shared-memory bytes of one pipeline stage: 128 chunk rows + one or two M tiles of 128 query rows, 128 B each (the
+// MMA addresses whole M tiles; rows past the padded batch are never loaded and only feed accumulator lanes nobody reads)
+__host__ __device__ inline uint32_t gemm_stage_bytes(int n_pad) {
+    return uint32_t(kGemmATileBytes) + uint32_t(n_pad > 128 ? 2 : 1) * 128u * 128u;
+}
 
 struct GemmWork {
     const int64_t* group_row;    // [n_groups + 1] first row of every doc-aligned group (<= 32 rows each)
@@ -122,18 +133,18 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_consta
     constexpr int kMaxStages = 8;
     __shared__ __align__(8) uint64_t s_full[kMaxStages], s_empty[kMaxStages], s_tfull[2], s_tempty[2];
     __shared__ uint32_t s_tmem_base;
-    __shared__ __align__(16) float s_tau[kGemmEpiWarps][256];
     __shared__ uint64_t s_stage_key[kGemmEpiWarps][kGemmStage];
     __shared__ uint16_t s_stage_q[kGemmEpiWarps][kGemmStage];
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int n_pad = g.n_pad;
-    const uint32_t b_bytes = uint32_t(n_pad) * 128u;
-    const uint32_t stage_bytes = uint32_t(kGemmATileBytes) + b_bytes;
+    const uint32_t tx_bytes = uint32_t(kGemmATileBytes) + uint32_t(n_pad) * 128u;        // bytes TMA delivers per stage
+    const uint32_t stage_bytes = gemm_stage_bytes(n_pad);                                // a whole M tile of query rows is addressable
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gemm_smem_raw) + 1023) & ~uintptr_t(1023));
-    uint32_t tmem_cols = 32;
-    while (tmem_cols < uint32_t(2 * n_pad)) tmem_cols <<= 1;
+    const int MT = n_pad > 128 ? 2 : 1;                                   // M tiles of 128 queries
+    const uint32_t acc_cols = uint32_t(MT) * kGemmTileRows;               // accumulator columns per buffer
+    const uint32_t tmem_cols = 2 * acc_cols;                              // 256 or 512: a power of two
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < g.stages; ++s) { mbarrier_init(&s_full[s], 1); mbarrier_init(&s_empty[s], 1); }
@@ -164,7 +175,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_consta
                 for (int kb = 0; kb < kGemmKBlocks; ++kb) {
                     mbarrier_wait_backoff(&s_empty[stage], phase ^ 1u);
                     unsigned char* sa = smem + size_t(stage) * stage_bytes;
-                    mbarrier_expect_tx(&s_full[stage], stage_bytes);
+                    mbarrier_expect_tx(&s_full[stage], tx_bytes);
 #pragma unroll
                     for (int gi = 0; gi < 4; ++gi)
                         tma_load_2d(sa + gi * (kGemmGroupRows * 128), &map_e, kb * kGemmBlockK, rows[gi], &s_full[stage]);
@@ -176,7 +187,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_consta
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16_f32(kGemmTileRows, n_pad);
+            const uint32_t idesc = umma_idesc_bf16_f32(128, kGemmTileRows);   // M = 128 queries, N = 128 chunk rows
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -185,18 +196,20 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_consta
                 const uint32_t use = uint32_t(it >> 1);
                 mbarrier_wait_backoff(&s_tempty[buf], (use & 1u) ^ 1u);  // epilogue has drained this accumulator
                 tcgen05_fence_after();
-                const uint32_t tmem_d = tmem_base + uint32_t(buf * n_pad);
+                const uint32_t tmem_d = tmem_base + uint32_t(buf) * acc_cols;
                 for (int kb = 0; kb < kGemmKBlocks; ++kb) {
                     mbarrier_wait(&s_full[stage], phase);
                     tcgen05_fence_after();
-                    const uint32_t a_addr = smem_addr(smem + size_t(stage) * stage_bytes);
-                    const uint32_t b_addr = a_addr + kGemmATileBytes;
+                    const uint32_t e_addr = smem_addr(smem + size_t(stage) * stage_bytes);   // 128 chunk rows x 64
+                    const uint32_t q_addr = e_addr + kGemmATileBytes;                        // n_pad queries x 64
+                    for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
-                    for (int k = 0; k < kGemmBlockK / 16; ++k) {
-                        if (g.debug & 2) break;
-                        const uint64_t ad = umma_desc_sw128(a_addr + k * 32);
-                        const uint64_t bd = umma_desc_sw128(b_addr + k * 32);
-                        tcgen05_mma_bf16(tmem_d, ad, bd, idesc, (kb | k) ? 1u : 0u);
+                        for (int k = 0; k < kGemmBlockK / 16; ++k) {
+                            if (g.debug & 2) break;
+                            const uint64_t ad = umma_desc_sw128(q_addr + uint32_t(mt) * (128u * 128u) + k * 32);
+                            const uint64_t bd = umma_desc_sw128(e_addr + k * 32);
+                            tcgen05_mma_bf16(tmem_d + uint32_t(mt) * kGemmTileRows, ad, bd, idesc, (kb | k) ? 1u : 0u);
+                        }
                     }
                     tcgen05_commit(&s_empty[stage]);                      // frees the smem slot when the MMAs retire
                     if (++stage == g.stages) { stage = 0; phase ^= 1u; }
@@ -205,16 +218,20 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_consta
             }
         }
     } else {
-        // ===================== epilogue (warp w -> TMEM lane quarter w % 4) =====================
+        // ===================== epilogue (warp w -> TMEM lane quarter w % 4 = 32 queries of an M tile) ==========
         const int quarter = warp & 3;
         const int ew = warp - 2;                                          // 0..7
         const int half = ew >> 2;                                         // which of the quarter's two warps
         const unsigned lt_mask = (1u << lane) - 1u;
-        float* my_tau = s_tau[ew];
         uint64_t* st_key = s_stage_key[ew];
         uint16_t* st_q = s_stage_q[ew];
         int staged = 0;                                                   // uniform
         int rr = int((blockIdx.x * kGemmEpiWarps + ew) % g.n_real);       // round-robin cursor for bound refreshes
+        const int mt = MT == 2 ? half : 0;                                // this warp's M tile
+        const int g_lo = MT == 2 ? 0 : 2 * half, g_hi = MT == 2 ? 4 : 2 * half + 2;   // and its doc-aligned groups
+        const int my_q = mt * 128 + quarter * 32 + lane;                  // this thread's query (may be padding)
+        const bool q_real = my_q < g.n_real;
+        const bool warp_idle = mt * 128 + quarter * 32 >= g.n_real;       // no real query on these lanes
         auto flush = [&]() {
             if (staged == 0) return;
             unsigned long long base = 0;
@@ -232,92 +249,79 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_consta
         for (int64_t tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
             const uint32_t use = uint32_t(it >> 1);
-            if (half * 32 >= g.n_real) {                                  // small batch: this warp has no column chunk
+            if (warp_idle || (g.debug & 1)) {
                 mbarrier_wait_backoff(&s_tfull[buf], use & 1u);
                 if (lane == 0) mbarrier_arrive(&s_tempty[buf]);
                 continue;
             }
-            // this warp's doc-aligned group
-            const int64_t grp = tile * 4 + quarter;
-            int64_t r0 = dx.n_chunks, r1 = dx.n_chunks;
-            if (grp < g.n_groups) { r0 = g.group_row[grp]; r1 = g.group_row[grp + 1]; }
-            const int nrow = int(r1 - r0);
-            const bool valid = lane < nrow;
-            const int my_doc = valid ? dx.row_doc[r0 + lane] : (-2 - lane);
-            unsigned same = 0;                                            // bit s: lane-(1<<s) holds the same document
-            int src[5];                                                   // scan source lane per step (self when not the same doc)
-#pragma unroll
-            for (int s = 0; s < 5; ++s) {
-                const int od = __shfl_up_sync(0xffffffffu, my_doc, 1 << s);
-                const bool sm = lane >= (1 << s) && od == my_doc;
-                if (sm) same |= 1u << s;
-                src[s] = sm ? lane - (1 << s) : lane;
+            // this thread's running bound (padding lanes never pass)
+            float tau = INFINITY;
+            if (q_real) {
+                const uint32_t tk = w.use_tau ? ld_relaxed_u32(&w.ts.tau[g.q0 + my_q]) : 0u;
+                tau = tk ? key_to_float(tk) : -INFINITY;
             }
-            const int nd = __shfl_down_sync(0xffffffffu, my_doc, 1);
-            const bool is_tail = valid && (lane == 31 || nd != my_doc);   // groups hold whole documents
-            unsigned step_mask = 0;                                       // scan steps some lane needs (uniform)
+            // document layout of the warp's groups (lane i <-> row i of the group; warp-uniform masks)
+            int my_doc[4];
+            unsigned tails[4];
 #pragma unroll
-            for (int s = 0; s < 5; ++s)
-                if (__any_sync(0xffffffffu, (same >> s) & 1u)) step_mask |= 1u << s;
-            for (int c = lane; c < n_pad; c += 32) {                      // padded columns never pass
-                float t = INFINITY;
-                if (c < g.n_real) {
-                    const uint32_t tk = w.use_tau ? ld_relaxed_u32(&w.ts.tau[g.q0 + c]) : 0u;
-                    t = tk ? key_to_float(tk) : -INFINITY;
+            for (int gi = 0; gi < 4; ++gi) {
+                my_doc[gi] = -1; tails[gi] = 0u;
+                if (gi >= g_lo && gi < g_hi) {
+                    const int64_t grp = tile * 4 + gi;
+                    int64_t r0 = dx.n_chunks, r1 = dx.n_chunks;
+                    if (grp < g.n_groups) { r0 = g.group_row[grp]; r1 = g.group_row[grp + 1]; }
+                    const bool valid = lane < int(r1 - r0);
+                    const int d = valid ? dx.row_doc[r0 + lane] : (-2 - lane);
+                    const int nd = __shfl_down_sync(0xffffffffu, d, 1);
+                    my_doc[gi] = d;
+                    tails[gi] = __ballot_sync(0xffffffffu, valid && (lane == 31 || nd != d));   // last row of every document
                 }
-                my_tau[c] = t;
             }
-            __syncwarp();
             mbarrier_wait(&s_tfull[buf], use & 1u);
             tcgen05_fence_after();
-            for (int c0 = half * 32; c0 < ((g.debug & 1) ? 0 : g.n_real); c0 += 64) {
+#pragma unroll
+            for (int gi = 0; gi < 4; ++gi) {
+                if (gi < g_lo || gi >= g_hi || tails[gi] == 0u) continue;  // uniform
                 uint32_t r[32];
-                tmem_ld_32x32b_x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(buf * n_pad + c0), r);
-                float v[32];
+                tmem_ld_32x32b_x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(buf) * acc_cols +
+                                   uint32_t(mt * kGemmTileRows + gi * kGemmGroupRows), r);
+                const unsigned tl = tails[gi];
+                // straight-line pass over the 32 columns: running max of the current document (boundaries are
+                // warp-uniform bits), bit i of passmask = "column i closes a document whose max reaches my bound"
+                float mm[32];
+                unsigned passmask = 0u;
+                float m = -INFINITY;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-                // per-document max: segmented inclusive max-scan over the lanes, 32 columns in lock-step
-#pragma unroll
-                for (int s = 0; s < 5; ++s) {
-                    if (step_mask & (1u << s)) {                          // uniform
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], __shfl_sync(0xffffffffu, v[i], src[s]));
-                    }
+                for (int i = 0; i < 32; ++i) {
+                    m = fmaxf(m, __uint_as_float(r[i]));
+                    mm[i] = m;
+                    if (m >= tau) passmask |= 1u << i;                    // masked with the document ends below
+                    m = ((tl >> i) & 1u) ? -INFINITY : m;
                 }
-                uint32_t pmask = 0;                                       // bit i: this lane's value reaches tau[c0+i]
-                const float4* tau4 = reinterpret_cast<const float4*>(my_tau + c0);
-#pragma unroll
-                for (int i4 = 0; i4 < 8; ++i4) {
-                    const float4 t = tau4[i4];
-                    if (v[4 * i4 + 0] >= t.x) pmask |= 1u << (4 * i4 + 0);
-                    if (v[4 * i4 + 1] >= t.y) pmask |= 1u << (4 * i4 + 1);
-                    if (v[4 * i4 + 2] >= t.z) pmask |= 1u << (4 * i4 + 2);
-                    if (v[4 * i4 + 3] >= t.w) pmask |= 1u << (4 * i4 + 3);
-                }
-                pmask = is_tail ? pmask : 0u;                             // only the last row of a document emits
-                uint32_t colmask = __reduce_or_sync(0xffffffffu, pmask);
+                passmask &= tl;
+                unsigned colmask = __reduce_or_sync(0xffffffffu, passmask);
                 while (colmask) {                                         // stage (query, key) entries: no global round trip
                     const int i = __ffs(colmask) - 1;
                     colmask &= colmask - 1;
                     float vi = 0.f;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) vi = (j == i) ? v[j] : vi;
+                    for (int j = 0; j < 32; ++j) vi = (j == i) ? mm[j] : vi;
                     vi += 0.0f;
-                    const bool pass = (pmask >> i) & 1u;
+                    const bool pass = (passmask >> i) & 1u;
                     const unsigned pm = __ballot_sync(0xffffffffu, pass);
                     const int n = __popc(pm);
                     if (staged + n > kGemmStage) flush();
+                    const int doc = __shfl_sync(0xffffffffu, my_doc[gi], i);
                     if (pass) {
-                        const int q = g.q0 + c0 + i;
+                        const int q = g.q0 + my_q;
                         const uint32_t key = float_to_key(vi);
                         const int e = staged + __popc(pm & lt_mask);
-                        st_key[e] = make_key64(key, dx.doc_base + uint32_t(my_doc));
+                        st_key[e] = make_key64(key, dx.doc_base + uint32_t(doc));
                         st_q[e] = uint16_t(q);
                         if (w.use_tau) tau_count(w.ts, q, key);           // fire-and-forget histogram update
                     }
                     staged += n;
                 }
-                __syncwarp();
             }
             tcgen05_fence_before();
             __syncwarp();
