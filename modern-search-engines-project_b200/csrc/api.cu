@@ -455,7 +455,7 @@ int mse_bm25_load(mse_index* ix, int64_t n_terms, int64_t n_docs, int64_t doc_ba
         MSE_CUDA_TRY(cudaGetLastError());
     }
     if (n_terms > 0) {
-        bm25_validate_kernel<<<unsigned((n_terms + 7) / 8), 256, 0, st>>>(ix->term_off.as<int64_t>(), ix->post_doc.as<int32_t>(),
+        bm25_validate_kernel<<<unsigned(std::min<int64_t>((P + 255) / 256 + 1, 148 * 64)), 256, 0, st>>>(ix->term_off.as<int64_t>(), ix->post_doc.as<int32_t>(),
                                                                          ix->post_tf.as<int32_t>(), n_terms, n_docs, ix->misc.as<int32_t>());
         MSE_CUDA_TRY(cudaGetLastError());
     }

@@ -590,18 +590,23 @@ __global__ void bm25_interleave_kernel(const int32_t* __restrict__ post_doc, con
     else if (i < n_padded) post2[i] = make_int2(0, 1);
 }
 
-// postings must be strictly ascending inside a term and inside [0, n_docs); tf >= 1
+// postings must be strictly ascending inside a term and inside [0, n_docs); tf >= 1.  One thread per posting; a
+// descent (doc[i-1] >= doc[i]) is legal only where a new term starts, which a binary search over term_off decides.
 __global__ void bm25_validate_kernel(const int64_t* __restrict__ term_off, const int32_t* __restrict__ post_doc,
                                      const int32_t* __restrict__ post_tf, int64_t n_terms, int64_t n_docs,
                                      int32_t* __restrict__ bad) {
-    const int64_t t = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (t >= n_terms) return;
-    const int64_t a = term_off[t], e = term_off[t + 1];
-    if (e < a) { *bad = 1; return; }
-    for (int64_t i = a + lane_id(); i < e; i += 32) {
+    const int64_t P = term_off[n_terms];
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < P; i += int64_t(gridDim.x) * blockDim.x) {
         const int d = post_doc[i];
         if (d < 0 || d >= n_docs || post_tf[i] < 1) *bad = 2;
-        if (i > a && post_doc[i - 1] >= d) *bad = 3;
+        if (i > 0 && post_doc[i - 1] >= d) {
+            int64_t lo = 0, hi = n_terms;                       // is i the first posting of some term?
+            while (lo < hi) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (term_off[mid] < i) lo = mid + 1; else hi = mid;
+            }
+            if (lo >= n_terms || term_off[lo] != i) *bad = 3;
+        }
     }
 }
 

@@ -56,7 +56,7 @@ def idf_float32(total_docs: float, df: torch.Tensor) -> torch.Tensor:
 
 def make_bm25_corpus(n_docs: int, vocab: int = 200_000, mean_len: float = 256.0, sigma: float = 0.5,
                      zipf_s: float = 1.0, seed: int = 1234, device="cpu",
-                     always_frac: float = 0.0) -> SyntheticBm25:
+                     always_frac: float = 0.0, sort_limit: int = (1 << 31) - 1) -> SyntheticBm25:
     """Docs with log-normal lengths and iid Zipf tokens; ``always_frac`` > 0 adds one extra term
     (index ``vocab``) present in that fraction of docs with tf ~ 1 + Poisson(3) — the analogue of
     the "tübingen" term ``search_api.py:160-165`` appends to every query."""
@@ -68,21 +68,61 @@ def make_bm25_corpus(n_docs: int, vocab: int = 200_000, mean_len: float = 256.0,
     L = torch.clamp(torch.round(torch.exp(mu + sigma * z)), min=8).to(torch.int64)
     cdf = zipf_cdf(vocab, zipf_s, dev)
     n_tok = int(L.sum().item())
-    doc_of = torch.repeat_interleave(torch.arange(n_docs, device=dev, dtype=torch.int64), L)
-    keys = torch.empty(n_tok, dtype=torch.int64, device=dev)
     step = 1 << 26
-    for a in range(0, n_tok, step):              # slabs keep the fp64 uniforms small
-        e = min(n_tok, a + step)
-        u = torch.rand(e - a, generator=g, device=dev, dtype=torch.float64)
-        t = torch.searchsorted(cdf, u).clamp_(max=vocab - 1)
-        keys[a:e] = t * n_docs + doc_of[a:e]
-    del doc_of
-    keys, _ = torch.sort(keys)
-    uniq, counts = torch.unique_consecutive(keys, return_counts=True)
-    del keys
-    term = uniq // n_docs
-    post_doc = (uniq % n_docs).to(torch.int32)
-    post_tf = counts.to(torch.int32)
+
+    def slab_postings(d0: int, d1: int):
+        """(term int64, doc int32, tf int32) of docs [d0, d1), sorted by (term, doc)."""
+        Ls = L[d0:d1]
+        nt = int(Ls.sum().item())
+        doc_of = torch.repeat_interleave(torch.arange(d0, d1, device=dev, dtype=torch.int64), Ls)
+        keys = torch.empty(nt, dtype=torch.int64, device=dev)
+        for a in range(0, nt, step):             # slabs keep the fp64 uniforms small
+            e = min(nt, a + step)
+            u = torch.rand(e - a, generator=g, device=dev, dtype=torch.float64)
+            t = torch.searchsorted(cdf, u).clamp_(max=vocab - 1)
+            keys[a:e] = t * n_docs + doc_of[a:e]
+        del doc_of
+        keys = torch.sort(keys).values            # (the permutation is not needed: drop it right away)
+        uniq, counts = torch.unique_consecutive(keys, return_counts=True)
+        del keys
+        return uniq // n_docs, (uniq % n_docs).to(torch.int32), counts.to(torch.int32)
+
+    if n_tok < sort_limit:
+        term, post_doc, post_tf = slab_postings(0, n_docs)
+    else:
+        # torch.sort takes at most INT_MAX elements: generate doc-range slabs of <= sort_limit/2 tokens, each sorted by
+        # (term, doc), and interleave them term-major (slab order == doc order inside every term)
+        csum = torch.cumsum(L, 0)
+        bounds, lo_tok = [0], 0
+        while bounds[-1] < n_docs:
+            nxt = int(torch.searchsorted(csum, torch.tensor([lo_tok + max(1, sort_limit // 2)], device=dev)).item())
+            nxt = max(min(nxt, n_docs), bounds[-1] + 1)
+            bounds.append(nxt)
+            lo_tok = int(csum[nxt - 1].item())
+        slabs, dfs = [], []
+        for d0, d1 in zip(bounds[:-1], bounds[1:]):
+            t_s, d_s, f_s = slab_postings(d0, d1)
+            dfs.append(torch.bincount(t_s, minlength=vocab))
+            slabs.append((d_s, f_s))
+            del t_s
+        df_all = torch.stack(dfs).sum(0)
+        t_off = torch.zeros(vocab + 1, dtype=torch.int64, device=dev)
+        t_off[1:] = torch.cumsum(df_all, 0)
+        n_post = int(t_off[-1].item())
+        post_doc = torch.empty(n_post, dtype=torch.int32, device=dev)
+        post_tf = torch.empty(n_post, dtype=torch.int32, device=dev)
+        base = t_off[:-1].clone()
+        ar = torch.arange(vocab, device=dev, dtype=torch.int64)
+        for (d_s, f_s), df_s in zip(slabs, dfs):
+            s_off = torch.cumsum(df_s, 0) - df_s
+            t_s = torch.repeat_interleave(ar, df_s)
+            dest = torch.arange(d_s.numel(), device=dev, dtype=torch.int64) - s_off[t_s] + base[t_s]
+            post_doc[dest] = d_s
+            post_tf[dest] = f_s
+            base += df_s
+            del t_s, dest
+        del slabs
+        term = torch.repeat_interleave(ar, df_all)
     n_terms = vocab
     doc_len = L.clone()
     always_term = -1

@@ -149,3 +149,19 @@ def test_reference_arm_of_bench_runs_on_cpu():
     d = json.loads(r.stdout.strip().splitlines()[-1])
     assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["metric"] == "bm25_queries_per_sec"
+
+
+def test_synthetic_corpus_slab_path_is_a_valid_index():
+    """Corpora above torch.sort's element limit are generated in doc-range slabs; forced here with a tiny limit."""
+    import torch
+    from mse_b200 import synthetic
+    c = synthetic.make_bm25_corpus(2000, vocab=300, mean_len=24, seed=8, sort_limit=9000)
+    off = c.term_off.numpy()
+    doc, tf = c.post_doc.numpy(), c.post_tf.numpy()
+    assert off[0] == 0 and off[-1] == len(doc) and (np.diff(off) >= 0).all()
+    for t in range(0, 300, 7):
+        d = doc[off[t]:off[t + 1]]
+        assert (np.diff(d) > 0).all()                      # strictly ascending docs inside a term
+    assert np.array_equal(np.bincount(doc, weights=tf, minlength=2000).astype(np.int64), c.doc_len.numpy().astype(np.int64))
+    ref = synthetic.make_bm25_corpus(2000, vocab=300, mean_len=24, seed=8)
+    assert np.array_equal(ref.doc_len.numpy(), c.doc_len.numpy())   # same documents, tokens drawn in a different chunking
