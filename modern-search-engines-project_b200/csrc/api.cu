@@ -87,6 +87,7 @@ struct mse_index {
     DevBuf o_doc, o_score, o_count;          // device staging of results for MSE_HOST callers
     DevBuf best, dq;                         // dense scan
     DevBuf r_in[5], r_out[6];                // rerank staging
+    DevBuf r_split[6];                       // small-batch rerank: cosines / survivor lists between the two kernels
     DevBuf m_in[3];                          // merge staging
     DevBuf fb_q[3], fb_out[3];               // fallback sub-batches
 
@@ -348,6 +349,7 @@ int mse_index_destroy(mse_index* ix) {
         for (DevBuf* b : all) b->release();
         for (auto& b : ix->r_in) b.release();
         for (auto& b : ix->r_out) b.release();
+        for (auto& b : ix->r_split) b.release();
         for (auto& b : ix->m_in) b.release();
         for (auto& b : ix->fb_q) b.release();
         for (auto& b : ix->fb_out) b.release();
@@ -564,7 +566,10 @@ int mse_bm25_search_batch(mse_index* ix, int32_t B, const int32_t* q_off, const 
     }
 
     // candidate-list capacity: bounded workspace; overflowing queries are re-run below
-    int64_t cap = ix->opt_cand_cap > 0 ? ix->opt_cand_cap : std::max<int64_t>(32 * int64_t(top_k), 32768);
+    // (a small batch fits the device in one wave of warps: every sub-range of a query is scored before the running
+    // bound can rise, so only the impact-table seed filters and the lists are given the room a 512 MB workspace allows)
+    int64_t cap = ix->opt_cand_cap > 0 ? ix->opt_cand_cap
+                                       : std::max<int64_t>(std::max<int64_t>(32 * int64_t(top_k), 32768), (int64_t(512) << 20) / (8 * int64_t(B)));
     cap = std::min<int64_t>(cap, std::max<int64_t>(ix->bm.n_docs, 1));
     const int64_t budget = int64_t(2) << 30;
     cap = std::max<int64_t>(std::min<int64_t>(cap, budget / (8 * int64_t(B))), std::min<int64_t>(ix->bm.n_docs, int64_t(top_k)));
@@ -918,10 +923,33 @@ int mse_rerank_batch(mse_index* ix, int32_t B, const int32_t* cand_off, const in
         a.out_doc = out_doc; a.out_score = out_score; a.out_orig = out_orig; a.out_chunk = out_chunk;
         a.out_count = out_count; a.out_rows = out_rows;
     }
-    MSE_CUDA_TRY(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kRerankSmemBytes)));
+    const int slices = (B * 4 <= ix->sm_count && ix->dn.doc_base == 0) ? std::min(32, std::max(1, ix->sm_count / B)) : 1;
     timer_begin(ix, T_RERANK, st);
-    rerank_kernel<<<B, kRerankThreads, kRerankSmemBytes, st>>>(ix->dn, a);
-    MSE_CUDA_TRY(cudaGetLastError());
+    if (slices > 1) {
+        // Small batch: one CTA per query would leave most SMs idle (batch-1 latency).  Same two kernels as the
+        // multi-GPU path: cosines by `slices` CTAs per query, then the pool-wide fusion from the gathered cosines.
+        const size_t slots = size_t(B) * kRerankMaxCand;
+        if ((rc = ix->r_split[0].ensure(sizeof(float) * slots * kRerankMaxChunks))) return rc;
+        if ((rc = ix->r_split[1].ensure(sizeof(int32_t) * slots))) return rc;
+        if ((rc = ix->r_split[2].ensure(sizeof(int64_t) * slots))) return rc;
+        if ((rc = ix->r_split[3].ensure(sizeof(int32_t) * slots))) return rc;
+        if ((rc = ix->r_split[4].ensure(sizeof(float) * slots))) return rc;
+        if ((rc = ix->r_split[5].ensure(sizeof(int32_t) * size_t(B)))) return rc;
+        MSE_CUDA_TRY(cudaMemsetAsync(ix->r_split[1].p, 0, sizeof(int32_t) * slots, st));      // rows: 0 = not fetched
+        RerankShardArgs sa{a.cand_off, a.cand_doc, a.cand_bm25, a.url_group, a.q, max_chunks, ix->dn.doc_base + ix->dn.n_docs,
+                           ix->r_split[0].as<float>(), ix->r_split[1].as<int32_t>(), ix->r_split[2].as<int64_t>(),
+                           ix->r_split[3].as<int32_t>(), ix->r_split[4].as<float>(), ix->r_split[5].as<int32_t>()};
+        rerank_shard_cos_kernel<<<dim3(unsigned(B), unsigned(slices)), kRerankThreads, 0, st>>>(ix->dn, sa);
+        MSE_CUDA_TRY(cudaGetLastError());
+        RerankFuseArgs fa{sa.cos, sa.rows, sa.chunk0, sa.surv_doc, sa.surv_bm25, sa.surv_count, smoothing, max_out,
+                          a.out_doc, a.out_score, a.out_orig, a.out_chunk, a.out_count, a.out_rows};
+        rerank_shard_fuse_kernel<<<B, kRerankThreads, 0, st>>>(fa);
+        MSE_CUDA_TRY(cudaGetLastError());
+    } else {
+        MSE_CUDA_TRY(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kRerankSmemBytes)));
+        rerank_kernel<<<B, kRerankThreads, kRerankSmemBytes, st>>>(ix->dn, a);
+        MSE_CUDA_TRY(cudaGetLastError());
+    }
     timer_end(ix, T_RERANK, st);
     if (where == MSE_HOST) {
         const size_t n = size_t(B) * max_out;

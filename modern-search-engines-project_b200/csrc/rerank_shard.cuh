@@ -98,12 +98,14 @@ rerank_shard_cos_kernel(DenseDev dx, RerankShardArgs a) {
                 const int o = carry + incl - 1;
                 const int32_t g = int32_t(0x7fffffffu - uint32_t((k >> 10) & 0x7fffffffu));
                 s_doc[o] = g;
-                a.surv_doc[int64_t(qi) * kRerankMaxCand + o] = g;
-                a.surv_bm25[int64_t(qi) * kRerankMaxCand + o] = a.cand_bm25[c0 + (0x3ff - int(k & 0x3ffull))];
+                if (blockIdx.y == 0) {                     // (every slice of a query computes the same list)
+                    a.surv_doc[int64_t(qi) * kRerankMaxCand + o] = g;
+                    a.surv_bm25[int64_t(qi) * kRerankMaxCand + o] = a.cand_bm25[c0 + (0x3ff - int(k & 0x3ffull))];
+                }
             }
             carry += __shfl_sync(0xffffffffu, incl, 31);
         }
-        if (tid == 0) { s_ns = carry; a.surv_count[qi] = carry; }
+        if (tid == 0) { s_ns = carry; if (blockIdx.y == 0) a.surv_count[qi] = carry; }
     }
     __syncthreads();
     const int ns = s_ns;
@@ -122,7 +124,8 @@ rerank_shard_cos_kernel(DenseDev dx, RerankShardArgs a) {
         }
     qq = warp_sum(qq);
     const float qn = sqrtf(qq);
-    for (int i = warp_id(); i < ns; i += NT / 32) {
+    // gridDim.y > 1 (small batches on one GPU): the survivors of a query are dealt out to gridDim.y CTAs
+    for (int i = int(blockIdx.y) * (NT / 32) + warp_id(); i < ns; i += int(gridDim.y) * (NT / 32)) {
         const int64_t d = int64_t(s_doc[i]) - int64_t(dx.doc_base);
         if (d < 0 || d >= dx.n_docs) continue;             // another rank owns this document
         const int64_t ra = dx.doc_chunk_off[d], re = dx.doc_chunk_off[d + 1];
