@@ -23,9 +23,10 @@
 //     and a "touched list".  Doc ids are unique inside a term, so a term is applied with plain
 //     read-modify-write and terms are separated by __syncwarp: deterministic summation in the
 //     reference's term order;
-//   * accumulators rest at -0.0f (x + -0.0 == x, +0.0 + -0.0 == +0.0): a document whose score is
-//     exactly zero (idf == 0, kept by the reference) is distinguishable from an untouched one
-//     (never returned).  The first posting that finds -0.0 appends the doc to the touched list,
+//   * accumulators hold the NEGATED score and rest at +0.0f (all-zero bits, so re-arming is a store of
+//     the zero register); contributions are added with round-toward-minus-infinity FMAs, where
+//     (+0.0) + (-0.0) == -0.0: a document whose score is exactly zero (idf == 0, kept by the
+//     reference) is distinguishable from an untouched one (never returned).  The first posting that finds -0.0 appends the doc to the touched list,
 //     and the read-out walks that list only (no scan over RS accumulators), re-arming as it goes;
 //   * read-out emits only candidates with score >= tau[q], a per-query lower bound of the final
 //     k-th best score, raised on the fly from a per-query histogram of emitted candidates (any
@@ -248,19 +249,13 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
     const int QC = w.queries_per_item;
     const int chunks = (w.n_queries + QC - 1) / QC;
     const int n_items = w.n_sub * chunks;
-    const float neg0 = __uint_as_float(kUntouchedBits);
     const unsigned lt_mask = (1u << lane) - 1u;
     const float c0 = ix.norm_c0, c1 = ix.norm_c1;
     const int2* __restrict__ g_post = ix.post2;          // {doc, tf}: one 8-byte load per posting
     constexpr int MP = kPrefetchSlots;
     const int scan_iters = RS >> 7;
 
-    // the re-arm pattern lives in four registers for the whole kernel (opaque to the compiler, which would
-    // otherwise rebuild it with four moves in front of every 16-byte store of the read-out pass)
-    int4 zq;
-    asm volatile("mov.b32 %0, 0x80000000;\n\tmov.b32 %1, 0x80000000;\n\tmov.b32 %2, 0x80000000;\n\tmov.b32 %3, 0x80000000;"
-                 : "=r"(zq.x), "=r"(zq.y), "=r"(zq.z), "=r"(zq.w));
-    for (int i = lane; i < RS; i += 32) s_acc[i] = neg0;
+    for (int i = lane; i < RS; i += 32) s_acc[i] = 0.f;
     if (lane == 0) *s_cnt = 0;
     __syncwarp();
     int cur_j = -1;
@@ -286,8 +281,8 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
     // stage comes from a shared-memory counter; what does not fit goes straight to the list.  Do NOT call this from
     // a loop whose trip count differs between lanes: that variant faulted sporadically ("illegal instruction") on
     // sm_100a under heavy emission (shared + global atomics with results inside a divergent loop).
-    auto emit_one = [&](int q, int vb, int d) {
-        const uint32_t key = float_to_key(__int_as_float(vb) + 0.0f);
+    auto emit_one = [&](int q, int vb, int d) {                        // vb: bits of the NEGATED score
+        const uint32_t key = float_to_key(0.0f - __int_as_float(vb));
         const uint64_t k64 = make_key64(key, ix.doc_base + uint32_t(lo + d));
         const int slot = atomicAdd(s_cnt, 1);
         if (slot < kEmitStage) {
@@ -306,10 +301,11 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
             const int d = dd - lo;
             const float tf = float(tfi);
             const float norm = LEN16 ? fmaf(float(s_len[d]), c1, c0) : float(s_len[d]);
-            // idf*qtf*(k1+1) * tf / (tf + k1*(1-b+b*dl/avgdl)); tf + norm >= 1, rcp.approx: <= 1 ulp
+            // idf*qtf*(k1+1) * tf / (tf + k1*(1-b+b*dl/avgdl)); tf + norm >= 1, rcp.approx: <= 1 ulp.
+            // The accumulator holds MINUS the score; round-down keeps "touched, score 0" at -0.0 (rest state: +0.0)
             float r;
             asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(tf + norm));
-            s_acc[d] = fmaf(wt * tf, r, s_acc[d]);
+            s_acc[d] = __fmaf_rd(-(wt * tf), r, s_acc[d]);
         }
     };
     // postings 32.. of a slice: the loads of up to four rounds are issued before the first is applied
@@ -431,29 +427,30 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
                 // ---- read-out: scan the accumulators 128 per round, re-arm them, stage candidates >= tau ----
                 if (touched) {
                     const float tau_f = key_to_float(tau_key);
-                    const int tau_i = __float_as_int(tau_f);
-                    const bool fast = tau_i >= 0;        // tau is +0.0 or positive: one signed compare also rejects
-                                                         // -0.0 (untouched) and every negative score
-                    int4* a4 = reinterpret_cast<int4*>(s_acc) + lane;
-                    const int4 z4 = make_int4(zq.x, zq.y, zq.z, zq.w);
+                    const uint32_t tau_u = __float_as_uint(tau_f) | 0x80000000u;   // bits of -tau when tau >= +0.0
+                    const bool fast = __float_as_int(tau_f) >= 0;   // tau is +0.0 or positive: the accumulators hold minus the
+                                                                     // score, so "score >= tau" is one UNSIGNED compare that also
+                                                                     // rejects 0 (untouched) and every negative score (sign bit clear)
+                    uint4* a4 = reinterpret_cast<uint4*>(s_acc) + lane;
+                    const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+                    auto passes = [&](uint32_t bits) {
+                        return fast ? (bits >= tau_u) : (bits != 0u && (0.0f - __uint_as_float(bits)) >= tau_f);
+                    };
                     // pass 1: re-arm every 4-doc group that holds no candidate, flag the (rare) others
                     uint32_t flag = 0;
                     if (fast) {
 #pragma unroll 8
                         for (int it = 0; it < scan_iters; ++it) {
-                            const int4 v = a4[it * 32];
-                            const bool p = max(max(v.x, v.y), max(v.z, v.w)) >= tau_i;
+                            const uint4 v = a4[it * 32];
+                            const bool p = max(max(v.x, v.y), max(v.z, v.w)) >= tau_u;
                             if (!p) a4[it * 32] = z4;
                             flag |= uint32_t(p) << it;
                         }
                     } else {
 #pragma unroll 1
                         for (int it = 0; it < scan_iters; ++it) {
-                            const int4 v = a4[it * 32];
-                            const bool p = (uint32_t(v.x) != kUntouchedBits && __int_as_float(v.x) >= tau_f) ||
-                                           (uint32_t(v.y) != kUntouchedBits && __int_as_float(v.y) >= tau_f) ||
-                                           (uint32_t(v.z) != kUntouchedBits && __int_as_float(v.z) >= tau_f) ||
-                                           (uint32_t(v.w) != kUntouchedBits && __int_as_float(v.w) >= tau_f);
+                            const uint4 v = a4[it * 32];
+                            const bool p = passes(v.x) || passes(v.y) || passes(v.z) || passes(v.w);
                             if (!p) a4[it * 32] = z4;
                             flag |= uint32_t(p) << it;
                         }
@@ -463,16 +460,13 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
                         if (flag == 0u) continue;
                         const int it = __ffs(int(flag)) - 1;
                         flag &= flag - 1u;
-                        const int4 v = a4[it * 32];
+                        const uint4 v = a4[it * 32];
                         a4[it * 32] = z4;
                         const int d0 = (it * 32 + lane) * 4;
-                        const int vv[4] = {v.x, v.y, v.z, v.w};
+                        const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const bool pass = fast ? (vv[u] >= tau_i)
-                                                   : (uint32_t(vv[u]) != kUntouchedBits && __int_as_float(vv[u]) >= tau_f);
-                            if (pass) emit_one(q, vv[u], d0 + u);
-                        }
+                        for (int u = 0; u < 4; ++u)
+                            if (passes(vv[u])) emit_one(q, int(vv[u]), d0 + u);
                     }
                     __syncwarp();
                     const int emitted = *s_cnt;

@@ -121,7 +121,8 @@ def test_synthetic_batch_vs_oracle(corpus20k, opts, top_k, min_score):
     dict(bm25_range_docs=2048),                               # skip table with two entries per sub-range
 ])
 def test_kernel_variants_agree(corpus20k, opts):
-    """Every variant returns exactly what the default configuration returns (same summation order)."""
+    """Every variant returns what the default configuration returns (same summation order; the staged kernel rounds
+    its accumulation to nearest, the default one rounds down, so scores may differ by a few ulp of the largest term)."""
     c, ix = corpus20k
     q_off, q_term, q_tf = synthetic.make_bm25_queries(c, 64, terms_per_query=4, min_rank=8, seed=21,
                                                        repeat_frac=0.2, add_always=True)
@@ -131,7 +132,7 @@ def test_kernel_variants_agree(corpus20k, opts):
         bm.native.set_option(k, v)
     got = bm.search_batch_terms(q_off, q_term, q_tf, 200, 0.0)
     assert np.array_equal(ref[2], got[2])
-    np.testing.assert_allclose(got[1], ref[1], rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(got[1], ref[1], rtol=2e-6, atol=4e-6)
     assert np.mean(ref[0] == got[0]) > 0.995
     _check_batch(ix, q_off, q_term, q_tf, got[0], got[1], got[2], 200, 0.0)
     bm.close()
