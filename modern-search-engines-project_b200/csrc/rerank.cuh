@@ -77,7 +77,8 @@ rerank_kernel(DenseDev dx, RerankArgs a) {
     int32_t* s_doc = reinterpret_cast<int32_t*>(s_cos + kRerankMaxRows);     // [1024] local doc, ascending
     float* s_bm = reinterpret_cast<float*>(s_doc + kRerankMaxCand);          // [1024]
     int32_t* s_row0 = reinterpret_cast<int32_t*>(s_bm + kRerankMaxCand);     // [1025] first row of cand i
-    uint16_t* s_rowcand = reinterpret_cast<uint16_t*>(s_row0 + kRerankMaxCand + 1);  // [kRerankMaxRows]
+    uint8_t* s_best = reinterpret_cast<uint8_t*>(s_row0 + kRerankMaxCand + 1);       // [1024] best row of cand i
+    int64_t* s_rowstart = reinterpret_cast<int64_t*>(s_key);                 // [1024] first chunk row of cand i (steps 2-3 only)
     __shared__ float s_tmp[NT / 32];
     __shared__ int s_ns, s_rows;
 
@@ -157,6 +158,7 @@ rerank_kernel(DenseDev dx, RerankArgs a) {
             if (i < ns) {
                 const int64_t ra = dx.doc_chunk_off[s_doc[i]], re = dx.doc_chunk_off[s_doc[i] + 1];
                 n = int(re - ra) < max_chunks ? int(re - ra) : max_chunks;
+                s_rowstart[i] = ra;
             }
             const int incl = warp_incl_scan(n);
             if (i < ns) s_row0[i] = carry + incl - n;
@@ -174,8 +176,6 @@ rerank_kernel(DenseDev dx, RerankArgs a) {
         }
         return;
     }
-    for (int i = tid; i < ns; i += NT)
-        for (int r = s_row0[i]; r < s_row0[i + 1]; ++r) s_rowcand[r] = uint16_t(i);
 
     // ---- 3. cosine of every fetched row ----------------------------------------------------------
     const float* qv = a.q + int64_t(qi) * kDim;
@@ -191,31 +191,35 @@ rerank_kernel(DenseDev dx, RerankArgs a) {
     qq = warp_sum(qq);
     const float qn = sqrtf(qq);
     __syncthreads();
-    constexpr int RIF = 4;                                 // rows in flight per warp (12 x 128-bit loads per lane)
-    for (int r0 = warp_id() * RIF; r0 < T; r0 += (NT / 32) * RIF) {
-        uint4 v[RIF][3];
+    // one warp per candidate: the <= 10 rows of a document are contiguous (1.5 KB each), their addresses come from
+    // shared memory (no dependent global load), and up to five rows (15 x 128-bit loads per lane) are in flight
+    constexpr int RIF = 5;
+    for (int i = warp_id(); i < ns; i += NT / 32) {
+        const int r_begin = s_row0[i], n = s_row0[i + 1] - r_begin;
+        const int64_t row0 = s_rowstart[i];
+        for (int b = 0; b < n; b += RIF) {
+            uint4 v[RIF][3];
 #pragma unroll
-        for (int k = 0; k < RIF; ++k) {
-            const int r = (r0 + k) < T ? (r0 + k) : (T - 1);
-            const int i = s_rowcand[r];
-            const int64_t row = dx.doc_chunk_off[s_doc[i]] + (r - s_row0[i]);
-            const uint4* p = reinterpret_cast<const uint4*>(dx.emb + row * kDim) + lane_id();
+            for (int k = 0; k < RIF; ++k) {
+                const int kk = (b + k) < n ? (b + k) : (n - 1);
+                const uint4* p = reinterpret_cast<const uint4*>(dx.emb + (row0 + kk) * kDim) + lane_id();
 #pragma unroll
-            for (int j = 0; j < 3; ++j) v[k][j] = ldg_stream(p + j * 32);
-        }
-#pragma unroll
-        for (int k = 0; k < RIF; ++k) {
-            float dot = 0.f, ee = 0.f;
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                float f[8];
-                bf16x8_to_float(v[k][j], f);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) { dot = fmaf(f[e], qf[j * 8 + e], dot); ee = fmaf(f[e], f[e], ee); }
+                for (int j = 0; j < 3; ++j) v[k][j] = ldg_stream(p + j * 32);
             }
-            dot = warp_sum(dot);
-            ee = warp_sum(ee);
-            if (lane_id() == 0 && (r0 + k) < T) s_cos[r0 + k] = dot / (sqrtf(ee) * qn);
+#pragma unroll
+            for (int k = 0; k < RIF; ++k) {
+                float dot = 0.f, ee = 0.f;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    float f[8];
+                    bf16x8_to_float(v[k][j], f);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) { dot = fmaf(f[e], qf[j * 8 + e], dot); ee = fmaf(f[e], f[e], ee); }
+                }
+                dot = warp_sum(dot);
+                ee = warp_sum(ee);
+                if (lane_id() == 0 && (b + k) < n) s_cos[r_begin + b + k] = dot / (sqrtf(ee) * qn);
+            }
         }
     }
     __syncthreads();
@@ -260,7 +264,7 @@ rerank_kernel(DenseDev dx, RerankArgs a) {
             // sort key: score desc, doc asc; low 10 bits = survivor slot
             key = (uint64_t(float_to_key(sc)) << 32) | (uint64_t(0x3fffffu - (uint32_t(i) & 0x3fffffu)) << 10) | uint64_t(i);
             s_cos[ra] = sc;                                 // row slots reused for per-doc outputs
-            s_rowcand[ra] = uint16_t(bi);
+            s_best[i] = uint8_t(bi);
             s_bm[i] = float(oldn);
         }
         s_key[i] = key;
@@ -283,7 +287,7 @@ rerank_kernel(DenseDev dx, RerankArgs a) {
             a.out_doc[dst] = int32_t(dx.doc_base + uint32_t(s_doc[i]));
             a.out_score[dst] = s_cos[ra];
             a.out_orig[dst] = s_bm[i];
-            a.out_chunk[dst] = dx.chunk_base + dx.doc_chunk_off[s_doc[i]] + int64_t(s_rowcand[ra]);
+            a.out_chunk[dst] = dx.chunk_base + dx.doc_chunk_off[s_doc[i]] + int64_t(s_best[i]);
         } else {
             a.out_doc[dst] = -1; a.out_score[dst] = 0.f; a.out_orig[dst] = 0.f; a.out_chunk[dst] = -1;
         }
@@ -293,6 +297,6 @@ rerank_kernel(DenseDev dx, RerankArgs a) {
 
 constexpr size_t kRerankSmemBytes =
     sizeof(uint64_t) * kRerankMaxCand + sizeof(float) * kRerankMaxRows + sizeof(int32_t) * kRerankMaxCand +
-    sizeof(float) * kRerankMaxCand + sizeof(int32_t) * (kRerankMaxCand + 1) + sizeof(uint16_t) * kRerankMaxRows + 16;
+    sizeof(float) * kRerankMaxCand + sizeof(int32_t) * (kRerankMaxCand + 1) + sizeof(uint8_t) * kRerankMaxCand + 16;
 
 }  // namespace mse
