@@ -155,7 +155,7 @@ def dense_scan_supplement(nat, dev, peak, n_chunks=10_000_000, chunks_per_doc=5,
             "results": out}
 
 
-def hybrid_supplement(nat, dev, dev_batches, peak, steps=5, chunks_per_doc=5, max_out=100):
+def hybrid_supplement(nat, dev, dev_batches, peak, steps=20, chunks_per_doc=5, max_out=100):
     """End-to-end hybrid query (BASELINE.json configs[4] shape at the C2 corpus size): BM25 top-1000 over the
     1M-doc index -> gathered rerank of <= 10 chunks/doc (768-d bf16) with min-max fusion -> top-100, batches of
     1024 queries, everything device-resident."""
