@@ -89,6 +89,18 @@ int mse_bm25_load(mse_index* idx, int64_t n_terms, int64_t n_docs, int64_t doc_b
                   const int64_t* term_off, const int32_t* post_doc, const int32_t* post_tf,
                   const int32_t* doc_len, const float* idf, float avgdl, float k1, float b, int where);
 
+/* Index aggregation on the device (replaces the aggregation half of BM25.build_index,
+ * indexer/bm25_indexer.py:181-211 and :283-343; tokenisation and the term dictionary stay with the caller).
+ *   doc_tok_off[n_docs+1], tok_term[T]   documents as a CSR of term ids, T = doc_tok_off[n_docs] < 2^31
+ *   term_off[n_terms+1]                  out: CSR offsets of the posting arrays (term-major, doc ascending)
+ *   post_doc[>=T], post_tf[>=T]          out: postings (dense doc index, term frequency); *n_postings entries are written
+ *   total_freq[n_terms]                  out: bm25_term_stats.total_freq; doc_freq is term_off[t+1] - term_off[t]
+ * The float32 corpus statistics and the float32 log10 IDF (:130-147, :346-369) are V- / N-sized: the caller forms
+ * them from these outputs exactly as the reference does.  Needs no mse_index; `device` selects the GPU. */
+int mse_bm25_aggregate(int device, int64_t n_docs, int64_t n_terms, const int64_t* doc_tok_off, const int32_t* tok_term,
+                       int64_t* term_off, int32_t* post_doc, int32_t* post_tf, int64_t* total_freq, int64_t* n_postings,
+                       int where, void* stream);
+
 /* Scores a batch of tokenised queries and returns, per query, the top_k documents with
  * score >= min_score among documents holding at least one posting of a valid query term
  * (:436-456, :480), ordered by score descending, ties by ascending doc (:484).

@@ -64,6 +64,7 @@ _SIGNATURES = {
                                 C.c_float, C.c_float, C.c_float, C.c_int]),
     "mse_bm25_search_batch": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, C.c_int32, C.c_float, _vp, _vp, _vp, C.c_int, _vp]),
     "mse_bm25_last_stats": (C.c_int, [_vp, _i64p]),
+    "mse_bm25_aggregate": (C.c_int, [C.c_int, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _i64p, C.c_int, _vp]),
     "mse_kernel_time": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), _i64p]),
     "mse_dense_load": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp, C.c_int, _vp, C.c_int]),
     "mse_dense_scan_batch": (C.c_int, [_vp, C.c_int32, _vp, C.c_int32, _vp, _vp, _vp, C.c_int, _vp]),
@@ -140,6 +141,24 @@ def _stream_ptr(where: int):
         import torch
         return C.c_void_p(torch.cuda.current_stream().cuda_stream)
     return None
+
+
+def bm25_aggregate(doc_tok_off, tok_term, n_terms: int, device: int = 0):
+    """Device aggregation of tokenised documents (CSR of term ids) into the CSR posting arrays of the BM25 index
+    (``mse_bm25_aggregate``).  Host arrays in, host arrays out: (term_off int64[V+1], post_doc int32[P], post_tf int32[P],
+    total_freq int64[V])."""
+    doc_tok_off = np.ascontiguousarray(doc_tok_off, dtype=np.int64)
+    tok_term = np.ascontiguousarray(tok_term, dtype=np.int32)
+    n_docs, T = int(doc_tok_off.shape[0]) - 1, int(tok_term.shape[0])
+    term_off = np.empty(n_terms + 1, np.int64)
+    post_doc, post_tf = np.empty(max(T, 1), np.int32), np.empty(max(T, 1), np.int32)
+    total_freq = np.empty(max(n_terms, 1), np.int64)
+    n_post = C.c_int64(0)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    _check(lib().mse_bm25_aggregate(int(device), n_docs, int(n_terms), vp(doc_tok_off), vp(tok_term), vp(term_off), vp(post_doc),
+                                    vp(post_tf), vp(total_freq), C.byref(n_post), MSE_HOST, None))
+    P = int(n_post.value)
+    return term_off, post_doc[:P].copy(), post_tf[:P].copy(), total_freq[:n_terms]
 
 
 class NativeIndex:

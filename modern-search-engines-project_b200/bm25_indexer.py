@@ -219,30 +219,38 @@ class BM25:
 
     # ------------------------------------------------------------------ index build (:252-369)
     def build_index(self, batch_size: int = 5000):
-        """Host-side build of the four bm25_* tables from ``urlsDB`` (tokenise, per-doc tf, df /
-        total_freq, float32 corpus stats, float32 log10 IDF), then upload.  The text front-end
-        stays on the host as in the reference; see SURVEY.md §8f N4."""
+        """Build of the four bm25_* tables from ``urlsDB``, then upload.  The text front-end (tokenisation, term
+        dictionary) stays on the host as in the reference; the aggregation of the tokens into per-document term
+        frequencies, document frequencies and total frequencies runs on the GPU (``mse_bm25_aggregate``,
+        SURVEY.md §8f N4); the float32 corpus statistics and the float32 log10 IDF are formed here exactly as
+        ``bm25_indexer.py:130-147, 346-369`` do."""
         if not isinstance(self.store, SqlStore):
             raise RuntimeError("build_index needs an SQL store holding urlsDB")
-        doc_rows, tf_rows = [], []
-        df: Dict[str, int] = defaultdict(int)
-        tot: Dict[str, int] = defaultdict(int)
+        vocab: Dict[str, int] = {}
+        doc_ids: List[int] = []
+        tok_off: List[int] = [0]
+        tok_term: List[int] = []
         for doc_id, title, text in self.store.iter_documents():
             s = f"{title or ''} {text or ''}".lower().replace("tuebingen", "tübingen").replace("tubingen", "tübingen")[:1_000_000]
             toks = self._tokenize(s)
             if not toks:
                 continue
-            counts: Dict[str, int] = defaultdict(int)
-            for w in toks:
-                counts[w] += 1
-            doc_rows.append((doc_id, len(toks)))
-            for w, c in counts.items():
-                tf_rows.append((doc_id, w, c)); df[w] += 1; tot[w] += c
-        n = len(doc_rows)
-        avg = float(np.float32(np.mean([r[1] for r in doc_rows]))) if n else 0.0
+            doc_ids.append(doc_id)
+            tok_term.extend(vocab.setdefault(w, len(vocab)) for w in toks)
+            tok_off.append(len(tok_term))
+        n = len(doc_ids)
+        terms = list(vocab)                                   # term id -> string (insertion order)
+        term_off, post_doc, post_tf, total_freq = _native.bm25_aggregate(np.asarray(tok_off, np.int64), np.asarray(tok_term, np.int32),
+                                                                         len(terms), self.device)
+        doc_len = np.diff(np.asarray(tok_off, np.int64))
+        df = np.diff(term_off)
+        avg = float(np.float32(np.mean(doc_len))) if n else 0.0
         n32 = float(np.float32(n))
         idf_of = lambda d: float(np.float32(math.log10((n32 - d + 0.5) / (d + 0.5))))
-        self.store.write_bm25(doc_rows, tf_rows, [(w, df[w], tot[w]) for w in df], avg, n, idf_of)
+        doc_rows = [(doc_ids[i], int(doc_len[i])) for i in range(n)]
+        term_of_post = np.repeat(np.arange(len(terms)), df)
+        tf_rows = [(doc_ids[int(d)], terms[int(t)], int(f)) for t, d, f in zip(term_of_post, post_doc, post_tf)]
+        self.store.write_bm25(doc_rows, tf_rows, [(terms[t], int(df[t]), int(total_freq[t])) for t in range(len(terms))], avg, n, idf_of)
         self.reload()
 
     def _require_loaded(self):

@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include "bm25.cuh"
 #include "bm25_staged.cuh"
+#include "build.cuh"
 #include "common.cuh"
 #include "dense.cuh"
 #include "gemm.cuh"
@@ -513,6 +514,87 @@ int mse_bm25_load(mse_index* ix, int64_t n_terms, int64_t n_docs, int64_t doc_ba
     ix->bm.n_terms = n_terms; ix->bm.n_docs = n_docs; ix->bm.n_postings = P;
     ix->bm.doc_base = uint32_t(doc_base); ix->bm.k1 = k1;
     ix->has_bm25 = true;
+    return MSE_OK;
+}
+
+int mse_bm25_aggregate(int device, int64_t n_docs, int64_t n_terms, const int64_t* doc_tok_off, const int32_t* tok_term,
+                       int64_t* term_off, int32_t* post_doc, int32_t* post_tf, int64_t* total_freq, int64_t* n_postings,
+                       int where, void* stream) {
+    MSE_REQUIRE(where == MSE_HOST || where == MSE_DEVICE, "bad `where`");
+    MSE_REQUIRE(n_docs >= 0 && n_docs < (int64_t(1) << 31) && n_terms >= 0 && n_terms < (int64_t(1) << 31), "n_docs/n_terms out of range");
+    MSE_REQUIRE(doc_tok_off && term_off && total_freq && n_postings, "null argument");
+    int ndev = 0;
+    int rc = mse_device_count(&ndev);
+    if (rc) return rc;
+    if (ndev == 0) { set_error("no CUDA device: this library has no CPU fallback"); return MSE_ERR_CUDA; }
+    MSE_REQUIRE(device >= 0 && device < ndev, "device %d out of range (have %d)", device, ndev);
+    DeviceGuard g(device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int64_t T = 0;
+    MSE_CUDA_TRY(cudaMemcpyAsync(&T, doc_tok_off + n_docs, sizeof(int64_t), where == MSE_HOST ? cudaMemcpyHostToHost : cudaMemcpyDeviceToHost, st));
+    MSE_CUDA_TRY(cudaStreamSynchronize(st));
+    MSE_REQUIRE(T >= 0 && T < (int64_t(1) << 31), "token count %lld out of range (one call aggregates < 2^31 tokens)", (long long)T);
+    MSE_REQUIRE(T == 0 || (tok_term && post_doc && post_tf), "null token / posting arrays");
+    DevBuf d_off, d_tok, keys, keys2, uniq, counts, tmp, misc, o_toff, o_pd, o_pt, o_tot;
+    if ((rc = misc.ensure(64))) return rc;
+    MSE_CUDA_TRY(cudaMemsetAsync(misc.p, 0, 64, st));
+    const int64_t* p_off = doc_tok_off; const int32_t* p_tok = tok_term;
+    int64_t* p_toff = term_off; int32_t* p_pd = post_doc; int32_t* p_pt = post_tf; int64_t* p_tot = total_freq;
+    const size_t Tn = size_t(std::max<int64_t>(T, 1));
+    if (where == MSE_HOST) {
+        if ((rc = d_off.ensure(sizeof(int64_t) * (n_docs + 1)))) return rc;
+        if ((rc = d_tok.ensure(sizeof(int32_t) * Tn))) return rc;
+        if ((rc = o_toff.ensure(sizeof(int64_t) * (n_terms + 1)))) return rc;
+        if ((rc = o_pd.ensure(sizeof(int32_t) * Tn))) return rc;
+        if ((rc = o_pt.ensure(sizeof(int32_t) * Tn))) return rc;
+        if ((rc = o_tot.ensure(sizeof(int64_t) * std::max<int64_t>(n_terms, 1)))) return rc;
+        if ((rc = copy_in(d_off.p, doc_tok_off, sizeof(int64_t) * (n_docs + 1), where, st))) return rc;
+        if ((rc = copy_in(d_tok.p, tok_term, sizeof(int32_t) * T, where, st))) return rc;
+        p_off = d_off.as<int64_t>(); p_tok = d_tok.as<int32_t>();
+        p_toff = o_toff.as<int64_t>(); p_pd = o_pd.as<int32_t>(); p_pt = o_pt.as<int32_t>(); p_tot = o_tot.as<int64_t>();
+    }
+    if ((rc = keys.ensure(sizeof(uint64_t) * Tn))) return rc;
+    if ((rc = keys2.ensure(sizeof(uint64_t) * Tn))) return rc;
+    if ((rc = uniq.ensure(sizeof(uint64_t) * Tn))) return rc;
+    if ((rc = counts.ensure(sizeof(int32_t) * Tn))) return rc;
+    int32_t* d_bad = misc.as<int32_t>();
+    int32_t* d_runs = misc.as<int32_t>() + 4;
+    if (n_docs > 0) {
+        build_keys_kernel<<<unsigned((n_docs + 7) / 8), 256, 0, st>>>(p_off, p_tok, n_docs, n_terms, keys.as<uint64_t>(), d_bad);
+        MSE_CUDA_TRY(cudaGetLastError());
+    }
+    int term_bits = 1;
+    while ((int64_t(1) << term_bits) < std::max<int64_t>(n_terms, 2)) ++term_bits;
+    size_t tb1 = 0, tb2 = 0;
+    MSE_CUDA_TRY(cub::DeviceRadixSort::SortKeys(nullptr, tb1, keys.as<uint64_t>(), keys2.as<uint64_t>(), int(T), 0, 32 + term_bits, st));
+    MSE_CUDA_TRY(cub::DeviceRunLengthEncode::Encode(nullptr, tb2, keys2.as<uint64_t>(), uniq.as<uint64_t>(), counts.as<int32_t>(), d_runs, int(T), st));
+    if ((rc = tmp.ensure(std::max(tb1, tb2) + 16))) return rc;
+    size_t tb = std::max(tb1, tb2) + 16;
+    if (T > 0) {
+        MSE_CUDA_TRY(cub::DeviceRadixSort::SortKeys(tmp.p, tb, keys.as<uint64_t>(), keys2.as<uint64_t>(), int(T), 0, 32 + term_bits, st));
+        tb = std::max(tb1, tb2) + 16;
+        MSE_CUDA_TRY(cub::DeviceRunLengthEncode::Encode(tmp.p, tb, keys2.as<uint64_t>(), uniq.as<uint64_t>(), counts.as<int32_t>(), d_runs, int(T), st));
+        build_split_kernel<<<148 * 8, 256, 0, st>>>(uniq.as<uint64_t>(), counts.as<int32_t>(), d_runs, p_pd, p_pt);
+        MSE_CUDA_TRY(cudaGetLastError());
+    }
+    build_offsets_kernel<<<unsigned((n_terms + 1 + 255) / 256), 256, 0, st>>>(uniq.as<uint64_t>(), d_runs, keys2.as<uint64_t>(), T, n_terms, p_toff, p_tot);
+    MSE_CUDA_TRY(cudaGetLastError());
+    int32_t h_misc[8] = {0};
+    MSE_CUDA_TRY(cudaMemcpyAsync(h_misc, misc.p, sizeof(h_misc), cudaMemcpyDeviceToHost, st));
+    MSE_CUDA_TRY(cudaStreamSynchronize(st));
+    MSE_REQUIRE(h_misc[0] == 0, "malformed token CSR (code %d): offsets must be monotone, term ids within [0, n_terms)", h_misc[0]);
+    const int64_t P = h_misc[4];
+    *n_postings = P;
+    if (where == MSE_HOST) {
+        MSE_CUDA_TRY(cudaMemcpyAsync(term_off, p_toff, sizeof(int64_t) * (n_terms + 1), cudaMemcpyDeviceToHost, st));
+        MSE_CUDA_TRY(cudaMemcpyAsync(total_freq, p_tot, sizeof(int64_t) * n_terms, cudaMemcpyDeviceToHost, st));
+        if (P > 0) {
+            MSE_CUDA_TRY(cudaMemcpyAsync(post_doc, p_pd, sizeof(int32_t) * P, cudaMemcpyDeviceToHost, st));
+            MSE_CUDA_TRY(cudaMemcpyAsync(post_tf, p_pt, sizeof(int32_t) * P, cudaMemcpyDeviceToHost, st));
+        }
+        MSE_CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    for (DevBuf* b : {&d_off, &d_tok, &keys, &keys2, &uniq, &counts, &tmp, &misc, &o_toff, &o_pd, &o_pt, &o_tot}) b->release();
     return MSE_OK;
 }
 

@@ -286,3 +286,25 @@ def test_full_size_c2_properties_and_sampled_parity(n_docs):
     d2, s2, c2 = nat.bm25_search(sub_off, sub_term, sub_tf, 1000, 0.0)
     np.testing.assert_array_equal(d2, doc[sample]); np.testing.assert_array_equal(s2, score[sample])
     nat.close()
+
+
+def test_device_index_aggregation_matches_host_statement():
+    """N4: mse_bm25_aggregate (tokens -> CSR postings, df, total_freq) against a numpy statement of
+    bm25_indexer.py:181-211 / 283-343, and the façade's build_index() against the oracle's host build."""
+    rng = np.random.default_rng(3)
+    n_docs, V = 3000, 700
+    lens = rng.integers(0, 90, n_docs)
+    lens[::97] = 0                                              # empty documents
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    tok = np.minimum((rng.pareto(1.1, int(off[-1])) * 3).astype(np.int64), V - 1).astype(np.int32)
+    term_off, post_doc, post_tf, total_freq = _native.bm25_aggregate(off, tok, V)
+    doc_of = np.repeat(np.arange(n_docs), lens)
+    key, cnt = np.unique(tok.astype(np.int64) * n_docs + doc_of, return_counts=True)
+    assert np.array_equal(post_doc, (key % n_docs).astype(np.int32)) and np.array_equal(post_tf, cnt.astype(np.int32))
+    df = np.bincount((key // n_docs).astype(np.int64), minlength=V)
+    assert np.array_equal(np.diff(term_off), df) and term_off[0] == 0
+    assert np.array_equal(total_freq, np.bincount(tok, minlength=V))
+    with pytest.raises(_native.NativeError):                   # term id outside the dictionary
+        _native.bm25_aggregate(off, np.where(np.arange(len(tok)) == 5, V + 3, tok).astype(np.int32), V)
+    e0, o0, f0, t0 = _native.bm25_aggregate(np.zeros(1, np.int64), np.zeros(0, np.int32), 4)      # nothing to aggregate
+    assert e0.tolist() == [0, 0, 0, 0, 0] and len(o0) == 0 and t0.tolist() == [0, 0, 0, 0]
