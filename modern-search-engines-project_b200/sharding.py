@@ -30,6 +30,43 @@ def all_gather_topk(doc, score, count, group=None):
     return g_doc, g_score, g_count
 
 
+def exchange_topk(doc, score, count, top_k: int, merge, group=None, slack: float = 2.0, extra: int = 32):
+    """Exchange step of a doc-sharded top-k: all-gather + merge, exact, with a truncated first attempt.
+
+    With W shards a rank contributes ~top_k/W entries to the global top-k, so the first attempt gathers only the first
+    m = slack*top_k/W + extra entries of every rank (W times less data, a W times shorter merge).  The attempt is exact
+    unless some rank was cut (it holds more than m entries) and its m-th score is still >= the merged k-th score (or
+    the merged list is short): that rank could own more of the top-k, so the full lists are exchanged instead.  The
+    decision is taken from all-gathered values and is therefore the same on every rank.
+    ``merge(g_doc, g_score, g_count, top_k)`` is ``NativeIndex.topk_merge`` on CUDA tensors."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    k_local = int(doc.shape[1])
+    m = max(1, min(k_local, int(slack * top_k / world) + extra))
+    if world == 1 or m >= k_local:
+        return merge(*all_gather_topk(doc, score, count, group), top_k)
+    cut = torch.clamp(count, max=m)
+    g_doc, g_score, g_cut = all_gather_topk(doc[:, :m].contiguous(), score[:, :m].contiguous(), cut, group)
+    g_full = torch.empty((world,) + tuple(count.shape), dtype=count.dtype, device=count.device)
+    if count.is_cuda:
+        dist.all_gather_into_tensor(g_full, count.contiguous(), group=group)
+    else:
+        dist.all_gather([g_full[w] for w in range(world)], count.contiguous(), group=group)
+    out_doc, out_score, out_count = merge(g_doc, g_score, g_cut, top_k)
+    out_doc, out_score, out_count = (torch.as_tensor(x) for x in (out_doc, out_score, out_count))
+    B = int(count.shape[0])
+    rows = torch.arange(B, device=out_score.device)
+    full = out_count.to(torch.int64) >= top_k
+    kth = out_score[rows, torch.clamp(out_count.to(torch.int64) - 1, min=0)]          # merged k-th score (valid where `full`)
+    truncated = g_full.to(out_score.device) > m                                        # [W, B]
+    mth = g_score[:, :, m - 1].to(out_score.device)                                    # m-th score of every rank
+    unsafe = truncated & (~full.unsqueeze(0) | (mth >= kth.unsqueeze(0)))
+    if bool(unsafe.any()):
+        return merge(*all_gather_topk(doc, score, count, group), top_k)
+    return out_doc, out_score, out_count
+
+
 def merge_topk_host(g_doc: np.ndarray, g_score: np.ndarray, g_count: np.ndarray, top_k: int):
     """Host statement of the merge rule (used by the gloo tests to check the collective plumbing, and
     as the specification of ``mse_topk_merge``): concatenate valid entries, order by (score desc,
@@ -56,8 +93,7 @@ class ShardedSearcher:
     def _merge(self, doc, score, count, top_k):
         if self.world == 1:
             return doc, score, count
-        g_doc, g_score, g_count = all_gather_topk(doc, score, count, self.group)
-        return self.native.topk_merge(g_doc, g_score, g_count, top_k)
+        return exchange_topk(doc, score, count, top_k, self.native.topk_merge, self.group)
 
     def bm25_search(self, q_off, q_term, q_tf, top_k: int, min_score: float = 0.0):
         doc, score, count = self.native.bm25_search(q_off, q_term, q_tf, top_k, min_score)

@@ -43,6 +43,12 @@ def _worker(rank, world, port, out):
         count[i] = len(res)
     g_doc, g_score, g_count = sharding.all_gather_topk(doc, score, count)
     m_doc, m_score, m_count = sharding.merge_topk_host(g_doc.numpy(), g_score.numpy(), g_count.numpy(), k)
+    # the truncated-first exchange must give the same answer (slack 0 forces cuts and exercises the exact fallback)
+    host_merge = lambda a, b, c, kk: sharding.merge_topk_host(a.numpy(), b.numpy(), c.numpy(), kk)
+    for slack, extra in ((2.0, 32), (1.2, 0), (0.3, 0)):     # full lists / mostly safe cuts / cuts that force the fallback
+        x_doc, x_score, x_count = sharding.exchange_topk(doc, score, count, k, host_merge, slack=slack, extra=extra)
+        assert np.array_equal(np.asarray(x_doc), m_doc) and np.array_equal(np.asarray(x_count), m_count)
+        assert np.array_equal(np.asarray(x_score), m_score)
     if rank == 0:
         ok = True
         for i, q in enumerate(queries):
