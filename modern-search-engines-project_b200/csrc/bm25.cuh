@@ -6,31 +6,33 @@
 // over the documents that hold at least one posting of a valid query term, kept when
 // score >= min_score.
 //
-// Layout in HBM: term_off int64[V+1]; postings as two int32 arrays (doc, tf), ascending doc
-// inside a term; per-doc length (uint16 when every length fits, else the fp32 norm
-// k1*(1-b+b*dl/avgdl)); idf float32[V] verbatim from bm25_term_stats.
+// Layout in HBM: term_off int64[V+1]; postings as ONE interleaved {int32 doc, int32 tf} array, ascending
+// doc inside a term (built at load from the two arrays the ABI receives); per-doc length (uint16 when every
+// length fits, else the fp32 norm k1*(1-b+b*dl/avgdl)); idf float32[V] verbatim from bm25_term_stats; a skip
+// table for heavy terms and a per-term impact table (both derived at load time, neither changes a result).
 //
 // Execution model ("warp tasks", no CTA barrier, no atomics on accumulators):
-//   * the doc space is cut into sub-ranges of RS docs (default 768); a (sub-range, query) pair
+//   * the doc space is cut into sub-ranges of RS docs (default 1024); a (sub-range, query) pair
 //     is one task and a warp owns a task outright.  Persistent warps pull (sub-range,
 //     query-chunk) items from an atomic counter in sub-range-major order;
-//   * bm25_prepare_kernel finds, once per (query term, sub-range boundary), where each posting
-//     list crosses each boundary (two-level binary search) and writes {first posting, count}
-//     records sub-range-major; a warp stages the records of its item with one coalesced load and
+//   * bm25_prepare_kernel writes, once per (query term, sub-range), a {first posting, count} record,
+//     sub-range-major (skip-table read for heavy terms, one-pass bucketing for short lists, two-level
+//     binary search otherwise); a warp stages the records of its item with one coalesced load and
 //     then streams exactly its task's postings.  Posting loads are software-pipelined one query
 //     ahead, so HBM latency overlaps the previous query's work;
-//   * per-warp accumulators live in shared memory (fp32[RS]) next to the sub-range's doc lengths
-//     and a "touched list".  Doc ids are unique inside a term, so a term is applied with plain
-//     read-modify-write and terms are separated by __syncwarp: deterministic summation in the
-//     reference's term order;
+//   * per-warp accumulators live in shared memory (fp32[RS]) next to the sub-range's doc lengths.
+//     Doc ids are unique inside a term, so a term is applied with plain read-modify-write and terms
+//     are separated by __syncwarp: deterministic summation in the reference's term order;
 //   * accumulators hold the NEGATED score and rest at +0.0f (all-zero bits, so re-arming is a store of
 //     the zero register); contributions are added with round-toward-minus-infinity FMAs, where
 //     (+0.0) + (-0.0) == -0.0: a document whose score is exactly zero (idf == 0, kept by the
-//     reference) is distinguishable from an untouched one (never returned).  The first posting that finds -0.0 appends the doc to the touched list,
-//     and the read-out walks that list only (no scan over RS accumulators), re-arming as it goes;
+//     reference) is distinguishable from an untouched one (never returned);
+//   * read-out scans the RS accumulators 128 per warp round (LDS.128): groups of four without a candidate
+//     are re-armed on the spot, the rare others are flagged and handled by their lanes;
 //   * read-out emits only candidates with score >= tau[q], a per-query lower bound of the final
-//     k-th best score, raised on the fly from a per-query histogram of emitted candidates (any
-//     value tau ever took is a valid bound, so no inter-warp synchronisation is needed).
+//     k-th best score: seeded from the impact table, then raised on the fly from a per-query histogram
+//     of emitted candidates (any value tau ever took is a valid bound, so no inter-warp
+//     synchronisation is needed).
 #pragma once
 #include <type_traits>
 #include "common.cuh"
