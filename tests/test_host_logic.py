@@ -165,3 +165,62 @@ def test_synthetic_corpus_slab_path_is_a_valid_index():
     assert np.array_equal(np.bincount(doc, weights=tf, minlength=2000).astype(np.int64), c.doc_len.numpy().astype(np.int64))
     ref = synthetic.make_bm25_corpus(2000, vocab=300, mean_len=24, seed=8)
     assert np.array_equal(ref.doc_len.numpy(), c.doc_len.numpy())   # same documents, tokens drawn in a different chunking
+
+
+class _OracleNative:
+    """Test double for ``NativeIndex`` (tests only): answers ``rerank`` from the pinned oracle so that the host
+    layer above the C ABI — id mapping, urlsDB filter, response objects, diversification, HTTP status codes — can be
+    exercised without a GPU.  The product never constructs this."""
+
+    def __init__(self, dense):
+        self.dense = dense
+
+    def dense_load(self, emb, off):
+        assert emb.shape[0] == int(off[-1])
+
+    def rerank(self, cand_off, cand_doc, cand_bm25, q, url_group, smoothing, max_chunks, max_out):
+        B = len(cand_off) - 1
+        o_doc = np.full((B, max_out), -1, np.int32); o_score = np.zeros((B, max_out), np.float32)
+        o_orig = np.zeros((B, max_out), np.float32); o_chunk = np.full((B, max_out), -1, np.int64)
+        o_count = np.zeros(B, np.int32); o_rows = np.zeros(B, np.int32)
+        for i in range(B):
+            a, e = int(cand_off[i]), int(cand_off[i + 1])
+            ref = ro.rerank(self.dense, cand_doc[a:e], cand_bm25[a:e], q[i], smoothing, max_chunks, faithful=True)
+            if ref is None:
+                continue
+            n = min(len(ref.doc), max_out)
+            o_doc[i, :n], o_score[i, :n], o_orig[i, :n] = ref.doc[:n], ref.score[:n], ref.orig[:n]
+            o_chunk[i, :n] = np.searchsorted(self.dense.chunk_ids, ref.best_chunk[:n])
+            o_count[i], o_rows[i] = n, ref.total_rows
+        return o_doc, o_score, o_orig, o_chunk, o_count, o_rows
+
+
+def test_rerank_http_surface_matches_the_hosted_reference():
+    """POST /rerank (reranker_api.py:336-417): schema, diversified order and scores equal to the fixture produced by
+    the unmodified reference; 401 when nothing is found, 500 on any other failure, unknown request keys ignored."""
+    from fastapi.testclient import TestClient
+    dense, j = helpers.load_rerank_small()
+    st = store.ArrayStore(doc_id_array=dense.doc_ids, url_list=j["urls"])
+    vec = {}
+    rr = reranker.Reranker(st, dense.doc_ids, native=_OracleNative(dense), embed=lambda text: vec[text],
+                           dense_tables=store.DenseTables(dense.emb, dense.chunk_ids, dense.doc_chunk_off))
+    client = TestClient(reranker.make_app(rr))
+    assert client.get("/health").status_code == 200
+    for n, case in enumerate(j["cases"]):
+        vec[f"q{n}"] = np.asarray(case["q"], np.float32)
+        r = client.post("/rerank", json={"doc_ids": [str(x) for x in case["cand_ids"]], "similarities": case["sims"],
+                                         "query": f"q{n}", "call_api": True})      # search_api.py:91-96 sends call_api too
+        assert r.status_code == 200, r.text
+        body, g = r.json(), case["div"]
+        assert body["total_documents"] == g["total_documents"] and body["total_windows"] == g["total_windows"]
+        assert [int(d["doc_id"]) for d in body["document_scores"]] == g["doc_id"]
+        np.testing.assert_allclose([d["similarity_score"] for d in body["document_scores"]], g["score"], atol=2e-6)
+        np.testing.assert_allclose([d["original_similarity"] for d in body["document_scores"]], g["orig"], atol=2e-6)
+        assert [d["most_relevant_window"]["window_index"] for d in body["document_scores"]] == g["window"]
+        assert [d["url"] for d in body["document_scores"]] == g["url"]
+        assert [w["doc_id"] for w in body["top_windows"]] == [d["doc_id"] for d in body["document_scores"]][:100]
+    miss = client.post("/rerank", json={"doc_ids": ["999999999"], "similarities": [1.0], "query": "q0"})
+    assert miss.status_code == 401 and "No documents found" in miss.json()["detail"]
+    bad = client.post("/rerank", json={"doc_ids": ["not-a-number"], "similarities": [1.0], "query": "q0"})
+    assert bad.status_code == 500 and bad.json()["detail"].startswith("Internal server error")
+    assert client.post("/rerank", json={"doc_ids": ["1"]}).status_code == 422          # pydantic: query is required
