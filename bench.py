@@ -3,8 +3,13 @@
 
 Workload (BASELINE.json configs[1]): BM25-only, 1M synthetic docs, Zipf(1.0) vocabulary of 200k,
 ~256 tokens/doc (~192M postings), batches of 1024 four-term queries, top-1000, on one B200.
-A "step" = one batch of 1024 queries through prepare -> score -> select (-> all-gather + merge on
-N > 1 GPUs, where the 1M-doc corpus is sharded by doc range: strong scaling).
+A "step" = one batch of queries through prepare -> score -> select.  On N > 1 GPUs the 1M-doc corpus is
+sharded by doc range (global idf / avgdl) and the batch is N x 1024 queries (weak scaling: every GPU traverses
+the same number of postings per step as the single GPU does): each rank scores the whole replicated batch
+against its shard, keeps m = 2k/N + 32 entries per query, the lists travel to the rank that owns the query
+(one NCCL all-to-all over NVLink) and are merged there to the exact global top-1000 (a step whose cut could
+have hidden a result is repeated with full lists).  `--exchange allgather` runs the all-gather + merge-everywhere
+variant instead (batch 1024 at every N: strong scaling).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
@@ -242,7 +247,7 @@ def run_reference_arm(args, rank, world):
     sample = f"{per_step} of the {BATCH} queries per step, full {n_docs}-doc index, faithful Python-loop port"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
+        "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "queries_per_step": per_step},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
@@ -272,6 +277,9 @@ def main():
     ap.add_argument("--cand-cap", type=int, default=0)
     ap.add_argument("--no-tau", action="store_true")
     ap.add_argument("--no-dense", action="store_true", help="skip the supplementary dense-scan (C3) measurements")
+    ap.add_argument("--exchange", default="owner", choices=["owner", "allgather"],
+                    help="N > 1: query-owner merge of an N x 1024 batch (weak scaling) or all-gather + merge of a 1024 batch")
+    ap.add_argument("--exchange-slack", type=float, default=2.0, help="owner exchange: shard list length = slack*k/N + 32")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -316,10 +324,13 @@ def main():
     setup_s = time.perf_counter() - t0
 
     # ---- query batches: a different batch every step (no reuse of a step's postings in L2) -------
+    owner = world > 1 and args.exchange == "owner"
+    GB = BATCH * world if owner else BATCH                  # queries per step over the whole job
+    m_local = max(1, min(TOP_K, int(args.exchange_slack * TOP_K / world) + 32)) if owner else TOP_K
     n_batches = args.steps + args.warmup
     host_batches, dev_batches, postings_per_batch = [], [], []
     for i in range(n_batches):
-        q_off, q_term, q_tf = synthetic.make_bm25_queries(c, BATCH, seed=SEED + 1 + i)
+        q_off, q_term, q_tf = synthetic.make_bm25_queries(c, GB, seed=SEED + 1 + i)
         host_batches.append((q_off, q_term, q_tf))
         dev_batches.append(tuple(torch.from_numpy(a).to(dev) for a in (q_off, q_term, q_tf)))
         postings_per_batch.append(int(df_global[q_term].sum()))
@@ -330,6 +341,8 @@ def main():
         q_off, q_term, q_tf = dev_batches[i]
         if world == 1:
             return nat.bm25_search(q_off, q_term, q_tf, TOP_K, 0.0, out=out)
+        if owner:
+            return searcher.bm25_search_owner(q_off, q_term, q_tf, TOP_K, 0.0, slack=args.exchange_slack)
         return searcher.bm25_search(q_off, q_term, q_tf, TOP_K, 0.0)
 
     def sync_all():
@@ -359,7 +372,7 @@ def main():
     select_ms, _ = nat.kernel_time("topk_select")
     prep_ms, _ = nat.kernel_time("bm25_prepare")
     stats = nat.bm25_stats()
-    value = args.steps * BATCH / (ms / 1000.0)
+    value = args.steps * GB / (ms / 1000.0)
 
     # ---- e2e: host buffers through the C ABI (H2D + D2H inside the timed region) ----------------------
     pin = lambda a: torch.from_numpy(a).pin_memory()
@@ -373,7 +386,10 @@ def main():
             nat.bm25_search(q_off, q_term, q_tf, TOP_K, 0.0, out=h_out)      # MSE_HOST path: copies + sync inside
         else:
             d = tuple(t.to(dev, non_blocking=True) for t in (q_off, q_term, q_tf))
-            r = searcher.bm25_search(d[0], d[1], d[2], TOP_K, 0.0)
+            if owner:                                                        # this rank's block of the batch comes back
+                r = searcher.bm25_search_owner(d[0], d[1], d[2], TOP_K, 0.0, slack=args.exchange_slack)
+            else:
+                r = searcher.bm25_search(d[0], d[1], d[2], TOP_K, 0.0)
             for dst, src in zip(h_out, r):
                 dst.copy_(src, non_blocking=True)
             torch.cuda.synchronize()
@@ -392,9 +408,11 @@ def main():
         t = torch.tensor([e2e_s], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_value = args.steps * BATCH / e2e_s
-    h2d = int(np.mean([sum(a.nbytes for a in b) for b in host_batches[args.warmup:]]))
-    d2h = BATCH * TOP_K * 8 + BATCH * 4
+    e2e_value = args.steps * GB / e2e_s
+    # whole-job bytes: every rank uploads the (replicated) query CSR; with the owner exchange each rank reads back its
+    # own 1024-query block, with the all-gather variant every rank reads back the replicated result
+    h2d = world * int(np.mean([sum(a.nbytes for a in b) for b in host_batches[args.warmup:]]))
+    d2h = (BATCH * TOP_K * 8 + BATCH * 4) * world
     sampler.stop()
 
     # ---- roofline of the dominant kernel -----------------------------------------------------------------
@@ -402,7 +420,7 @@ def main():
     timed_post = postings_per_batch[args.warmup:]
     # algorithmic bytes per launch: 12 B per posting of THIS rank's shard + 8 B per emitted result
     frac_local = n_postings_local / max(1, int(c.n_postings))
-    alg_bytes = 12.0 * float(np.mean(timed_post)) * frac_local + 8.0 * TOP_K * BATCH
+    alg_bytes = 12.0 * float(np.mean(timed_post)) * frac_local + 8.0 * m_local * GB
     avg_score_ms = score_ms / max(1, score_n)
     achieved = alg_bytes / (avg_score_ms * 1e-3) / 1e9 if avg_score_ms > 0 else 0.0
     traffic = None
@@ -412,6 +430,21 @@ def main():
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
+
+    # ---- N > 1: the owner exchange against the all-gather + merge-everywhere exchange on one batch (outside the
+    # timed regions; both are exact, so this rank's block must be identical bit for bit) -----------------------
+    exchange_check = None
+    if owner:
+        q_off, q_term, q_tf = dev_batches[args.warmup]
+        o_doc, o_score, o_count = searcher.bm25_search_owner(q_off, q_term, q_tf, TOP_K, 0.0, slack=args.exchange_slack)
+        a_doc, a_score, a_count = searcher.bm25_search(q_off, q_term, q_tf, TOP_K, 0.0)
+        blk = slice(rank * BATCH, (rank + 1) * BATCH)
+        valid = torch.arange(TOP_K, device=dev).unsqueeze(0) < o_count.unsqueeze(1)
+        same = torch.equal(o_count, a_count[blk]) and torch.equal(o_doc[valid], a_doc[blk][valid]) and \
+            torch.equal(o_score[valid], a_score[blk][valid])
+        t = torch.tensor([0 if same else 1], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        exchange_check = {"queries": GB, "ranks_differing_from_allgather_merge": int(t.item())}
 
     # ---- parity spot-check + CPU baseline (rank 0, N=1) -------------------------------------------------
     cpu_baseline = None
@@ -469,23 +502,30 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak" if (owner or world == 1) else "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "n_docs": N_DOCS, "vocab": VOCAB, "postings": int(c.n_postings), "batch": BATCH,
-                       "top_k": TOP_K, "sharding": f"doc-range x{world}" if world > 1 else "none",
+                       "global_batch": GB, "top_k": TOP_K,
+                       "sharding": ("none" if world == 1 else
+                                    f"doc-range x{world}, {GB}-query batch replicated, query-owner merge: NCCL all-to-all of "
+                                    f"{m_local}-entry shard lists, exact (full-list repeat when a cut could hide a result)"
+                                    if owner else f"doc-range x{world}, all-gather + merge on every rank"),
+                       "exchange_fallback_steps": int(getattr(searcher, "fallbacks", 0)),
                        "l2_policy": "inputs larger than L2: 1.5 GB index, a different query batch every step",
-                       "postings_per_query": float(np.mean(timed_post)) / BATCH},
+                       "postings_per_query": float(np.mean(timed_post)) / GB},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": args.steps * (3 + (1 if world > 1 else 0)),
+            "gpu_launches": args.steps * (3 + (1 if world > 1 else 0)) * world,   # prepare, score, select (+ merge) per rank
             "roofline": {"bound": "hbm", "kernel": "bm25_score_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": avg_score_ms},
             "cpu_baseline": cpu_baseline,
             "clocks": sampler.summary(),
             "breakdown": {"prepare_ms": prep_ms / max(1, score_n), "score_ms": avg_score_ms, "select_ms": select_ms / max(1, score_n),
-                          "candidates_emitted_per_query": stats["emitted"] / BATCH, "rerun_queries": stats["rerun_queries"],
+                          "candidates_emitted_per_query": stats["emitted"] / GB, "rerun_queries": stats["rerun_queries"],
                           "ranges": stats["ranges"], "score_ctas": stats["ctas"], "setup_s": setup_s},
             "parity": parity,
+            "exchange_check": exchange_check,
             "hybrid": hybrid,
             "dense_scan": dense,
         }

@@ -1,5 +1,5 @@
-"""world_size-2 gloo test of the multi-GPU exchange step on CPU tensors: all-gather of per-rank
-top-k lists + the merge rule == the unsharded oracle.  The per-rank scoring is
+"""world_size-2 gloo test of the multi-GPU exchange step on CPU tensors: all-gather (and the query-owner
+all-to-all) of per-rank top-k lists + the merge rule == the unsharded oracle.  The per-rank scoring is
 done by the oracle here (no GPU in this container); the collective plumbing is the code under test."""
 import os
 import sys
@@ -49,6 +49,22 @@ def _worker(rank, world, port, out):
         x_doc, x_score, x_count = sharding.exchange_topk(doc, score, count, k, host_merge, slack=slack, extra=extra)
         assert np.array_equal(np.asarray(x_doc), m_doc) and np.array_equal(np.asarray(x_count), m_count)
         assert np.array_equal(np.asarray(x_score), m_score)
+    # query-owner exchange (all-to-all): every rank receives the shard lists of ITS block of the batch; lists cut to
+    # m entries stand for a shard-local search with top_k = m; an unsafe cut is repeated with full lists
+    nq = (len(queries) // world) * world
+    bq = nq // world
+    blk = slice(rank * bq, (rank + 1) * bq)
+    outcomes = []
+    for m_cut in (k, 12, 3):
+        cut = lambda t: t[:nq, :m_cut].contiguous()
+        o_doc, o_score, o_count, unsafe = sharding.exchange_topk_owner(cut(doc), cut(score), torch.clamp(count[:nq], max=m_cut), k, host_merge)
+        outcomes.append(bool(unsafe))
+        if bool(unsafe):
+            o_doc, o_score, o_count, again = sharding.exchange_topk_owner(doc[:nq].contiguous(), score[:nq].contiguous(), count[:nq].contiguous(), k, host_merge)
+            assert not bool(again)
+        assert np.array_equal(np.asarray(o_doc), m_doc[blk]) and np.array_equal(np.asarray(o_count), m_count[blk])
+        assert np.array_equal(np.asarray(o_score), m_score[blk])
+    assert outcomes[0] is False and outcomes[2] is True      # full lists are always safe; 2 x 3 entries cannot cover k = 20
     if rank == 0:
         ok = True
         for i, q in enumerate(queries):

@@ -255,6 +255,35 @@ def test_sharded_equals_unsharded(corpus20k):
     whole.close()
 
 
+def test_shard_lists_cut_to_m_merge_exactly_when_the_rule_says_so(corpus20k):
+    """Query-owner exchange (sharding.exchange_topk_owner) without the collective: shard-local searches with
+    top_k = m < k, merged; whenever ``cut_could_hide_a_result`` reports the cut safe the merge equals the unsharded
+    top-k bit for bit, and m == k is always safe."""
+    from mse_b200.bm25_indexer import shard_bounds
+    from mse_b200.sharding import cut_could_hide_a_result
+    c, ix = corpus20k
+    K, W = 200, 4
+    q_off, q_term, q_tf = synthetic.make_bm25_queries(c, 32, min_rank=8, seed=15, add_always=True)
+    whole = _facade(ix)
+    ref = whole.search_batch_terms(q_off, q_term, q_tf, K, 0.0)
+    bounds = shard_bounds(np.bincount(ix.post_doc, minlength=ix.n_docs), W)
+    shards = [_facade(ix, doc_range=(bounds[r], bounds[r + 1])) for r in range(W)]
+    verdicts = {}
+    for m in (K, 2 * K // W + 32, K // W + 8, 5):
+        parts = [sh.search_batch_terms(q_off, q_term, q_tf, m, 0.0) for sh in shards]
+        g = [np.stack([p[i] for p in parts]) for i in range(3)]
+        merged = whole.native.topk_merge(g[0], g[1], g[2], K)
+        unsafe = bool(cut_could_hide_a_result(g[1], g[2], merged[1], merged[2], K)) if m < K else False
+        verdicts[m] = unsafe
+        if not unsafe:
+            for a, b in zip(ref, merged):
+                np.testing.assert_array_equal(a, b)
+    assert verdicts[K] is False and verdicts[2 * K // W + 32] is False and verdicts[5] is True
+    for sh in shards:
+        sh.close()
+    whole.close()
+
+
 @pytest.mark.parametrize("n_docs", [1_000_000])
 def test_full_size_c2_properties_and_sampled_parity(n_docs):
     """BASELINE.json configs[1]: 1M docs, Zipf vocab 200k, batch 1024, top-1000.  Checks
