@@ -269,8 +269,12 @@ int bm25_run(mse_index* ix, int32_t B, const int32_t* d_q_off, const int32_t* d_
         timer_end(ix, T_SCORE, st);
     } else {
         const size_t smem = size_t(kBm25Warps) * bm25_score_warp_bytes(RS, len16);
-        const void* kfn = len16 ? (RS == 1024 ? (const void*)bm25_score_kernel<true, 1024> : (const void*)bm25_score_kernel<true, 0>)
-                                : (const void*)bm25_score_kernel<false, 0>;
+        const bool hits = ix->opt_readout != 0;        // candidates found while the postings are applied (default) or by a scan
+        const void* kfn;
+        if (hits) kfn = len16 ? (RS == 1024 ? (const void*)bm25_score_kernel<true, 1024, true> : (const void*)bm25_score_kernel<true, 0, true>)
+                              : (const void*)bm25_score_kernel<false, 0, true>;
+        else kfn = len16 ? (RS == 1024 ? (const void*)bm25_score_kernel<true, 1024, false> : (const void*)bm25_score_kernel<true, 0, false>)
+                         : (const void*)bm25_score_kernel<false, 0, false>;
         MSE_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         int per_sm = 0;
         MSE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kBm25Threads, smem));

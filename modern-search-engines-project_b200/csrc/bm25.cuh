@@ -233,7 +233,15 @@ __host__ __device__ inline size_t bm25_score_warp_bytes(int rs, bool len16) {
     return size_t(kMetaSlots) * 16 + size_t(2 * kEmitStage) * 8 + 16 + size_t(rs) * (len16 ? 6 : 8);
 }
 
-template <bool LEN16, int RS_T>                  // RS_T: sub-range size known at compile time (0 = take it from the workspace)
+// RS_T: sub-range size known at compile time (0 = take it from the workspace).
+// HITS: candidates are found while the postings are applied instead of by a scan of the accumulators.  When every
+// weight of the query is >= 0 an accumulator only moves away from zero, so a document reaches the bound iff its LAST
+// update does: each round compares the value it stores with the bound and a lane remembers how many of its updates
+// reached it and the document of the last one (compare, select, predicated add — no vote, no branch).  When no lane
+// saw more than one (the usual case: ~2.5 candidates per task) the read-out visits those documents (duplicates from
+// several terms are dropped with match.any) and re-arms the sub-range with plain stores — no loads.  Queries with a
+// negative weight or a negative bound (min_score < 0), and tasks where a lane saw two, take the scan read-out.
+template <bool LEN16, int RS_T, bool HITS>
 __global__ void __launch_bounds__(kBm25Threads, 4)
 bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
     using LenT = typename std::conditional<LEN16, uint16_t, float>::type;
@@ -297,6 +305,8 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
         if (w.use_tau) atomicAdd(&w.ts.hist[int64_t(q) * kHistBins + (key >> kHistShift)], 1u);   // maxbin[q] is preset
     };
 
+    uint32_t hit_tau = 0xffffffffu;                  // bits of minus the bound of the current query (HITS), or "never"
+    int hc = 0, hd = 0;                              // this lane's updates that reached the bound in the current task; doc of the last
     // one warp-round: up to 32 postings of one term; docs are unique inside a term (no race)
     auto apply = [&](int dd, int tfi, bool valid, float wt) {
         if (valid) {
@@ -307,7 +317,13 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
             // The accumulator holds MINUS the score; round-down keeps "touched, score 0" at -0.0 (rest state: +0.0)
             float r;
             asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(tf + norm));
-            s_acc[d] = __fmaf_rd(-(wt * tf), r, s_acc[d]);
+            const float nv = __fmaf_rd(-(wt * tf), r, s_acc[d]);
+            s_acc[d] = nv;
+            if (HITS) {
+                const bool hit = __float_as_uint(nv) >= hit_tau;
+                hd = hit ? d : hd;
+                hc += int(hit);
+            }
         }
     };
     // postings 32.. of a slice: the loads of up to four rounds are issued before the first is applied
@@ -398,6 +414,14 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
                     }
                 }
                 // ---- apply the query's terms in order ---------------------------------------------------
+                const float tau_f = key_to_float(tau_key);
+                const uint32_t tau_u = __float_as_uint(tau_f) | 0x80000000u;   // bits of -tau when tau >= +0.0
+                const bool fast = __float_as_int(tau_f) >= 0;   // tau is +0.0 or positive: the accumulators hold minus the
+                                                                 // score, so "score >= tau" is one UNSIGNED compare that also
+                                                                 // rejects 0 (untouched) and every negative score (sign bit clear)
+                if (HITS) { hit_tau = fast ? tau_u : 0xffffffffu; hc = 0; }
+                uint32_t wneg = 0u;                             // sign bit set: a negative weight was applied (the last update
+                                                                // of a document need not be its largest then)
                 int touched = 0;
 #pragma unroll
                 for (int t = 0; t < MP; ++t) {
@@ -407,6 +431,7 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
                         if (n > 0) {
                             const float wt = __uint_as_float(m.z);
                             touched = 1;
+                            if (HITS) wneg |= m.z;
                             apply(pd_cur[t], pt_cur[t], lane < n, wt);
                             if (n > 32) apply_rest(m.x, n, wt);
                             __syncwarp();                                   // next term may touch the same docs
@@ -420,6 +445,7 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
                     if (n == 0) continue;
                     const float wt = __uint_as_float(m.z);
                     touched = 1;
+                    if (HITS) wneg |= m.z;
                     int dd = 0, tfi = 0;
                     if (lane < n) { const int2 p = ldg_stream_i2(g_post + m.x + lane); dd = p.x; tfi = p.y; }
                     apply(dd, tfi, lane < n, wt);
@@ -428,13 +454,21 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
                 }
                 // ---- read-out: scan the accumulators 128 per round, re-arm them, stage candidates >= tau ----
                 if (touched) {
-                    const float tau_f = key_to_float(tau_key);
-                    const uint32_t tau_u = __float_as_uint(tau_f) | 0x80000000u;   // bits of -tau when tau >= +0.0
-                    const bool fast = __float_as_int(tau_f) >= 0;   // tau is +0.0 or positive: the accumulators hold minus the
-                                                                     // score, so "score >= tau" is one UNSIGNED compare that also
-                                                                     // rejects 0 (untouched) and every negative score (sign bit clear)
                     uint4* a4 = reinterpret_cast<uint4*>(s_acc) + lane;
                     const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+                    if (HITS && fast && int(wneg) >= 0 && !__any_sync(0xffffffffu, hc > 1)) {
+                        // hit read-out: the remembered documents are the only ones that can reach the bound
+                        if (__any_sync(0xffffffffu, hc == 1)) {
+                            int d = -1 - lane;                               // idle lanes: distinct keys
+                            uint32_t bits = 0u;
+                            if (hc == 1) { d = hd; bits = reinterpret_cast<const uint32_t*>(s_acc)[d]; }
+                            const unsigned same = __match_any_sync(0xffffffffu, d);
+                            if (hc == 1 && (same & lt_mask) == 0u && bits >= tau_u) emit_one(q, int(bits), d);
+                            __syncwarp();                                    // accumulators read before they are re-armed
+                        }
+#pragma unroll 8
+                        for (int it = 0; it < scan_iters; ++it) a4[it * 32] = z4;
+                    } else {
                     auto passes = [&](uint32_t bits) {
                         return fast ? (bits >= tau_u) : (bits != 0u && (0.0f - __uint_as_float(bits)) >= tau_f);
                     };
@@ -457,18 +491,20 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
                             flag |= uint32_t(p) << it;
                         }
                     }
-                    // pass 2 (lanes that hold flagged groups only)
+                    // pass 2 (lanes that hold flagged groups only): one candidate per lane and round, a single emission site
                     while (__any_sync(0xffffffffu, flag != 0u)) {
                         if (flag == 0u) continue;
                         const int it = __ffs(int(flag)) - 1;
-                        flag &= flag - 1u;
                         const uint4 v = a4[it * 32];
-                        a4[it * 32] = z4;
-                        const int d0 = (it * 32 + lane) * 4;
-                        const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            if (passes(vv[u])) emit_one(q, int(vv[u]), d0 + u);
+                        const uint32_t pm = uint32_t(passes(v.x)) | (uint32_t(passes(v.y)) << 1) | (uint32_t(passes(v.z)) << 2) |
+                                            (uint32_t(passes(v.w)) << 3);      // != 0 for a flagged group
+                        const int u = __ffs(int(pm)) - 1;
+                        const uint32_t bits = u == 0 ? v.x : (u == 1 ? v.y : (u == 2 ? v.z : v.w));
+                        const int d = (it * 32 + lane) * 4 + u;
+                        emit_one(q, int(bits), d);
+                        if (pm & (pm - 1u)) reinterpret_cast<uint32_t*>(s_acc)[d] = 0u;   // more in this group: come back for them
+                        else { a4[it * 32] = z4; flag &= flag - 1u; }
+                    }
                     }
                     __syncwarp();
                     const int emitted = *s_cnt;
