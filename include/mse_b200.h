@@ -66,8 +66,8 @@ int mse_index_destroy(mse_index* idx);
  *   "bm25_cand_cap"          per-query capacity of the candidate list between scoring and selection
  *   "bm25_use_tau"           1 (default) = running k-th-score bound filters candidates, 0 = emit all
  *   "bm25_tau_init"          1 (default) = seed the bound from the per-term impact table built at load time, 0 = off
- *   "bm25_kernel"            1 (default) = warp-task score kernel, 2 = experimental bulk-copy staged kernel
- *   "bm25_stage_cap", "bm25_stage_buffers", "bm25_warps_per_cta", "bm25_readout"   knobs of kernel 2 only
+ *   "bm25_readout"           1 (default) = candidates are found while the postings are applied, 0 = by a scan of the
+ *                            accumulators (identical results)
  *   "dense_scan_ctas_per_sm" persistent CTAs per SM of the scan kernel
  *   "dense_gemm_min_batch"   smallest batch routed to the tcgen05 GEMM kernel
  *   "reset_timers"           any value: zero the accumulated kernel timers

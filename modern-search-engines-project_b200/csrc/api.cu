@@ -9,7 +9,6 @@
 
 #include <cstdlib>
 #include "bm25.cuh"
-#include "bm25_staged.cuh"
 #include "build.cuh"
 #include "common.cuh"
 #include "dense.cuh"
@@ -72,8 +71,7 @@ struct mse_index {
 
     bool has_bm25 = false;
     Bm25Dev bm{};
-    DevBuf term_off, post_doc, post_tf, post2, skip, skip_row, imp_levels, doc_norm, doc_len16, idf;
-    bool len16_ok = false;
+    DevBuf term_off, post_doc, post_tf, post2, skip, skip_row, imp_levels, doc_norm, idf;
     std::vector<int64_t> h_term_off;
 
     bool has_dense = false;
@@ -92,7 +90,7 @@ struct mse_index {
     DevBuf m_in[3];                          // merge staging
     DevBuf fb_q[3], fb_out[3];               // fallback sub-batches
 
-    int64_t opt_bm25_kernel = 1, opt_stage_cap = 0, opt_nbuf = 0, opt_bm25_warps = 0, opt_readout = 1, opt_debug_skip = 0, opt_tau_init = 1;
+    int64_t opt_readout = 1, opt_tau_init = 1;
     int64_t opt_range_docs = 0, opt_qpi = 0, opt_cand_cap = 0, opt_use_tau = 1, opt_scan_ctas = 0, opt_gemm_min_batch = 0, opt_gemm_debug = 0;
     int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
@@ -183,18 +181,10 @@ int bm25_run(mse_index* ix, int32_t B, const int32_t* d_q_off, const int32_t* d_
              int32_t S, int32_t max_terms, int32_t top_k, float min_score, int32_t cap, int use_tau,
              int32_t* d_out_doc, float* d_out_score, int32_t* d_out_count, bool mark_overflow, cudaStream_t st) {
     const Bm25Dev& bm = ix->bm;
-    const bool len16 = ix->len16_ok;
-    const bool staged = ix->opt_bm25_kernel != 1;
-    int RS;
-    if (staged) {                                      // sub-ranges of whole 128-doc scan rows, at most 32 of them
-        RS = ix->opt_range_docs > 0 ? round_up(std::min<int64_t>(ix->opt_range_docs, 4096), 128) : 1024;
-        if (bm.n_docs < RS) RS = std::max(128, round_up(bm.n_docs, 128));
-    } else {
-        RS = ix->opt_range_docs > 0 ? round_up(std::min<int64_t>(ix->opt_range_docs, 4096), 128) : 1024;
-        if (bm.n_docs < RS) RS = std::max(128, round_up(bm.n_docs, 128));
-    }
+    int RS = ix->opt_range_docs > 0 ? round_up(std::min<int64_t>(ix->opt_range_docs, 4096), 128) : kBm25DefaultRange;
+    if (bm.n_docs < RS) RS = std::max(128, round_up(bm.n_docs, 128));
     const int n_sub = int((bm.n_docs + RS - 1) / RS);
-    const int qpi = int(std::min<int64_t>(31, ix->opt_qpi > 0 ? ix->opt_qpi : (staged ? 31 : 8)));
+    const int qpi = int(std::min<int64_t>(31, ix->opt_qpi > 0 ? ix->opt_qpi : 8));
     int rc;
     if ((rc = ix->slot_w.ensure(sizeof(float) * size_t(S + 1)))) return rc;
     if ((rc = ix->rec.ensure(sizeof(uint2) * (size_t(S) * n_sub + 1)))) return rc;
@@ -207,10 +197,7 @@ int bm25_run(mse_index* ix, int32_t B, const int32_t* d_q_off, const int32_t* d_
 
     MSE_CUDA_TRY(cudaMemsetAsync(ix->cand_count.p, 0, sizeof(int32_t) * 2 * size_t(B), st));
     MSE_CUDA_TRY(cudaMemsetAsync(ix->misc.p, 0, 64, st));
-    if (use_tau && !staged) MSE_CUDA_TRY(cudaMemsetAsync(ix->hist.p, 0, sizeof(uint32_t) * size_t(B) * kHistBins, st));   // maxbin: prepare kernel
-    // staged kernel: the bound is refreshed by reading the candidate lists while they grow; a slot that has been
-    // reserved but not written yet must read as "no candidate"
-    if (use_tau && staged) MSE_CUDA_TRY(cudaMemsetAsync(ix->cand.p, 0, sizeof(uint64_t) * size_t(B) * cap, st));
+    if (use_tau) MSE_CUDA_TRY(cudaMemsetAsync(ix->hist.p, 0, sizeof(uint32_t) * size_t(B) * kHistBins, st));   // maxbin: prepare kernel
 
     Bm25Work w{};
     w.q_off = d_q_off; w.q_term = d_q_term; w.q_tf = d_q_tf;
@@ -221,7 +208,6 @@ int bm25_run(mse_index* ix, int32_t B, const int32_t* d_q_off, const int32_t* d_
     w.stats = reinterpret_cast<unsigned long long*>(ix->misc.as<char>() + 16);
     w.n_queries = B; w.n_slots = S; w.n_sub = n_sub; w.sub_docs = RS; w.queries_per_item = qpi;
     w.cap = cap; w.min_key = float_to_key(min_score + 0.0f); w.use_tau = use_tau;
-    w.debug_skip = int32_t(ix->opt_debug_skip);
 
     timer_begin(ix, T_PREPARE, st);
     {
@@ -238,43 +224,12 @@ int bm25_run(mse_index* ix, int32_t B, const int32_t* d_q_off, const int32_t* d_
     const int chunks = (B + qpi - 1) / qpi;
     const int64_t n_items = int64_t(n_sub) * chunks;
     int grid = 0;
-    if (staged) {
-        const int nbuf = ix->opt_nbuf == 3 ? 3 : 2;
-        int cap_st = ix->opt_stage_cap > 0 ? round_up(std::min<int64_t>(ix->opt_stage_cap, 16384), 32) : std::max(128, round_up(RS / 4, 32));
-        const int slots = std::max(1, std::min(32, max_terms));
-        w.stage_cap = cap_st;
-        w.stage_slots = slots;
-        w.readout_mode = ix->opt_readout ? 1 : 0;
-        w.debug_skip = int32_t(ix->opt_debug_skip);
-        const size_t per_warp = bm25_staged_warp_bytes(RS, cap_st, slots, nbuf, len16);
-        const size_t smem_max = 227 * 1024 - kStTailSlack;
-        int warps = int(std::min<size_t>(32, smem_max / per_warp));
-        if (ix->opt_bm25_warps > 0) warps = int(std::min<int64_t>(warps, ix->opt_bm25_warps));
-        if (warps < 1) { set_error("bm25 staged kernel does not fit (sub-range %d docs, staging %d postings)", RS, cap_st); return MSE_ERR_INVALID; }
-        const size_t smem = per_warp * size_t(warps) + kStTailSlack;
-        const bool big = warps > 16;                   // more than 16 warps per CTA: the 64-register build
-        const void* kfn;
-        if (len16) kfn = nbuf == 3 ? (big ? (const void*)bm25_score_staged_kernel<true, 3, 32> : (const void*)bm25_score_staged_kernel<true, 3, 16>)
-                                   : (big ? (const void*)bm25_score_staged_kernel<true, 2, 32> : (const void*)bm25_score_staged_kernel<true, 2, 16>);
-        else kfn = nbuf == 3 ? (big ? (const void*)bm25_score_staged_kernel<false, 3, 32> : (const void*)bm25_score_staged_kernel<false, 3, 16>)
-                             : (big ? (const void*)bm25_score_staged_kernel<false, 2, 32> : (const void*)bm25_score_staged_kernel<false, 2, 16>);
-        MSE_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        int per_sm = 0;
-        MSE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, warps * 32, smem));
-        if (per_sm < 1) { set_error("bm25 staged kernel does not fit (%zu bytes of shared memory)", smem); return MSE_ERR_INVALID; }
-        grid = int(std::min<int64_t>((n_items + warps - 1) / warps, int64_t(per_sm) * ix->sm_count));
-        timer_begin(ix, T_SCORE, st);
-        void* args[] = {(void*)&bm, (void*)&w};
-        MSE_CUDA_TRY(cudaLaunchKernel(kfn, dim3(unsigned(grid)), dim3(unsigned(warps * 32)), args, smem, st));
-        timer_end(ix, T_SCORE, st);
-    } else {
-        const size_t smem = size_t(kBm25Warps) * bm25_score_warp_bytes(RS, len16);
+    {
+        const size_t smem = size_t(kBm25Warps) * bm25_score_warp_bytes(RS);
         const bool hits = ix->opt_readout != 0;        // candidates found while the postings are applied (default) or by a scan
         const void* kfn;
-        if (hits) kfn = len16 ? (RS == 1024 ? (const void*)bm25_score_kernel<true, 1024, true> : (const void*)bm25_score_kernel<true, 0, true>)
-                              : (const void*)bm25_score_kernel<false, 0, true>;
-        else kfn = len16 ? (RS == 1024 ? (const void*)bm25_score_kernel<true, 1024, false> : (const void*)bm25_score_kernel<true, 0, false>)
-                         : (const void*)bm25_score_kernel<false, 0, false>;
+        if (hits) kfn = RS == kBm25DefaultRange ? (const void*)bm25_score_kernel<kBm25DefaultRange, true> : (const void*)bm25_score_kernel<0, true>;
+        else kfn = RS == kBm25DefaultRange ? (const void*)bm25_score_kernel<kBm25DefaultRange, false> : (const void*)bm25_score_kernel<0, false>;
         MSE_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         int per_sm = 0;
         MSE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kBm25Threads, smem));
@@ -286,7 +241,7 @@ int bm25_run(mse_index* ix, int32_t B, const int32_t* d_q_off, const int32_t* d_
         timer_end(ix, T_SCORE, st);
     }
 
-    if ((rc = debug_sync(st, staged ? "bm25_score_staged_kernel" : "bm25_score_kernel"))) return rc;
+    if ((rc = debug_sync(st, "bm25_score_kernel"))) return rc;
     ListLoader ld{w.cand, w.cand_count, int64_t(cap), cap};
     timer_begin(ix, T_SELECT, st);
     topk_select_kernel<ListLoader><<<B, kSelectThreads, 0, st>>>(ld, top_k, d_out_doc, d_out_score, d_out_count,
@@ -347,7 +302,7 @@ int mse_index_destroy(mse_index* ix) {
     {
         DeviceGuard g(ix->device);
         cudaDeviceSynchronize();
-        DevBuf* all[] = {&ix->term_off, &ix->post_doc, &ix->post_tf, &ix->post2, &ix->skip, &ix->skip_row, &ix->imp_levels, &ix->doc_norm, &ix->doc_len16, &ix->idf, &ix->emb, &ix->doc_chunk_off, &ix->row_doc, &ix->tile_row, &ix->group_row, &ix->qb16, &ix->log_key, &ix->log_q,
+        DevBuf* all[] = {&ix->term_off, &ix->post_doc, &ix->post_tf, &ix->post2, &ix->skip, &ix->skip_row, &ix->imp_levels, &ix->doc_norm, &ix->idf, &ix->emb, &ix->doc_chunk_off, &ix->row_doc, &ix->tile_row, &ix->group_row, &ix->qb16, &ix->log_key, &ix->log_q,
                          &ix->q_off, &ix->q_term, &ix->q_tf, &ix->slot_w, &ix->rec, &ix->tau, &ix->hist,
                          &ix->maxbin, &ix->cand, &ix->cand_count, &ix->overflow, &ix->misc, &ix->o_doc, &ix->o_score,
                          &ix->o_count, &ix->best, &ix->dq};
@@ -370,12 +325,7 @@ int mse_index_set_option(mse_index* ix, const char* name, int64_t value) {
     if (!ix || !name) { set_error("null argument"); return MSE_ERR_INVALID; }
     std::lock_guard<std::mutex> lk(ix->mu);
     if (!strcmp(name, "bm25_range_docs")) ix->opt_range_docs = value;
-    else if (!strcmp(name, "bm25_kernel")) ix->opt_bm25_kernel = value;
-    else if (!strcmp(name, "bm25_stage_cap")) ix->opt_stage_cap = value;
-    else if (!strcmp(name, "bm25_stage_buffers")) ix->opt_nbuf = value;
-    else if (!strcmp(name, "bm25_warps_per_cta")) ix->opt_bm25_warps = value;
     else if (!strcmp(name, "bm25_readout")) ix->opt_readout = value;
-    else if (!strcmp(name, "bm25_debug_skip")) ix->opt_debug_skip = value;
     else if (!strcmp(name, "bm25_tau_init")) { ix->opt_tau_init = value; ix->bm.imp_levels = (value && ix->has_bm25) ? ix->imp_levels.as<float>() : nullptr; }
     else if (!strcmp(name, "bm25_queries_per_item")) ix->opt_qpi = value;
     else if (!strcmp(name, "bm25_cand_cap")) ix->opt_cand_cap = value;
@@ -433,7 +383,6 @@ int mse_bm25_load(mse_index* ix, int64_t n_terms, int64_t n_docs, int64_t doc_ba
     if ((rc = ix->post_tf.ensure(sizeof(int32_t) * (std::max<int64_t>(P, 1) + 8)))) return rc;
     if ((rc = ix->post2.ensure(sizeof(int2) * (std::max<int64_t>(P, 1) + 8)))) return rc;
     if ((rc = ix->doc_norm.ensure(sizeof(float) * (std::max<int64_t>(n_docs, 1) + 8)))) return rc;
-    if ((rc = ix->doc_len16.ensure(sizeof(uint16_t) * (std::max<int64_t>(n_docs, 1) + 16)))) return rc;
     if ((rc = ix->misc.ensure(64))) return rc;
     MSE_CUDA_TRY(cudaMemsetAsync(ix->misc.p, 0, 64, st));
     if ((rc = ix->idf.ensure(sizeof(float) * std::max<int64_t>(n_terms, 1)))) return rc;
@@ -450,15 +399,15 @@ int mse_bm25_load(mse_index* ix, int64_t n_terms, int64_t n_docs, int64_t doc_ba
     for (auto& v : h_idf) v = v + 0.0f;
     MSE_CUDA_TRY(cudaMemcpyAsync(ix->idf.p, h_idf.data(), sizeof(float) * n_terms, cudaMemcpyHostToDevice, st));
     if (n_docs > 0) {
-        bm25_norm_kernel<<<unsigned((n_docs + 255) / 256), 256, 0, st>>>(d_len.as<int32_t>(), ix->doc_norm.as<float>(),
-                                                                        ix->doc_len16.as<uint16_t>(), n_docs, double(k1), double(b),
-                                                                        double(avgdl), ix->misc.as<int32_t>() + 1);
+        bm25_norm_kernel<<<unsigned((n_docs + 255) / 256), 256, 0, st>>>(d_len.as<int32_t>(), ix->doc_norm.as<float>(), n_docs,
+                                                                        double(k1), double(b), double(avgdl));
         MSE_CUDA_TRY(cudaGetLastError());
     }
     {
         const int64_t np = P + 8;
         bm25_interleave_kernel<<<unsigned((np + 255) / 256), 256, 0, st>>>(ix->post_doc.as<int32_t>(), ix->post_tf.as<int32_t>(),
-                                                                          ix->post2.as<int2>(), P, np);
+                                                                          d_len.as<int32_t>(), ix->post2.as<int2>(), P, np, n_docs,
+                                                                          double(k1), double(b), double(avgdl));
         MSE_CUDA_TRY(cudaGetLastError());
     }
     if (n_terms > 0) {
@@ -471,7 +420,6 @@ int mse_bm25_load(mse_index* ix, int64_t n_terms, int64_t n_docs, int64_t doc_ba
     MSE_CUDA_TRY(cudaStreamSynchronize(st));
     d_len.release();
     const int32_t bad = flags[0];
-    ix->len16_ok = flags[1] == 0;                 // every doc length fits 16 bits
     MSE_REQUIRE(bad == 0, "malformed postings (code %d): doc ids must be strictly ascending inside a term, within [0,n_docs), tf >= 1", bad);
     if ((rc = ix->imp_levels.ensure(sizeof(float) * kImpLevels * size_t(std::max<int64_t>(n_terms, 1))))) return rc;
     if (n_terms > 0 && n_docs > 0) {                     // needs doc_norm (bm25_norm_kernel above, same stream)
@@ -503,16 +451,14 @@ int mse_bm25_load(mse_index* ix, int64_t n_terms, int64_t n_docs, int64_t doc_ba
             ix->bm.skip_docs = kSkipDocs; ix->bm.n_skip = n_skip;
         }
     }
-    // the kernels read the interleaved {doc, tf} array only; the separate copies were needed by the load-time kernels
+    // the search kernels read the interleaved {doc, impact} array only; the separate copies and the norms were needed
+    // by the load-time kernels
     ix->post_doc.release();
     ix->post_tf.release();
+    ix->doc_norm.release();
     ix->bm.post_doc = nullptr;
     ix->bm.post_tf = nullptr;
     ix->bm.post2 = ix->post2.as<int2>();
-    ix->bm.doc_norm = ix->doc_norm.as<float>();
-    ix->bm.doc_len16 = ix->doc_len16.as<uint16_t>();
-    ix->bm.norm_c0 = float(double(k1) * (1.0 - double(b)));
-    ix->bm.norm_c1 = float(double(k1) * double(b) / double(avgdl));
     ix->bm.idf = ix->idf.as<float>();
     ix->bm.imp_levels = (ix->opt_tau_init && n_terms > 0 && n_docs > 0) ? ix->imp_levels.as<float>() : nullptr;
     ix->bm.n_terms = n_terms; ix->bm.n_docs = n_docs; ix->bm.n_postings = P;

@@ -6,10 +6,13 @@
 // over the documents that hold at least one posting of a valid query term, kept when
 // score >= min_score.
 //
-// Layout in HBM: term_off int64[V+1]; postings as ONE interleaved {int32 doc, int32 tf} array, ascending
-// doc inside a term (built at load from the two arrays the ABI receives); per-doc length (uint16 when every
-// length fits, else the fp32 norm k1*(1-b+b*dl/avgdl)); idf float32[V] verbatim from bm25_term_stats; a skip
-// table for heavy terms and a per-term impact table (both derived at load time, neither changes a result).
+// Layout in HBM: term_off int64[V+1]; postings as ONE interleaved {int32 doc, fp32 impact} array, ascending
+// doc inside a term, built at load from the (doc, tf) arrays and the doc lengths the ABI receives:
+//     impact = tf / (tf + k1*(1 - b + b*dl_d/avgdl))        (formed in float64, rounded once)
+// i.e. the length-normalised tf factor of the posting, which depends only on load-time quantities (k1, b and avgdl
+// are fixed per index, as in the reference's constructor) — a posting is one 8-byte load and its contribution one
+// FMA, with no per-document gather; idf float32[V] verbatim from bm25_term_stats; a skip table for heavy terms and a
+// per-term impact table (both derived at load time, neither changes a result).
 //
 // Execution model ("warp tasks", no CTA barrier, no atomics on accumulators):
 //   * the doc space is cut into sub-ranges of RS docs (default 1024); a (sub-range, query) pair
@@ -20,7 +23,7 @@
 //     binary search otherwise); a warp stages the records of its item with one coalesced load and
 //     then streams exactly its task's postings.  Posting loads are software-pipelined one query
 //     ahead, so HBM latency overlaps the previous query's work;
-//   * per-warp accumulators live in shared memory (fp32[RS]) next to the sub-range's doc lengths.
+//   * per-warp accumulators live in shared memory (fp32[RS]).
 //     Doc ids are unique inside a term, so a term is applied with plain read-modify-write and terms
 //     are separated by __syncwarp: deterministic summation in the reference's term order;
 //   * accumulators hold the NEGATED score and rest at +0.0f (all-zero bits, so re-arming is a store of
@@ -42,16 +45,16 @@ namespace mse {
 
 constexpr int kBm25Threads = 256;
 constexpr int kBm25Warps = kBm25Threads / 32;
+constexpr int kBm25DefaultRange = 1536;          // docs per sub-range (the compile-time specialisation of the score kernel):
+                                                 // 6 KB of accumulators per warp, 32 warps per SM
 constexpr int kBm25MaxPrefetchSlots = 8;         // terms per query whose postings are prefetched
 constexpr int kImpLevels = 8;                    // ranks 64, 128, ..., 4096 (7 used) of the per-term impact table
 
 struct Bm25Dev {                                 // device-resident index of one shard
     const int64_t* term_off;
-    const int32_t* post_doc;
-    const int32_t* post_tf;
-    const int2* post2;           // the same postings interleaved {doc, tf} (staged kernel: one bulk copy per slice)
-    const float* doc_norm;       // fp32 norm per doc (always present)
-    const uint16_t* doc_len16;   // doc length per doc, or null when some length >= 65536
+    const int32_t* post_doc;     // load time only
+    const int32_t* post_tf;      // load time only
+    const int2* post2;           // postings interleaved {doc, bits of the fp32 impact tf/(tf+norm)}
     const float* idf;
     const uint32_t* skip;        // skip table: for every "heavy" term, the offset (relative to the term's first posting) of the
     const int64_t* skip_row;     //   first posting with doc >= g * skip_docs, g = 0..n_skip; skip_row[t] = first entry of term t, -1 = none
@@ -60,7 +63,6 @@ struct Bm25Dev {                                 // device-resident index of one
     int64_t n_terms, n_docs, n_postings;
     uint32_t doc_base;
     float k1;
-    float norm_c0, norm_c1;      // norm = c0 + c1 * len   (c0 = k1*(1-b), c1 = k1*b/avgdl)
 };
 
 struct Bm25Work {                                // per-call workspace
@@ -78,10 +80,6 @@ struct Bm25Work {                                // per-call workspace
     int32_t n_queries, n_slots, n_sub, sub_docs, queries_per_item, cap;
     uint32_t min_key;
     int32_t use_tau;
-    int32_t stage_cap;           // staged kernel: postings per staging buffer
-    int32_t stage_slots;         // staged kernel: slice-table entries per staging buffer
-    int32_t debug_skip;          // staged kernel, timing experiments only: 1 = no scoring, 2 = no read-out, 4 = no copies, 8 = no emission
-    int32_t readout_mode;        // staged kernel: 0 = always scan the accumulators, 1 = walk staged postings when possible
 };
 
 // ---- prepare: slot weights, per-(sub-range, slot) task records, tau init ---------------------------
@@ -92,7 +90,7 @@ struct Bm25Work {                                // per-call workspace
 // (consecutive slots of one sub-range) are contiguous.
 constexpr int kPrepThreads = 256;
 constexpr int kPrepCoarse = 32;
-constexpr int kSkipDocs = 1024;                  // granularity of the skip table == default sub-range size
+constexpr int kSkipDocs = 512;                   // granularity of the skip table; sub-ranges that are a multiple of it read it
 constexpr int kSkipMinDf = 4096;                 // terms with fewer postings are bucketed on the fly (one pass over the list)
 constexpr int kPrepCountMaxSub = 12000;          // the on-the-fly path keeps one counter per sub-range in shared memory
 
@@ -229,8 +227,8 @@ constexpr int kMetaSlots = 32;                   // slot records staged per warp
 constexpr int kPrefetchSlots = 4;                // terms per query whose first 32 postings are prefetched
 constexpr int kEmitStage = 24;                   // candidates of one task staged in shared memory (deferred write-out)
 
-__host__ __device__ inline size_t bm25_score_warp_bytes(int rs, bool len16) {
-    return size_t(kMetaSlots) * 16 + size_t(2 * kEmitStage) * 8 + 16 + size_t(rs) * (len16 ? 6 : 8);
+__host__ __device__ inline size_t bm25_score_warp_bytes(int rs) {
+    return size_t(kMetaSlots) * 16 + size_t(2 * kEmitStage) * 8 + 16 + size_t(rs) * 4;
 }
 
 // RS_T: sub-range size known at compile time (0 = take it from the workspace).
@@ -241,34 +239,30 @@ __host__ __device__ inline size_t bm25_score_warp_bytes(int rs, bool len16) {
 // saw more than one (the usual case: ~2.5 candidates per task) the read-out visits those documents (duplicates from
 // several terms are dropped with match.any) and re-arms the sub-range with plain stores — no loads.  Queries with a
 // negative weight or a negative bound (min_score < 0), and tasks where a lane saw two, take the scan read-out.
-template <bool LEN16, int RS_T, bool HITS>
+template <int RS_T, bool HITS>
 __global__ void __launch_bounds__(kBm25Threads, 4)
 bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
-    using LenT = typename std::conditional<LEN16, uint16_t, float>::type;
     extern __shared__ __align__(16) unsigned char bm25_smem[];
     const int RS = RS_T ? RS_T : w.sub_docs;     // multiple of 128
     const int lane = lane_id();
-    unsigned char* my = bm25_smem + bm25_score_warp_bytes(RS, LEN16) * warp_id();
+    unsigned char* my = bm25_smem + bm25_score_warp_bytes(RS) * warp_id();
     uint4* s_meta = reinterpret_cast<uint4*>(my);                                  // {begin, count, weight bits, -}
     uint64_t* s_emit = reinterpret_cast<uint64_t*>(my + kMetaSlots * 16);          // [2][kEmitStage] staged candidates
     int* s_cnt = reinterpret_cast<int*>(my + kMetaSlots * 16 + size_t(2 * kEmitStage) * 8);   // candidates staged by the current task
     unsigned char* body = my + kMetaSlots * 16 + size_t(2 * kEmitStage) * 8 + 16;
     float* s_acc = reinterpret_cast<float*>(body);
-    LenT* s_len = reinterpret_cast<LenT*>(body + size_t(RS) * 4);
 
     const int QC = w.queries_per_item;
     const int chunks = (w.n_queries + QC - 1) / QC;
     const int n_items = w.n_sub * chunks;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const float c0 = ix.norm_c0, c1 = ix.norm_c1;
-    const int2* __restrict__ g_post = ix.post2;          // {doc, tf}: one 8-byte load per posting
+    const int2* __restrict__ g_post = ix.post2;          // {doc, impact}: one 8-byte load per posting
     constexpr int MP = kPrefetchSlots;
     const int scan_iters = RS >> 7;
 
     for (int i = lane; i < RS; i += 32) s_acc[i] = 0.f;
     if (lane == 0) *s_cnt = 0;
     __syncwarp();
-    int cur_j = -1;
     int lo = 0;
     // Deferred emission: the slot-reserving atomicAdd of task t is issued without waiting for its
     // result; the staged candidates are written out at the end of task t+1, when it has long returned.
@@ -311,13 +305,9 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
     auto apply = [&](int dd, int tfi, bool valid, float wt) {
         if (valid) {
             const int d = dd - lo;
-            const float tf = float(tfi);
-            const float norm = LEN16 ? fmaf(float(s_len[d]), c1, c0) : float(s_len[d]);
-            // idf*qtf*(k1+1) * tf / (tf + k1*(1-b+b*dl/avgdl)); tf + norm >= 1, rcp.approx: <= 1 ulp.
+            // idf*qtf*(k1+1) * [tf / (tf + k1*(1-b+b*dl/avgdl))]: the bracket is the posting's precomputed impact.
             // The accumulator holds MINUS the score; round-down keeps "touched, score 0" at -0.0 (rest state: +0.0)
-            float r;
-            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(tf + norm));
-            const float nv = __fmaf_rd(-(wt * tf), r, s_acc[d]);
+            const float nv = __fmaf_rd(-wt, __int_as_float(tfi), s_acc[d]);
             s_acc[d] = nv;
             if (HITS) {
                 const bool hit = __float_as_uint(nv) >= hit_tau;
@@ -351,19 +341,11 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
         if (item >= n_items) break;
         const int j = item / chunks, c = item - j * chunks;
         lo = j * RS;
-        const int nd = (ix.n_docs - lo) < RS ? int(ix.n_docs - lo) : RS;
         const int q0 = c * QC;
         const int q1 = (q0 + QC) < w.n_queries ? (q0 + QC) : w.n_queries;
         const int nq = q1 - q0;
         const int qo_reg = (lane <= nq) ? w.q_off[q0 + lane] : 0;          // CSR offsets of the chunk (QC <= 31)
         const uint32_t tau_reg = (lane < nq && w.use_tau) ? ld_relaxed_u32(&w.ts.tau[q0 + lane]) : w.min_key;
-        if (j != cur_j) {                                                   // stage this sub-range's doc lengths (16-byte loads;
-            const uint4* src = LEN16 ? reinterpret_cast<const uint4*>(ix.doc_len16 + lo)   // lo % 128 == 0, arrays padded)
-                                     : reinterpret_cast<const uint4*>(ix.doc_norm + lo);
-            const int n16 = (nd * int(sizeof(LenT)) + 15) >> 4;
-            for (int i = lane; i < n16; i += 32) reinterpret_cast<uint4*>(s_len)[i] = __ldg(src + i);
-            cur_j = j;
-        }
         const uint2* __restrict__ rec = w.rec + int64_t(j) * w.n_slots;
 
         int qa = 0;                                                         // queries are indexed relative to q0 below
@@ -528,15 +510,10 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
 }
 
 // ---- load-time kernels ----------------------------------------------------------------------------------
-__global__ void bm25_norm_kernel(const int32_t* __restrict__ doc_len, float* __restrict__ norm, uint16_t* __restrict__ len16,
-                                 int64_t n, double k1, double b, double avgdl, int32_t* __restrict__ max_len) {
+__global__ void bm25_norm_kernel(const int32_t* __restrict__ doc_len, float* __restrict__ norm, int64_t n, double k1, double b,
+                                 double avgdl) {
     int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i < n) {
-        const int32_t l = doc_len[i];
-        norm[i] = float(k1 * (1.0 - b + b * double(l) / avgdl));
-        len16[i] = uint16_t(l < 0 ? 0 : (l > 65535 ? 65535 : l));
-        if (l > 65535 || l < 0) atomicMax(max_len, 65536);
-    }
+    if (i < n) norm[i] = float(k1 * (1.0 - b + b * double(doc_len[i]) / avgdl));
 }
 
 // Skip table (load time): one CTA per heavy term; entry g = number of postings of the term with doc < g * skip_docs.
@@ -615,11 +592,22 @@ bm25_impact_levels_kernel(const int64_t* __restrict__ term_off, const int32_t* _
     }
 }
 
+// The device-resident posting array: {doc, fp32 impact}, impact = tf / (tf + k1*(1 - b + b*dl/avgdl)) as in
+// bm25_indexer.py:470-476, formed in float64 and rounded once.  Runs before the validation kernel, hence the guards.
 __global__ void bm25_interleave_kernel(const int32_t* __restrict__ post_doc, const int32_t* __restrict__ post_tf,
-                                       int2* __restrict__ post2, int64_t n, int64_t n_padded) {
+                                       const int32_t* __restrict__ doc_len, int2* __restrict__ post2, int64_t n, int64_t n_padded,
+                                       int64_t n_docs, double k1, double b, double avgdl) {
     const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i < n) post2[i] = make_int2(post_doc[i], post_tf[i]);
-    else if (i < n_padded) post2[i] = make_int2(0, 1);
+    if (i < n) {
+        const int d = post_doc[i];
+        float imp = 0.f;
+        if (d >= 0 && d < n_docs) {
+            const double tf = double(post_tf[i]);
+            const double den = tf + k1 * (1.0 - b + b * double(doc_len[d]) / avgdl);
+            imp = den > 0.0 ? float(tf / den) : 0.f;
+        }
+        post2[i] = make_int2(d, __float_as_int(imp));
+    } else if (i < n_padded) post2[i] = make_int2(0, 0);
 }
 
 // postings must be strictly ascending inside a term and inside [0, n_docs); tf >= 1.  One thread per posting; a

@@ -115,14 +115,13 @@ def test_synthetic_batch_vs_oracle(corpus20k, opts, top_k, min_score):
 
 @pytest.mark.parametrize("opts", [
     dict(bm25_tau_init=0),                                    # no impact-table seed: the running bound alone
-    dict(bm25_kernel=2),                                      # experimental bulk-copy staged score kernel
-    dict(bm25_kernel=2, bm25_range_docs=512, bm25_readout=0, bm25_stage_buffers=3),
-    dict(bm25_kernel=2, bm25_range_docs=2048, bm25_stage_cap=64),   # slices larger than the staging buffer
+    dict(bm25_readout=0),                                     # candidates by a scan of the accumulators
+    dict(bm25_readout=0, bm25_range_docs=512, bm25_queries_per_item=3),
+    dict(bm25_range_docs=1536),                               # sub-ranges that are not a power of two
     dict(bm25_range_docs=2048),                               # skip table with two entries per sub-range
 ])
 def test_kernel_variants_agree(corpus20k, opts):
-    """Every variant returns what the default configuration returns (same summation order; the staged kernel rounds
-    its accumulation to nearest, the default one rounds down, so scores may differ by a few ulp of the largest term)."""
+    """Every variant returns what the default configuration returns (same summation order)."""
     c, ix = corpus20k
     q_off, q_term, q_tf = synthetic.make_bm25_queries(c, 64, terms_per_query=4, min_rank=8, seed=21,
                                                        repeat_frac=0.2, add_always=True)

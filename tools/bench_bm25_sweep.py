@@ -6,7 +6,7 @@ prepare / score / select kernels (CUDA events recorded inside the library) and t
 The first configuration's results are the comparison baseline: every other configuration must return
 the same doc ids (ties aside) and scores within 1e-6 relative.
 
-    python tools/bench_bm25_sweep.py --configs "kernel=1;kernel=2;kernel=2,range=2048,cap=768"
+    python tools/bench_bm25_sweep.py --configs "readout=1;readout=0;range=2048,qpi=4"
 """
 from __future__ import annotations
 
@@ -20,15 +20,14 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-KEYS = {"kernel": "bm25_kernel", "range": "bm25_range_docs", "cap": "bm25_stage_cap", "nbuf": "bm25_stage_buffers",
-        "warps": "bm25_warps_per_cta", "readout": "bm25_readout", "qpi": "bm25_queries_per_item", "tau": "bm25_use_tau",
-        "candcap": "bm25_cand_cap", "skip": "bm25_debug_skip", "init": "bm25_tau_init"}
-DEFAULTS = {"kernel": 2, "range": 0, "cap": 0, "nbuf": 0, "warps": 0, "readout": 1, "qpi": 0, "tau": 1, "candcap": 0, "skip": 0, "init": 1}
+KEYS = {"range": "bm25_range_docs", "readout": "bm25_readout", "qpi": "bm25_queries_per_item", "tau": "bm25_use_tau",
+        "candcap": "bm25_cand_cap", "init": "bm25_tau_init"}
+DEFAULTS = {"range": 0, "readout": 1, "qpi": 0, "tau": 1, "candcap": 0, "init": 1}
 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="kernel=1;kernel=2")
+    ap.add_argument("--configs", default="readout=1;readout=0")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--docs", type=int, default=1_000_000)
