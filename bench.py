@@ -3,13 +3,19 @@
 
 Workload (BASELINE.json configs[1]): BM25-only, 1M synthetic docs, Zipf(1.0) vocabulary of 200k,
 ~256 tokens/doc (~192M postings), batches of 1024 four-term queries, top-1000, on one B200.
-A "step" = one batch of queries through prepare -> score -> select.  On N > 1 GPUs the 1M-doc corpus is
-sharded by doc range (global idf / avgdl) and the batch is N x 1024 queries (weak scaling: every GPU traverses
-the same number of postings per step as the single GPU does): each rank scores the whole replicated batch
-against its shard, keeps m = 2k/N + 32 entries per query, the lists travel to the rank that owns the query
-(one NCCL all-to-all over NVLink) and are merged there to the exact global top-1000 (a step whose cut could
-have hidden a result is repeated with full lists).  `--exchange allgather` runs the all-gather + merge-everywhere
-variant instead (batch 1024 at every N: strong scaling).
+A "step" = one batch of queries through prepare -> score -> select.  On N > 1 GPUs (weak scaling: every GPU
+traverses the same number of postings per step as the single GPU does, the job processes N x 1024 queries):
+  * `--layout replicated` (what `auto` picks when the index fits one GPU, as the 1.5 GB C2 index does): the
+    QUERIES are the sharded unit — every rank holds the whole index and answers its own 1024-query batch, no
+    data-path collective;
+  * `--layout doc-sharded` (what `auto` picks for an index that does not fit): the corpus is sharded by doc range
+    (global idf / avgdl), each rank scores the whole replicated N x 1024 batch against its shard, keeps
+    m = 2k/N + 32 entries per query, the lists travel to the rank that owns the query (NCCL all-to-all over
+    NVLink) and are merged there to the exact global top-1000 (a step whose cut could have hidden a result is
+    repeated with full lists).  `--exchange allgather` runs all-gather + merge-everywhere instead (batch 1024 at
+    every N: strong scaling).
+With the replicated layout the doc-sharded exchange is still measured on the same GPUs for a few steps and
+reported as the `doc_sharded` supplement of the JSON line.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
@@ -215,6 +221,57 @@ def hybrid_supplement(nat, dev, dev_batches, peak, steps=20, chunks_per_doc=5, m
             "rerank_frac_of_hbm_peak": alg / (rr_ms * 1e-3) / 1e9 / peak}
 
 
+def doc_sharded_supplement(args, c, rank, world, dev, local_rank, steps=20, warmup=3):
+    """The N x 1024-query batch against the corpus sharded by doc range over the same N GPUs (the layout an index that
+    does not fit one GPU needs): shard-local search cut to m entries, NCCL all-to-all to the query-owning rank, merge,
+    exact repeat when a cut could hide a result — and a bit-for-bit check against all-gather + merge everywhere."""
+    import torch
+    import torch.distributed as dist
+    from mse_b200 import _native, synthetic
+    from mse_b200.sharding import ShardedSearcher
+    term_off, post_doc, post_tf, doc_len, doc_base = shard_corpus(c, rank, world)
+    nat = _native.NativeIndex(local_rank)
+    nat.bm25_load(term_off, post_doc, post_tf, doc_len, c.idf, c.avgdl, doc_base=doc_base)
+    searcher = ShardedSearcher(nat, rank, world)
+    GB = BATCH * world
+    m_local = max(1, min(TOP_K, int(args.exchange_slack * TOP_K / world) + 32))
+    batches = [tuple(torch.from_numpy(a).to(dev) for a in synthetic.make_bm25_queries(c, GB, seed=SEED + 7001 + i))
+               for i in range(steps + warmup)]
+    run = lambda b: searcher.bm25_search_owner(b[0], b[1], b[2], TOP_K, 0.0, slack=args.exchange_slack)
+    for i in range(warmup):
+        run(batches[i])
+    dist.barrier(); torch.cuda.synchronize()
+    nat.set_option("reset_timers", 1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        o_doc, o_score, o_count = run(batches[warmup + i])
+    e1.record()
+    dist.barrier(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    score_ms, n = nat.kernel_time("bm25_score")
+    select_ms, _ = nat.kernel_time("topk_select")
+    prep_ms, _ = nat.kernel_time("bm25_prepare")
+    b = batches[warmup]
+    o_doc, o_score, o_count = run(b)
+    a_doc, a_score, a_count = searcher.bm25_search(b[0], b[1], b[2], TOP_K, 0.0)
+    blk = slice(rank * BATCH, (rank + 1) * BATCH)
+    valid = torch.arange(TOP_K, device=dev).unsqueeze(0) < o_count.unsqueeze(1)
+    same = torch.equal(o_count, a_count[blk]) and torch.equal(o_doc[valid], a_doc[blk][valid]) and \
+        torch.equal(o_score[valid], a_score[blk][valid])
+    d = torch.tensor([0 if same else 1], device=dev)
+    dist.all_reduce(d, op=dist.ReduceOp.SUM)
+    nat.close()
+    return {"workload": f"{GB}-query batch replicated, corpus in {world} doc-range shards, NCCL all-to-all of {m_local}-entry shard "
+                        f"lists to the query-owning rank, exact merge",
+            "queries_per_s": GB / (ms / 1e3), "ms_per_step": ms, "steps": steps,
+            "score_ms": score_ms / max(1, n), "select_ms": select_ms / max(1, n), "prepare_ms": prep_ms / max(1, n),
+            "exchange_fallback_steps": int(getattr(searcher, "fallbacks", 0)),
+            "ranks_differing_from_allgather_merge": int(d.item())}
+
+
 def run_reference_arm(args, rank, world):
     """The reference's CPU path for this workload: the oracle port of BM25.search's Python loop
     (the reference is pure Python; nothing compiles to oracle/_ref), one process per host core."""
@@ -277,6 +334,9 @@ def main():
     ap.add_argument("--cand-cap", type=int, default=0)
     ap.add_argument("--no-tau", action="store_true")
     ap.add_argument("--no-dense", action="store_true", help="skip the supplementary dense-scan (C3) measurements")
+    ap.add_argument("--layout", default="auto", choices=["auto", "replicated", "doc-sharded"],
+                    help="N > 1: replicate the index and shard the queries, or shard the corpus by doc range (auto: replicate "
+                         "when the index fits a quarter of one GPU's memory)")
     ap.add_argument("--exchange", default="owner", choices=["owner", "allgather"],
                     help="N > 1: query-owner merge of an N x 1024 batch (weak scaling) or all-gather + merge of a 1024 batch")
     ap.add_argument("--exchange-slack", type=float, default=2.0, help="owner exchange: shard list length = slack*k/N + 32")
@@ -309,6 +369,16 @@ def main():
     # ---- corpus + index ------------------------------------------------------------------------
     t0 = time.perf_counter()
     c = gen_corpus(dev)
+    index_bytes = 8 * int(c.n_postings)
+    layout = args.layout
+    if layout == "auto":
+        layout = "replicated" if index_bytes * 4 <= torch.cuda.get_device_properties(dev).total_memory else "doc-sharded"
+    replicated = world > 1 and layout == "replicated"
+    full_corpus = c
+    if replicated:                                   # every rank is a whole single-GPU engine with its own query batches
+        job_world, job_rank, world, rank = world, rank, 1, 0
+    else:
+        job_world, job_rank = world, rank
     term_off, post_doc, post_tf, doc_len, doc_base = shard_corpus(c, rank, world)
     nat = _native.NativeIndex(local_rank)
     nat.bm25_load(term_off, post_doc, post_tf, doc_len, c.idf, c.avgdl, doc_base=doc_base)
@@ -325,12 +395,12 @@ def main():
 
     # ---- query batches: a different batch every step (no reuse of a step's postings in L2) -------
     owner = world > 1 and args.exchange == "owner"
-    GB = BATCH * world if owner else BATCH                  # queries per step over the whole job
+    GB = BATCH * world if owner else BATCH                  # queries per step over the whole job (replicated: per rank)
     m_local = max(1, min(TOP_K, int(args.exchange_slack * TOP_K / world) + 32)) if owner else TOP_K
     n_batches = args.steps + args.warmup
     host_batches, dev_batches, postings_per_batch = [], [], []
     for i in range(n_batches):
-        q_off, q_term, q_tf = synthetic.make_bm25_queries(c, GB, seed=SEED + 1 + i)
+        q_off, q_term, q_tf = synthetic.make_bm25_queries(c, GB, seed=SEED + 1 + i + (100_000 * job_rank if replicated else 0))
         host_batches.append((q_off, q_term, q_tf))
         dev_batches.append(tuple(torch.from_numpy(a).to(dev) for a in (q_off, q_term, q_tf)))
         postings_per_batch.append(int(df_global[q_term].sum()))
@@ -346,9 +416,16 @@ def main():
         return searcher.bm25_search(q_off, q_term, q_tf, TOP_K, 0.0)
 
     def sync_all():
-        if world > 1:
+        if job_world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if job_world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     # ---- value: inputs resident in HBM ----------------------------------------------------------------
     for i in range(args.warmup):
@@ -363,16 +440,13 @@ def main():
     e1.record()
     sync_all()
     sampler.active.clear()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    job_q = GB * (job_world if replicated else 1)           # queries per step over the whole job
     score_ms, score_n = nat.kernel_time("bm25_score")
     select_ms, _ = nat.kernel_time("topk_select")
     prep_ms, _ = nat.kernel_time("bm25_prepare")
     stats = nat.bm25_stats()
-    value = args.steps * GB / (ms / 1000.0)
+    value = args.steps * job_q / (ms / 1000.0)
 
     # ---- e2e: host buffers through the C ABI (H2D + D2H inside the timed region) ----------------------
     pin = lambda a: torch.from_numpy(a).pin_memory()
@@ -404,15 +478,12 @@ def main():
     sync_all()
     e2e_s = time.perf_counter() - t0
     sampler.active.clear()
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = args.steps * GB / e2e_s
+    e2e_s = max_over_ranks(e2e_s)
+    e2e_value = args.steps * job_q / e2e_s
     # whole-job bytes: every rank uploads the (replicated) query CSR; with the owner exchange each rank reads back its
     # own 1024-query block, with the all-gather variant every rank reads back the replicated result
-    h2d = world * int(np.mean([sum(a.nbytes for a in b) for b in host_batches[args.warmup:]]))
-    d2h = (BATCH * TOP_K * 8 + BATCH * 4) * world
+    h2d = job_world * int(np.mean([sum(a.nbytes for a in b) for b in host_batches[args.warmup:]]))
+    d2h = (BATCH * TOP_K * 8 + BATCH * 4) * job_world
     sampler.stop()
 
     # ---- roofline of the dominant kernel -----------------------------------------------------------------
@@ -449,7 +520,7 @@ def main():
     # ---- parity spot-check + CPU baseline (rank 0, N=1) -------------------------------------------------
     cpu_baseline = None
     parity = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if job_rank == 0 and job_world == 1 and not args.no_cpu_baseline:
         from oracle import bm25_oracle as bo
         ix = bo.Bm25Arrays(c.term_off.cpu().numpy(), c.post_doc.cpu().numpy(), c.post_tf.cpu().numpy(), c.doc_len.cpu().numpy(),
                            c.idf.cpu().numpy(), c.avgdl, c.total_docs, c.doc_ids.cpu().numpy())
@@ -489,7 +560,7 @@ def main():
     # ---- supplementary: dense exhaustive scan (BASELINE.json configs[2]) on rank 0 at N=1 ------------------
     dense = None
     hybrid = None
-    if rank == 0 and world == 1 and not args.no_dense:
+    if job_rank == 0 and job_world == 1 and not args.no_dense:
         try:
             hybrid = hybrid_supplement(nat, dev, dev_batches, peak)
         except Exception as e:  # noqa: BLE001 - the headline number must not depend on the supplements
@@ -499,15 +570,25 @@ def main():
         except Exception as e:  # noqa: BLE001
             dense = {"error": repr(e)}
 
-    if rank == 0:
+    # ---- N > 1, replicated layout: the doc-sharded exchange measured on the same GPUs as a supplement ------------
+    doc_sharded = None
+    if replicated and not args.no_dense:
+        try:
+            doc_sharded = doc_sharded_supplement(args, full_corpus, job_rank, job_world, dev, local_rank)
+        except Exception as e:  # noqa: BLE001 - the headline number must not depend on the supplements
+            doc_sharded = {"error": repr(e)}
+
+    if job_rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": job_world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak" if (owner or world == 1) else "strong", "vs_baseline": None,
+            "scaling": "weak" if (owner or replicated or world == 1) else "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "n_docs": N_DOCS, "vocab": VOCAB, "postings": int(c.n_postings), "batch": BATCH,
-                       "global_batch": GB, "top_k": TOP_K,
-                       "sharding": ("none" if world == 1 else
+                       "global_batch": job_q, "top_k": TOP_K, "layout": layout if job_world > 1 else "single GPU",
+                       "sharding": (f"index replicated on {job_world} GPUs ({index_bytes / 1e9:.2f} GB of postings fits one), queries sharded: "
+                                    f"{BATCH} per rank and step, no data-path collective" if replicated else
+                                    "none" if world == 1 else
                                     f"doc-range x{world}, {GB}-query batch replicated, query-owner merge: NCCL all-to-all of "
                                     f"{m_local}-entry shard lists, exact (full-list repeat when a cut could hide a result)"
                                     if owner else f"doc-range x{world}, all-gather + merge on every rank"),
@@ -515,7 +596,7 @@ def main():
                        "l2_policy": "inputs larger than L2: 1.5 GB index, a different query batch every step",
                        "postings_per_query": float(np.mean(timed_post)) / GB},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": args.steps * (3 + (1 if world > 1 else 0)) * world,   # prepare, score, select (+ merge) per rank
+            "gpu_launches": args.steps * (3 + (1 if world > 1 else 0)) * job_world,   # prepare, score, select (+ merge) per rank
             "roofline": {"bound": "hbm", "kernel": "bm25_score_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": avg_score_ms},
@@ -526,11 +607,12 @@ def main():
                           "ranges": stats["ranges"], "score_ctas": stats["ctas"], "setup_s": setup_s},
             "parity": parity,
             "exchange_check": exchange_check,
+            "doc_sharded": doc_sharded,
             "hybrid": hybrid,
             "dense_scan": dense,
         }
         print(json.dumps(line))
-    if world > 1:
+    if job_world > 1:
         dist.barrier()
         dist.destroy_process_group()
 

@@ -61,7 +61,7 @@ int mse_index_create(int device, mse_index** out);
 int mse_index_destroy(mse_index* idx);
 
 /* Tuning knobs (all optional; 0 restores the automatic choice unless stated):
- *   "bm25_range_docs"        docs per shared-memory accumulator range (rounded up to a multiple of 128, default 1024)
+ *   "bm25_range_docs"        docs per shared-memory accumulator range (rounded up to a multiple of 128, default 1536)
  *   "bm25_queries_per_item"  queries a warp scores per scheduled work item (<= 31, default 8)
  *   "bm25_cand_cap"          per-query capacity of the candidate list between scoring and selection
  *   "bm25_use_tau"           1 (default) = running k-th-score bound filters candidates, 0 = emit all
