@@ -89,14 +89,16 @@ class BM25:
     def reload(self):
         """(Re)reads the bm25_* tables and uploads the CSR index to HBM."""
         all_ids = self.store.all_doc_ids() if hasattr(self.store, "all_doc_ids") else None
+        self.fingerprint = self.store.bm25_fingerprint() if hasattr(self.store, "bm25_fingerprint") else None
         full = None
         if self.cache_path:
             from .store import load_bm25_cache, save_bm25_cache
-            full = load_bm25_cache(self.cache_path, expect_docs=None if all_ids is None else len(all_ids))
+            full = load_bm25_cache(self.cache_path, expect_docs=None if all_ids is None else len(all_ids),
+                                   fingerprint=self.fingerprint)
         if full is None:
             full = self.store.load_bm25(all_ids)
             if self.cache_path:
-                save_bm25_cache(self.cache_path, full)
+                save_bm25_cache(self.cache_path, full, self.fingerprint or "")
         self.global_doc_ids = full.doc_ids
         self._df_global = np.diff(full.term_off)
         t = full
@@ -114,6 +116,18 @@ class BM25:
                               np.ascontiguousarray(t.doc_len, dtype=np.int32),
                               np.ascontiguousarray(t.idf, dtype=np.float32),
                               t.avgdl, self.k1, self.b, doc_base=self.doc_base)
+
+    def refresh(self) -> bool:
+        """Reloads the index when the bm25_* tables have changed since it was read (new ``processed_at`` /
+        ``last_updated`` stamps, row counts or corpus statistics — `SqlStore.bm25_fingerprint`); returns whether it
+        did.  The reference re-reads the tables on every query, so an index rebuilt by ``index_all.py`` is picked up
+        at once there; here a serving process calls this between batches (one cheap aggregate query per table)."""
+        if not hasattr(self.store, "bm25_fingerprint") or not self.store.has_table("bm25_term_freq"):
+            return False
+        if self.tables is not None and self.store.bm25_fingerprint() == getattr(self, "fingerprint", None):
+            return False
+        self.reload()
+        return True
 
     # ------------------------------------------------------------------ tokenisation (host)
     def _tokenize(self, text: str) -> List[str]:

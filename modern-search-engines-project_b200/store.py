@@ -57,6 +57,17 @@ class SqlStore:
             return False
 
     # -- BM25 tables
+    def bm25_fingerprint(self) -> str:
+        """Cheap description of the state of the bm25_* tables: row counts, the newest ``processed_at`` /
+        ``last_updated`` stamps (``bm25_indexer.py:90,105,115``) and the corpus statistics.  Two equal fingerprints
+        mean the loaded CSR index (and an on-disk cache of it) is still current; `build_index` changes at least one
+        of the fields (every run re-stamps ``bm25_corpus_stats`` and recomputes all idf values, ``:346-369``)."""
+        d = self._all("SELECT COUNT(*), MAX(processed_at) FROM bm25_doc_stats")[0]
+        t = self._all("SELECT COUNT(*), MAX(last_updated), SUM(doc_freq) FROM bm25_term_stats")[0]
+        c = sorted((str(r[0]), repr(float(r[1])), str(r[2])) for r in
+                   self._all("SELECT stat_name, stat_value, last_updated FROM bm25_corpus_stats"))
+        return repr((int(d[0]), str(d[1]), int(t[0]), str(t[1]), int(t[2] or 0), c))
+
     def load_bm25(self, doc_ids: Optional[np.ndarray] = None) -> Bm25Tables:
         stats = dict(self._all("SELECT stat_name, stat_value FROM bm25_corpus_stats"))
         trows = self._all("SELECT term, doc_freq, total_freq, idf_score FROM bm25_term_stats ORDER BY term")
@@ -85,6 +96,13 @@ class SqlStore:
                           float(np.float32(stats.get("avg_doc_length", 1.0))), float(np.float32(stats.get("total_docs", 1))))
 
     # -- dense tables
+    def dense_fingerprint(self) -> str:
+        """Row counts and id range of the chunk / embedding tables (``indexer/embedder.py:31-52``; they carry no
+        timestamps: chunks are only ever appended with increasing ``chunk_id``)."""
+        c = self._all("SELECT COUNT(*), MAX(chunk_id) FROM chunks_optimized")[0]
+        e = self._all("SELECT COUNT(*), MAX(chunk_id) FROM embeddings")[0]
+        return repr((int(c[0]), int(c[1] or 0), int(e[0]), int(e[1] or 0)))
+
     def load_dense(self, doc_ids: np.ndarray) -> DenseTables:
         rows = self._all("SELECT c.doc_id, c.chunk_id, e.embedding FROM chunks_optimized c "
                          "JOIN embeddings e ON c.chunk_id = e.chunk_id ORDER BY c.doc_id, c.chunk_id")
@@ -223,18 +241,23 @@ class ArrayStore:
 
 
 # ---- on-disk cache of the loaded arrays ---------------------------------------------
-def save_bm25_cache(path: str, t: Bm25Tables) -> None:
-    """Persist the CSR arrays beside the database so the next start-up skips the SQL scan.  The cache is
-    keyed by (n_docs, n_postings, n_terms, avgdl, total_docs): `load_bm25_cache` returns None on mismatch."""
+def save_bm25_cache(path: str, t: Bm25Tables, fingerprint: str = "") -> None:
+    """Persist the CSR arrays beside the database so the next start-up skips the SQL scan.  ``fingerprint``
+    (`SqlStore.bm25_fingerprint`) records the table state the arrays were read from: `load_bm25_cache` returns None
+    when the tables have changed since (or on a size mismatch)."""
     np.savez(path, term_off=t.term_off, post_doc=t.post_doc, post_tf=t.post_tf, doc_ids=t.doc_ids, doc_len=t.doc_len,
              idf=t.idf, total_freq=t.total_freq, scalars=np.asarray([t.avgdl, t.total_docs], dtype=np.float64),
-             terms=np.asarray(t.terms if t.terms is not None else [], dtype=object))
+             terms=np.asarray(t.terms if t.terms is not None else [], dtype=object),
+             fingerprint=np.asarray(fingerprint))
 
 
-def load_bm25_cache(path: str, expect_docs: Optional[int] = None, expect_terms: Optional[int] = None) -> Optional[Bm25Tables]:
+def load_bm25_cache(path: str, expect_docs: Optional[int] = None, expect_terms: Optional[int] = None,
+                    fingerprint: Optional[str] = None) -> Optional[Bm25Tables]:
     if not os.path.exists(path):
         return None
     z = np.load(path, allow_pickle=True)
+    if fingerprint is not None and ("fingerprint" not in z.files or str(z["fingerprint"]) != fingerprint):
+        return None
     t = Bm25Tables(list(z["terms"]) or None, z["term_off"], z["post_doc"], z["post_tf"], z["doc_ids"], z["doc_len"], z["idf"],
                    z["total_freq"], float(z["scalars"][0]), float(z["scalars"][1]))
     if expect_docs is not None and len(t.doc_ids) != expect_docs:
@@ -242,6 +265,43 @@ def load_bm25_cache(path: str, expect_docs: Optional[int] = None, expect_terms: 
     if expect_terms is not None and len(t.term_off) - 1 != expect_terms:
         return None
     return t
+
+
+def f32_to_bf16_bits(x: np.ndarray) -> np.ndarray:
+    """float32 -> bfloat16 bit patterns (uint16), round to nearest even — the conversion `mse_dense_load` applies to
+    float32 input on the device (`__float2bfloat16_rn`), so a cache written here uploads to the same table."""
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    nan = (u & 0x7FFFFFFF) > 0x7F800000
+    r = (u + (((u >> 16) & 1) + 0x7FFF)) >> 16
+    r[nan] = (u[nan] >> 16) | 0x0040                      # quiet NaN, payload kept
+    return r.astype(np.uint16)
+
+
+def save_dense_cache(path: str, d: DenseTables, fingerprint: str = "") -> None:
+    """Persist the chunk table as bf16 (half the size of the FLOAT[768] column) with its chunk ids and doc offsets."""
+    emb = d.emb
+    if hasattr(emb, "detach"):                            # torch tensor (bf16 or fp32)
+        import torch
+        bits = emb.detach().to(torch.bfloat16).cpu().contiguous().view(torch.int16).numpy().view(np.uint16)
+    else:
+        bits = f32_to_bf16_bits(np.asarray(emb, dtype=np.float32))
+    np.savez(path, emb_bf16=bits, chunk_ids=np.asarray(d.chunk_ids, dtype=np.int64),
+             doc_chunk_off=np.asarray(d.doc_chunk_off, dtype=np.int64), fingerprint=np.asarray(fingerprint))
+
+
+def load_dense_cache(path: str, expect_docs: Optional[int] = None, fingerprint: Optional[str] = None) -> Optional[DenseTables]:
+    """-> DenseTables whose ``emb`` is a torch bf16 tensor (uploaded as is), or None when absent / stale."""
+    if not os.path.exists(path):
+        return None
+    z = np.load(path, allow_pickle=False)
+    if fingerprint is not None and str(z["fingerprint"]) != fingerprint:
+        return None
+    off = z["doc_chunk_off"]
+    if expect_docs is not None and len(off) - 1 != expect_docs:
+        return None
+    import torch
+    emb = torch.from_numpy(z["emb_bf16"].view(np.int16)).view(torch.bfloat16)
+    return DenseTables(emb, z["chunk_ids"], off)
 
 
 def open_store(db_path: str, read_only: bool = True):

@@ -224,3 +224,87 @@ def test_rerank_http_surface_matches_the_hosted_reference():
     bad = client.post("/rerank", json={"doc_ids": ["not-a-number"], "similarities": [1.0], "query": "q0"})
     assert bad.status_code == 500 and bad.json()["detail"].startswith("Internal server error")
     assert client.post("/rerank", json={"doc_ids": ["1"]}).status_code == 422          # pydantic: query is required
+
+
+def _sqlite_store_with_small_index():
+    ix, j, z = helpers.load_bm25_small()
+    conn = sqlite3.connect(":memory:")
+    st = store.SqlStore(conn)
+    conn.execute("CREATE TABLE urlsDB (id INTEGER PRIMARY KEY, url TEXT, title TEXT, text TEXT)")
+    conn.executemany("INSERT INTO urlsDB VALUES (?, ?, ?, ?)", [(int(d), f"https://h{int(d) % 7}.x/{int(d)}", f"t{int(d)}", "body")
+                                                              for d in ix.doc_ids])
+    names = j["terms"]
+    df = np.diff(ix.term_off)
+    st.write_bm25([(int(d), int(l)) for d, l in zip(ix.doc_ids, ix.doc_len)],
+                  [(int(ix.doc_ids[d]), names[t], int(f)) for t in range(len(names))
+                   for d, f in zip(ix.post_doc[ix.term_off[t]:ix.term_off[t + 1]], ix.post_tf[ix.term_off[t]:ix.term_off[t + 1]])],
+                  [(names[t], int(df[t]), int(ix.post_tf[ix.term_off[t]:ix.term_off[t + 1]].sum())) for t in range(len(names))],
+                  ix.avgdl, int(ix.total_docs), lambda d: float(ix.idf[0]))
+    return st, ix
+
+
+def test_fingerprint_tracks_the_bm25_tables_and_keys_the_cache(tmp_path):
+    """the on-disk cache and `BM25.refresh` are keyed on the state of the bm25_* tables
+    (row counts, newest processed_at / last_updated stamps, corpus statistics)."""
+    st, ix = _sqlite_store_with_small_index()
+    fp0 = st.bm25_fingerprint()
+    assert fp0 == st.bm25_fingerprint()                                   # stable while nothing changes
+    t = st.load_bm25(st.all_doc_ids())
+    p = str(tmp_path / "c.npz")
+    store.save_bm25_cache(p, t, fp0)
+    assert store.load_bm25_cache(p, fingerprint=fp0) is not None
+    # an indexing run adds a document: new doc row with a newer stamp, new postings, re-stamped corpus stats
+    new_id = int(ix.doc_ids.max()) + 1
+    st.conn.execute("INSERT INTO bm25_doc_stats (doc_id, doc_length, processed_at) VALUES (?, ?, '2099-01-01 00:00:00')", [new_id, 7])
+    fp1 = st.bm25_fingerprint()
+    assert fp1 != fp0
+    assert store.load_bm25_cache(p, fingerprint=fp1) is None              # the cache no longer describes the tables
+    # a statistics-only change (idf recalculation, bm25_indexer.py:130-147) is seen too
+    st.conn.execute("UPDATE bm25_corpus_stats SET stat_value = stat_value + 1 WHERE stat_name = 'total_docs'")
+    assert st.bm25_fingerprint() not in (fp0, fp1)
+
+
+def test_refresh_reloads_only_when_the_tables_changed():
+    class _CountingNative:                         # stands in for the device index: counts uploads (tests only)
+        loads = 0
+
+        def bm25_load(self, *a, **k):
+            _CountingNative.loads += 1
+
+        def close(self):
+            pass
+
+    from mse_b200.bm25_indexer import BM25
+    st, ix = _sqlite_store_with_small_index()
+    bm = BM25(None, store=st, load=False, tokenizer=str.split)
+    bm.native = _CountingNative()
+    bm.reload()
+    assert _CountingNative.loads == 1 and bm.refresh() is False and _CountingNative.loads == 1
+    n_before = len(bm.tables.doc_ids)
+    new_id = int(ix.doc_ids.max()) + 1
+    st.conn.execute("INSERT INTO urlsDB VALUES (?, 'https://new.x/1', 'new', 'body')", [new_id])
+    st.conn.execute("INSERT INTO bm25_doc_stats (doc_id, doc_length, processed_at) VALUES (?, 3, '2099-01-01 00:00:00')", [new_id])
+    st.conn.execute("INSERT INTO bm25_term_freq (doc_id, term, freq) VALUES (?, ?, 3)", [new_id, bm.tables.terms[0]])
+    assert bm.refresh() is True and _CountingNative.loads == 2
+    assert len(bm.tables.doc_ids) == n_before + 1 and bm.refresh() is False
+
+
+def test_dense_cache_is_bf16_round_to_nearest_even(tmp_path):
+    import torch
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((257, 768)).astype(np.float32)
+    x[0, :4] = [0.0, -0.0, np.inf, -np.inf]
+    x[1, 0] = np.float32(1.0) + np.float32(2.0 ** -8)          # exactly halfway between two bf16 values: ties to even
+    x[1, 1] = np.float32(1.0) + np.float32(3 * 2.0 ** -8)
+    bits = store.f32_to_bf16_bits(x)
+    want = torch.from_numpy(x).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+    np.testing.assert_array_equal(bits, want)
+    d = store.DenseTables(x, np.arange(257, dtype=np.int64) * 2 + 5, np.asarray([0, 100, 100, 257], dtype=np.int64))
+    p = str(tmp_path / "dense.npz")
+    store.save_dense_cache(p, d, "fp")
+    back = store.load_dense_cache(p, expect_docs=3, fingerprint="fp")
+    assert back.emb.dtype == torch.bfloat16 and tuple(back.emb.shape) == (257, 768)
+    np.testing.assert_array_equal(back.emb.view(torch.int16).numpy().view(np.uint16), want)
+    np.testing.assert_array_equal(back.chunk_ids, d.chunk_ids)
+    np.testing.assert_array_equal(back.doc_chunk_off, d.doc_chunk_off)
+    assert store.load_dense_cache(p, fingerprint="other") is None and store.load_dense_cache(p, expect_docs=4) is None
