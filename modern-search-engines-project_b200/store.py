@@ -49,6 +49,19 @@ class SqlStore:
     def _all(self, sql, params=()):
         return self.conn.execute(sql, list(params)).fetchall()
 
+    def _columns(self, sql, params=()) -> List[np.ndarray]:
+        """Result of a query with numeric columns as one numpy array per column.  A DuckDB cursor hands the columns
+        over without a Python object per row (``fetchnumpy``); anything else (sqlite3) goes through ``fetchall``."""
+        cur = self.conn.execute(sql, list(params))
+        if hasattr(cur, "fetchnumpy"):
+            d = cur.fetchnumpy()
+            return [np.ma.getdata(v) if isinstance(v, np.ma.MaskedArray) else np.asarray(v) for v in d.values()]
+        rows = cur.fetchall()
+        n_cols = len(cur.description) if getattr(cur, "description", None) else (len(rows[0]) if rows else 0)
+        if not rows:
+            return [np.zeros(0, dtype=np.int64) for _ in range(n_cols)]
+        return [np.asarray(c) for c in zip(*rows)]
+
     def has_table(self, name: str) -> bool:
         try:
             self.conn.execute(f"SELECT 1 FROM {name} LIMIT 1").fetchall()
@@ -80,12 +93,15 @@ class SqlStore:
             all_ids = ids
         doc_len = np.zeros(len(all_ids), dtype=np.int32)
         doc_len[np.searchsorted(all_ids, ids)] = np.asarray([r[1] for r in drows], dtype=np.int32)
-        # sort in numpy rather than ORDER BY term: python's str order == the order of `terms`
-        prows = self._all("SELECT term, doc_id, freq FROM bm25_term_freq")
-        tix = {t: i for i, t in enumerate(terms)}
-        pt = np.asarray([tix[r[0]] for r in prows], dtype=np.int64)
-        pd_ = np.searchsorted(all_ids, np.asarray([r[1] for r in prows], dtype=np.int64)).astype(np.int64)
-        pf = np.asarray([r[2] for r in prows], dtype=np.int32)
+        # postings as three integer columns: the term is replaced by its rank in `ORDER BY term` inside the database
+        # (the same ordering the `terms` list above was read in), so no Python object is made per posting; postings of
+        # a term without a bm25_term_stats row drop out of the join — such a term is unknown to search() anyway
+        # (bm25_indexer.py:412-432).  The (term, doc) sort is done in numpy.
+        cols = self._columns("SELECT s.rn, f.doc_id, f.freq FROM bm25_term_freq f JOIN "
+                             "(SELECT term, ROW_NUMBER() OVER (ORDER BY term) - 1 AS rn FROM bm25_term_stats) s ON f.term = s.term")
+        pt = cols[0].astype(np.int64)
+        pd_ = np.searchsorted(all_ids, cols[1].astype(np.int64)).astype(np.int64)
+        pf = cols[2].astype(np.int32)
         order = np.lexsort((pd_, pt))
         term_off = np.zeros(len(terms) + 1, dtype=np.int64)
         np.add.at(term_off, pt + 1, 1)
@@ -104,9 +120,13 @@ class SqlStore:
         return repr((int(c[0]), int(c[1] or 0), int(e[0]), int(e[1] or 0)))
 
     def load_dense(self, doc_ids: np.ndarray) -> DenseTables:
-        rows = self._all("SELECT c.doc_id, c.chunk_id, e.embedding FROM chunks_optimized c "
-                         "JOIN embeddings e ON c.chunk_id = e.chunk_id ORDER BY c.doc_id, c.chunk_id")
+        sql = ("SELECT c.doc_id, c.chunk_id, e.embedding FROM chunks_optimized c "
+               "JOIN embeddings e ON c.chunk_id = e.chunk_id ORDER BY c.doc_id, c.chunk_id")
         doc_ids = np.asarray(doc_ids, dtype=np.int64)
+        cur = self.conn.execute(sql, [])
+        if hasattr(cur, "fetch_arrow_table"):             # DuckDB: FLOAT[768] arrives as one Arrow (fixed-size) list column
+            return dense_from_arrow(cur.fetch_arrow_table(), doc_ids)
+        rows = cur.fetchall()
         cd = np.asarray([r[0] for r in rows], dtype=np.int64)
         keep = np.isin(cd, doc_ids)
         chunk_ids = np.asarray([r[1] for r in rows], dtype=np.int64)[keep]
@@ -265,6 +285,30 @@ def load_bm25_cache(path: str, expect_docs: Optional[int] = None, expect_terms: 
     if expect_terms is not None and len(t.term_off) - 1 != expect_terms:
         return None
     return t
+
+
+def dense_from_arrow(table, doc_ids: np.ndarray, dim: int = 768) -> DenseTables:
+    """(doc_id, chunk_id, embedding) Arrow table ordered by (doc_id, chunk_id) -> DenseTables without a Python object
+    per row: the list column's child values are one contiguous float buffer."""
+    import pyarrow as pa
+    doc_ids = np.asarray(doc_ids, dtype=np.int64)
+    cd = table.column(0).to_numpy().astype(np.int64)
+    chunk_ids = table.column(1).to_numpy().astype(np.int64)
+    col = table.column(2).combine_chunks()
+    if isinstance(col, pa.ChunkedArray):
+        col = col.chunk(0) if col.num_chunks else pa.array([], type=pa.list_(pa.float32()))
+    n = len(col)
+    if not pa.types.is_fixed_size_list(col.type):
+        lengths = np.diff(col.offsets.to_numpy())
+        if n and not np.all(lengths == dim):
+            raise ValueError(f"embedding rows must have {dim} values (found lengths {np.unique(lengths)[:4]})")
+    flat = col.flatten().to_numpy(zero_copy_only=False).astype(np.float32, copy=False)
+    emb = flat.reshape(n, dim) if n else np.zeros((0, dim), dtype=np.float32)
+    keep = np.isin(cd, doc_ids)
+    counts = np.bincount(np.searchsorted(doc_ids, cd[keep]), minlength=len(doc_ids))
+    off = np.zeros(len(doc_ids) + 1, dtype=np.int64)
+    off[1:] = np.cumsum(counts)
+    return DenseTables(np.ascontiguousarray(emb[keep]), chunk_ids[keep], off)
 
 
 def f32_to_bf16_bits(x: np.ndarray) -> np.ndarray:

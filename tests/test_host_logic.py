@@ -308,3 +308,63 @@ def test_dense_cache_is_bf16_round_to_nearest_even(tmp_path):
     np.testing.assert_array_equal(back.chunk_ids, d.chunk_ids)
     np.testing.assert_array_equal(back.doc_chunk_off, d.doc_chunk_off)
     assert store.load_dense_cache(p, fingerprint="other") is None and store.load_dense_cache(p, expect_docs=4) is None
+
+
+class _ColumnarCursor:
+    """What a DuckDB cursor offers beyond DB-API (tests only; duckdb is not installed in the build image)."""
+
+    def __init__(self, cur):
+        self._cur = cur
+        self.description = cur.description
+
+    def fetchall(self):
+        return self._cur.fetchall()
+
+    def fetchnumpy(self):
+        rows = self._cur.fetchall()
+        names = [d[0] for d in self.description]
+        cols = list(zip(*rows)) if rows else [[] for _ in names]
+        return {n: np.ma.masked_array(np.asarray(c)) for n, c in zip(names, cols)}
+
+    def fetch_arrow_table(self):
+        import pyarrow as pa
+        rows = self._cur.fetchall()
+        emb = pa.array([np.frombuffer(r[2], dtype=np.float32).tolist() for r in rows], type=pa.list_(pa.float32(), 768))
+        return pa.table({"doc_id": pa.array([r[0] for r in rows], pa.int64()), "chunk_id": pa.array([r[1] for r in rows], pa.int64()),
+                         "embedding": emb})
+
+
+class _ColumnarConn:
+    def __init__(self, conn):
+        self._conn = conn
+
+    def execute(self, sql, params=()):
+        return _ColumnarCursor(self._conn.execute(sql, params))
+
+
+def test_columnar_loaders_equal_the_row_loaders():
+    """The DuckDB fast paths (fetchnumpy for the postings, one Arrow list column for FLOAT[768]) build the same arrays as
+    the DB-API row paths sqlite3 takes."""
+    st, ix = _sqlite_store_with_small_index()
+    rng = np.random.default_rng(5)
+    ids = st.all_doc_ids()
+    st.conn.execute("CREATE TABLE chunks_optimized (chunk_id INTEGER PRIMARY KEY, doc_id INTEGER, chunk_text TEXT)")
+    st.conn.execute("CREATE TABLE embeddings (chunk_id INTEGER PRIMARY KEY, embedding BLOB)")
+    cid = 0
+    for d in ids[:40].tolist() + [10 ** 9]:                       # the last chunk belongs to a doc that is not indexed
+        for _ in range(int(rng.integers(0, 4))):
+            st.conn.execute("INSERT INTO chunks_optimized VALUES (?, ?, '')", [cid, d])
+            st.conn.execute("INSERT INTO embeddings VALUES (?, ?)", [cid, rng.standard_normal(768).astype(np.float32).tobytes()])
+            cid += 1
+    fast = store.SqlStore(_ColumnarConn(st.conn))
+    a, b = st.load_bm25(ids), fast.load_bm25(ids)
+    assert a.terms == b.terms and a.avgdl == b.avgdl
+    for x, y in ((a.term_off, b.term_off), (a.post_doc, b.post_doc), (a.post_tf, b.post_tf), (a.doc_len, b.doc_len), (a.idf, b.idf)):
+        np.testing.assert_array_equal(x, y)
+    np.testing.assert_array_equal(a.term_off, ix.term_off)
+    np.testing.assert_array_equal(a.post_doc, ix.post_doc)
+    da, db = st.load_dense(ids), fast.load_dense(ids)
+    assert da.emb.shape == db.emb.shape and da.emb.shape[0] > 0
+    np.testing.assert_array_equal(da.emb, db.emb)
+    np.testing.assert_array_equal(da.chunk_ids, db.chunk_ids)
+    np.testing.assert_array_equal(da.doc_chunk_off, db.doc_chunk_off)
