@@ -368,3 +368,38 @@ def test_columnar_loaders_equal_the_row_loaders():
     np.testing.assert_array_equal(da.emb, db.emb)
     np.testing.assert_array_equal(da.chunk_ids, db.chunk_ids)
     np.testing.assert_array_equal(da.doc_chunk_off, db.doc_chunk_off)
+
+
+def test_cut_rule_is_sound_under_ties():
+    """Property behind the truncated exchanges: whenever `cut_could_hide_a_result` calls a cut safe, merging
+    the cut shard lists gives exactly the merge of the full lists — including when scores tie across shards (few
+    distinct score values force ties at the k-th place)."""
+    import torch
+    rng = np.random.default_rng(11)
+    safe_seen = unsafe_seen = 0
+    for trial in range(300):
+        W, B = int(rng.integers(2, 6)), int(rng.integers(1, 5))
+        k_full, top_k = int(rng.integers(4, 40)), int(rng.integers(1, 30))
+        m = int(rng.integers(1, k_full + 1))
+        levels = int(rng.integers(2, 12))
+        g_doc = np.full((W, B, k_full), -1, np.int32); g_score = np.zeros((W, B, k_full), np.float32)
+        g_count = rng.integers(0, k_full + 1, size=(W, B)).astype(np.int32)
+        for w in range(W):
+            for q in range(B):
+                n = int(g_count[w, q])
+                sc = np.sort(rng.integers(0, levels, size=n).astype(np.float32))[::-1]
+                docs = w * 1000 + np.sort(rng.choice(1000, size=n, replace=False))
+                order = np.lexsort((docs, -sc))                    # a shard list is (score desc, doc asc)
+                g_doc[w, q, :n], g_score[w, q, :n] = docs[order], sc[order]
+        full = sharding.merge_topk_host(g_doc, g_score, g_count, top_k)
+        c_doc, c_score, c_count = g_doc[:, :, :m].copy(), g_score[:, :, :m].copy(), np.minimum(g_count, m)
+        cut = sharding.merge_topk_host(c_doc, c_score, c_count, top_k)
+        unsafe = bool(sharding.cut_could_hide_a_result(torch.from_numpy(c_score), torch.from_numpy(c_count),
+                                                       torch.from_numpy(cut[1]), torch.from_numpy(cut[2]), top_k))
+        if unsafe:
+            unsafe_seen += 1
+            continue
+        safe_seen += 1
+        for a, b in zip(full, cut):
+            np.testing.assert_array_equal(a, b)
+    assert safe_seen > 30 and unsafe_seen > 30
