@@ -84,7 +84,10 @@ int mse_index_set_option(mse_index* idx, const char* name, int64_t value);
  *   idf[n_terms]         bm25_term_stats.idf_score verbatim (float32 log10, may be <= 0; :140)
  *   avgdl                bm25_corpus_stats 'avg_doc_length' (float32; GLOBAL, never per shard)
  *   k1, b                BM25.__init__ parameters (:57)
- * `where` tells whether the five arrays are host (MSE_HOST) or device (MSE_DEVICE) memory. */
+ * `where` tells whether the five arrays are host (MSE_HOST) or device (MSE_DEVICE) memory.
+ * The arrays are only read during the call.  The library keeps the postings as one {doc, fp32 impact} array with
+ * impact = tf / (tf + k1*(1 - b + b*doc_len/avgdl)) (the tf factor of bm25_indexer.py:470-476, formed in float64 and
+ * rounded once), so k1, b and avgdl are fixed per loaded index: load again after the corpus statistics change. */
 int mse_bm25_load(mse_index* idx, int64_t n_terms, int64_t n_docs, int64_t doc_base,
                   const int64_t* term_off, const int32_t* post_doc, const int32_t* post_tf,
                   const int32_t* doc_len, const float* idf, float avgdl, float k1, float b, int where);
