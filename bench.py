@@ -190,8 +190,6 @@ def hybrid_supplement(nat, dev, dev_batches, peak, steps=20, chunks_per_doc=5, m
     for i in range(5):
         step(i)
     torch.cuda.synchronize()
-    import gc
-    gc.collect()                                   # the CPU-baseline leg above leaves a few million Python objects behind
     nat.set_option("reset_timers", 1)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
     ev[0].record()
@@ -334,7 +332,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpu-sample", type=int, default=16, help="queries timed by the CPU baseline")
+    ap.add_argument("--cpu-sample", type=int, default=128, help="queries timed by the CPU baseline (~10-15 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--range-docs", type=int, default=0)
     ap.add_argument("--queries-per-item", type=int, default=0)
@@ -563,6 +561,12 @@ def main():
                         "sample": f"{n_s} of the {BATCH} queries of one batch, full 1M-doc index, faithful Python-loop port of "
                                   f"bm25_indexer.py:435-485 (no SQL cost)",
                         "vectorised_numpy_value": n_s / fast_s}
+
+    # the CPU-baseline leg leaves millions of Python objects behind: collect now and keep the survivors out of later
+    # collections, so that no generation-2 pass lands inside a timed supplement loop (one cost ~28 ms when it did)
+    import gc
+    gc.collect()
+    gc.freeze()
 
     # ---- supplementary: dense exhaustive scan (BASELINE.json configs[2]) on rank 0 at N=1 ------------------
     dense = None
