@@ -403,3 +403,29 @@ def test_cut_rule_is_sound_under_ties():
         for a, b in zip(full, cut):
             np.testing.assert_array_equal(a, b)
     assert safe_seen > 30 and unsafe_seen > 30
+
+
+def test_committed_bench_lines_carry_every_contract_key():
+    """The bench lines kept under profiles/ (produced by bench.py on a B200) have the keys the measurement contract
+    names; guards against drift between bench.py and the documented samples."""
+    import json
+    prof = os.path.join(ROOT, "profiles")
+    lines = [json.load(open(os.path.join(prof, "bench_r01c_sample.json")))]
+    for name in ("bench_n2_r01c.jsonl", "bench_n4_r01c.jsonl"):
+        lines += [json.loads(l) for l in open(os.path.join(prof, name)) if l.strip()]
+    for j in lines:
+        for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                  "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "clocks"):
+            assert k in j, k
+        assert j["metric"] == "bm25_queries_per_sec" and j["unit"] == "queries/s" and j["higher_is_better"] is True
+        assert "workload" in j["config"] and "model" not in j["config"]
+        assert set(j["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
+        assert j["e2e"]["h2d_bytes_per_step"] > 0 and j["e2e"]["d2h_bytes_per_step"] > 0 and j["e2e"]["value"] < j["value"]
+        r = j["roofline"]
+        assert set(r) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"} and r["bound"] == "hbm"
+        assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and 0 < r["frac"] < 1.2
+        assert j["gpu_launches"] > 0 and j["clocks"]["sm_mhz"] and not set(j["clocks"]["reasons"]) & {
+            "hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    one = lines[0]
+    assert one["n_gpus"] == 1 and one["cpu_baseline"]["kind"] == "port" and one["cpu_baseline"]["cores"] >= 1
+    assert one["parity"]["queries_failing"] == 0 and one["parity"]["max_rel_err"] < 1e-5
