@@ -429,3 +429,63 @@ def test_committed_bench_lines_carry_every_contract_key():
     one = lines[0]
     assert one["n_gpus"] == 1 and one["cpu_baseline"]["kind"] == "port" and one["cpu_baseline"]["cores"] >= 1
     assert one["parity"]["queries_failing"] == 0 and one["parity"]["max_rel_err"] < 1e-5
+
+
+class _OracleBm25Native:
+    """Test double for the device index below `BM25` (tests only): answers `bm25_search` from the pinned oracle, so the
+    façade's own logic — tokenise, qtf counts, unknown terms, id mapping, snippets, urlsDB filter — runs without a GPU."""
+
+    def bm25_load(self, term_off, post_doc, post_tf, doc_len, idf, avgdl, k1=1.2, b=0.75, doc_base=0):
+        self.ix = bo.Bm25Arrays(term_off, post_doc, post_tf, doc_len, idf, float(avgdl), float(len(doc_len)),
+                                np.arange(len(doc_len), dtype=np.int64))
+        self.k1, self.b = k1, b
+
+    def bm25_search(self, q_off, q_term, q_tf, top_k, min_score):
+        B = len(q_off) - 1
+        doc = np.full((B, top_k), -1, np.int32); score = np.zeros((B, top_k), np.float32); count = np.zeros(B, np.int32)
+        for i in range(B):
+            terms = [int(t) for s in range(q_off[i], q_off[i + 1]) for t in [q_term[s]] * int(q_tf[s])]
+            res = bo.search_fast(self.ix, terms, top_k=top_k, min_score=min_score, k1=self.k1, b=self.b)
+            for r, (d, sc) in enumerate(res):
+                doc[i, r], score[i, r] = d, sc
+            count[i] = len(res)
+        return doc, score, count
+
+    def close(self):
+        pass
+
+
+def test_bm25_facade_returns_the_references_known_answers():
+    """`BM25.search` above a test double of the device index == the reference's own results: ids,
+    scores, snippets; `[]` for no tokens / unknown terms / nothing above min_score; ids missing from urlsDB dropped."""
+    from mse_b200.bm25_indexer import BM25, whitespace_tokenizer
+    ix, e = helpers.load_appendix_e()
+    conn = sqlite3.connect(":memory:")
+    conn.execute("CREATE TABLE urlsDB (id BIGINT PRIMARY KEY, url TEXT, title TEXT, text TEXT)")
+    conn.executemany("INSERT INTO urlsDB VALUES (?,?,?,?)", [(i, f"http://x/{i}", "", t) for i, t in e["docs"]])
+    st = store.SqlStore(conn)
+    st.write_bm25(e["doc_stats"], [(r[1], r[0], r[2]) for r in e["term_freq"]], [(r[0], r[1], r[2]) for r in e["term_stats"]],
+                  e["corpus_stats"]["avg_doc_length"], int(e["corpus_stats"]["total_docs"]),
+                  lambda df: float(np.float32(np.log10((float(np.float32(e["corpus_stats"]["total_docs"])) - df + 0.5) / (df + 0.5)))))
+    bm = BM25(None, store=st, tokenizer=whitespace_tokenizer, load=False)
+    bm.native = _OracleBm25Native()
+    bm.reload()
+    assert len(e["searches"]) >= 4
+    for s in e["searches"]:
+        got = bm.search(s["query"], top_k=s["top_k"], min_score=s["min_score"])
+        assert [g["doc_id"] for g in got] == [r[0] for r in s["result"]], s["query"]
+        np.testing.assert_allclose([g["score"] for g in got], [r[1] for r in s["result"]], rtol=1e-6, atol=1e-7)
+        assert [g["text_snippet"] for g in got] == [r[2] for r in s["result"]]
+    assert bm.search("") == [] and bm.search("   ") == []                      # no tokens (:396-397)
+    assert bm.search("nosuchterm anotherunknown") == []                          # no known terms (:431-432)
+    assert bm.search("gamma", min_score=1e9) == []                               # no survivors (:487-488)
+    assert bm.search("beta") == []                                               # idf < 0 only: every score negative
+    full = bm.search("gamma delta", top_k=10)
+    assert len(full) >= 3
+    conn.execute("DELETE FROM urlsDB WHERE id = ?", [full[0]["doc_id"]])
+    assert [g["doc_id"] for g in bm.search("gamma delta", top_k=10)] == [g["doc_id"] for g in full[1:]]    # (:506)
+    long_id = full[1]["doc_id"]
+    conn.execute("UPDATE urlsDB SET title = 'T', text = ? WHERE id = ?", ["x" * 250, long_id])
+    hit = [g for g in bm.search("gamma delta", top_k=10) if g["doc_id"] == long_id]
+    assert hit and hit[0]["text_snippet"] == "T: " + "x" * 200 + "..."          # (:508-510)
+    assert bm.get_term_stats("beta")["document_frequency"] == 4 and bm.get_term_stats("nosuchterm") is None
