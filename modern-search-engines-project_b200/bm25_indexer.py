@@ -64,6 +64,9 @@ def slice_bm25_tables(t: Bm25Tables, lo: int, hi: int) -> Bm25Tables:
                       t.doc_ids[lo:hi], t.doc_len[lo:hi], t.idf, t.total_freq, t.avgdl, t.total_docs)
 
 
+MAX_QUERY_TERMS = 32          # distinct valid terms per query the score kernel stages (csrc/bm25.cuh kMetaSlots)
+
+
 class BM25:
     def __init__(self, db_path: Optional[str], k1: float = 1.2, b: float = 0.75, read_only: bool = True, *,
                  store=None, tokenizer: Optional[Callable[[str], List[str]]] = None, device: int = 0,
@@ -93,8 +96,9 @@ class BM25:
         full = None
         if self.cache_path:
             from .store import load_bm25_cache, save_bm25_cache
-            full = load_bm25_cache(self.cache_path, expect_docs=None if all_ids is None else len(all_ids),
-                                   fingerprint=self.fingerprint)
+            # staleness is decided by the fingerprint; the doc count of the cached index is union(urlsDB, doc_stats)
+            # and need not equal len(urlsDB)
+            full = load_bm25_cache(self.cache_path, fingerprint=self.fingerprint)
         if full is None:
             full = self.store.load_bm25(all_ids)
             if self.cache_path:
@@ -164,7 +168,55 @@ class BM25:
         """CSR term-id batch -> (doc index [B,k] int32 (global dense index, -1 padded), score [B,k] fp32,
         count [B]).  Accepts numpy (host) or torch CUDA tensors (device-resident, no copies)."""
         self._require_loaded()
+        if not _native._is_torch(q_off) and len(q_off) > 1 and int(np.max(np.diff(q_off))) > MAX_QUERY_TERMS:
+            return self._search_long_queries(np.asarray(q_off), np.asarray(q_term), np.asarray(q_tf), top_k, min_score)
         return self.native.bm25_search(q_off, q_term, q_tf, top_k, min_score)
+
+    def _search_long_queries(self, q_off, q_term, q_tf, top_k: int, min_score: float):
+        """The kernel takes <= 32 distinct terms per query; the reference's ``search`` accepts any length (a pasted
+        paragraph).  A longer query is cut into pieces of <= 32 terms, every piece is scored WITHOUT a cut
+        (top_k = all docs it touches, min_score = -inf), the piece scores of a document are summed in piece order on
+        the host and the reference's filter / order / slice (:480-485) is applied to the sums.  Short queries of the
+        same batch still go through one batched call."""
+        B = len(q_off) - 1
+        n_terms = np.diff(q_off)
+        long_q = np.flatnonzero(n_terms > MAX_QUERY_TERMS)
+        short_q = np.flatnonzero(n_terms <= MAX_QUERY_TERMS)
+        doc = np.full((B, top_k), -1, np.int32); score = np.zeros((B, top_k), np.float32); count = np.zeros(B, np.int32)
+        if len(short_q):
+            so = np.zeros(len(short_q) + 1, np.int32); st, sf = [], []
+            for j, q in enumerate(short_q):
+                st.append(q_term[q_off[q]:q_off[q + 1]]); sf.append(q_tf[q_off[q]:q_off[q + 1]]); so[j + 1] = so[j] + n_terms[q]
+            d, s, c = self.native.bm25_search(so, np.concatenate(st).astype(np.int32) if so[-1] else np.zeros(0, np.int32),
+                                              np.concatenate(sf).astype(np.int32) if so[-1] else np.zeros(0, np.int32), top_k, min_score)
+            doc[short_q], score[short_q], count[short_q] = d, s, c
+        n_docs = len(self.tables.doc_len)
+        k_all = min(_native.MAX_TOPK, max(1, n_docs))
+        for q in long_q:
+            lo, hi = int(q_off[q]), int(q_off[q + 1])
+            total: Dict[int, float] = {}
+            for a in range(lo, hi, MAX_QUERY_TERMS):
+                e = min(hi, a + MAX_QUERY_TERMS)
+                po = np.asarray([0, e - a], np.int32)
+                d, s, c = self.native.bm25_search(po, np.ascontiguousarray(q_term[a:e], np.int32),
+                                                  np.ascontiguousarray(q_tf[a:e], np.int32), k_all, -3.0e38)
+                if int(c[0]) >= k_all and n_docs > k_all:
+                    # the piece may touch more documents than one call can return: fail THIS query only (count 0),
+                    # never the batch (search_api's batch path would lose every query of the file)
+                    import warnings
+                    warnings.warn(f"query {int(q)} has {hi - lo} distinct terms and a {e - a}-term piece touches more than "
+                                  f"{k_all} documents: not supported, returning no results for it")
+                    total = None
+                    break
+                for dd, ss in zip(d[0, :int(c[0])].tolist(), s[0, :int(c[0])].tolist()):
+                    total[dd] = total.get(dd, 0.0) + ss
+            if total is None:
+                continue
+            keep = sorted(((sc, dd) for dd, sc in total.items() if sc >= min_score), key=lambda x: (-x[0], x[1]))[:top_k]
+            count[q] = len(keep)
+            for r, (sc, dd) in enumerate(keep):
+                doc[q, r], score[q, r] = dd, sc
+        return doc, score, count
 
     def search_batch(self, queries: Sequence, top_k: int = 1000, min_score: float = 0.0):
         """Batched ``search``: returns (doc_ids [B,k] int64 urlsDB ids, scores [B,k], counts [B])."""

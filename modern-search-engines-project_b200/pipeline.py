@@ -44,6 +44,17 @@ class HybridSearch:
     def __init__(self, bm25: BM25, reranker: Reranker, embed: Optional[Callable[[str], np.ndarray]] = None,
                  top_k_retrieval: int = TOP_K_RETRIEVAL):
         self.bm25, self.reranker, self.embed, self.top_k_retrieval = bm25, reranker, embed or reranker.embed, top_k_retrieval
+        # BM25 results are positions in bm25.global_doc_ids; the reranker indexes reranker.doc_ids.  The two are the same
+        # array when the Reranker is built with doc_ids=bm25.global_doc_ids; when they differ (a
+        # bm25_doc_stats id missing from urlsDB, bm25_indexer.py:506) positions are translated through the ids and
+        # candidates unknown to the reranker are dropped, as the reference's JOIN on urlsDB drops them
+        # (reranker_api.py:36-47).
+        self._remap = None
+        bm_ids = np.asarray(getattr(bm25, "global_doc_ids", reranker.doc_ids), dtype=np.int64)
+        if not np.array_equal(bm_ids, reranker.doc_ids):
+            rr = reranker.doc_ids
+            pos = np.minimum(np.searchsorted(rr, bm_ids), max(len(rr) - 1, 0))
+            self._remap = np.where(rr[pos] == bm_ids, pos, -1).astype(np.int64) if len(rr) else np.full(len(bm_ids), -1, np.int64)
 
     def search_batch(self, queries: Sequence[str], query_vecs: Optional[np.ndarray] = None, preprocess: bool = True):
         """Returns, per query, the reranked ``[(doc_id, url, score)]`` list (<= 100 entries)."""
@@ -54,6 +65,10 @@ class HybridSearch:
             query_vecs = np.stack([self.embed(q) for q in qs])
         cand = [doc[i, :count[i]] for i in range(len(qs))]
         sims = [score[i, :count[i]] for i in range(len(qs))]
+        if self._remap is not None:
+            for i in range(len(qs)):
+                m = self._remap[cand[i]]
+                cand[i], sims[i] = m[m >= 0].astype(np.int32), sims[i][m >= 0]
         o_doc, o_score, o_orig, o_chunk, o_count, o_rows = self.reranker.rerank_batch(cand, sims, query_vecs)
         results = []
         for i in range(len(qs)):

@@ -100,8 +100,19 @@ class SqlStore:
         cols = self._columns("SELECT s.rn, f.doc_id, f.freq FROM bm25_term_freq f JOIN "
                              "(SELECT term, ROW_NUMBER() OVER (ORDER BY term) - 1 AS rn FROM bm25_term_stats) s ON f.term = s.term")
         pt = cols[0].astype(np.int64)
-        pd_ = np.searchsorted(all_ids, cols[1].astype(np.int64)).astype(np.int64)
+        raw_doc = cols[1].astype(np.int64)
         pf = cols[2].astype(np.int32)
+        # the reference's candidate query inner-joins bm25_doc_stats (bm25_indexer.py:442-444): a posting whose doc has
+        # no doc_stats row never reaches the scoring loop.  Drop such rows here instead of attributing them to a
+        # neighbouring doc (a partly built or inconsistent index).
+        if len(ids):
+            pos = np.minimum(np.searchsorted(ids, raw_doc), len(ids) - 1)
+            ok = ids[pos] == raw_doc
+        else:
+            ok = np.zeros(len(raw_doc), dtype=bool)
+        if not bool(np.all(ok)):
+            pt, raw_doc, pf = pt[ok], raw_doc[ok], pf[ok]
+        pd_ = np.searchsorted(all_ids, raw_doc).astype(np.int64)
         order = np.lexsort((pd_, pt))
         term_off = np.zeros(len(terms) + 1, dtype=np.int64)
         np.add.at(term_off, pt + 1, 1)
@@ -267,7 +278,7 @@ def save_bm25_cache(path: str, t: Bm25Tables, fingerprint: str = "") -> None:
     when the tables have changed since (or on a size mismatch)."""
     np.savez(path, term_off=t.term_off, post_doc=t.post_doc, post_tf=t.post_tf, doc_ids=t.doc_ids, doc_len=t.doc_len,
              idf=t.idf, total_freq=t.total_freq, scalars=np.asarray([t.avgdl, t.total_docs], dtype=np.float64),
-             terms=np.asarray(t.terms if t.terms is not None else [], dtype=object),
+             terms=np.asarray(t.terms if t.terms is not None else [], dtype=str),     # fixed-width unicode: no pickle
              fingerprint=np.asarray(fingerprint))
 
 
@@ -275,10 +286,14 @@ def load_bm25_cache(path: str, expect_docs: Optional[int] = None, expect_terms: 
                     fingerprint: Optional[str] = None) -> Optional[Bm25Tables]:
     if not os.path.exists(path):
         return None
-    z = np.load(path, allow_pickle=True)
-    if fingerprint is not None and ("fingerprint" not in z.files or str(z["fingerprint"]) != fingerprint):
+    try:
+        z = np.load(path, allow_pickle=False)          # the cache sits beside the database: never unpickle it
+        if fingerprint is not None and ("fingerprint" not in z.files or str(z["fingerprint"]) != fingerprint):
+            return None
+        terms = [str(x) for x in z["terms"]]
+    except ValueError:                                 # a cache written with pickled object arrays: treat as stale
         return None
-    t = Bm25Tables(list(z["terms"]) or None, z["term_off"], z["post_doc"], z["post_tf"], z["doc_ids"], z["doc_len"], z["idf"],
+    t = Bm25Tables(terms or None, z["term_off"], z["post_doc"], z["post_tf"], z["doc_ids"], z["doc_len"], z["idf"],
                    z["total_freq"], float(z["scalars"][0]), float(z["scalars"][1]))
     if expect_docs is not None and len(t.doc_ids) != expect_docs:
         return None
