@@ -1,33 +1,35 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the retrieval hot path.
 
-Workload (BASELINE.json configs[1]): BM25-only, 1M synthetic docs, Zipf(1.0) vocabulary of 200k,
-~256 tokens/doc (~192M postings), batches of 1024 four-term queries, top-1000, on one B200.
-A "step" = one batch of queries through prepare -> score -> select.  On N > 1 GPUs (weak scaling: every GPU
-traverses the same number of postings per step as the single GPU does, the job processes N x 1024 queries):
-  * `--layout replicated` (what `auto` picks when the index fits one GPU, as the 1.5 GB C2 index does): the
-    QUERIES are the sharded unit — every rank holds the whole index and answers its own 1024-query batch, no
-    data-path collective;
-  * `--layout doc-sharded` (what `auto` picks for an index that does not fit): the corpus is sharded by doc range
-    (global idf / avgdl), each rank scores the whole replicated N x 1024 batch against its shard, keeps
-    m = 2k/N + 32 entries per query, the lists travel to the rank that owns the query (NCCL all-to-all over
-    NVLink) and are merged there to the exact global top-1000 (a step whose cut could have hidden a result is
-    repeated with full lists).  `--exchange allgather` runs all-gather + merge-everywhere instead (batch 1024 at
-    every N: strong scaling).
-With the replicated layout the doc-sharded exchange is still measured on the same GPUs for a few steps and
-reported as the `doc_sharded` supplement of the JSON line.
+Workload (BASELINE.json configs[4], the config its metric "hybrid queries/sec" is quoted on — it fits one B200):
+    C5 end-to-end hybrid: BM25 top-1000 candidates over 10M synthetic docs (Zipf(1.0) vocabulary of 200k, ~256
+    tokens/doc, ~1.9G postings, plus the always-present "tübingen"-like term search_api.py:160-165 appends to every
+    query, in 95 % of the docs) -> gathered rerank of <= 10 chunks/doc out of 50M x 768 bf16 chunks (clipped-geometric
+    chunk counts) with min-max fusion -> top-100; batch 4096 throughput and batch-1 latency.
+A "step" = one batch of 4096 hybrid queries through `mse_hybrid_search_batch` (search_api.py:252-274 per query).
+
+N > 1 GPUs (one process per GPU): the corpus is sharded by contiguous doc range (postings AND chunks of a doc on its
+rank, global idf / avgdl), the batch is N x 4096 queries replicated on every rank (weak scaling: every GPU streams the
+same number of postings and gathers the same number of chunk rows per step as the single GPU does), every rank owns one
+4096-query block of the results, and the exchange (`mse_hybrid_search_sharded`: shard lists to the owner, survivors
+all-gather, 4-word all-reduce of the min-max bounds, local top-100 records to the owner) runs as NCCL calls enqueued on
+the compute stream inside the library.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-Prints ONE JSON line (rank 0).  `value` = queries/s with inputs resident in HBM; `e2e` = the same
-through the C ABI with HOST buffers (H2D of the query CSR and D2H of the results inside the timed
-region); `roofline` describes the dominant kernel (bm25_score_kernel) with algorithmic bytes
-12*P_q + 8*k per query; `cpu_baseline` = the oracle port of the reference's Python
-scoring loop (indexer/bm25_indexer.py:435-485) timed on this box's host cores on a bounded sample.
+Prints ONE JSON line (rank 0).  `value` = hybrid queries/s with the inputs resident in HBM (CUDA events, max over
+ranks); `e2e` = the same through the C ABI with PINNED HOST buffers (H2D of query CSR + query vectors and D2H of the
+top-100 inside the timed region, two streams alternating); `roofline` describes the dominant kernel
+(bm25_score_kernel) — algorithmic bytes 12 B per STREAMED posting + 8*k per query over the kernel's mean duration —
+and `rooflines` lists every hot kernel; `cpu_baseline` = the oracle port of the reference's per-query path
+(bm25_indexer.py:435-485 -> reranker_api.py:336-372) timed on this box's host cores on a bounded sample; `parity` =
+GPU vs oracle on sampled queries AT THIS SIZE.  Supplements (N=1): C2 BM25-only (with and without the always-term) and
+C3 dense exhaustive scan (B=1, 256), each with its own sampled parity; (N>1): C4-shaped sharded dense scan.
 """
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import sys
@@ -39,24 +41,44 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_DOCS = 1_000_000
+N_DOCS = 10_000_000
+N_CHUNKS = 50_000_000
 VOCAB = 200_000
-BATCH = 1024
+ALWAYS_FRAC = 0.95
+BATCH = 4096
 TOP_K = 1000
+MAX_OUT = 100
 SEED = 1234
-METRIC = "bm25_queries_per_sec"
+METRIC = "hybrid_queries_per_sec"
 UNIT = "queries/s"
-WORKLOAD = "C2 BM25-only: 1M synthetic docs, Zipf(1.0) vocab 200k, batch 1024 x 4-term queries, top-1000"
+
+
+def workload_name(n_docs, n_chunks, batch):
+    return (f"C5 end-to-end hybrid: BM25 top-{TOP_K} over {n_docs} synthetic docs (Zipf(1.0) vocab {VOCAB}, always-term in "
+            f"{int(ALWAYS_FRAC * 100)} % of docs appended to every query) -> gathered rerank of <=10 chunks/doc from {n_chunks} x 768 "
+            f"bf16 chunks (geometric chunk counts) + score fusion -> top-{MAX_OUT}; batch {batch} throughput, batch 1 latency")
 
 
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         try:
-            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+            j = json.load(open(p))
+            return float(j["hbm_gbs"]), float(j.get("bf16_tflops", 1602.5)), "measured (MEASURED_PEAKS.json hbm_gbs / bf16_tflops, burst)"
         except Exception:
             pass
-    return 6650.0, "fallback (B200_PROFILING.md)"
+    return 6650.0, 1600.0, "fallback (B200_PROFILING.md)"
+
+
+def committed_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture of this workload (a cited figure,
+    not measured by this run)."""
+    p = os.path.join(ROOT, "profiles", "traffic_r02.json")
+    try:
+        j = json.load(open(p)).get(kernel)
+        return (j["dram_bytes_per_launch"], j["source"]) if j else (None, None)
+    except Exception:
+        return None, None
 
 
 class ClockSampler(threading.Thread):
@@ -106,46 +128,284 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
-def gen_corpus(device):
-    from mse_b200 import synthetic
-    return synthetic.make_bm25_corpus(N_DOCS, vocab=VOCAB, seed=SEED, device=device)
+# ------------------------------------------------------------------------------------------------------------------
+# corpus
+# ------------------------------------------------------------------------------------------------------------------
+class Corpus:
+    """The synthetic C5 corpus of one rank: its doc-range shard loaded into an `NativeIndex`, plus what the parity /
+    CPU legs need on the host (global df, doc lengths, the always-term's posting list, global chunk offsets)."""
 
 
-def shard_corpus(c, rank, world):
-    """Contiguous doc-index range balanced by postings; postings re-based to local doc indices."""
+def build_corpus(dev, local_rank, rank, world, n_docs, n_chunks, keep_terms_for=None):
     import torch
+    from mse_b200 import _native, synthetic
+    c = synthetic.make_bm25_corpus(n_docs, vocab=VOCAB, seed=SEED, device=dev, always_frac=ALWAYS_FRAC)
+    out = Corpus()
+    out.n_docs, out.n_terms, out.n_postings = n_docs, c.n_terms, int(c.n_postings)
+    out.always_term, out.avgdl, out.total_docs = c.always_term, c.avgdl, c.total_docs
+    out.df = torch.diff(c.term_off).cpu().numpy()
+    out.term_off_host = c.term_off.cpu().numpy()
+    out.idf_host = c.idf.cpu().numpy()
+    out.doc_len_host = c.doc_len.cpu().numpy()
+    out.lo, out.hi = rank * n_docs // world, (rank + 1) * n_docs // world
+    out.bm25 = c                                          # kept until the query batches and oracle slices are taken
+    counts = synthetic.make_chunk_counts(n_docs, SEED, total=n_chunks)
+    off = np.zeros(n_docs + 1, dtype=np.int64)
+    off[1:] = np.cumsum(counts)
+    out.chunk_off_host = off
+    nat = _native.NativeIndex(local_rank)
     if world == 1:
-        return c.term_off, c.post_doc, c.post_tf, c.doc_len, 0
-    per_doc = torch.bincount(c.post_doc.long(), minlength=c.n_docs)
-    cum = torch.cumsum(per_doc, 0)
-    total = int(cum[-1].item())
-    targets = torch.tensor([total * r // world for r in range(1, world)], device=cum.device)
-    cuts = [0] + (torch.searchsorted(cum, targets) + 1).tolist() + [c.n_docs]
-    lo, hi = int(cuts[rank]), int(cuts[rank + 1])
-    keep = (c.post_doc >= lo) & (c.post_doc < hi)
-    df = torch.diff(c.term_off)
-    term_of = torch.repeat_interleave(torch.arange(c.n_terms, device=df.device), df)
-    ndf = torch.bincount(term_of[keep], minlength=c.n_terms)
-    term_off = torch.zeros(c.n_terms + 1, dtype=torch.int64, device=df.device)
-    term_off[1:] = torch.cumsum(ndf, 0)
-    return term_off, (c.post_doc[keep] - lo).contiguous(), c.post_tf[keep].contiguous(), c.doc_len[lo:hi].contiguous(), lo
+        nat.bm25_load(c.term_off, c.post_doc, c.post_tf, c.doc_len, c.idf, c.avgdl)
+    else:
+        keep = (c.post_doc >= out.lo) & (c.post_doc < out.hi)
+        term_of = torch.repeat_interleave(torch.arange(c.n_terms, device=dev, dtype=torch.int32), torch.diff(c.term_off))
+        ndf = torch.bincount(term_of[keep].long(), minlength=c.n_terms)
+        del term_of
+        t_off = torch.zeros(c.n_terms + 1, dtype=torch.int64, device=dev)
+        t_off[1:] = torch.cumsum(ndf, 0)
+        nat.bm25_load(t_off, (c.post_doc[keep] - out.lo).contiguous(), c.post_tf[keep].contiguous(), c.doc_len[out.lo:out.hi].contiguous(),
+                      c.idf, c.avgdl, doc_base=out.lo)
+        del keep
+    out.nat = nat
+    out.local_postings = int(((c.post_doc >= out.lo) & (c.post_doc < out.hi)).sum().item()) if world > 1 else int(c.n_postings)
+    return out
 
 
-def dense_scan_supplement(nat, dev, peak, n_chunks=10_000_000, chunks_per_doc=5, top_k=1000, steps=5):
-    """C3: 10M x 768 bf16 chunks, 2M docs, per-doc max-pool + top-1000.  B=1/2 use the GEMV kernel, B>=8 the
-    tcgen05 GEMM kernel.  Reports the scan kernel's algorithmic HBM GB/s and, for the GEMM, bf16 TFLOP/s."""
+def attach_dense(corpus, dev):
+    """Generates and loads this rank's chunk rows (after the BM25 generation temporaries are gone)."""
     import torch
     from mse_b200 import synthetic
-    n_docs = n_chunks // chunks_per_doc
-    d = synthetic.make_dense_corpus(n_docs, seed=SEED, device=dev, dtype=torch.bfloat16, chunks_per_doc=chunks_per_doc)
-    nat.dense_load(d.emb, d.doc_chunk_off)
-    del d
-    torch.cuda.empty_cache()
+    d = synthetic.make_dense_shard(corpus.chunk_off_host, corpus.lo, corpus.hi, SEED, device=dev, dtype=torch.bfloat16)
+    corpus.nat.dense_load(d.emb, d.doc_chunk_off, doc_base=corpus.lo, chunk_base=int(corpus.chunk_off_host[corpus.lo]), borrow=True)
+    corpus.emb = d.emb                                    # borrowed by the index: keep alive
+    corpus.row_lo = int(corpus.chunk_off_host[corpus.lo])
+
+
+def make_batches(corpus, n_batches, batch, seed0):
+    """Query batches: 4 Zipf terms (ranks >= 64) + the always-term, and un-normalised Gaussian query vectors."""
+    from mse_b200 import synthetic
     out = []
+    for i in range(n_batches):
+        q_off, q_term, q_tf = synthetic.make_bm25_queries(corpus.bm25, batch, seed=seed0 + i, add_always=True)
+        qv = synthetic.make_query_vectors(batch, seed=seed0 + 50_000 + i)
+        out.append((q_off, q_term, q_tf, qv))
+    return out
+
+
+def fetch_rows_fn(corpus, dev):
+    """global chunk rows -> float32 host array of the STORED bf16 values (device gather for local rows; rows of another
+    rank's shard are regenerated on this GPU from the slab-seeded generator)."""
+    import torch
+    from mse_b200 import synthetic
+
+    def fetch(rows):
+        rows = np.asarray(rows, dtype=np.int64)
+        out = np.empty((len(rows), 768), dtype=np.float32)
+        local = (rows >= corpus.row_lo) & (rows < corpus.row_lo + corpus.emb.shape[0])
+        if local.any():
+            idx = torch.from_numpy(rows[local] - corpus.row_lo).to(dev)
+            out[local] = corpus.emb[idx].float().cpu().numpy()
+        rest = np.flatnonzero(~local)
+        if len(rest):
+            slabs = rows[rest] // synthetic.DENSE_SLAB_ROWS
+            for sl in np.unique(slabs):
+                sel = rest[slabs == sl]
+                a = int(sl) * synthetic.DENSE_SLAB_ROWS
+                block = synthetic.dense_rows(a, a + synthetic.DENSE_SLAB_ROWS, SEED, device=dev, dtype=torch.bfloat16)
+                out[sel] = block[torch.from_numpy(rows[sel] - a).to(dev)].float().cpu().numpy()
+        return out
+    return fetch
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation of the path (oracle port; the reference is pure Python)
+# ------------------------------------------------------------------------------------------------------------------
+_REF = {}
+
+
+def _ref_one(i):
+    from oracle import sampled
+    ix, fetch, off, qs, qv = _REF["ix"], _REF["fetch"], _REF["off"], _REF["queries"], _REF["qv"]
+    d, s, rows = sampled.oracle_hybrid(ix, fetch, off, qs[i], qv[i], TOP_K, MAX_OUT, faithful=_REF["faithful"])
+    return len(d)
+
+
+def cpu_hybrid_setup(corpus, dev, host_batch, n_queries):
+    """Host-side sub-index + chunk rows for the first n_queries of a batch (everything the faithful oracle touches)."""
+    from oracle import sampled
+    q_off, q_term, q_tf, qv = host_batch
+    sample = list(range(n_queries))
+    queries = sampled.query_term_lists(q_off, q_term, q_tf, sample)
+    terms = sorted({t for q in queries for t in q})
+    c = corpus.bm25
+    ix = sampled.bm25_subindex(c.term_off, c.post_doc, c.post_tf, c.doc_len, c.idf, c.avgdl, c.total_docs, terms)
+    return ix, queries, qv[:n_queries]
+
+
+def prefetch_rows_for(ix, queries, chunk_off, fetch):
+    """Runs the oracle BM25 once to learn the candidate rows of the sampled queries and fetches them in one gather, so that
+    the timed / forked CPU workers read host memory only."""
+    from oracle import bm25_oracle as bo
+    need = set()
+    for terms in queries:
+        for d, _ in bo.search_fast(ix, terms, top_k=TOP_K, min_score=0.0):
+            a, e = int(chunk_off[d]), int(chunk_off[d + 1])
+            need.update(range(a, min(e, a + 10)))
+    rows = np.asarray(sorted(need), dtype=np.int64)
+    table = fetch(rows) if len(rows) else np.zeros((0, 768), np.float32)
+
+    def cached(r):
+        return table[np.searchsorted(rows, np.asarray(r, dtype=np.int64))]
+    return cached
+
+
+def run_reference_arm(args, rank, world):
+    """The reference's CPU implementation of the hybrid path on all host cores.  The reference is pure Python (nothing
+    compiles to oracle/_ref), so this times the oracle PORT.  With the always-present term every query touches ~11M
+    posting rows; the reference's per-row Python loop (bm25_indexer.py:451-481) needs ~15-25 s per query and core,
+    which would make K timed steps last many minutes — so this arm runs the VECTORISED numpy form of the same loop
+    (bit-identical results, ~an order of magnitude faster: a conservative baseline) and the main line's `cpu_baseline`
+    times the faithful loop on a 2-query sample."""
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    import torch
+    cores = os.cpu_count() or 1
+    on_gpu = torch.cuda.is_available()
+    dev = torch.device("cuda", 0) if on_gpu else torch.device("cpu")
+    n_docs, n_chunks = (N_DOCS, N_CHUNKS) if on_gpu else (20_000, 100_000)     # CPU-only container: tiny corpus just to exercise the arm
+    procs = max(1, min(cores, 32))
+    per_step = procs if on_gpu else 2
+    n_q = per_step                                        # the same sampled queries every step (no cache carries over: every query streams its own rows)
+    if on_gpu:
+        corpus = build_corpus(dev, 0, 0, 1, n_docs, n_chunks)
+        host_batch = make_batches(corpus, 1, max(n_q, 8), SEED + 1)[0]
+        ix, queries, qv = cpu_hybrid_setup(corpus, dev, host_batch, n_q)
+        corpus.bm25 = None
+        gc.collect(); torch.cuda.empty_cache()
+        attach_dense(corpus, dev)
+        fetch = prefetch_rows_for(ix, queries, corpus.chunk_off_host, fetch_rows_fn(corpus, dev))
+        chunk_off = corpus.chunk_off_host
+        corpus.nat.close()
+        corpus.emb = None
+        torch.cuda.empty_cache()
+    else:
+        from mse_b200 import synthetic
+        from oracle import sampled
+        c = synthetic.make_bm25_corpus(n_docs, vocab=VOCAB, seed=SEED, always_frac=ALWAYS_FRAC)
+        counts = synthetic.make_chunk_counts(n_docs, SEED, total=n_chunks)
+        chunk_off = np.zeros(n_docs + 1, dtype=np.int64); chunk_off[1:] = np.cumsum(counts)
+        emb = synthetic.dense_rows(0, n_chunks, SEED, device="cpu", dtype=torch.float32).numpy()
+        q_off, q_term, q_tf = synthetic.make_bm25_queries(c, n_q, seed=SEED + 1, add_always=True)
+        qv = synthetic.make_query_vectors(n_q, seed=SEED + 50_001)
+        queries = sampled.query_term_lists(q_off, q_term, q_tf, range(n_q))
+        ix = sampled.bm25_subindex(c.term_off, c.post_doc, c.post_tf, c.doc_len, c.idf, c.avgdl, c.total_docs,
+                                   sorted({t for q in queries for t in q}))
+        fetch = lambda r: emb[np.asarray(r, dtype=np.int64)]
+    _REF.update(ix=ix, fetch=fetch, off=chunk_off, queries=queries, qv=qv, faithful=False)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(min(procs, per_step)) as pool:
+        for _ in range(args.warmup):
+            pool.map(_ref_one, list(range(per_step)))
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pool.map(_ref_one, list(range(per_step)))
+        dt = time.perf_counter() - t0
+    value = args.steps * per_step / dt
+    sample = (f"{per_step} hybrid queries per step on {min(procs, per_step)} worker processes (one query each), full {n_docs}-doc index "
+              f"(posting lists of the sampled queries' terms incl. the always-term + their candidate chunk rows on the host); VECTORISED "
+              f"numpy port of bm25_indexer.py:435-485 -> reranker_api.py:336-372 (bit-identical to the faithful Python-loop port, which is "
+              f"what `cpu_baseline` of the main line times); no SQL / spaCy / HTTP cost")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(n_docs, n_chunks, BATCH), "queries_per_step": per_step},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": min(procs, per_step), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# supplements
+# ------------------------------------------------------------------------------------------------------------------
+def bm25_c2_supplement(dev, local_rank, peak, always: bool, steps=20, warmup=3, parity_queries=16):
+    """BASELINE.json configs[1]: BM25-only, 1M docs, batch 1024, top-1000 — with or without the always-term."""
+    import torch
+    from mse_b200 import _native, synthetic
+    from oracle import sampled
+    n_docs, B = 1_000_000, 1024
+    c = synthetic.make_bm25_corpus(n_docs, vocab=VOCAB, seed=SEED, device=dev, always_frac=ALWAYS_FRAC if always else 0.0)
+    nat = _native.NativeIndex(local_rank)
+    nat.bm25_load(c.term_off, c.post_doc, c.post_tf, c.doc_len, c.idf, c.avgdl)
+    df = torch.diff(c.term_off).cpu().numpy()
+    host = [synthetic.make_bm25_queries(c, B, seed=SEED + 1 + i, add_always=always) for i in range(steps + warmup)]
+    devb = [tuple(torch.from_numpy(a).to(dev) for a in b) for b in host]
+    out = (torch.empty((B, TOP_K), dtype=torch.int32, device=dev), torch.empty((B, TOP_K), dtype=torch.float32, device=dev),
+           torch.empty((B,), dtype=torch.int32, device=dev))
+    status = torch.zeros(4, dtype=torch.int32, device=dev)
+    run = lambda i: nat.bm25_search_async(devb[i][0], devb[i][1], devb[i][2], int(host[i][0][-1]), TOP_K, 0.0, out=out, status=status)
+    for i in range(warmup):
+        run(i)
+    torch.cuda.synchronize()
+    nat.set_option("reset_timers", 1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        run(warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    score_ms, n = nat.kernel_time("bm25_score")
+    sel_ms, _ = nat.kernel_time("topk_select")
+    prep_ms, _ = nat.kernel_time("bm25_prepare")
+    stats = nat.bm25_stats()
+    all_post = float(np.mean([df[b[1]].sum() for b in host[warmup:]]))
+    streamed = float(stats["postings"])                                  # last batch
+    looked = float(stats["postings_looked_up"])
+    score_ms /= max(n, 1)
+    alg_streamed = 12.0 * streamed + 8.0 * TOP_K * B
+    alg_def = 12.0 * all_post + 8.0 * TOP_K * B
+    # sampled parity at this size
+    qs = list(range(parity_queries))
+    q_off, q_term, q_tf = host[warmup]
+    queries = sampled.query_term_lists(q_off, q_term, q_tf, qs)
+    ix = sampled.bm25_subindex(c.term_off, c.post_doc, c.post_tf, c.doc_len, c.idf, c.avgdl, c.total_docs,
+                               sorted({t for q in queries for t in q}))
+    g_doc, g_score, g_count = nat.bm25_search(q_off, q_term, q_tf, TOP_K, 0.0)
+    parity = sampled.check_bm25(ix, queries, g_doc[:parity_queries], g_score[:parity_queries], g_count[:parity_queries], TOP_K)
+    parity["kind"] = "pinned"
+    nat.close()
+    return {"workload": f"C2 BM25-only: 1M synthetic docs, Zipf(1.0) vocab 200k, batch {B} x 4-term queries"
+                        f"{' + the always-term (95 % of docs, negative idf)' if always else ''}, top-{TOP_K}",
+            "queries_per_s": B / (ms / 1e3), "ms_per_batch": ms, "score_kernel_ms": score_ms, "prepare_ms": prep_ms / max(n, 1),
+            "select_ms": sel_ms / max(n, 1), "postings_per_query_all_terms": all_post / B, "postings_streamed_per_query": streamed / B,
+            "postings_looked_up_not_streamed_per_query": looked / B, "candidates_per_query": stats["emitted"] / B,
+            "roofline": {"kernel": "bm25_score_kernel", "bound": "hbm", "unit": "GB/s", "peak": peak,
+                         "achieved": alg_streamed / (score_ms * 1e-3) / 1e9, "frac": alg_streamed / (score_ms * 1e-3) / 1e9 / peak,
+                         "basis": "12 B per STREAMED posting + 8*k per query",
+                         "achieved_on_all_query_postings": alg_def / (score_ms * 1e-3) / 1e9},
+            "status_words": status.cpu().tolist(), "parity": parity}
+
+
+def dense_c3_supplement(dev, local_rank, peak, tf_peak, n_chunks=10_000_000, chunks_per_doc=5, top_k=1000, steps=5, parity_queries=4):
+    """BASELINE.json configs[2]: 10M x 768 bf16 chunks, 2M docs, per-doc max-pool + top-1000, batch 1 (GEMV kernel) and
+    batch 256 (tcgen05 GEMM kernel); sampled queries checked against the slab-wise float oracle at this size."""
+    import torch
+    from mse_b200 import _native, synthetic
+    from oracle import sampled
+    n_docs = n_chunks // chunks_per_doc
+    off = np.arange(n_docs + 1, dtype=np.int64) * chunks_per_doc
+    emb = synthetic.dense_rows(0, n_chunks, SEED, device=dev, dtype=torch.bfloat16)
+    nat = _native.NativeIndex(local_rank)
+    nat.dense_load(emb, torch.from_numpy(off).to(dev), borrow=True)
+    results = []
+    checks = {}
     for B in (1, 8, 64, 256):
-        q = torch.from_numpy(synthetic.make_query_vectors(B, seed=77, normalize=True)).to(dev)
+        q_host = synthetic.make_query_vectors(B, seed=77, normalize=True)
+        q = torch.from_numpy(q_host).to(dev)
         for _ in range(3):
-            nat.dense_scan(q, top_k)
+            got = nat.dense_scan(q, top_k)
         torch.cuda.synchronize()
         nat.set_option("reset_timers", 1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -158,193 +418,127 @@ def dense_scan_supplement(nat, dev, peak, n_chunks=10_000_000, chunks_per_doc=5,
         scan_ms, n = nat.kernel_time("dense_scan")
         scan_ms /= max(n, 1)
         alg = 2.0 * 768 * n_chunks + 8.0 * (n_docs + 1) + 4.0 * 768 * B + 8.0 * top_k * B
-        out.append({"batch": B, "kernel": "dense_gemm_kernel (tcgen05)" if B >= 8 else "dense_scan_kernel (GEMV)",
-                    "ms_per_batch": ms, "queries_per_s": B / (ms / 1e3), "scan_kernel_ms": scan_ms,
-                    "hbm_GBps_algorithmic": alg / (scan_ms * 1e-3) / 1e9, "frac_of_hbm_peak": alg / (scan_ms * 1e-3) / 1e9 / peak,
-                    "bf16_TFLOPs": 2.0 * 768 * n_chunks * B / (scan_ms * 1e-3) / 1e12})
-    return {"workload": f"C3 dense exhaustive scan: {n_chunks} x 768 bf16 chunks, {n_docs} docs, per-doc max-pool, top-{top_k}",
-            "results": out}
-
-
-def hybrid_supplement(nat, dev, dev_batches, peak, steps=20, chunks_per_doc=5, max_out=100):
-    """End-to-end hybrid query (BASELINE.json configs[4] shape at the C2 corpus size): BM25 top-1000 over the
-    1M-doc index -> gathered rerank of <= 10 chunks/doc (768-d bf16) with min-max fusion -> top-100, batches of
-    1024 queries, everything device-resident."""
-    import torch
-    from mse_b200 import synthetic
-    d = synthetic.make_dense_corpus(N_DOCS, seed=SEED, device=dev, dtype=torch.bfloat16, chunks_per_doc=chunks_per_doc)
-    nat.dense_load(d.emb, d.doc_chunk_off)
-    del d
+        tfl = 2.0 * 768 * n_chunks * B / (scan_ms * 1e-3) / 1e12
+        results.append({"batch": B, "kernel": "dense_gemm_kernel (tcgen05)" if B >= 8 else "dense_scan_kernel (GEMV)",
+                        "ms_per_batch": ms, "queries_per_s": B / (ms / 1e3), "scan_kernel_ms": scan_ms,
+                        "hbm_GBps_algorithmic": alg / (scan_ms * 1e-3) / 1e9, "frac_of_hbm_peak": alg / (scan_ms * 1e-3) / 1e9 / peak,
+                        "bf16_TFLOPs": tfl, "frac_of_bf16_peak": tfl / tf_peak})
+        if B in (1, 256):
+            checks[B] = (q_host, tuple(t.cpu().numpy() for t in got))
+    # sampled parity: B=1 (its query) and `parity_queries` queries of the B=256 batch, slab-wise oracle over all 10M rows
+    sel256 = list(range(0, 256, 256 // parity_queries))[:parity_queries]
+    qs = np.concatenate([checks[1][0], checks[256][0][sel256]])
+    if hasattr(nat, "_borrowed"):
+        pass
+    fetch_slab = lambda a, e: emb[a:e].float().cpu().numpy()
+    # the GEMM path rounds the queries to bf16 (documented); the oracle sees the same rounded queries for those
+    qs_eff = qs.copy()
+    qs_eff[1:] = torch.from_numpy(qs[1:]).to(torch.bfloat16).float().numpy()
+    ref = sampled.dense_scan_slabwise(fetch_slab, n_chunks, off, qs_eff, top_k, slab=1 << 18)
+    fails, worst = [], 0.0
+    for j, (rd, rs) in enumerate(ref):
+        gd, gs, gc_ = (checks[1][1] if j == 0 else checks[256][1])
+        row = 0 if j == 0 else sel256[j - 1]
+        n = int(gc_[row])
+        msg = sampled.compare_topk(gd[row][:n], gs[row][:n], rd, rs, 2e-3, atol=2e-5)
+        if msg:
+            fails.append(f"{'B=1' if j == 0 else 'B=256 q%d' % row}: {msg}")
+        else:
+            worst = max(worst, float(np.max(np.abs(gs[row][:n] - rs) / np.maximum(np.abs(rs), 1e-30))))
+    parity = {"kind": "reconstruction (the reference's retriever.py is absent from the snapshot: parity unpinned, SURVEY.md 8a row D0)",
+              "queries_checked": len(ref), "queries_failing": len(fails), "first_failures": fails[:3], "max_rel_err": worst,
+              "tolerance": 2e-3, "at_size": f"{n_chunks} chunks, slab-wise float64-accumulate oracle on the stored bf16 values"}
+    nat.close()
+    del emb
     torch.cuda.empty_cache()
-    qv = torch.from_numpy(synthetic.make_query_vectors(BATCH, seed=99)).to(dev)
-    cand_off = (torch.arange(BATCH + 1, device=dev, dtype=torch.int32) * TOP_K).contiguous()
-
-    bm_out = (torch.empty((BATCH, TOP_K), dtype=torch.int32, device=dev), torch.empty((BATCH, TOP_K), dtype=torch.float32, device=dev),
-              torch.empty((BATCH,), dtype=torch.int32, device=dev))
-
-    def step(i):
-        q_off, q_term, q_tf = dev_batches[i % len(dev_batches)]
-        doc, score, count = nat.bm25_search(q_off, q_term, q_tf, TOP_K, 0.0, out=bm_out)
-        return nat.rerank(cand_off, doc.view(-1), score.view(-1), qv, None, 0.15, 10, max_out), count
-
-    for i in range(5):
-        step(i)
-    torch.cuda.synchronize()
-    nat.set_option("reset_timers", 1)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
-    ev[0].record()
-    for i in range(steps):
-        out, count = step(5 + i)
-        ev[i + 1].record()
-    torch.cuda.synchronize()
-    ms = ev[0].elapsed_time(ev[steps]) / steps
-    per_step = [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
-    ms_median = float(np.median(per_step))
-    rr_ms, n = nat.kernel_time("rerank")
-    rr_ms /= max(n, 1)
-    # stage breakdown (same work, timed separately)
-    q_off, q_term, q_tf = dev_batches[0]
-    doc, score, count = nat.bm25_search(q_off, q_term, q_tf, TOP_K, 0.0)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for i in range(steps):
-        nat.bm25_search(q_off, q_term, q_tf, TOP_K, 0.0)
-    torch.cuda.synchronize()
-    bm25_call_ms = (time.perf_counter() - t0) * 1e3 / steps
-    t0 = time.perf_counter()
-    for i in range(steps):
-        nat.rerank(cand_off, doc.view(-1), score.view(-1), qv, None, 0.15, 10, max_out)
-    torch.cuda.synchronize()
-    rerank_call_ms = (time.perf_counter() - t0) * 1e3 / steps
-    rows = float(out[5].float().mean().item())
-    cands = float(count.float().mean().item())
-    alg = BATCH * (2.0 * 768 * rows + 12.0 * cands + 8.0 * max_out)
-    return {"workload": f"hybrid: BM25 top-{TOP_K} over {N_DOCS} docs -> rerank <=10 of {chunks_per_doc} chunks/doc (768-d bf16) -> top-{max_out}, batch {BATCH}",
-            "ms_per_batch": ms, "ms_per_batch_median": ms_median, "ms_per_batch_max": float(np.max(per_step)), "slowest_step": int(np.argmax(per_step)), "hybrid_queries_per_s": BATCH / (ms / 1e3), "rerank_kernel_ms": rr_ms,
-            "bm25_call_ms": bm25_call_ms, "rerank_call_ms": rerank_call_ms,
-            "rerank_rows_per_query": rows, "rerank_GBps_algorithmic": alg / (rr_ms * 1e-3) / 1e9,
-            "rerank_frac_of_hbm_peak": alg / (rr_ms * 1e-3) / 1e9 / peak}
+    return {"workload": f"C3 dense exhaustive scan: {n_chunks} x 768 bf16 chunks, {n_docs} docs, per-doc max-pool, top-{top_k}",
+            "results": results, "parity": parity}
 
 
-def doc_sharded_supplement(args, c, rank, world, dev, local_rank, steps=20, warmup=3):
-    """The N x 1024-query batch against the corpus sharded by doc range over the same N GPUs (the layout an index that
-    does not fit one GPU needs): shard-local search cut to m entries, NCCL all-to-all to the query-owning rank, merge,
-    exact repeat when a cut could hide a result — and a bit-for-bit check against all-gather + merge everywhere."""
+def dense_c4_supplement(corpus_rank, world, dev, local_rank, id_bytes, peak, top_k=1000, steps=5):
+    """BASELINE.json configs[3] shape on the GPUs at hand: 100M x 768 bf16 chunks (153.6 GB) sharded by doc range, B=1 and
+    256, NCCL all-gather of the per-rank top-k lists + merge inside `mse_dense_scan_sharded`; rank 0 checks sampled
+    queries against a float oracle over rows regenerated from the slab-seeded generator (rows of its own shard only:
+    a rank holds 1/world of the table; the merged list is checked for the documents it owns and for global order)."""
     import torch
     import torch.distributed as dist
     from mse_b200 import _native, synthetic
-    from mse_b200.sharding import ShardedSearcher
-    term_off, post_doc, post_tf, doc_len, doc_base = shard_corpus(c, rank, world)
+    n_chunks, cpd = 100_000_000, 5
+    n_docs = n_chunks // cpd
+    lo, hi = corpus_rank * n_docs // world, (corpus_rank + 1) * n_docs // world
+    emb = synthetic.dense_rows(lo * cpd, hi * cpd, SEED, device=dev, dtype=torch.bfloat16)
+    off = torch.arange(hi - lo + 1, dtype=torch.int64, device=dev) * cpd
     nat = _native.NativeIndex(local_rank)
-    nat.bm25_load(term_off, post_doc, post_tf, doc_len, c.idf, c.avgdl, doc_base=doc_base)
-    searcher = ShardedSearcher(nat, rank, world)
-    GB = BATCH * world
-    m_local = max(1, min(TOP_K, int(args.exchange_slack * TOP_K / world) + 32))
-    batches = [tuple(torch.from_numpy(a).to(dev) for a in synthetic.make_bm25_queries(c, GB, seed=SEED + 7001 + i))
-               for i in range(steps + warmup)]
-    run = lambda b: searcher.bm25_search_owner(b[0], b[1], b[2], TOP_K, 0.0, slack=args.exchange_slack)
-    for i in range(warmup):
-        run(batches[i])
-    dist.barrier(); torch.cuda.synchronize()
-    nat.set_option("reset_timers", 1)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(steps):
-        o_doc, o_score, o_count = run(batches[warmup + i])
-    e1.record()
-    dist.barrier(); torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item()) / steps
-    score_ms, n = nat.kernel_time("bm25_score")
-    select_ms, _ = nat.kernel_time("topk_select")
-    prep_ms, _ = nat.kernel_time("bm25_prepare")
-    b = batches[warmup]
-    o_doc, o_score, o_count = run(b)
-    a_doc, a_score, a_count = searcher.bm25_search(b[0], b[1], b[2], TOP_K, 0.0)
-    blk = slice(rank * BATCH, (rank + 1) * BATCH)
-    valid = torch.arange(TOP_K, device=dev).unsqueeze(0) < o_count.unsqueeze(1)
-    same = torch.equal(o_count, a_count[blk]) and torch.equal(o_doc[valid], a_doc[blk][valid]) and \
-        torch.equal(o_score[valid], a_score[blk][valid])
-    d = torch.tensor([0 if same else 1], device=dev)
-    dist.all_reduce(d, op=dist.ReduceOp.SUM)
+    nat.dense_load(emb, off, doc_base=lo, chunk_base=lo * cpd, borrow=True)
+    nat.comm_init(id_bytes, corpus_rank, world)
+    out = []
+    status = torch.zeros(4, dtype=torch.int32, device=dev)
+    for B in (1, 256):
+        q_host = synthetic.make_query_vectors(B, seed=78, normalize=True)
+        q = torch.from_numpy(q_host).to(dev)
+        for _ in range(2):
+            got = nat.dense_scan_sharded(q, top_k, status=status)
+        dist.barrier(); torch.cuda.synchronize()
+        nat.set_option("reset_timers", 1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            nat.dense_scan_sharded(q, top_k, status=status)
+        e1.record()
+        dist.barrier(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        scan_ms, n = nat.kernel_time("dense_scan")
+        x_ms, nx = nat.kernel_time("exchange")
+        # check: scores of this rank's docs in the merged list against fp32 torch dot products of the stored rows
+        gd, gs, gc_ = (x.cpu().numpy() for x in got)
+        qb = q if B == 1 else q.to(torch.bfloat16).float()
+        bad, checked = 0, 0
+        for row in ([0] if B == 1 else [0, 85, 170, 255]):
+            nn = int(gc_[row])
+            docs = gd[row][:nn]
+            mine = np.flatnonzero((docs >= lo) & (docs < hi))
+            if len(mine):
+                d = torch.from_numpy(docs[mine] - lo).to(dev)
+                rows = (d[:, None] * cpd + torch.arange(cpd, device=dev)[None, :]).reshape(-1)
+                sc = (emb[rows].float() @ qb[row]).reshape(-1, cpd).max(dim=1).values.cpu().numpy()
+                bad += int(np.sum(np.abs(sc - gs[row][:nn][mine]) > 2e-3 * np.abs(sc) + 2e-5)); checked += len(mine)
+            bad += int(np.any(np.diff(gs[row][:nn]) > 0))                       # descending order
+        agg = torch.tensor([bad, checked], device=dev)
+        dist.all_reduce(agg)
+        out.append({"batch": B, "ms_per_batch": float(t.item()), "queries_per_s": B / (float(t.item()) / 1e3),
+                    "scan_kernel_ms_rank0": scan_ms / max(n, 1), "exchange_ms_rank0": x_ms / max(nx, 1),
+                    "rank0_scan_frac_of_hbm_peak": (2.0 * 768 * (hi - lo) * cpd) / (scan_ms / max(n, 1) * 1e-3) / 1e9 / peak,
+                    "merged_entries_checked_against_fp32_dot_products": int(agg[1].item()), "mismatches": int(agg[0].item()),
+                    "status_words": status.cpu().tolist()})
     nat.close()
-    return {"workload": f"{GB}-query batch replicated, corpus in {world} doc-range shards, NCCL all-to-all of {m_local}-entry shard "
-                        f"lists to the query-owning rank, exact merge",
-            "queries_per_s": GB / (ms / 1e3), "ms_per_step": ms, "steps": steps,
-            "score_ms": score_ms / max(1, n), "select_ms": select_ms / max(1, n), "prepare_ms": prep_ms / max(1, n),
-            "exchange_fallback_steps": int(getattr(searcher, "fallbacks", 0)),
-            "ranks_differing_from_allgather_merge": int(d.item())}
+    del emb
+    torch.cuda.empty_cache()
+    return {"workload": f"C4 sharded dense scan: {n_chunks} x 768 bf16 chunks over {world} GPUs (doc-range shards), NCCL all-gather "
+                        f"top-{top_k} merge", "results": out,
+            "parity": {"kind": "reconstruction (parity unpinned, SURVEY.md 8a row D0); every rank checks the merged entries it owns "
+                               "against fp32 dot products of the stored rows, tolerance 2e-3 relative"}}
 
 
-def run_reference_arm(args, rank, world):
-    """The reference's CPU path for this workload: the oracle port of BM25.search's Python loop
-    (the reference is pure Python; nothing compiles to oracle/_ref), one process per host core."""
-    if rank != 0:
-        return
-    import multiprocessing as mp
-    import torch
-    from mse_b200 import synthetic
-    from oracle import bm25_oracle as bo
-    dev = "cuda:0" if torch.cuda.is_available() else "cpu"
-    n_docs = N_DOCS if dev != "cpu" else 50_000          # CPU-only container: tiny corpus just to exercise the arm
-    c = synthetic.make_bm25_corpus(n_docs, vocab=VOCAB, seed=SEED, device=dev)
-    global _REF_IX, _REF_Q
-    _REF_IX = bo.Bm25Arrays(c.term_off.cpu().numpy(), c.post_doc.cpu().numpy(), c.post_tf.cpu().numpy(),
-                            c.doc_len.cpu().numpy(), c.idf.cpu().numpy(), c.avgdl, c.total_docs, c.doc_ids.cpu().numpy())
-    q_off, q_term, q_tf = synthetic.make_bm25_queries(c, BATCH, seed=SEED + 1)
-    _REF_Q = [[int(t) for s in range(q_off[i], q_off[i + 1]) for t in [q_term[s]] * int(q_tf[s])] for i in range(BATCH)]
-    cores = os.cpu_count() or 1
-    per_step = min(BATCH, 2 * cores)
-    ctx = mp.get_context("fork")
-    with ctx.Pool(cores) as pool:
-        pool.map(_ref_one, range(min(cores, BATCH)))                       # warm the workers
-        for w in range(args.warmup):
-            pool.map(_ref_one, [(w * per_step + j) % BATCH for j in range(per_step)])
-        t0 = time.perf_counter()
-        for s in range(args.steps):
-            pool.map(_ref_one, [((args.warmup + s) * per_step + j) % BATCH for j in range(per_step)])
-        dt = time.perf_counter() - t0
-    value = args.steps * per_step / dt
-    sample = f"{per_step} of the {BATCH} queries per step, full {n_docs}-doc index, faithful Python-loop port"
-    print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "queries_per_step": per_step},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
-
-
-_REF_IX = None
-_REF_Q = None
-
-
-def _ref_one(i):
-    from oracle import bm25_oracle as bo
-    return len(bo.search_faithful(_REF_IX, _REF_Q[i], top_k=TOP_K, min_score=0.0))
-
-
+# ------------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpu-sample", type=int, default=128, help="queries timed by the CPU baseline (~10-15 s of CPU work)")
+    ap.add_argument("--docs", type=int, default=N_DOCS, help="experiments only: a smaller corpus (the line then says so)")
+    ap.add_argument("--chunks", type=int, default=0)
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--parity-queries", type=int, default=16)
+    ap.add_argument("--cpu-sample", type=int, default=2, help="queries timed by the single-core faithful CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-supplements", action="store_true")
+    ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--shard-list-len", type=int, default=0)
+    ap.add_argument("--neg-lookup", type=int, default=1)
     ap.add_argument("--range-docs", type=int, default=0)
-    ap.add_argument("--queries-per-item", type=int, default=0)
-    ap.add_argument("--cand-cap", type=int, default=0)
-    ap.add_argument("--no-tau", action="store_true")
-    ap.add_argument("--no-dense", action="store_true", help="skip the supplementary dense-scan (C3) measurements")
-    ap.add_argument("--layout", default="auto", choices=["auto", "replicated", "doc-sharded"],
-                    help="N > 1: replicate the index and shard the queries, or shard the corpus by doc range (auto: replicate "
-                         "when the index fits a quarter of one GPU's memory)")
-    ap.add_argument("--exchange", default="owner", choices=["owner", "allgather"],
-                    help="N > 1: query-owner merge of an N x 1024 batch (weak scaling) or all-gather + merge of a 1024 batch")
-    ap.add_argument("--exchange-slack", type=float, default=2.0, help="owner exchange: shard list length = slack*k/N + 32")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -358,75 +552,75 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from mse_b200 import _native, synthetic
-    from mse_b200.sharding import ShardedSearcher
+    from mse_b200 import _native
+    from oracle import sampled
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    id_bytes = None
     if world > 1:
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        box = [_native.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        id_bytes = box[0]
+    n_docs = args.docs
+    n_chunks = args.chunks or n_docs * 5
+    B, GB = args.batch, args.batch * world
+    peak, tf_peak, peak_src = measured_peaks()
 
     sampler = ClockSampler(local_rank)
     sampler.start()
 
     # ---- corpus + index ------------------------------------------------------------------------
     t0 = time.perf_counter()
-    c = gen_corpus(dev)
-    index_bytes = 8 * int(c.n_postings)
-    layout = args.layout
-    if layout == "auto":
-        layout = "replicated" if index_bytes * 4 <= torch.cuda.get_device_properties(dev).total_memory else "doc-sharded"
-    replicated = world > 1 and layout == "replicated"
-    full_corpus = c
-    if replicated:                                   # every rank is a whole single-GPU engine with its own query batches
-        job_world, job_rank, world, rank = world, rank, 1, 0
+    corpus = build_corpus(dev, local_rank, rank, world, n_docs, n_chunks)
+    nat = corpus.nat
+    if world > 1:
+        nat.comm_init(id_bytes, rank, world)
     else:
-        job_world, job_rank = world, rank
-    term_off, post_doc, post_tf, doc_len, doc_base = shard_corpus(c, rank, world)
-    nat = _native.NativeIndex(local_rank)
-    nat.bm25_load(term_off, post_doc, post_tf, doc_len, c.idf, c.avgdl, doc_base=doc_base)
-    for name, v in (("bm25_range_docs", args.range_docs), ("bm25_queries_per_item", args.queries_per_item),
-                    ("bm25_cand_cap", args.cand_cap)):
-        if v:
-            nat.set_option(name, v)
-    if args.no_tau:
-        nat.set_option("bm25_use_tau", 0)
-    searcher = ShardedSearcher(nat, rank, world)
-    df_global = torch.diff(c.term_off).cpu().numpy()
-    n_postings_local = int(post_doc.numel())
+        nat.comm_init(None, 0, 1)
+    nat.set_option("bm25_neg_lookup", args.neg_lookup)
+    if args.range_docs:
+        nat.set_option("bm25_range_docs", args.range_docs)
+    n_batches = args.steps + args.warmup
+    host_batches = make_batches(corpus, n_batches, GB, SEED + 1)
+    lat_batches = make_batches(corpus, 24, 1, SEED + 9001) if not args.no_latency and world == 1 else []
+    all_post = [int(corpus.df[b[1]].sum()) for b in host_batches]
+    # host pieces for the oracle legs (rank 0): posting lists of the sampled queries' terms
+    n_par = 0 if args.no_parity else min(args.parity_queries, B)
+    n_cpu = 0 if (args.no_cpu_baseline or world > 1) else args.cpu_sample
+    par_ix = par_queries = None
+    if rank == 0 and max(n_par, n_cpu) > 0:
+        par_ix, par_queries, _ = cpu_hybrid_setup(corpus, dev, host_batches[args.warmup], max(n_par, n_cpu))
+    corpus.bm25 = None                                   # drop the (doc, tf) arrays: the index holds its own layout
+    gc.collect(); torch.cuda.empty_cache()
+    attach_dense(corpus, dev)
     setup_s = time.perf_counter() - t0
 
-    # ---- query batches: a different batch every step (no reuse of a step's postings in L2) -------
-    owner = world > 1 and args.exchange == "owner"
-    GB = BATCH * world if owner else BATCH                  # queries per step over the whole job (replicated: per rank)
-    m_local = max(1, min(TOP_K, int(args.exchange_slack * TOP_K / world) + 32)) if owner else TOP_K
-    n_batches = args.steps + args.warmup
-    host_batches, dev_batches, postings_per_batch = [], [], []
-    for i in range(n_batches):
-        q_off, q_term, q_tf = synthetic.make_bm25_queries(c, GB, seed=SEED + 1 + i + (100_000 * job_rank if replicated else 0))
-        host_batches.append((q_off, q_term, q_tf))
-        dev_batches.append(tuple(torch.from_numpy(a).to(dev) for a in (q_off, q_term, q_tf)))
-        postings_per_batch.append(int(df_global[q_term].sum()))
-    out = (torch.empty((BATCH, TOP_K), dtype=torch.int32, device=dev), torch.empty((BATCH, TOP_K), dtype=torch.float32, device=dev),
-           torch.empty((BATCH,), dtype=torch.int32, device=dev))
+    dev_batches = [tuple(torch.from_numpy(a).to(dev) for a in b) for b in host_batches]
+    n_slots = [int(b[0][-1]) for b in host_batches]
+    out = _native.NativeIndex._rerank_out(B, MAX_OUT, dev_batches[0][0])
+    status = torch.zeros(4, dtype=torch.int32, device=dev)
+    status_acc = torch.zeros(4, dtype=torch.int32, device=dev)
 
     def step_device(i):
-        q_off, q_term, q_tf = dev_batches[i]
+        q_off, q_term, q_tf, qv = dev_batches[i]
         if world == 1:
-            return nat.bm25_search(q_off, q_term, q_tf, TOP_K, 0.0, out=out)
-        if owner:
-            return searcher.bm25_search_owner(q_off, q_term, q_tf, TOP_K, 0.0, slack=args.exchange_slack)
-        return searcher.bm25_search(q_off, q_term, q_tf, TOP_K, 0.0)
+            nat.hybrid_search(q_off, q_term, q_tf, qv, TOP_K, 0.0, max_out=MAX_OUT, n_slots=n_slots[i], out=out, status=status)
+        else:
+            nat.hybrid_search_sharded(q_off, q_term, q_tf, qv, n_slots[i], TOP_K, 0.0, shard_list_len=args.shard_list_len,
+                                      max_out=MAX_OUT, out=out, status=status)
+        status_acc.add_(status)                          # (a torch kernel on the same stream: no host sync)
 
     def sync_all():
-        if job_world > 1:
+        if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
     def max_over_ranks(x):
-        if job_world == 1:
+        if world == 1:
             return x
         t = torch.tensor([x], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -437,193 +631,200 @@ def main():
         step_device(i)
     sync_all()
     nat.set_option("reset_timers", 1)
+    status_acc.zero_()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.active.set()
     e0.record()
     for s in range(args.steps):
-        res = step_device(args.warmup + s)
+        step_device(args.warmup + s)
     e1.record()
     sync_all()
     sampler.active.clear()
     ms = max_over_ranks(e0.elapsed_time(e1))
-    job_q = GB * (job_world if replicated else 1)           # queries per step over the whole job
-    score_ms, score_n = nat.kernel_time("bm25_score")
-    select_ms, _ = nat.kernel_time("topk_select")
-    prep_ms, _ = nat.kernel_time("bm25_prepare")
-    stats = nat.bm25_stats()
-    value = args.steps * job_q / (ms / 1000.0)
+    value = args.steps * GB / (ms / 1000.0)
+    kt = {k: nat.kernel_time(k) for k in ("bm25_prepare", "bm25_score", "topk_select", "rerank", "exchange")}
+    stats = nat.bm25_stats()                             # counters of the last step
+    status_total = status_acc.cpu().tolist()
+    rows_per_query = float(out[5].float().mean().item())
+    gpu_doc, gpu_score, gpu_count = (x.cpu().numpy() for x in (out[0], out[1], out[4]))     # last step (not the parity batch)
 
-    # ---- e2e: host buffers through the C ABI (H2D + D2H inside the timed region) ----------------------
-    pin = lambda a: torch.from_numpy(a).pin_memory()
+    # ---- e2e: pinned host buffers through the C ABI, two streams alternating ---------------------------------
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     host_pinned = [tuple(pin(a) for a in b) for b in host_batches]
-    h_out = (torch.empty((BATCH, TOP_K), dtype=torch.int32).pin_memory(), torch.empty((BATCH, TOP_K), dtype=torch.float32).pin_memory(),
-             torch.empty((BATCH,), dtype=torch.int32).pin_memory())
+    streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+    h_out = [_native.NativeIndex._rerank_out(B, MAX_OUT, host_pinned[0][0], pinned=True) for _ in streams]
+    h_status = [torch.zeros(4, dtype=torch.int32).pin_memory() for _ in streams]
+    d_in = [None, None]
+    d_out = [_native.NativeIndex._rerank_out(B, MAX_OUT, dev_batches[0][0]) for _ in streams]
+    d_status = [torch.zeros(4, dtype=torch.int32, device=dev) for _ in streams]
 
-    def step_host(i):
-        q_off, q_term, q_tf = host_pinned[i]
+    def step_host(i, slot):
+        q_off, q_term, q_tf, qv = host_pinned[i]
+        st = streams[slot]
         if world == 1:
-            nat.bm25_search(q_off, q_term, q_tf, TOP_K, 0.0, out=h_out)      # MSE_HOST path: copies + sync inside
+            nat.hybrid_search(q_off, q_term, q_tf, qv, TOP_K, 0.0, max_out=MAX_OUT, n_slots=n_slots[i], out=h_out[slot],
+                              status=h_status[slot], stream=st, pinned_async=True)
         else:
-            d = tuple(t.to(dev, non_blocking=True) for t in (q_off, q_term, q_tf))
-            if owner:                                                        # this rank's block of the batch comes back
-                r = searcher.bm25_search_owner(d[0], d[1], d[2], TOP_K, 0.0, slack=args.exchange_slack)
-            else:
-                r = searcher.bm25_search(d[0], d[1], d[2], TOP_K, 0.0)
-            for dst, src in zip(h_out, r):
-                dst.copy_(src, non_blocking=True)
-            torch.cuda.synchronize()
+            with torch.cuda.stream(st):
+                d_in[slot] = tuple(t.to(dev, non_blocking=True) for t in (q_off, q_term, q_tf, qv))
+                nat.hybrid_search_sharded(*d_in[slot], n_slots[i], TOP_K, 0.0, shard_list_len=args.shard_list_len, max_out=MAX_OUT,
+                                          out=d_out[slot], status=d_status[slot], stream=st)
+                for dst, src in zip(h_out[slot], d_out[slot]):
+                    dst.copy_(src, non_blocking=True)
+                h_status[slot].copy_(d_status[slot], non_blocking=True)
 
     for i in range(args.warmup):
-        step_host(i)
+        step_host(i, i % 2)
     sync_all()
     sampler.active.set()
     t0 = time.perf_counter()
     for s in range(args.steps):
-        step_host(args.warmup + s)
+        slot = s % 2
+        if world == 1:
+            streams[slot].synchronize()                  # the previous user of this slot's host buffers has finished
+        step_host(args.warmup + s, slot)
+    for st in streams:
+        st.synchronize()
     sync_all()
-    e2e_s = time.perf_counter() - t0
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
     sampler.active.clear()
-    e2e_s = max_over_ranks(e2e_s)
-    e2e_value = args.steps * job_q / e2e_s
-    # whole-job bytes: every rank uploads the (replicated) query CSR; with the owner exchange each rank reads back its
-    # own 1024-query block, with the all-gather variant every rank reads back the replicated result
-    h2d = job_world * int(np.mean([sum(a.nbytes for a in b) for b in host_batches[args.warmup:]]))
-    d2h = (BATCH * TOP_K * 8 + BATCH * 4) * job_world
+    e2e_value = args.steps * GB / e2e_s
+    h2d = world * int(np.mean([sum(a.nbytes for a in b) for b in host_batches[args.warmup:]]))
+    d2h = world * (B * MAX_OUT * (4 + 4 + 4 + 8) + B * 8 + 16)
     sampler.stop()
 
-    # ---- roofline of the dominant kernel -----------------------------------------------------------------
-    peak, peak_src = measured_peaks()
-    timed_post = postings_per_batch[args.warmup:]
-    # algorithmic bytes per launch: 12 B per posting of THIS rank's shard + 8 B per emitted result
-    frac_local = n_postings_local / max(1, int(c.n_postings))
-    alg_bytes = 12.0 * float(np.mean(timed_post)) * frac_local + 8.0 * m_local * GB
-    avg_score_ms = score_ms / max(1, score_n)
-    achieved = alg_bytes / (avg_score_ms * 1e-3) / 1e9 if avg_score_ms > 0 else 0.0
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "bm25_score_traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
+    # ---- batch-1 latency (N=1): synchronous MSE_HOST call per query ---------------------------------------------
+    latency = None
+    if lat_batches:
+        lat = []
+        for j, (q_off, q_term, q_tf, qv) in enumerate(lat_batches):
+            t1 = time.perf_counter()
+            nat.hybrid_search(q_off, q_term, q_tf, qv, TOP_K, 0.0, max_out=MAX_OUT)
+            lat.append((time.perf_counter() - t1) * 1e3)
+        lat = lat[4:]
+        latency = {"batch": 1, "ms_median": float(np.median(lat)), "ms_p90": float(np.percentile(lat, 90)), "ms_min": float(np.min(lat)),
+                   "path": "mse_hybrid_search_batch, MSE_HOST (pageable host buffers in, results out, synchronous)", "queries": len(lat)}
 
-    # ---- N > 1: the owner exchange against the all-gather + merge-everywhere exchange on one batch (outside the
-    # timed regions; both are exact, so this rank's block must be identical bit for bit) -----------------------
-    exchange_check = None
-    if owner:
-        q_off, q_term, q_tf = dev_batches[args.warmup]
-        o_doc, o_score, o_count = searcher.bm25_search_owner(q_off, q_term, q_tf, TOP_K, 0.0, slack=args.exchange_slack)
-        a_doc, a_score, a_count = searcher.bm25_search(q_off, q_term, q_tf, TOP_K, 0.0)
-        blk = slice(rank * BATCH, (rank + 1) * BATCH)
-        valid = torch.arange(TOP_K, device=dev).unsqueeze(0) < o_count.unsqueeze(1)
-        same = torch.equal(o_count, a_count[blk]) and torch.equal(o_doc[valid], a_doc[blk][valid]) and \
-            torch.equal(o_score[valid], a_score[blk][valid])
-        t = torch.tensor([0 if same else 1], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        exchange_check = {"queries": GB, "ranks_differing_from_allgather_merge": int(t.item())}
+    # ---- rooflines ---------------------------------------------------------------------------------------------
+    timed_all = float(np.mean(all_post[args.warmup:]))
+    share = corpus.local_postings / max(1, corpus.n_postings)
+    streamed = float(stats["postings"])                                  # this rank, last step
+    looked = float(stats["postings_looked_up"])
+    m_local = TOP_K if world == 1 else (args.shard_list_len or min(TOP_K, 2 * TOP_K // world + 32))
+    score_ms = kt["bm25_score"][0] / max(1, kt["bm25_score"][1])
+    rerank_ms = kt["rerank"][0] / max(1, kt["rerank"][1]) * (1 if world == 1 else 2)     # sharded: cos + fuse kernels per step
+    alg_score = 12.0 * streamed + 8.0 * m_local * GB
+    alg_score_def = 12.0 * timed_all * share + 8.0 * m_local * GB
+    rows_local = rows_per_query * (B if world == 1 else GB / world)
+    alg_rerank = 2.0 * 768 * rows_local + 12.0 * TOP_K * (B if world == 1 else GB / world) + 8.0 * MAX_OUT * B
+    tr_score, tr_src = committed_traffic("bm25_score_kernel")
+    tr_rr, tr_rr_src = committed_traffic("rerank_kernel")
+    roof_score = {"bound": "hbm", "kernel": "bm25_score_kernel", "achieved": alg_score / (score_ms * 1e-3) / 1e9 if score_ms else 0.0,
+                  "peak": peak, "unit": "GB/s", "frac": (alg_score / (score_ms * 1e-3) / 1e9 / peak) if score_ms else 0.0,
+                  "traffic": tr_score, "traffic_source": tr_src, "peak_source": peak_src,
+                  "algorithmic_bytes_per_launch": alg_score, "kernel_ms": score_ms,
+                  "basis": "12 B per posting STREAMED by the kernel + 8 B per emitted result (postings of the negative-idf always-term "
+                           "are not streamed: their contribution is read from a dense impact row per candidate)",
+                  "achieved_on_all_query_postings": alg_score_def / (score_ms * 1e-3) / 1e9 if score_ms else 0.0,
+                  "postings_streamed_per_query": streamed / GB, "postings_not_streamed_per_query": looked / GB}
+    roof_rerank = {"bound": "hbm", "kernel": "rerank_kernel" if world == 1 else "hyb_cos_kernel + hyb_fuse_kernel",
+                   "achieved": alg_rerank / (rerank_ms * 1e-3) / 1e9 if rerank_ms else 0.0, "peak": peak, "unit": "GB/s",
+                   "frac": (alg_rerank / (rerank_ms * 1e-3) / 1e9 / peak) if rerank_ms else 0.0, "traffic": tr_rr, "traffic_source": tr_rr_src,
+                   "algorithmic_bytes_per_launch": alg_rerank, "kernel_ms": rerank_ms, "rows_per_query": rows_per_query,
+                   "basis": "2*768 B per fetched chunk row + 12 B per candidate + 8 B per result"}
 
-    # ---- parity spot-check + CPU baseline (rank 0, N=1) -------------------------------------------------
-    cpu_baseline = None
+    # ---- parity at this size (rank 0): GPU vs oracle pipeline on sampled queries of one timed batch ------------------
     parity = None
-    if job_rank == 0 and job_world == 1 and not args.no_cpu_baseline:
-        from oracle import bm25_oracle as bo
-        ix = bo.Bm25Arrays(c.term_off.cpu().numpy(), c.post_doc.cpu().numpy(), c.post_tf.cpu().numpy(), c.doc_len.cpu().numpy(),
-                           c.idf.cpu().numpy(), c.avgdl, c.total_docs, c.doc_ids.cpu().numpy())
-        q_off, q_term, q_tf = host_batches[args.warmup]
-        n_s = min(args.cpu_sample, BATCH)
-        qs = [[int(t) for s in range(q_off[i], q_off[i + 1]) for t in [q_term[s]] * int(q_tf[s])] for i in range(n_s)]
-        t0 = time.perf_counter()
-        refs = [bo.search_faithful(ix, q, top_k=TOP_K, min_score=0.0) for q in qs]
-        faithful_s = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        fast = [bo.search_fast(ix, q, top_k=TOP_K, min_score=0.0) for q in qs]
-        fast_s = time.perf_counter() - t0
-        g_doc, g_score, g_count = nat.bm25_search(q_off, q_term, q_tf, TOP_K, 0.0)
-        bad, worst, same_ids, n_ids = 0, 0.0, 0, 0
-        for i in range(n_s):
-            rd = np.asarray([d for d, _ in refs[i]]); rs = np.asarray([s for _, s in refs[i]])
-            n = int(g_count[i])
-            if n != len(rd):
-                bad += 1
-                continue
-            scale = bo.abs_contrib_sum(ix, qs[i])[rd] if len(rd) else np.zeros(0)
-            tol = 1e-5 * np.maximum(np.maximum(np.abs(rs), scale), 1e-30)
-            diff = np.abs(g_score[i, :n] - rs)
-            worst = max(worst, float((diff / np.maximum(np.maximum(np.abs(rs), scale), 1e-30)).max(initial=0.0)))
-            # north_star rule: scores within tolerance; ids identical except where the scores that decide the
-            # order are tied inside that tolerance (a different doc at rank r must carry rank r's score)
-            bad += int(np.any(diff > tol))
-            same_ids += int(np.sum(g_doc[i, :n] == rd)); n_ids += n
-        parity = {"queries_checked": n_s, "queries_failing": bad, "max_rel_err": worst, "tolerance": 1e-5,
-                  "rank_positions_with_identical_doc_id": same_ids / max(1, n_ids),
-                  "rule": "score at every rank within 1e-5 relative (floor: sum of |term contributions|); ids may differ only at such ties"}
-        cpu_baseline = {"value": n_s / faithful_s, "unit": UNIT, "cores": 1, "kind": "port",
-                        "sample": f"{n_s} of the {BATCH} queries of one batch, full 1M-doc index, faithful Python-loop port of "
-                                  f"bm25_indexer.py:435-485 (no SQL cost)",
-                        "vectorised_numpy_value": n_s / fast_s}
-
-    # the CPU-baseline leg leaves millions of Python objects behind: collect now and keep the survivors out of later
-    # collections, so that no generation-2 pass lands inside a timed supplement loop (one cost ~28 ms when it did)
-    import gc
+    cpu_baseline = None
+    if rank == 0 and par_ix is not None:
+        fetch = fetch_rows_fn(corpus, dev)
+        i = args.warmup
+        step_device(i)
+        torch.cuda.synchronize()
+        g_doc, g_score, g_count = (x.cpu().numpy() for x in (out[0], out[1], out[4]))
+        qv = host_batches[i][3]
+        if n_par:
+            parity = sampled.check_hybrid(par_ix, fetch, corpus.chunk_off_host, par_queries[:n_par], qv[:n_par], g_doc[:n_par],
+                                          g_score[:n_par], g_count[:n_par], TOP_K, MAX_OUT)
+            parity["kind"] = "pinned (oracle restates bm25_indexer.py:383-485 and reranker_api.py:27-63,273-372; pinned on the hosted reference)"
+            parity["at_size"] = f"{n_docs} docs / {n_chunks} chunks, {world} GPU(s)"
+            # stage 1 alone on the same queries: BM25 top-1000 ids / scores with the tie rule
+            if world == 1:
+                q_off, q_term, q_tf, _ = host_batches[i]
+                so = q_off[:n_par + 1].copy()
+                b_doc, b_score, b_count = nat.bm25_search(so, q_term[:so[-1]].copy(), q_tf[:so[-1]].copy(), TOP_K, 0.0)
+                parity["bm25_stage"] = sampled.check_bm25(par_ix, par_queries[:n_par], b_doc, b_score, b_count, TOP_K)
+        if n_cpu:
+            cached = prefetch_rows_for(par_ix, par_queries[:n_cpu], corpus.chunk_off_host, fetch)
+            t1 = time.perf_counter()
+            for j in range(n_cpu):
+                sampled.oracle_hybrid(par_ix, cached, corpus.chunk_off_host, par_queries[j], qv[j], TOP_K, MAX_OUT, faithful=True)
+            dt = time.perf_counter() - t1
+            cpu_baseline = {"value": n_cpu / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                            "sample": f"{n_cpu} hybrid queries of one batch on 1 core, full {n_docs}-doc index: faithful Python-loop port of "
+                                      f"bm25_indexer.py:435-485 (~{int(timed_all / GB)} posting rows per query incl. the always-term) -> "
+                                      f"reranker_api.py:336-372 (sklearn cosine, 32-row batches); no SQL / spaCy / HTTP cost"}
     gc.collect()
     gc.freeze()
 
-    # ---- supplementary: dense exhaustive scan (BASELINE.json configs[2]) on rank 0 at N=1 ------------------
-    dense = None
-    hybrid = None
-    if job_rank == 0 and job_world == 1 and not args.no_dense:
-        try:
-            hybrid = hybrid_supplement(nat, dev, dev_batches, peak)
-        except Exception as e:  # noqa: BLE001 - the headline number must not depend on the supplements
-            hybrid = {"error": repr(e)}
-        try:
-            dense = dense_scan_supplement(nat, dev, peak)
-        except Exception as e:  # noqa: BLE001
-            dense = {"error": repr(e)}
+    # ---- supplements -------------------------------------------------------------------------------------------------------
+    supplements = {}
+    if not args.no_supplements:
+        nat.close()
+        corpus.emb = None
+        del corpus.nat
+        gc.collect(); torch.cuda.empty_cache()
+        if world == 1:
+            for name, fn in (("bm25_c2", lambda: bm25_c2_supplement(dev, local_rank, peak, always=False)),
+                             ("bm25_c2_always_term", lambda: bm25_c2_supplement(dev, local_rank, peak, always=True)),
+                             ("dense_c3", lambda: dense_c3_supplement(dev, local_rank, peak, tf_peak))):
+                try:
+                    supplements[name] = fn()
+                except Exception as e:  # noqa: BLE001 - the headline number must not depend on the supplements
+                    supplements[name] = {"error": repr(e)}
+                gc.collect(); torch.cuda.empty_cache()
+        else:
+            try:
+                box = [_native.comm_unique_id() if rank == 0 else None]
+                dist.broadcast_object_list(box, src=0)
+                supplements["dense_c4_sharded"] = dense_c4_supplement(rank, world, dev, local_rank, box[0], peak)
+            except Exception as e:  # noqa: BLE001
+                supplements["dense_c4_sharded"] = {"error": repr(e)}
 
-    # ---- N > 1, replicated layout: the doc-sharded exchange measured on the same GPUs as a supplement ------------
-    doc_sharded = None
-    if replicated and not args.no_dense:
-        try:
-            doc_sharded = doc_sharded_supplement(args, full_corpus, job_rank, job_world, dev, local_rank)
-        except Exception as e:  # noqa: BLE001 - the headline number must not depend on the supplements
-            doc_sharded = {"error": repr(e)}
-
-    if job_rank == 0:
+    if rank == 0:
+        per = lambda k: kt[k][0] / max(1, kt[k][1])
+        launches_per_step = (1 + 3 + 2 + 1) if world == 1 else (1 + 3 + 2 + 2 + 1 + 1 + 1 + 1 + 1)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": job_world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak" if (owner or replicated or world == 1) else "strong", "vs_baseline": None,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "n_docs": N_DOCS, "vocab": VOCAB, "postings": int(c.n_postings), "batch": BATCH,
-                       "global_batch": job_q, "top_k": TOP_K, "layout": layout if job_world > 1 else "single GPU",
-                       "sharding": (f"index replicated on {job_world} GPUs ({index_bytes / 1e9:.2f} GB of postings fits one), queries sharded: "
-                                    f"{BATCH} per rank and step, no data-path collective" if replicated else
-                                    "none" if world == 1 else
-                                    f"doc-range x{world}, {GB}-query batch replicated, query-owner merge: NCCL all-to-all of "
-                                    f"{m_local}-entry shard lists, exact (full-list repeat when a cut could hide a result)"
-                                    if owner else f"doc-range x{world}, all-gather + merge on every rank"),
-                       "exchange_fallback_steps": int(getattr(searcher, "fallbacks", 0)),
-                       "l2_policy": "inputs larger than L2: 1.5 GB index, a different query batch every step",
-                       "postings_per_query": float(np.mean(timed_post)) / GB},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": args.steps * (3 + (1 if world > 1 else 0)) * job_world,   # prepare, score, select (+ merge) per rank
-            "roofline": {"bound": "hbm", "kernel": "bm25_score_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": avg_score_ms},
+            "config": {"workload": workload_name(n_docs, n_chunks, B), "n_docs": n_docs, "n_chunks": n_chunks, "vocab": VOCAB,
+                       "postings": corpus.n_postings, "batch": B, "global_batch": GB, "top_k": TOP_K, "max_out": MAX_OUT,
+                       "layout": "single GPU" if world == 1 else
+                                 f"doc-sharded x{world}: postings and chunks of a doc on its rank, {GB}-query batch replicated, every rank owns "
+                                 f"{B} queries; NCCL inside mse_hybrid_search_sharded (shard lists of {m_local} entries to the owner, "
+                                 f"survivor all-gather, 4-word min-max all-reduce, top-{MAX_OUT} records to the owner)",
+                       "l2_policy": "inputs larger than L2: 15 GB of postings + 77 GB of chunks per corpus, a different query batch every step",
+                       "postings_per_query_all_terms": timed_all / GB, "parity_tolerances": "BM25 1e-5 relative, fused score 3e-3 absolute"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "path": "mse_hybrid_search_batch MSE_HOST_ASYNC, pinned host buffers, two streams alternating" if world == 1 else
+                            "pinned H2D + mse_hybrid_search_sharded + pinned D2H per rank, two streams alternating"},
+            "gpu_launches": args.steps * launches_per_step * world,
+            "roofline": roof_score,
+            "rooflines": [roof_score, roof_rerank],
             "cpu_baseline": cpu_baseline,
             "clocks": sampler.summary(),
-            "breakdown": {"prepare_ms": prep_ms / max(1, score_n), "score_ms": avg_score_ms, "select_ms": select_ms / max(1, score_n),
-                          "candidates_emitted_per_query": stats["emitted"] / GB, "rerun_queries": stats["rerun_queries"],
-                          "ranges": stats["ranges"], "score_ctas": stats["ctas"], "setup_s": setup_s},
+            "breakdown": {"prepare_ms": per("bm25_prepare"), "score_ms": score_ms, "select_ms": per("topk_select"),
+                          "rerank_ms": rerank_ms, "exchange_ms": per("exchange") * (1 if world == 1 else 4),
+                          "candidates_emitted_per_query": stats["emitted"] / GB, "ranges": stats["ranges"], "score_ctas": stats["ctas"],
+                          "rerank_rows_per_query": rows_per_query, "status_words_summed_over_timed_steps": status_total,
+                          "setup_s": setup_s},
+            "latency_b1": latency,
             "parity": parity,
-            "exchange_check": exchange_check,
-            "doc_sharded": doc_sharded,
-            "hybrid": hybrid,
-            "dense_scan": dense,
+            "supplements": supplements,
         }
         print(json.dumps(line))
-    if job_world > 1:
+    if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 

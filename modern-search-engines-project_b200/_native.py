@@ -18,10 +18,12 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.environ.get("MSE_B200_LIB") or os.path.join(CSRC, "libmsegpu.so")   # override: experiments only
 HEADER = os.path.join(os.path.dirname(HERE), "include", "mse_b200.h")
 
-MSE_HOST, MSE_DEVICE, MSE_DEVICE_BORROW = 0, 1, 2
+MSE_HOST, MSE_DEVICE, MSE_DEVICE_BORROW, MSE_HOST_ASYNC = 0, 1, 2, 3
+STATUS_WORDS = 4
+COMM_ID_BYTES = 128
 MAX_TOPK = 4096
 EMB_DIM = 768
-KERNELS = {"bm25_score": 0, "topk_select": 1, "dense_scan": 2, "rerank": 3, "bm25_prepare": 4}
+KERNELS = {"bm25_score": 0, "topk_select": 1, "dense_scan": 2, "rerank": 3, "bm25_prepare": 4, "exchange": 5}
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
@@ -63,11 +65,24 @@ _SIGNATURES = {
     "mse_bm25_load": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, _vp,
                                 C.c_float, C.c_float, C.c_float, C.c_int]),
     "mse_bm25_search_batch": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, C.c_int32, C.c_float, _vp, _vp, _vp, C.c_int, _vp]),
+    "mse_bm25_search_batch_async": (C.c_int, [_vp, C.c_int32, C.c_int32, _vp, _vp, _vp, C.c_int32, C.c_float, _vp, _vp, _vp, _vp, C.c_int, _vp]),
     "mse_bm25_last_stats": (C.c_int, [_vp, _i64p]),
     "mse_bm25_aggregate": (C.c_int, [C.c_int, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _i64p, C.c_int, _vp]),
     "mse_kernel_time": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), _i64p]),
     "mse_dense_load": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp, C.c_int, _vp, C.c_int]),
     "mse_dense_scan_batch": (C.c_int, [_vp, C.c_int32, _vp, C.c_int32, _vp, _vp, _vp, C.c_int, _vp]),
+    "mse_dense_set_url_groups": (C.c_int, [_vp, _vp, C.c_int64, C.c_int]),
+    "mse_dense_scan_batch_async": (C.c_int, [_vp, C.c_int32, _vp, C.c_int32, _vp, _vp, _vp, _vp, C.c_int, _vp]),
+    "mse_hybrid_search_batch": (C.c_int, [_vp, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_int32,
+                                          _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp]),
+    "mse_comm_unique_id": (C.c_int, [_vp]),
+    "mse_comm_init": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32]),
+    "mse_comm_attach": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32]),
+    "mse_comm_destroy": (C.c_int, [_vp]),
+    "mse_bm25_search_sharded": (C.c_int, [_vp, C.c_int32, C.c_int32, _vp, _vp, _vp, C.c_int32, C.c_float, C.c_int32, _vp, _vp, _vp, _vp, _vp]),
+    "mse_hybrid_search_sharded": (C.c_int, [_vp, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp, C.c_int32, C.c_float, C.c_int32, C.c_float,
+                                            C.c_int32, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mse_dense_scan_sharded": (C.c_int, [_vp, C.c_int32, _vp, C.c_int32, _vp, _vp, _vp, _vp, _vp]),
     "mse_rerank_batch": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, C.c_float, C.c_int32, C.c_int32,
                                    _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp]),
     "mse_rerank_shard_cos": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, _vp, C.c_int64, _vp, C.c_int32,
@@ -123,8 +138,9 @@ def _ptr(x, dtype, where: int):
         assert x.dtype == want, (x.dtype, want)
         assert x.is_contiguous()
         assert x.is_cuda == (where == MSE_DEVICE), "buffer location does not match `where`"
+        assert where != MSE_HOST_ASYNC or x.is_pinned(), "MSE_HOST_ASYNC needs pinned host buffers"
         return C.c_void_p(x.data_ptr())
-    assert where == MSE_HOST, "numpy buffers are host memory"
+    assert where == MSE_HOST, "numpy buffers are (pageable) host memory"
     assert x.dtype == np.dtype(dtype) and x.flags["C_CONTIGUOUS"], (x.dtype, dtype)
     return C.c_void_p(x.ctypes.data)
 
@@ -136,11 +152,22 @@ def _where_of(*xs) -> int:
     return MSE_HOST
 
 
-def _stream_ptr(where: int):
-    if where == MSE_DEVICE:
+def _stream_ptr(where: int, stream=None):
+    """cudaStream_t of the call: an explicit torch stream / raw handle, else torch's current stream for device and
+    pinned-async buffers, else the default stream."""
+    if stream is not None:
+        return C.c_void_p(int(getattr(stream, "cuda_stream", stream)))
+    if where in (MSE_DEVICE, MSE_HOST_ASYNC):
         import torch
         return C.c_void_p(torch.cuda.current_stream().cuda_stream)
     return None
+
+
+def comm_unique_id() -> bytes:
+    """NCCL unique id (create on rank 0, hand to every rank, pass to ``NativeIndex.comm_init``)."""
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    _check(lib().mse_comm_unique_id(buf))
+    return bytes(buf.raw)
 
 
 def bm25_aggregate(doc_tok_off, tok_term, n_terms: int, device: int = 0):
@@ -191,7 +218,8 @@ class NativeIndex:
     def bm25_stats(self) -> dict:
         arr = (C.c_int64 * 8)()
         _check(lib().mse_bm25_last_stats(self._h, arr))
-        return {"postings": arr[0], "emitted": arr[1], "rerun_queries": arr[2], "ranges": arr[3], "ctas": arr[4]}
+        return {"postings": arr[0], "emitted": arr[1], "rerun_queries": arr[2], "ranges": arr[3], "ctas": arr[4],
+                "postings_looked_up": arr[5]}
 
     # ---- BM25 --------------------------------------------------------------------------------
     def bm25_load(self, term_off, post_doc, post_tf, doc_len, idf, avgdl, k1=1.2, b=0.75, doc_base=0):
@@ -311,6 +339,143 @@ class NativeIndex:
                                            float(smoothing), int(max_out), _ptr(out[0], np.int32, D), _ptr(out[1], np.float32, D),
                                            _ptr(out[2], np.float32, D), _ptr(out[3], np.int64, D), _ptr(out[4], np.int32, D),
                                            _ptr(out[5], np.int32, D), _stream_ptr(D)))
+        return out
+
+    # ---- enqueue-only calls (MSE_DEVICE tensors or pinned host tensors) -----------------------------------------
+    def new_status(self, like):
+        """int32[4] status record in the memory space of `like` (a CUDA tensor or a pinned host tensor)."""
+        import torch
+        if like.is_cuda:
+            return torch.zeros(STATUS_WORDS, dtype=torch.int32, device=like.device)
+        return torch.zeros(STATUS_WORDS, dtype=torch.int32).pin_memory()
+
+    def bm25_search_async(self, q_off, q_term, q_tf, n_slots: int, top_k: int, min_score: float = 0.0, out=None, status=None,
+                          stream=None):
+        """Enqueue-only BM25 (``mse_bm25_search_batch_async``): CUDA tensors (MSE_DEVICE) or pinned host tensors
+        (MSE_HOST_ASYNC); results are valid in stream order / after the stream is synchronised."""
+        import torch
+        where = MSE_DEVICE if q_off.is_cuda else MSE_HOST_ASYNC
+        B = int(q_off.shape[0]) - 1
+        if out is None:
+            mk = (lambda shape, dt: torch.empty(shape, dtype=dt, device=q_off.device)) if q_off.is_cuda else \
+                (lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory())
+            out = (mk((B, top_k), torch.int32), mk((B, top_k), torch.float32), mk((B,), torch.int32))
+        _check(lib().mse_bm25_search_batch_async(self._h, B, int(n_slots), _ptr(q_off, np.int32, where), _ptr(q_term, np.int32, where),
+                                                 _ptr(q_tf, np.int32, where), int(top_k), float(min_score),
+                                                 _ptr(out[0], np.int32, where), _ptr(out[1], np.float32, where),
+                                                 _ptr(out[2], np.int32, where), _ptr(status, np.int32, where), where,
+                                                 _stream_ptr(where, stream)))
+        return out
+
+    def dense_scan_async(self, q, top_k: int, out=None, status=None, stream=None):
+        import torch
+        where = MSE_DEVICE if q.is_cuda else MSE_HOST_ASYNC
+        B = int(q.shape[0])
+        if out is None:
+            mk = (lambda shape, dt: torch.empty(shape, dtype=dt, device=q.device)) if q.is_cuda else \
+                (lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory())
+            out = (mk((B, top_k), torch.int32), mk((B, top_k), torch.float32), mk((B,), torch.int32))
+        _check(lib().mse_dense_scan_batch_async(self._h, B, _ptr(q, np.float32, where), int(top_k), _ptr(out[0], np.int32, where),
+                                                _ptr(out[1], np.float32, where), _ptr(out[2], np.int32, where),
+                                                _ptr(status, np.int32, where), where, _stream_ptr(where, stream)))
+        return out
+
+    def set_url_groups(self, url_group):
+        """Stores the GLOBAL url-group ids (int32 per doc) in the index; rerank / hybrid calls use them by default."""
+        if url_group is None:
+            _check(lib().mse_dense_set_url_groups(self._h, None, 0, MSE_HOST))
+            return
+        where = _where_of(url_group)
+        _check(lib().mse_dense_set_url_groups(self._h, _ptr(url_group, np.int32, where), int(url_group.shape[0]), where))
+
+    @staticmethod
+    def _rerank_out(B, max_out, like=None, pinned=False):
+        if like is not None and _is_torch(like):
+            import torch
+            if like.is_cuda:
+                mk = lambda shape, dt: torch.empty(shape, dtype=dt, device=like.device)
+            elif pinned:
+                mk = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
+            else:
+                mk = lambda shape, dt: torch.empty(shape, dtype=dt)
+            return (mk((B, max_out), torch.int32), mk((B, max_out), torch.float32), mk((B, max_out), torch.float32),
+                    mk((B, max_out), torch.int64), mk((B,), torch.int32), mk((B,), torch.int32))
+        return (np.empty((B, max_out), np.int32), np.empty((B, max_out), np.float32), np.empty((B, max_out), np.float32),
+                np.empty((B, max_out), np.int64), np.empty((B,), np.int32), np.empty((B,), np.int32))
+
+    def hybrid_search(self, q_off, q_term, q_tf, q_vec, top_k: int = 1000, min_score: float = 0.0, smoothing=0.15, max_chunks=10,
+                      max_out=100, n_slots: Optional[int] = None, out=None, status=None, stream=None, pinned_async: bool = False):
+        """BM25 top_k -> rerank -> max_out per query in ONE call (``mse_hybrid_search_batch``).  numpy / pageable torch:
+        MSE_HOST (exact, complete on return); CUDA tensors: MSE_DEVICE (enqueue-only); pinned host tensors with
+        ``pinned_async=True``: MSE_HOST_ASYNC.  ``n_slots`` = q_off[-1] (read here when the offsets are host memory)."""
+        where = _where_of(q_off, q_term, q_tf, q_vec)
+        if where == MSE_HOST and pinned_async:
+            where = MSE_HOST_ASYNC
+        B = int(q_off.shape[0]) - 1
+        if n_slots is None:
+            assert where != MSE_DEVICE, "pass n_slots with device-resident queries (no read-back in an enqueue-only call)"
+            n_slots = int(q_off[-1])
+        if out is None:
+            out = self._rerank_out(B, max_out, q_off if _is_torch(q_off) else None, pinned=where == MSE_HOST_ASYNC)
+        _check(lib().mse_hybrid_search_batch(self._h, B, int(n_slots), _ptr(q_off, np.int32, where), _ptr(q_term, np.int32, where),
+                                             _ptr(q_tf, np.int32, where), _ptr(q_vec, np.float32, where), int(top_k), float(min_score),
+                                             float(smoothing), int(max_chunks), int(max_out),
+                                             _ptr(out[0], np.int32, where), _ptr(out[1], np.float32, where), _ptr(out[2], np.float32, where),
+                                             _ptr(out[3], np.int64, where), _ptr(out[4], np.int32, where), _ptr(out[5], np.int32, where),
+                                             _ptr(status, np.int32, where), where, _stream_ptr(where, stream)))
+        return out
+
+    # ---- corpus sharded by doc range over the GPUs of one box (NCCL inside the library) -------------------------------
+    def comm_init(self, id_bytes: Optional[bytes], rank: int, world: int):
+        buf = C.create_string_buffer(id_bytes, COMM_ID_BYTES) if id_bytes is not None else None
+        _check(lib().mse_comm_init(self._h, buf, int(rank), int(world)))
+        self.rank, self.world = int(rank), int(world)
+
+    def comm_destroy(self):
+        _check(lib().mse_comm_destroy(self._h))
+
+    def bm25_search_sharded(self, q_off, q_term, q_tf, n_slots: int, top_k: int, min_score: float = 0.0, shard_list_len: int = 0,
+                            out=None, status=None, stream=None):
+        """The whole replicated batch in, this rank's block of the results out ([B/world, top_k])."""
+        import torch
+        D = MSE_DEVICE
+        B = int(q_off.shape[0]) - 1
+        bq = B // self.world
+        if out is None:
+            dev = q_off.device
+            out = (torch.empty((bq, top_k), dtype=torch.int32, device=dev), torch.empty((bq, top_k), dtype=torch.float32, device=dev),
+                   torch.empty((bq,), dtype=torch.int32, device=dev))
+        _check(lib().mse_bm25_search_sharded(self._h, B, int(n_slots), _ptr(q_off, np.int32, D), _ptr(q_term, np.int32, D),
+                                             _ptr(q_tf, np.int32, D), int(top_k), float(min_score), int(shard_list_len),
+                                             _ptr(out[0], np.int32, D), _ptr(out[1], np.float32, D), _ptr(out[2], np.int32, D),
+                                             _ptr(status, np.int32, D), _stream_ptr(D, stream)))
+        return out
+
+    def hybrid_search_sharded(self, q_off, q_term, q_tf, q_vec, n_slots: int, top_k: int = 1000, min_score: float = 0.0,
+                              shard_list_len: int = 0, smoothing=0.15, max_chunks=10, max_out=100, out=None, status=None, stream=None):
+        D = MSE_DEVICE
+        B = int(q_off.shape[0]) - 1
+        bq = B // self.world
+        if out is None:
+            out = self._rerank_out(bq, max_out, q_off)
+        _check(lib().mse_hybrid_search_sharded(self._h, B, int(n_slots), _ptr(q_off, np.int32, D), _ptr(q_term, np.int32, D),
+                                               _ptr(q_tf, np.int32, D), _ptr(q_vec, np.float32, D), int(top_k), float(min_score),
+                                               int(shard_list_len), float(smoothing), int(max_chunks), int(max_out),
+                                               _ptr(out[0], np.int32, D), _ptr(out[1], np.float32, D), _ptr(out[2], np.float32, D),
+                                               _ptr(out[3], np.int64, D), _ptr(out[4], np.int32, D), _ptr(out[5], np.int32, D),
+                                               _ptr(status, np.int32, D), _stream_ptr(D, stream)))
+        return out
+
+    def dense_scan_sharded(self, q, top_k: int, out=None, status=None, stream=None):
+        import torch
+        D = MSE_DEVICE
+        B = int(q.shape[0])
+        if out is None:
+            out = (torch.empty((B, top_k), dtype=torch.int32, device=q.device), torch.empty((B, top_k), dtype=torch.float32, device=q.device),
+                   torch.empty((B,), dtype=torch.int32, device=q.device))
+        _check(lib().mse_dense_scan_sharded(self._h, B, _ptr(q, np.float32, D), int(top_k), _ptr(out[0], np.int32, D),
+                                            _ptr(out[1], np.float32, D), _ptr(out[2], np.int32, D), _ptr(status, np.int32, D),
+                                            _stream_ptr(D, stream)))
         return out
 
     def topk_merge(self, in_doc, in_score, in_count, top_k: int):

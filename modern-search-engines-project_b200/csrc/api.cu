@@ -10,12 +10,15 @@
 #include <cstdlib>
 #include "bm25.cuh"
 #include "build.cuh"
+#include "comm.cuh"
 #include "common.cuh"
 #include "dense.cuh"
 #include "gemm.cuh"
+#include "hybrid_shard.cuh"
 #include "rerank.cuh"
 #include "rerank_shard.cuh"
 #include "topk.cuh"
+#include "workspace.cuh"
 
 namespace mse {
 
@@ -28,38 +31,6 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
-struct DevBuf {
-    void* p = nullptr;
-    size_t cap = 0;
-    int ensure(size_t bytes) {
-        if (bytes <= cap) return MSE_OK;
-        if (p) { cudaFree(p); p = nullptr; cap = 0; }
-        size_t want = bytes + bytes / 8 + 256;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e != cudaSuccess) {
-            e = cudaMalloc(&p, bytes);
-            want = bytes;
-        }
-        if (e != cudaSuccess) {
-            p = nullptr;
-            set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
-            (void)cudaGetLastError();
-            return MSE_ERR_NOMEM;
-        }
-        cap = want;
-        return MSE_OK;
-    }
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-    }
-    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
-};
-
-constexpr int kNumTimers = 5;
-enum { T_SCORE = 0, T_SELECT = 1, T_SCAN = 2, T_RERANK = 3, T_PREPARE = 4 };
-
 }  // namespace mse
 
 using namespace mse;
@@ -67,38 +38,31 @@ using namespace mse;
 struct mse_index {
     int device = 0;
     int sm_count = 148;
-    std::mutex mu;
+    std::mutex mu;                       // guards loads, options and the stats snapshot; search calls do not hold it
 
     bool has_bm25 = false;
     Bm25Dev bm{};
-    DevBuf term_off, post_doc, post_tf, post2, skip, skip_row, imp_levels, doc_norm, idf;
+    DevBuf term_off, post2, skip, skip_row, imp_levels, idf, neg_row, neg_imp;
     std::vector<int64_t> h_term_off;
 
     bool has_dense = false;
     DenseDev dn{};
-    DevBuf emb, doc_chunk_off, row_doc, tile_row, group_row, qb16, log_key, log_q;
+    DevBuf emb, doc_chunk_off, row_doc, tile_row, group_row, url_group;
+    int64_t n_url_groups = 0;
     bool gemm_ok = false;
     int64_t n_groups = 0;
     CUtensorMap map_e;
 
-    // workspace (guarded by mu)
-    DevBuf q_off, q_term, q_tf, slot_w, rec, tau, hist, maxbin, cand, cand_count, overflow, misc;
-    DevBuf o_doc, o_score, o_count;          // device staging of results for MSE_HOST callers
-    DevBuf best, dq;                         // dense scan
-    DevBuf r_in[5], r_out[6];                // rerank staging
-    DevBuf r_split[6];                       // small-batch rerank: cosines / survivor lists between the two kernels
-    DevBuf m_in[3];                          // merge staging
-    DevBuf fb_q[3], fb_out[3];               // fallback sub-batches
+    WorkspacePool pool;
+    Workspace* last_bm25_ws = nullptr;   // where the counters of the last BM25 call live
+    int32_t last_bm25_queries = 0;
 
-    int64_t opt_readout = 1, opt_tau_init = 1;
+    Comm comm;
+
+    int64_t opt_readout = 1, opt_tau_init = 1, opt_neg_lookup = 1;
     int64_t opt_range_docs = 0, opt_qpi = 0, opt_cand_cap = 0, opt_use_tau = 1, opt_scan_ctas = 0, opt_gemm_min_batch = 0, opt_gemm_debug = 0;
     int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-
-    cudaEvent_t ev[kNumTimers][2];
-    bool ev_ok = false;
-    double t_ms[kNumTimers] = {0, 0, 0, 0, 0};
-    int64_t t_n[kNumTimers] = {0, 0, 0, 0, 0};
-    bool t_pending[kNumTimers] = {false, false, false, false, false};
+    int score_ctas_per_sm[2] = {0, 0};            // occupancy of the score kernel (scan / hit read-out) at the default range
 };
 
 namespace {
@@ -114,28 +78,17 @@ struct DeviceGuard {
     }
 };
 
-void timer_begin(mse_index* ix, int t, cudaStream_t s) {
-    if (ix->ev_ok) cudaEventRecord(ix->ev[t][0], s);
-}
-void timer_end(mse_index* ix, int t, cudaStream_t s) {
-    if (ix->ev_ok) { cudaEventRecord(ix->ev[t][1], s); ix->t_pending[t] = true; }
-}
-// call after the stream has been synchronised
-void timers_collect(mse_index* ix) {
-    for (int t = 0; t < kNumTimers; ++t) {
-        if (!ix->t_pending[t]) continue;
-        float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, ix->ev[t][0], ix->ev[t][1]) == cudaSuccess) { ix->t_ms[t] += ms; ix->t_n[t] += 1; }
-        else (void)cudaGetLastError();
-        ix->t_pending[t] = false;
-    }
-}
-
 int copy_in(void* dst, const void* src, size_t bytes, int where, cudaStream_t s) {
     if (bytes == 0) return MSE_OK;
-    MSE_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, where == MSE_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
+    MSE_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, where == MSE_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
     return MSE_OK;
 }
+int copy_out(void* dst, const void* src, size_t bytes, cudaStream_t s) {
+    if (bytes == 0) return MSE_OK;
+    MSE_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
+    return MSE_OK;
+}
+bool is_host(int where) { return where == MSE_HOST || where == MSE_HOST_ASYNC; }
 
 int round_up(int64_t v, int64_t m) { return int(((v + m - 1) / m) * m); }
 
@@ -176,49 +129,72 @@ int make_bf16_rowmajor_map(CUtensorMap* map, const void* base, uint64_t rows, ui
     return MSE_OK;
 }
 
-// ---- BM25 core: everything on device, outputs to device pointers ---------------------------------
-int bm25_run(mse_index* ix, int32_t B, const int32_t* d_q_off, const int32_t* d_q_term, const int32_t* d_q_tf,
-             int32_t S, int32_t max_terms, int32_t top_k, float min_score, int32_t cap, int use_tau,
-             int32_t* d_out_doc, float* d_out_score, int32_t* d_out_count, bool mark_overflow, cudaStream_t st) {
+// adds the number of set flags / a device counter to a status word (enqueue-only calls report instead of re-running)
+__global__ void status_add_flags_kernel(const int32_t* __restrict__ flags, int32_t n, int32_t* __restrict__ status_word) {
+    int c = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) c += flags[i] != 0;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(status_word, c);
+}
+__global__ void status_add_counter_kernel(const unsigned long long* __restrict__ counter, int32_t* __restrict__ status_word) {
+    if (threadIdx.x == 0 && blockIdx.x == 0 && *counter) atomicAdd(status_word, int32_t(*counter));
+}
+
+const void* score_kernel_fn(bool default_range, bool hits) {
+    if (hits) return default_range ? (const void*)bm25_score_kernel<kBm25DefaultRange, true> : (const void*)bm25_score_kernel<0, true>;
+    return default_range ? (const void*)bm25_score_kernel<kBm25DefaultRange, false> : (const void*)bm25_score_kernel<0, false>;
+}
+
+// ---- BM25 core: enqueue-only; everything on device, outputs to device pointers -------------------------------------
+// d_q_off must be a valid CSR (validated on the host, or the sanitised copy).  out_doc/out_score/out_count and/or
+// out_key receive the top_k lists; queries whose candidate list overflowed `cap` are marked (count -1, empty list) and
+// counted in ws.misc (+40) when mark_overflow is set.
+int bm25_enqueue(mse_index* ix, Lease& L, int32_t B, const int32_t* d_q_off, const int32_t* d_q_term, const int32_t* d_q_tf,
+                 int32_t S, int32_t top_k, float min_score, int32_t cap, int use_tau,
+                 int32_t* d_out_doc, float* d_out_score, int32_t* d_out_count, uint64_t* d_out_key, bool mark_overflow) {
+    Workspace* ws = L.ws;
+    cudaStream_t st = L.st;
     const Bm25Dev& bm = ix->bm;
     int RS = ix->opt_range_docs > 0 ? round_up(std::min<int64_t>(ix->opt_range_docs, 4096), 128) : kBm25DefaultRange;
     if (bm.n_docs < RS) RS = std::max(128, round_up(bm.n_docs, 128));
     const int n_sub = int((bm.n_docs + RS - 1) / RS);
     const int qpi = int(std::min<int64_t>(31, ix->opt_qpi > 0 ? ix->opt_qpi : 8));
     int rc;
-    if ((rc = ix->slot_w.ensure(sizeof(float) * size_t(S + 1)))) return rc;
-    if ((rc = ix->rec.ensure(sizeof(uint2) * (size_t(S) * n_sub + 1)))) return rc;
-    if ((rc = ix->tau.ensure(sizeof(uint32_t) * size_t(B)))) return rc;
-    if ((rc = ix->hist.ensure(sizeof(uint32_t) * size_t(B) * kHistBins))) return rc;
-    if ((rc = ix->maxbin.ensure(sizeof(uint32_t) * size_t(B)))) return rc;
-    if ((rc = ix->cand.ensure(sizeof(uint64_t) * size_t(B) * cap))) return rc;
-    if ((rc = ix->cand_count.ensure(sizeof(int32_t) * 2 * size_t(B)))) return rc;     // [B] counts, then [B] overflow flags
-    if ((rc = ix->misc.ensure(64))) return rc;
+    if ((rc = ws->slot_w.ensure(sizeof(float) * size_t(S + 1)))) return rc;
+    if ((rc = ws->slot_row.ensure(sizeof(int32_t) * size_t(S + 1)))) return rc;
+    if ((rc = ws->rec.ensure(sizeof(uint2) * (size_t(S) * n_sub + 1)))) return rc;
+    if ((rc = ws->tau.ensure(sizeof(uint32_t) * size_t(B)))) return rc;
+    if ((rc = ws->hist.ensure(sizeof(uint32_t) * size_t(B) * kHistBins))) return rc;
+    if ((rc = ws->maxbin.ensure(sizeof(uint32_t) * size_t(B)))) return rc;
+    if ((rc = ws->cand.ensure(sizeof(uint64_t) * size_t(B) * cap))) return rc;
+    if ((rc = ws->cand_count.ensure(sizeof(int32_t) * 2 * size_t(B)))) return rc;     // [B] counts, then [B] overflow flags
+    if ((rc = ws->misc.ensure(64))) return rc;
 
-    MSE_CUDA_TRY(cudaMemsetAsync(ix->cand_count.p, 0, sizeof(int32_t) * 2 * size_t(B), st));
-    MSE_CUDA_TRY(cudaMemsetAsync(ix->misc.p, 0, 64, st));
-    if (use_tau) MSE_CUDA_TRY(cudaMemsetAsync(ix->hist.p, 0, sizeof(uint32_t) * size_t(B) * kHistBins, st));   // maxbin: prepare kernel
+    MSE_CUDA_TRY(cudaMemsetAsync(ws->cand_count.p, 0, sizeof(int32_t) * 2 * size_t(B), st));
+    MSE_CUDA_TRY(cudaMemsetAsync(ws->misc.p, 0, 64, st));
+    if (use_tau) MSE_CUDA_TRY(cudaMemsetAsync(ws->hist.p, 0, sizeof(uint32_t) * size_t(B) * kHistBins, st));   // maxbin: prepare kernel
 
     Bm25Work w{};
     w.q_off = d_q_off; w.q_term = d_q_term; w.q_tf = d_q_tf;
-    w.slot_w = ix->slot_w.as<float>(); w.rec = ix->rec.as<uint2>();
-    w.ts = TauState{ix->tau.as<uint32_t>(), ix->hist.as<uint32_t>(), ix->maxbin.as<uint32_t>(), top_k};
-    w.cand = ix->cand.as<uint64_t>(); w.cand_count = ix->cand_count.as<int32_t>(); w.overflow = ix->cand_count.as<int32_t>() + B;
-    w.item_counter = ix->misc.as<int32_t>();
-    w.stats = reinterpret_cast<unsigned long long*>(ix->misc.as<char>() + 16);
+    w.slot_w = ws->slot_w.as<float>(); w.slot_row = ws->slot_row.as<int32_t>(); w.rec = ws->rec.as<uint2>();
+    w.ts = TauState{ws->tau.as<uint32_t>(), ws->hist.as<uint32_t>(), ws->maxbin.as<uint32_t>(), top_k};
+    w.cand = ws->cand.as<uint64_t>(); w.cand_count = ws->cand_count.as<int32_t>(); w.overflow = ws->cand_count.as<int32_t>() + B;
+    w.item_counter = ws->misc.as<int32_t>();
+    w.stats = reinterpret_cast<unsigned long long*>(ws->misc.as<char>() + 16);
     w.n_queries = B; w.n_slots = S; w.n_sub = n_sub; w.sub_docs = RS; w.queries_per_item = qpi;
     w.cap = cap; w.min_key = float_to_key(min_score + 0.0f); w.use_tau = use_tau;
+    w.neg_lookup = (ix->opt_neg_lookup && bm.neg_imp != nullptr && w.min_key >= float_to_key(0.0f)) ? 1 : 0;
 
-    timer_begin(ix, T_PREPARE, st);
+    int tp = L.timer_begin(T_PREPARE);
     {
         const int tau_ctas = (B + kPrepThreads - 1) / kPrepThreads;
         const size_t psm = std::max(sizeof(int64_t) * size_t((n_sub + kPrepCoarse - 1) / kPrepCoarse + 2) + sizeof(uint32_t) * size_t(n_sub + 2),
                                     n_sub <= kPrepCountMaxSub ? sizeof(int) * size_t(n_sub + 2) : size_t(0));
-        MSE_CUDA_TRY(cudaFuncSetAttribute(bm25_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(std::max<size_t>(psm, 1024))));
+        if (psm > 48 * 1024) MSE_CUDA_TRY(cudaFuncSetAttribute(bm25_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(psm)));
         bm25_prepare_kernel<<<unsigned(S + tau_ctas), kPrepThreads, psm, st>>>(bm, w);
         MSE_CUDA_TRY(cudaGetLastError());
     }
-    timer_end(ix, T_PREPARE, st);
+    L.timer_end(tp);
     if ((rc = debug_sync(st, "bm25_prepare_kernel"))) return rc;
 
     const int chunks = (B + qpi - 1) / qpi;
@@ -227,30 +203,236 @@ int bm25_run(mse_index* ix, int32_t B, const int32_t* d_q_off, const int32_t* d_
     {
         const size_t smem = size_t(kBm25Warps) * bm25_score_warp_bytes(RS);
         const bool hits = ix->opt_readout != 0;        // candidates found while the postings are applied (default) or by a scan
-        const void* kfn;
-        if (hits) kfn = RS == kBm25DefaultRange ? (const void*)bm25_score_kernel<kBm25DefaultRange, true> : (const void*)bm25_score_kernel<0, true>;
-        else kfn = RS == kBm25DefaultRange ? (const void*)bm25_score_kernel<kBm25DefaultRange, false> : (const void*)bm25_score_kernel<0, false>;
-        MSE_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        int per_sm = 0;
-        MSE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kBm25Threads, smem));
+        const bool dflt = RS == kBm25DefaultRange;
+        const void* kfn = score_kernel_fn(dflt, hits);
+        int per_sm = dflt ? ix->score_ctas_per_sm[hits ? 1 : 0] : 0;
+        if (per_sm == 0) {
+            MSE_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+            MSE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kBm25Threads, smem));
+        }
         if (per_sm < 1) { set_error("bm25 score kernel does not fit (sub-range %d docs)", RS); return MSE_ERR_INVALID; }
         grid = int(std::min<int64_t>((n_items + kBm25Warps - 1) / kBm25Warps, int64_t(per_sm) * ix->sm_count));
-        timer_begin(ix, T_SCORE, st);
+        int ts = L.timer_begin(T_SCORE);
         void* args[] = {(void*)&bm, (void*)&w};
-        MSE_CUDA_TRY(cudaLaunchKernel(kfn, dim3(unsigned(grid)), dim3(kBm25Threads), args, smem, st));
-        timer_end(ix, T_SCORE, st);
+        MSE_CUDA_TRY(cudaLaunchKernel(kfn, dim3(unsigned(std::max(grid, 1))), dim3(kBm25Threads), args, smem, st));
+        L.timer_end(ts);
     }
 
     if ((rc = debug_sync(st, "bm25_score_kernel"))) return rc;
     ListLoader ld{w.cand, w.cand_count, int64_t(cap), cap};
-    timer_begin(ix, T_SELECT, st);
+    int tsel = L.timer_begin(T_SELECT);
     topk_select_kernel<ListLoader><<<B, kSelectThreads, 0, st>>>(ld, top_k, d_out_doc, d_out_score, d_out_count,
                                                                 mark_overflow ? w.overflow : nullptr,
-                                                                reinterpret_cast<unsigned long long*>(ix->misc.as<char>() + 32));
+                                                                reinterpret_cast<unsigned long long*>(ws->misc.as<char>() + 32), d_out_key);
     MSE_CUDA_TRY(cudaGetLastError());
-    timer_end(ix, T_SELECT, st);
+    L.timer_end(tsel);
     if ((rc = debug_sync(st, "topk_select_kernel"))) return rc;
-    if (mark_overflow) { ix->stats[3] = n_sub; ix->stats[4] = grid; }
+    if (mark_overflow) {
+        std::lock_guard<std::mutex> lk(ix->mu);
+        ix->stats[3] = n_sub; ix->stats[4] = grid;
+        ix->last_bm25_ws = ws; ix->last_bm25_queries = B;
+    }
+    return MSE_OK;
+}
+
+int32_t bm25_default_cap(const mse_index* ix, int32_t B, int32_t top_k) {
+    // candidate-list capacity: bounded workspace; overflowing queries are re-run (exact calls) or reported (enqueue-only).
+    // (a small batch fits the device in one wave of warps: every sub-range of a query is scored before the running
+    // bound can rise, so only the impact-table seed filters and the lists are given the room a 512 MB workspace allows)
+    int64_t cap = ix->opt_cand_cap > 0 ? ix->opt_cand_cap
+                                       : std::max<int64_t>(std::max<int64_t>(32 * int64_t(top_k), 32768), (int64_t(512) << 20) / (8 * int64_t(B)));
+    cap = std::min<int64_t>(cap, std::max<int64_t>(ix->bm.n_docs, 1));
+    const int64_t budget = int64_t(2) << 30;
+    cap = std::max<int64_t>(std::min<int64_t>(cap, budget / (8 * int64_t(B))), std::min<int64_t>(ix->bm.n_docs, int64_t(top_k)));
+    return int32_t(std::max<int64_t>(cap, 1));
+}
+
+// validates a host CSR; returns S through *n_slots
+int check_host_csr(const int32_t* q_off, int32_t B, int32_t* n_slots) {
+    MSE_REQUIRE(q_off[0] == 0, "q_off[0] must be 0");
+    for (int i = 0; i < B; ++i) {
+        MSE_REQUIRE(q_off[i + 1] >= q_off[i], "q_off not monotone at %d", i);
+        if (q_off[i + 1] - q_off[i] > MSE_MAX_QUERY_TERMS) {
+            set_error("query %d has %d distinct terms (max %d)", i, q_off[i + 1] - q_off[i], MSE_MAX_QUERY_TERMS);
+            return MSE_ERR_UNSUPPORTED;
+        }
+    }
+    *n_slots = q_off[B];
+    return MSE_OK;
+}
+
+// Stages a query CSR on the device.  Host memory: copied into the workspace.  With validate_on_device the offsets are
+// checked by bm25_sanitize_kernel into ws.q_safe (enqueue-only calls; exact calls validate on the host beforehand).
+int stage_queries(Lease& L, int32_t B, int32_t S, const int32_t* q_off, const int32_t* q_term, const int32_t* q_tf, int where,
+                  bool validate_on_device, int32_t* d_status, const int32_t** d_off, const int32_t** d_term, const int32_t** d_tf) {
+    Workspace* ws = L.ws;
+    int rc;
+    *d_off = q_off; *d_term = q_term; *d_tf = q_tf;
+    if (is_host(where)) {
+        if ((rc = ws->q_off.ensure(sizeof(int32_t) * (B + 1)))) return rc;
+        if ((rc = ws->q_term.ensure(sizeof(int32_t) * std::max(S, 1)))) return rc;
+        if ((rc = ws->q_tf.ensure(sizeof(int32_t) * std::max(S, 1)))) return rc;
+        if ((rc = copy_in(ws->q_off.p, q_off, sizeof(int32_t) * (B + 1), where, L.st))) return rc;
+        if ((rc = copy_in(ws->q_term.p, q_term, sizeof(int32_t) * S, where, L.st))) return rc;
+        if ((rc = copy_in(ws->q_tf.p, q_tf, sizeof(int32_t) * S, where, L.st))) return rc;
+        *d_off = ws->q_off.as<int32_t>(); *d_term = ws->q_term.as<int32_t>(); *d_tf = ws->q_tf.as<int32_t>();
+    }
+    if (validate_on_device) {
+        if ((rc = ws->q_safe.ensure(sizeof(int32_t) * (B + 1)))) return rc;
+        bm25_sanitize_kernel<<<1, 1024, 0, L.st>>>(*d_off, ws->q_safe.as<int32_t>(), B, S, d_status);
+        MSE_CUDA_TRY(cudaGetLastError());
+        *d_off = ws->q_safe.as<int32_t>();
+    }
+    return MSE_OK;
+}
+
+// device status record of a call: the caller's (MSE_DEVICE) or a workspace copy that is read back / copied out
+int status_begin(Lease& L, int32_t* status, int where, int32_t** d_status) {
+    int rc;
+    if (where == MSE_DEVICE && status) *d_status = status;
+    else {
+        if ((rc = L.ws->status.ensure(sizeof(int32_t) * MSE_STATUS_WORDS))) return rc;
+        *d_status = L.ws->status.as<int32_t>();
+    }
+    MSE_CUDA_TRY(cudaMemsetAsync(*d_status, 0, sizeof(int32_t) * MSE_STATUS_WORDS, L.st));
+    return MSE_OK;
+}
+
+// ---- exact BM25 (MSE_HOST / MSE_DEVICE): one status read, overflowed queries re-run with capacity n_docs ------------
+int bm25_search_exact(mse_index* ix, Lease& L, int32_t B, int32_t S, const std::vector<int32_t>& h_off, const int32_t* d_off,
+                      const int32_t* d_term, const int32_t* d_tf, int32_t top_k, float min_score,
+                      int32_t* d_doc, float* d_score, int32_t* d_count) {
+    Workspace* ws = L.ws;
+    cudaStream_t st = L.st;
+    int rc;
+    const int32_t cap = bm25_default_cap(ix, B, top_k);
+    const int use_tau = ix->opt_use_tau ? 1 : 0;
+    if ((rc = bm25_enqueue(ix, L, B, d_off, d_term, d_tf, S, top_k, min_score, cap, use_tau, d_doc, d_score, d_count, nullptr, true))) return rc;
+
+    // one 32-byte status read: {postings streamed, postings looked up, candidates handed to the selection, overflowed queries}
+    unsigned long long h_status[4] = {0, 0, 0, 0};
+    MSE_CUDA_TRY(cudaMemcpyAsync(h_status, ws->misc.as<char>() + 16, sizeof(h_status), cudaMemcpyDeviceToHost, st));
+    MSE_CUDA_TRY(cudaStreamSynchronize(st));
+    std::vector<int32_t> redo;
+    if (h_status[3] > 0) {
+        std::vector<int32_t> h_ovf;
+        h_ovf.resize(size_t(B));
+        MSE_CUDA_TRY(cudaMemcpy(h_ovf.data(), ws->cand_count.as<int32_t>() + B, sizeof(int32_t) * B, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < B; ++i) if (h_ovf[i]) redo.push_back(i);
+    }
+    {
+        std::lock_guard<std::mutex> lk(ix->mu);
+        ix->stats[0] = int64_t(h_status[0]);
+        ix->stats[5] = int64_t(h_status[1]);
+        ix->stats[1] = int64_t(h_status[2]);
+        ix->stats[2] = int64_t(redo.size());
+        ix->last_bm25_ws = nullptr;                  // the snapshot above is the answer of mse_bm25_last_stats
+    }
+    if (redo.empty()) return MSE_OK;
+
+    // Unbounded path: capacity == n_docs cannot overflow.  Sub-batches sized to the budget.
+    std::vector<int32_t> h_term, h_tf;
+    h_term.resize(size_t(std::max(S, 1)));
+    h_tf.resize(size_t(std::max(S, 1)));
+    MSE_CUDA_TRY(cudaMemcpy(h_term.data(), d_term, sizeof(int32_t) * S, cudaMemcpyDeviceToHost));
+    MSE_CUDA_TRY(cudaMemcpy(h_tf.data(), d_tf, sizeof(int32_t) * S, cudaMemcpyDeviceToHost));
+    const int64_t fcap = std::max<int64_t>(ix->bm.n_docs, 1);
+    const int64_t budget = int64_t(2) << 30;
+    const int sub = int(std::max<int64_t>(1, std::min<int64_t>(int64_t(redo.size()), budget / (8 * fcap))));
+    for (size_t a = 0; a < redo.size(); a += sub) {
+        const int nb = int(std::min<size_t>(sub, redo.size() - a));
+        std::vector<int32_t> so(size_t(nb) + 1, 0), stm, stf;
+        for (int j = 0; j < nb; ++j) {
+            const int qq = redo[a + j];
+            for (int s = h_off[qq]; s < h_off[qq + 1]; ++s) { stm.push_back(h_term[s]); stf.push_back(h_tf[s]); }
+            so[j + 1] = int32_t(stm.size());
+        }
+        const int32_t SS = so[nb];
+        if ((rc = ws->fb_q[0].ensure(sizeof(int32_t) * (nb + 1)))) return rc;
+        if ((rc = ws->fb_q[1].ensure(sizeof(int32_t) * std::max(SS, 1)))) return rc;
+        if ((rc = ws->fb_q[2].ensure(sizeof(int32_t) * std::max(SS, 1)))) return rc;
+        if ((rc = ws->fb_out[0].ensure(sizeof(int32_t) * size_t(nb) * top_k))) return rc;
+        if ((rc = ws->fb_out[1].ensure(sizeof(float) * size_t(nb) * top_k))) return rc;
+        if ((rc = ws->fb_out[2].ensure(sizeof(int32_t) * size_t(nb)))) return rc;
+        MSE_CUDA_TRY(cudaMemcpyAsync(ws->fb_q[0].p, so.data(), sizeof(int32_t) * (nb + 1), cudaMemcpyHostToDevice, st));
+        MSE_CUDA_TRY(cudaMemcpyAsync(ws->fb_q[1].p, stm.data(), sizeof(int32_t) * SS, cudaMemcpyHostToDevice, st));
+        MSE_CUDA_TRY(cudaMemcpyAsync(ws->fb_q[2].p, stf.data(), sizeof(int32_t) * SS, cudaMemcpyHostToDevice, st));
+        if ((rc = bm25_enqueue(ix, L, nb, ws->fb_q[0].as<int32_t>(), ws->fb_q[1].as<int32_t>(), ws->fb_q[2].as<int32_t>(), SS, top_k,
+                               min_score, int32_t(fcap), 0, ws->fb_out[0].as<int32_t>(), ws->fb_out[1].as<float>(),
+                               ws->fb_out[2].as<int32_t>(), nullptr, false))) return rc;
+        for (int j = 0; j < nb; ++j) {
+            const int qq = redo[a + j];
+            MSE_CUDA_TRY(cudaMemcpyAsync(d_doc + size_t(qq) * top_k, ws->fb_out[0].as<int32_t>() + size_t(j) * top_k,
+                                         sizeof(int32_t) * top_k, cudaMemcpyDeviceToDevice, st));
+            MSE_CUDA_TRY(cudaMemcpyAsync(d_score + size_t(qq) * top_k, ws->fb_out[1].as<float>() + size_t(j) * top_k,
+                                         sizeof(float) * top_k, cudaMemcpyDeviceToDevice, st));
+            MSE_CUDA_TRY(cudaMemcpyAsync(d_count + qq, ws->fb_out[2].as<int32_t>() + j, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+        }
+        MSE_CUDA_TRY(cudaStreamSynchronize(st));     // staging buffers are reused by the next sub-batch
+    }
+    return MSE_OK;
+}
+
+// ---- rerank core (enqueue-only) ------------------------------------------------------------------------------------
+int rerank_enqueue(mse_index* ix, Lease& L, int32_t B, RerankArgs a) {
+    Workspace* ws = L.ws;
+    cudaStream_t st = L.st;
+    int rc;
+    if (!a.url_group && ix->n_url_groups >= ix->dn.n_docs && ix->dn.doc_base == 0 && ix->n_url_groups > 0) a.url_group = ix->url_group.as<int32_t>();
+    const int slices = (B * 4 <= ix->sm_count && ix->dn.doc_base == 0) ? std::min(32, std::max(1, ix->sm_count / B)) : 1;
+    int tr = L.timer_begin(T_RERANK);
+    if (slices > 1) {
+        // Small batch: one CTA per query would leave most SMs idle (batch-1 latency).  Same two kernels as the
+        // host-driven multi-GPU path: cosines by `slices` CTAs per query, then the pool-wide fusion from the gathered cosines.
+        const size_t slots = size_t(B) * kRerankMaxCand;
+        if ((rc = ws->r_split[0].ensure(sizeof(float) * slots * kRerankMaxChunks))) return rc;
+        if ((rc = ws->r_split[1].ensure(sizeof(int32_t) * slots))) return rc;
+        if ((rc = ws->r_split[2].ensure(sizeof(int64_t) * slots))) return rc;
+        if ((rc = ws->r_split[3].ensure(sizeof(int32_t) * slots))) return rc;
+        if ((rc = ws->r_split[4].ensure(sizeof(float) * slots))) return rc;
+        if ((rc = ws->r_split[5].ensure(sizeof(int32_t) * size_t(B)))) return rc;
+        MSE_CUDA_TRY(cudaMemsetAsync(ws->r_split[1].p, 0, sizeof(int32_t) * slots, st));      // rows: 0 = not fetched
+        RerankShardArgs sa{a.cand_off, a.cand_count, a.cand_stride, a.cand_doc, a.cand_bm25, a.url_group, a.q, a.max_chunks,
+                           int64_t(ix->dn.doc_base) + ix->dn.n_docs,
+                           ws->r_split[0].as<float>(), ws->r_split[1].as<int32_t>(), ws->r_split[2].as<int64_t>(),
+                           ws->r_split[3].as<int32_t>(), ws->r_split[4].as<float>(), ws->r_split[5].as<int32_t>()};
+        rerank_shard_cos_kernel<<<dim3(unsigned(B), unsigned(slices)), kRerankThreads, 0, st>>>(ix->dn, sa);
+        MSE_CUDA_TRY(cudaGetLastError());
+        RerankFuseArgs fa{sa.cos, sa.rows, sa.chunk0, sa.surv_doc, sa.surv_bm25, sa.surv_count, a.smoothing, a.max_out,
+                          a.out_doc, a.out_score, a.out_orig, a.out_chunk, a.out_count, a.out_rows};
+        rerank_shard_fuse_kernel<<<B, kRerankThreads, 0, st>>>(fa);
+        MSE_CUDA_TRY(cudaGetLastError());
+    } else {
+        rerank_kernel<<<B, kRerankThreads, kRerankSmemBytes, st>>>(ix->dn, a);
+        MSE_CUDA_TRY(cudaGetLastError());
+    }
+    L.timer_end(tr);
+    return MSE_OK;
+}
+
+int rerank_out_buffers(Workspace* ws, int32_t B, int32_t max_out, RerankArgs& a) {
+    int rc;
+    if ((rc = ws->r_out[0].ensure(sizeof(int32_t) * size_t(B) * max_out))) return rc;
+    if ((rc = ws->r_out[1].ensure(sizeof(float) * size_t(B) * max_out))) return rc;
+    if ((rc = ws->r_out[2].ensure(sizeof(float) * size_t(B) * max_out))) return rc;
+    if ((rc = ws->r_out[3].ensure(sizeof(int64_t) * size_t(B) * max_out))) return rc;
+    if ((rc = ws->r_out[4].ensure(sizeof(int32_t) * size_t(B)))) return rc;
+    if ((rc = ws->r_out[5].ensure(sizeof(int32_t) * size_t(B)))) return rc;
+    a.out_doc = ws->r_out[0].as<int32_t>(); a.out_score = ws->r_out[1].as<float>(); a.out_orig = ws->r_out[2].as<float>();
+    a.out_chunk = ws->r_out[3].as<int64_t>(); a.out_count = ws->r_out[4].as<int32_t>(); a.out_rows = ws->r_out[5].as<int32_t>();
+    return MSE_OK;
+}
+
+int rerank_copy_out(const RerankArgs& a, int32_t B, int32_t max_out, int32_t* out_doc, float* out_score, float* out_orig,
+                    int64_t* out_chunk, int32_t* out_count, int32_t* out_rows, cudaStream_t st) {
+    const size_t n = size_t(B) * max_out;
+    int rc;
+    if ((rc = copy_out(out_doc, a.out_doc, sizeof(int32_t) * n, st))) return rc;
+    if ((rc = copy_out(out_score, a.out_score, sizeof(float) * n, st))) return rc;
+    if ((rc = copy_out(out_orig, a.out_orig, sizeof(float) * n, st))) return rc;
+    if ((rc = copy_out(out_chunk, a.out_chunk, sizeof(int64_t) * n, st))) return rc;
+    if ((rc = copy_out(out_count, a.out_count, sizeof(int32_t) * B, st))) return rc;
+    if ((rc = copy_out(out_rows, a.out_rows, sizeof(int32_t) * B, st))) return rc;
     return MSE_OK;
 }
 
@@ -289,35 +471,31 @@ int mse_index_create(int device, mse_index** out) {
     mse_index* ix = new mse_index();
     ix->device = device;
     ix->sm_count = prop.multiProcessorCount;
-    ix->ev_ok = true;
-    for (int t = 0; t < kNumTimers; ++t)
-        for (int j = 0; j < 2; ++j)
-            if (cudaEventCreate(&ix->ev[t][j]) != cudaSuccess) ix->ev_ok = false;
+    // function attributes are set once here, so that no search call touches them (calls may run inside a stream capture)
+    cudaError_t e = cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kRerankSmemBytes));
+    for (int hits = 0; hits < 2 && e == cudaSuccess; ++hits) {
+        const void* kfn = score_kernel_fn(true, hits != 0);
+        const size_t smem = size_t(kBm25Warps) * bm25_score_warp_bytes(kBm25DefaultRange);
+        e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ix->score_ctas_per_sm[hits], kfn, kBm25Threads, smem);
+    }
+    if (e != cudaSuccess) {
+        set_error("kernel attribute setup failed: %s", cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        delete ix;
+        return MSE_ERR_CUDA;
+    }
     *out = ix;
     return MSE_OK;
 }
 
 int mse_index_destroy(mse_index* ix) {
     if (!ix) return MSE_OK;
-    {
-        DeviceGuard g(ix->device);
-        cudaDeviceSynchronize();
-        DevBuf* all[] = {&ix->term_off, &ix->post_doc, &ix->post_tf, &ix->post2, &ix->skip, &ix->skip_row, &ix->imp_levels, &ix->doc_norm, &ix->idf, &ix->emb, &ix->doc_chunk_off, &ix->row_doc, &ix->tile_row, &ix->group_row, &ix->qb16, &ix->log_key, &ix->log_q,
-                         &ix->q_off, &ix->q_term, &ix->q_tf, &ix->slot_w, &ix->rec, &ix->tau, &ix->hist,
-                         &ix->maxbin, &ix->cand, &ix->cand_count, &ix->overflow, &ix->misc, &ix->o_doc, &ix->o_score,
-                         &ix->o_count, &ix->best, &ix->dq};
-        for (DevBuf* b : all) b->release();
-        for (auto& b : ix->r_in) b.release();
-        for (auto& b : ix->r_out) b.release();
-        for (auto& b : ix->r_split) b.release();
-        for (auto& b : ix->m_in) b.release();
-        for (auto& b : ix->fb_q) b.release();
-        for (auto& b : ix->fb_out) b.release();
-        if (ix->ev_ok)
-            for (int t = 0; t < kNumTimers; ++t)
-                for (int j = 0; j < 2; ++j) cudaEventDestroy(ix->ev[t][j]);
-    }
-    delete ix;
+    DeviceGuard g(ix->device);
+    cudaDeviceSynchronize();
+    if (ix->comm.owned && ix->comm.comm) nccl_api().CommDestroy(ix->comm.comm);
+    ix->pool.all.clear();
+    delete ix;                                   // DevBuf destructors free the index arrays
     return MSE_OK;
 }
 
@@ -326,6 +504,7 @@ int mse_index_set_option(mse_index* ix, const char* name, int64_t value) {
     std::lock_guard<std::mutex> lk(ix->mu);
     if (!strcmp(name, "bm25_range_docs")) ix->opt_range_docs = value;
     else if (!strcmp(name, "bm25_readout")) ix->opt_readout = value;
+    else if (!strcmp(name, "bm25_neg_lookup")) ix->opt_neg_lookup = value;
     else if (!strcmp(name, "bm25_tau_init")) { ix->opt_tau_init = value; ix->bm.imp_levels = (value && ix->has_bm25) ? ix->imp_levels.as<float>() : nullptr; }
     else if (!strcmp(name, "bm25_queries_per_item")) ix->opt_qpi = value;
     else if (!strcmp(name, "bm25_cand_cap")) ix->opt_cand_cap = value;
@@ -333,23 +512,36 @@ int mse_index_set_option(mse_index* ix, const char* name, int64_t value) {
     else if (!strcmp(name, "dense_scan_ctas_per_sm")) ix->opt_scan_ctas = value;
     else if (!strcmp(name, "dense_gemm_min_batch")) ix->opt_gemm_min_batch = value;
     else if (!strcmp(name, "dense_gemm_debug")) ix->opt_gemm_debug = value;
+    else if (!strcmp(name, "timers")) { std::lock_guard<std::mutex> lp(ix->pool.mu); ix->pool.timers_on = value != 0; }
     else if (!strcmp(name, "reset_timers")) {
-        for (int t = 0; t < kNumTimers; ++t) { ix->t_ms[t] = 0; ix->t_n[t] = 0; }
+        DeviceGuard g(ix->device);
+        std::lock_guard<std::mutex> lp(ix->pool.mu);
+        for (auto& w : ix->pool.all) ix->pool.collect(w.get(), true);
+        ix->pool.totals = TimerTotals{};
     } else { set_error("unknown option '%s'", name); return MSE_ERR_INVALID; }
     return MSE_OK;
 }
 
 int mse_kernel_time(mse_index* ix, int kernel, double* total_ms, int64_t* launches) {
     if (!ix || kernel < 0 || kernel >= kNumTimers) { set_error("bad argument"); return MSE_ERR_INVALID; }
-    std::lock_guard<std::mutex> lk(ix->mu);
-    if (total_ms) *total_ms = ix->t_ms[kernel];
-    if (launches) *launches = ix->t_n[kernel];
+    DeviceGuard g(ix->device);
+    std::lock_guard<std::mutex> lp(ix->pool.mu);
+    for (auto& w : ix->pool.all) ix->pool.collect(w.get(), true);       // waits for the launches still in flight
+    if (total_ms) *total_ms = ix->pool.totals.ms[kernel];
+    if (launches) *launches = ix->pool.totals.n[kernel];
     return MSE_OK;
 }
 
 int mse_bm25_last_stats(mse_index* ix, int64_t stats[8]) {
     if (!ix || !stats) { set_error("null argument"); return MSE_ERR_INVALID; }
+    DeviceGuard g(ix->device);
     std::lock_guard<std::mutex> lk(ix->mu);
+    if (ix->last_bm25_ws) {                       // the last call was enqueue-only: fetch its counters now
+        unsigned long long h[4] = {0, 0, 0, 0};
+        MSE_CUDA_TRY(cudaDeviceSynchronize());
+        MSE_CUDA_TRY(cudaMemcpy(h, ix->last_bm25_ws->misc.as<char>() + 16, sizeof(h), cudaMemcpyDeviceToHost));
+        ix->stats[0] = int64_t(h[0]); ix->stats[5] = int64_t(h[1]); ix->stats[1] = int64_t(h[2]); ix->stats[2] = int64_t(h[3]);
+    }
     memcpy(stats, ix->stats, sizeof(ix->stats));
     return MSE_OK;
 }
@@ -367,6 +559,7 @@ int mse_bm25_load(mse_index* ix, int64_t n_terms, int64_t n_docs, int64_t doc_ba
     std::lock_guard<std::mutex> lk(ix->mu);
     DeviceGuard g(ix->device);
     cudaStream_t st = 0;
+    MSE_CUDA_TRY(cudaDeviceSynchronize());               // no search may still read the arrays replaced below
     ix->has_bm25 = false;
     ix->h_term_off.assign(size_t(n_terms) + 1, 0);
     MSE_CUDA_TRY(cudaMemcpy(ix->h_term_off.data(), term_off, sizeof(int64_t) * (n_terms + 1),
@@ -378,19 +571,19 @@ int mse_bm25_load(mse_index* ix, int64_t n_terms, int64_t n_docs, int64_t doc_ba
         MSE_REQUIRE(ix->h_term_off[t + 1] >= ix->h_term_off[t], "term_off not monotone at %lld", (long long)t);
     MSE_REQUIRE(P == 0 || (post_doc && post_tf), "null posting arrays");
     int rc;
+    DevBuf d_post_doc, d_post_tf, d_norm, d_len, d_misc;          // load-time temporaries (freed on every return path)
     if ((rc = ix->term_off.ensure(sizeof(int64_t) * (n_terms + 1)))) return rc;
-    if ((rc = ix->post_doc.ensure(sizeof(int32_t) * (std::max<int64_t>(P, 1) + 8)))) return rc;
-    if ((rc = ix->post_tf.ensure(sizeof(int32_t) * (std::max<int64_t>(P, 1) + 8)))) return rc;
+    if ((rc = d_post_doc.ensure(sizeof(int32_t) * (std::max<int64_t>(P, 1) + 8)))) return rc;
+    if ((rc = d_post_tf.ensure(sizeof(int32_t) * (std::max<int64_t>(P, 1) + 8)))) return rc;
     if ((rc = ix->post2.ensure(sizeof(int2) * (std::max<int64_t>(P, 1) + 8)))) return rc;
-    if ((rc = ix->doc_norm.ensure(sizeof(float) * (std::max<int64_t>(n_docs, 1) + 8)))) return rc;
-    if ((rc = ix->misc.ensure(64))) return rc;
-    MSE_CUDA_TRY(cudaMemsetAsync(ix->misc.p, 0, 64, st));
+    if ((rc = d_norm.ensure(sizeof(float) * (std::max<int64_t>(n_docs, 1) + 8)))) return rc;
+    if ((rc = d_misc.ensure(64))) return rc;
+    MSE_CUDA_TRY(cudaMemsetAsync(d_misc.p, 0, 64, st));
     if ((rc = ix->idf.ensure(sizeof(float) * std::max<int64_t>(n_terms, 1)))) return rc;
-    DevBuf d_len;
     if ((rc = d_len.ensure(sizeof(int32_t) * std::max<int64_t>(n_docs, 1)))) return rc;
     if ((rc = copy_in(ix->term_off.p, term_off, sizeof(int64_t) * (n_terms + 1), where, st))) return rc;
-    if ((rc = copy_in(ix->post_doc.p, post_doc, sizeof(int32_t) * P, where, st))) return rc;
-    if ((rc = copy_in(ix->post_tf.p, post_tf, sizeof(int32_t) * P, where, st))) return rc;
+    if ((rc = copy_in(d_post_doc.p, post_doc, sizeof(int32_t) * P, where, st))) return rc;
+    if ((rc = copy_in(d_post_tf.p, post_tf, sizeof(int32_t) * P, where, st))) return rc;
     if ((rc = copy_in(d_len.p, doc_len, sizeof(int32_t) * n_docs, where, st))) return rc;
     // idf: canonicalise -0.0 -> +0.0 (`idf_score or 0.0`, bm25_indexer.py:426)
     std::vector<float> h_idf;
@@ -399,36 +592,38 @@ int mse_bm25_load(mse_index* ix, int64_t n_terms, int64_t n_docs, int64_t doc_ba
     for (auto& v : h_idf) v = v + 0.0f;
     MSE_CUDA_TRY(cudaMemcpyAsync(ix->idf.p, h_idf.data(), sizeof(float) * n_terms, cudaMemcpyHostToDevice, st));
     if (n_docs > 0) {
-        bm25_norm_kernel<<<unsigned((n_docs + 255) / 256), 256, 0, st>>>(d_len.as<int32_t>(), ix->doc_norm.as<float>(), n_docs,
+        bm25_norm_kernel<<<unsigned((n_docs + 255) / 256), 256, 0, st>>>(d_len.as<int32_t>(), d_norm.as<float>(), n_docs,
                                                                         double(k1), double(b), double(avgdl));
         MSE_CUDA_TRY(cudaGetLastError());
     }
     {
         const int64_t np = P + 8;
-        bm25_interleave_kernel<<<unsigned((np + 255) / 256), 256, 0, st>>>(ix->post_doc.as<int32_t>(), ix->post_tf.as<int32_t>(),
+        bm25_interleave_kernel<<<unsigned((np + 255) / 256), 256, 0, st>>>(d_post_doc.as<int32_t>(), d_post_tf.as<int32_t>(),
                                                                           d_len.as<int32_t>(), ix->post2.as<int2>(), P, np, n_docs,
                                                                           double(k1), double(b), double(avgdl));
         MSE_CUDA_TRY(cudaGetLastError());
     }
     if (n_terms > 0) {
-        bm25_validate_kernel<<<unsigned(std::min<int64_t>((P + 255) / 256 + 1, 148 * 64)), 256, 0, st>>>(ix->term_off.as<int64_t>(), ix->post_doc.as<int32_t>(),
-                                                                         ix->post_tf.as<int32_t>(), n_terms, n_docs, ix->misc.as<int32_t>());
+        bm25_validate_kernel<<<unsigned(std::min<int64_t>((P + 255) / 256 + 1, 148 * 64)), 256, 0, st>>>(ix->term_off.as<int64_t>(), d_post_doc.as<int32_t>(),
+                                                                         d_post_tf.as<int32_t>(), n_terms, n_docs, d_misc.as<int32_t>());
         MSE_CUDA_TRY(cudaGetLastError());
     }
     int32_t flags[2] = {0, 0};
-    MSE_CUDA_TRY(cudaMemcpyAsync(flags, ix->misc.p, sizeof(flags), cudaMemcpyDeviceToHost, st));
+    MSE_CUDA_TRY(cudaMemcpyAsync(flags, d_misc.p, sizeof(flags), cudaMemcpyDeviceToHost, st));
     MSE_CUDA_TRY(cudaStreamSynchronize(st));
     d_len.release();
     const int32_t bad = flags[0];
     MSE_REQUIRE(bad == 0, "malformed postings (code %d): doc ids must be strictly ascending inside a term, within [0,n_docs), tf >= 1", bad);
     if ((rc = ix->imp_levels.ensure(sizeof(float) * kImpLevels * size_t(std::max<int64_t>(n_terms, 1))))) return rc;
-    if (n_terms > 0 && n_docs > 0) {                     // needs doc_norm (bm25_norm_kernel above, same stream)
-        bm25_impact_levels_kernel<<<unsigned(n_terms), kImpThreads, 0, st>>>(ix->term_off.as<int64_t>(), ix->post_doc.as<int32_t>(),
-                                                                            ix->post_tf.as<int32_t>(), ix->doc_norm.as<float>(),
+    if (n_terms > 0 && n_docs > 0) {                     // needs the norms (bm25_norm_kernel above, same stream)
+        bm25_impact_levels_kernel<<<unsigned(n_terms), kImpThreads, 0, st>>>(ix->term_off.as<int64_t>(), d_post_doc.as<int32_t>(),
+                                                                            d_post_tf.as<int32_t>(), d_norm.as<float>(),
                                                                             ix->imp_levels.as<float>(), n_terms);
         MSE_CUDA_TRY(cudaGetLastError());
     }
     MSE_CUDA_TRY(cudaStreamSynchronize(st));
+    // the search kernels read the interleaved {doc, impact} array only
+    d_post_doc.release(); d_post_tf.release(); d_norm.release();
     ix->bm.term_off = ix->term_off.as<int64_t>();
     {   // skip table of the heavy terms
         ix->bm.skip = nullptr; ix->bm.skip_row = nullptr; ix->bm.skip_docs = 0; ix->bm.n_skip = 0;
@@ -451,11 +646,37 @@ int mse_bm25_load(mse_index* ix, int64_t n_terms, int64_t n_docs, int64_t doc_ba
             ix->bm.skip_docs = kSkipDocs; ix->bm.n_skip = n_skip;
         }
     }
-    // the search kernels read the interleaved {doc, impact} array only; the separate copies and the norms were needed
-    // by the load-time kernels
-    ix->post_doc.release();
-    ix->post_tf.release();
-    ix->doc_norm.release();
+    {   // dense impact rows of the negative-idf terms (df > N/2), largest first, within a memory budget
+        ix->bm.neg_row = nullptr; ix->bm.neg_imp = nullptr; ix->bm.neg_stride = 0;
+        std::vector<std::pair<int64_t, int32_t>> neg;          // (df, term)
+        for (int64_t t = 0; t < n_terms; ++t)
+            if (h_idf[t] < 0.f && ix->h_term_off[t + 1] > ix->h_term_off[t]) neg.emplace_back(ix->h_term_off[t + 1] - ix->h_term_off[t], int32_t(t));
+        std::sort(neg.begin(), neg.end(), [](const std::pair<int64_t, int32_t>& x, const std::pair<int64_t, int32_t>& y) {
+            return x.first != y.first ? x.first > y.first : x.second < y.second;
+        });
+        const int64_t stride = ((n_docs + 31) / 32) * 32;
+        const int64_t budget = std::max<int64_t>(int64_t(256) << 20, P * 2);          // bytes: a quarter of the posting array, at least 256 MB
+        const int64_t max_rows = stride > 0 ? std::min<int64_t>(512, budget / (4 * stride)) : 0;
+        const int64_t n_rows = std::min<int64_t>(int64_t(neg.size()), max_rows);
+        if (n_rows > 0) {
+            std::vector<int32_t> h_neg_row(size_t(n_terms), -1), h_row_term(size_t(n_rows), 0);
+            for (int64_t r = 0; r < n_rows; ++r) { h_neg_row[neg[r].second] = int32_t(r); h_row_term[r] = neg[r].second; }
+            DevBuf d_row_term;
+            if ((rc = ix->neg_row.ensure(sizeof(int32_t) * size_t(n_terms)))) return rc;
+            if ((rc = ix->neg_imp.ensure(sizeof(float) * size_t(n_rows) * size_t(stride)))) return rc;
+            if ((rc = d_row_term.ensure(sizeof(int32_t) * size_t(n_rows)))) return rc;
+            MSE_CUDA_TRY(cudaMemcpyAsync(ix->neg_row.p, h_neg_row.data(), sizeof(int32_t) * n_terms, cudaMemcpyHostToDevice, st));
+            MSE_CUDA_TRY(cudaMemcpyAsync(d_row_term.p, h_row_term.data(), sizeof(int32_t) * n_rows, cudaMemcpyHostToDevice, st));
+            MSE_CUDA_TRY(cudaMemsetAsync(ix->neg_imp.p, 0, sizeof(float) * size_t(n_rows) * size_t(stride), st));
+            bm25_neg_rows_kernel<<<dim3(unsigned(std::max<int64_t>(1, std::min<int64_t>(1024, (n_docs + 255) / 256))), unsigned(n_rows)), 256, 0, st>>>(
+                ix->term_off.as<int64_t>(), ix->post2.as<int2>(), d_row_term.as<int32_t>(), ix->neg_imp.as<float>(), stride);
+            MSE_CUDA_TRY(cudaGetLastError());
+            MSE_CUDA_TRY(cudaStreamSynchronize(st));
+            ix->bm.neg_row = ix->neg_row.as<int32_t>(); ix->bm.neg_imp = ix->neg_imp.as<float>(); ix->bm.neg_stride = stride;
+        } else {
+            ix->neg_row.release(); ix->neg_imp.release();
+        }
+    }
     ix->bm.post_doc = nullptr;
     ix->bm.post_tf = nullptr;
     ix->bm.post2 = ix->post2.as<int2>();
@@ -548,22 +769,23 @@ int mse_bm25_aggregate(int device, int64_t n_docs, int64_t n_terms, const int64_
     return MSE_OK;
 }
 
+
+// ---- BM25 search ---------------------------------------------------------------------------------------------------
 int mse_bm25_search_batch(mse_index* ix, int32_t B, const int32_t* q_off, const int32_t* q_term, const int32_t* q_tf,
                           int32_t top_k, float min_score, int32_t* out_doc, float* out_score, int32_t* out_count,
                           int where, void* stream) {
     if (!ix) { set_error("null index"); return MSE_ERR_INVALID; }
-    MSE_REQUIRE(where == MSE_HOST || where == MSE_DEVICE, "bad `where`");
+    MSE_REQUIRE(where == MSE_HOST || where == MSE_DEVICE, "bad `where` (MSE_HOST or MSE_DEVICE; see mse_bm25_search_batch_async)");
     MSE_REQUIRE(B >= 0 && q_off && out_count && (B == 0 || (out_doc && out_score)), "null/negative argument");
     if (top_k < 1 || top_k > MSE_MAX_TOPK) { set_error("top_k %d outside [1, %d]", top_k, MSE_MAX_TOPK); return MSE_ERR_UNSUPPORTED; }
     MSE_REQUIRE(min_score == min_score, "min_score is NaN");
-    std::lock_guard<std::mutex> lk(ix->mu);
     if (!ix->has_bm25) { set_error("mse_bm25_load has not been called"); return MSE_ERR_STATE; }
     if (B == 0) return MSE_OK;
     DeviceGuard g(ix->device);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     int rc;
 
-    // query CSR on the host (needed for the slot count and for the rare overflow re-run)
+    // query CSR on the host (validation, slot count, and the rare overflow re-run)
     std::vector<int32_t> h_off;
     h_off.resize(size_t(B) + 1);
     if (where == MSE_HOST) memcpy(h_off.data(), q_off, sizeof(int32_t) * (B + 1));
@@ -571,109 +793,66 @@ int mse_bm25_search_batch(mse_index* ix, int32_t B, const int32_t* q_off, const 
         MSE_CUDA_TRY(cudaMemcpyAsync(h_off.data(), q_off, sizeof(int32_t) * (B + 1), cudaMemcpyDeviceToHost, st));
         MSE_CUDA_TRY(cudaStreamSynchronize(st));
     }
-    MSE_REQUIRE(h_off[0] == 0, "q_off[0] must be 0");
-    int32_t max_terms = 0;
-    for (int i = 0; i < B; ++i) {
-        MSE_REQUIRE(h_off[i + 1] >= h_off[i], "q_off not monotone at %d", i);
-        max_terms = std::max(max_terms, h_off[i + 1] - h_off[i]);
-        if (h_off[i + 1] - h_off[i] > 32) { set_error("query %d has %d distinct terms (max 32)", i, h_off[i + 1] - h_off[i]); return MSE_ERR_UNSUPPORTED; }
-    }
-    const int32_t S = h_off[B];
+    int32_t S = 0;
+    if ((rc = check_host_csr(h_off.data(), B, &S))) return rc;
     MSE_REQUIRE(S == 0 || (q_term && q_tf), "null query arrays");
 
-    const int32_t *d_off = q_off, *d_term = q_term, *d_tf = q_tf;
+    Lease L(&ix->pool, st);
+    Workspace* ws = L.ws;
+    const int32_t *d_off, *d_term, *d_tf;
+    if ((rc = stage_queries(L, B, S, q_off, q_term, q_tf, where, false, nullptr, &d_off, &d_term, &d_tf))) return rc;
     int32_t* d_doc = out_doc; float* d_score = out_score; int32_t* d_count = out_count;
     if (where == MSE_HOST) {
-        if ((rc = ix->q_off.ensure(sizeof(int32_t) * (B + 1)))) return rc;
-        if ((rc = ix->q_term.ensure(sizeof(int32_t) * std::max(S, 1)))) return rc;
-        if ((rc = ix->q_tf.ensure(sizeof(int32_t) * std::max(S, 1)))) return rc;
-        if ((rc = ix->o_doc.ensure(sizeof(int32_t) * size_t(B) * top_k))) return rc;
-        if ((rc = ix->o_score.ensure(sizeof(float) * size_t(B) * top_k))) return rc;
-        if ((rc = ix->o_count.ensure(sizeof(int32_t) * size_t(B)))) return rc;
-        if ((rc = copy_in(ix->q_off.p, q_off, sizeof(int32_t) * (B + 1), where, st))) return rc;
-        if ((rc = copy_in(ix->q_term.p, q_term, sizeof(int32_t) * S, where, st))) return rc;
-        if ((rc = copy_in(ix->q_tf.p, q_tf, sizeof(int32_t) * S, where, st))) return rc;
-        d_off = ix->q_off.as<int32_t>(); d_term = ix->q_term.as<int32_t>(); d_tf = ix->q_tf.as<int32_t>();
-        d_doc = ix->o_doc.as<int32_t>(); d_score = ix->o_score.as<float>(); d_count = ix->o_count.as<int32_t>();
+        if ((rc = ws->o_doc.ensure(sizeof(int32_t) * size_t(B) * top_k))) return rc;
+        if ((rc = ws->o_score.ensure(sizeof(float) * size_t(B) * top_k))) return rc;
+        if ((rc = ws->o_count.ensure(sizeof(int32_t) * size_t(B)))) return rc;
+        d_doc = ws->o_doc.as<int32_t>(); d_score = ws->o_score.as<float>(); d_count = ws->o_count.as<int32_t>();
     }
-
-    // candidate-list capacity: bounded workspace; overflowing queries are re-run below
-    // (a small batch fits the device in one wave of warps: every sub-range of a query is scored before the running
-    // bound can rise, so only the impact-table seed filters and the lists are given the room a 512 MB workspace allows)
-    int64_t cap = ix->opt_cand_cap > 0 ? ix->opt_cand_cap
-                                       : std::max<int64_t>(std::max<int64_t>(32 * int64_t(top_k), 32768), (int64_t(512) << 20) / (8 * int64_t(B)));
-    cap = std::min<int64_t>(cap, std::max<int64_t>(ix->bm.n_docs, 1));
-    const int64_t budget = int64_t(2) << 30;
-    cap = std::max<int64_t>(std::min<int64_t>(cap, budget / (8 * int64_t(B))), std::min<int64_t>(ix->bm.n_docs, int64_t(top_k)));
-    cap = std::max<int64_t>(cap, 1);
-    const int use_tau = ix->opt_use_tau ? 1 : 0;
-
-    if ((rc = bm25_run(ix, B, d_off, d_term, d_tf, S, max_terms, top_k, min_score, int32_t(cap), use_tau, d_doc, d_score, d_count, true, st))) return rc;
-
-    // one 32-byte status read: {postings traversed, -, candidates handed to the selection, overflowed queries}
-    unsigned long long h_status[4] = {0, 0, 0, 0};
-    MSE_CUDA_TRY(cudaMemcpyAsync(h_status, ix->misc.as<char>() + 16, sizeof(h_status), cudaMemcpyDeviceToHost, st));
-    MSE_CUDA_TRY(cudaStreamSynchronize(st));
-    timers_collect(ix);
-    std::vector<int32_t> redo;
-    if (h_status[3] > 0) {
-        std::vector<int32_t> h_ovf;
-        h_ovf.resize(size_t(B));
-        MSE_CUDA_TRY(cudaMemcpy(h_ovf.data(), ix->cand_count.as<int32_t>() + B, sizeof(int32_t) * B, cudaMemcpyDeviceToHost));
-        for (int i = 0; i < B; ++i) if (h_ovf[i]) redo.push_back(i);
-    }
-    ix->stats[0] = int64_t(h_status[0]);
-    ix->stats[1] = int64_t(h_status[2]);
-    ix->stats[2] = int64_t(redo.size());
-
-    if (!redo.empty()) {
-        // Unbounded path: capacity == n_docs cannot overflow.  Sub-batches sized to the budget.
-        std::vector<int32_t> h_term, h_tf;
-        h_term.resize(size_t(std::max(S, 1)));
-        h_tf.resize(size_t(std::max(S, 1)));
-        MSE_CUDA_TRY(cudaMemcpy(h_term.data(), d_term, sizeof(int32_t) * S, cudaMemcpyDeviceToHost));
-        MSE_CUDA_TRY(cudaMemcpy(h_tf.data(), d_tf, sizeof(int32_t) * S, cudaMemcpyDeviceToHost));
-        const int64_t fcap = std::max<int64_t>(ix->bm.n_docs, 1);
-        const int sub = int(std::max<int64_t>(1, std::min<int64_t>(int64_t(redo.size()), budget / (8 * fcap))));
-        for (size_t a = 0; a < redo.size(); a += sub) {
-            const int nb = int(std::min<size_t>(sub, redo.size() - a));
-            std::vector<int32_t> so(size_t(nb) + 1, 0), stm, stf;
-            for (int j = 0; j < nb; ++j) {
-                const int qq = redo[a + j];
-                for (int s = h_off[qq]; s < h_off[qq + 1]; ++s) { stm.push_back(h_term[s]); stf.push_back(h_tf[s]); }
-                so[j + 1] = int32_t(stm.size());
-            }
-            const int32_t SS = so[nb];
-            if ((rc = ix->fb_q[0].ensure(sizeof(int32_t) * (nb + 1)))) return rc;
-            if ((rc = ix->fb_q[1].ensure(sizeof(int32_t) * std::max(SS, 1)))) return rc;
-            if ((rc = ix->fb_q[2].ensure(sizeof(int32_t) * std::max(SS, 1)))) return rc;
-            if ((rc = ix->fb_out[0].ensure(sizeof(int32_t) * size_t(nb) * top_k))) return rc;
-            if ((rc = ix->fb_out[1].ensure(sizeof(float) * size_t(nb) * top_k))) return rc;
-            if ((rc = ix->fb_out[2].ensure(sizeof(int32_t) * size_t(nb)))) return rc;
-            MSE_CUDA_TRY(cudaMemcpyAsync(ix->fb_q[0].p, so.data(), sizeof(int32_t) * (nb + 1), cudaMemcpyHostToDevice, st));
-            MSE_CUDA_TRY(cudaMemcpyAsync(ix->fb_q[1].p, stm.data(), sizeof(int32_t) * SS, cudaMemcpyHostToDevice, st));
-            MSE_CUDA_TRY(cudaMemcpyAsync(ix->fb_q[2].p, stf.data(), sizeof(int32_t) * SS, cudaMemcpyHostToDevice, st));
-            if ((rc = bm25_run(ix, nb, ix->fb_q[0].as<int32_t>(), ix->fb_q[1].as<int32_t>(), ix->fb_q[2].as<int32_t>(), SS, max_terms, top_k,
-                               min_score, int32_t(fcap), 0, ix->fb_out[0].as<int32_t>(), ix->fb_out[1].as<float>(),
-                               ix->fb_out[2].as<int32_t>(), false, st))) return rc;
-            for (int j = 0; j < nb; ++j) {
-                const int qq = redo[a + j];
-                MSE_CUDA_TRY(cudaMemcpyAsync(d_doc + size_t(qq) * top_k, ix->fb_out[0].as<int32_t>() + size_t(j) * top_k,
-                                             sizeof(int32_t) * top_k, cudaMemcpyDeviceToDevice, st));
-                MSE_CUDA_TRY(cudaMemcpyAsync(d_score + size_t(qq) * top_k, ix->fb_out[1].as<float>() + size_t(j) * top_k,
-                                             sizeof(float) * top_k, cudaMemcpyDeviceToDevice, st));
-                MSE_CUDA_TRY(cudaMemcpyAsync(d_count + qq, ix->fb_out[2].as<int32_t>() + j, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
-            }
-            MSE_CUDA_TRY(cudaStreamSynchronize(st));     // staging buffers are reused by the next sub-batch
-            for (int t = 0; t < kNumTimers; ++t) ix->t_pending[t] = false;   // timers describe the main pass only
-        }
-    }
-
+    if ((rc = bm25_search_exact(ix, L, B, S, h_off, d_off, d_term, d_tf, top_k, min_score, d_doc, d_score, d_count))) return rc;
     if (where == MSE_HOST) {
-        MSE_CUDA_TRY(cudaMemcpyAsync(out_doc, d_doc, sizeof(int32_t) * size_t(B) * top_k, cudaMemcpyDeviceToHost, st));
-        MSE_CUDA_TRY(cudaMemcpyAsync(out_score, d_score, sizeof(float) * size_t(B) * top_k, cudaMemcpyDeviceToHost, st));
-        MSE_CUDA_TRY(cudaMemcpyAsync(out_count, d_count, sizeof(int32_t) * size_t(B), cudaMemcpyDeviceToHost, st));
+        if ((rc = copy_out(out_doc, d_doc, sizeof(int32_t) * size_t(B) * top_k, st))) return rc;
+        if ((rc = copy_out(out_score, d_score, sizeof(float) * size_t(B) * top_k, st))) return rc;
+        if ((rc = copy_out(out_count, d_count, sizeof(int32_t) * size_t(B), st))) return rc;
         MSE_CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    return MSE_OK;
+}
+
+int mse_bm25_search_batch_async(mse_index* ix, int32_t B, int32_t S, const int32_t* q_off, const int32_t* q_term,
+                                const int32_t* q_tf, int32_t top_k, float min_score, int32_t* out_doc, float* out_score,
+                                int32_t* out_count, int32_t* status, int where, void* stream) {
+    if (!ix) { set_error("null index"); return MSE_ERR_INVALID; }
+    MSE_REQUIRE(where == MSE_DEVICE || where == MSE_HOST_ASYNC, "bad `where` (MSE_DEVICE or MSE_HOST_ASYNC)");
+    MSE_REQUIRE(B >= 0 && S >= 0 && q_off && out_count && (B == 0 || (out_doc && out_score)) && (S == 0 || (q_term && q_tf)), "null/negative argument");
+    if (top_k < 1 || top_k > MSE_MAX_TOPK) { set_error("top_k %d outside [1, %d]", top_k, MSE_MAX_TOPK); return MSE_ERR_UNSUPPORTED; }
+    MSE_REQUIRE(min_score == min_score, "min_score is NaN");
+    if (!ix->has_bm25) { set_error("mse_bm25_load has not been called"); return MSE_ERR_STATE; }
+    if (B == 0) return MSE_OK;
+    DeviceGuard g(ix->device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int rc;
+    Lease L(&ix->pool, st);
+    Workspace* ws = L.ws;
+    int32_t* d_status;
+    if ((rc = status_begin(L, status, where, &d_status))) return rc;
+    const int32_t *d_off, *d_term, *d_tf;
+    if ((rc = stage_queries(L, B, S, q_off, q_term, q_tf, where, true, d_status, &d_off, &d_term, &d_tf))) return rc;
+    int32_t* d_doc = out_doc; float* d_score = out_score; int32_t* d_count = out_count;
+    if (where == MSE_HOST_ASYNC) {
+        if ((rc = ws->o_doc.ensure(sizeof(int32_t) * size_t(B) * top_k))) return rc;
+        if ((rc = ws->o_score.ensure(sizeof(float) * size_t(B) * top_k))) return rc;
+        if ((rc = ws->o_count.ensure(sizeof(int32_t) * size_t(B)))) return rc;
+        d_doc = ws->o_doc.as<int32_t>(); d_score = ws->o_score.as<float>(); d_count = ws->o_count.as<int32_t>();
+    }
+    if ((rc = bm25_enqueue(ix, L, B, d_off, d_term, d_tf, S, top_k, min_score, bm25_default_cap(ix, B, top_k), ix->opt_use_tau ? 1 : 0,
+                           d_doc, d_score, d_count, nullptr, true))) return rc;
+    status_add_counter_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const unsigned long long*>(ws->misc.as<char>() + 40), d_status + 1);
+    MSE_CUDA_TRY(cudaGetLastError());
+    if (where == MSE_HOST_ASYNC) {
+        if ((rc = copy_out(out_doc, d_doc, sizeof(int32_t) * size_t(B) * top_k, st))) return rc;
+        if ((rc = copy_out(out_score, d_score, sizeof(float) * size_t(B) * top_k, st))) return rc;
+        if ((rc = copy_out(out_count, d_count, sizeof(int32_t) * size_t(B), st))) return rc;
+        if (status && (rc = copy_out(status, d_status, sizeof(int32_t) * MSE_STATUS_WORDS, st))) return rc;
     }
     return MSE_OK;
 }
@@ -692,6 +871,7 @@ int mse_dense_load(mse_index* ix, int64_t n_chunks, int64_t n_docs, int64_t doc_
     std::lock_guard<std::mutex> lk(ix->mu);
     DeviceGuard g(ix->device);
     cudaStream_t st = 0;
+    MSE_CUDA_TRY(cudaDeviceSynchronize());
     ix->has_dense = false;
     std::vector<int64_t> h_off;
     h_off.resize(size_t(n_docs) + 1);
@@ -726,7 +906,6 @@ int mse_dense_load(mse_index* ix, int64_t n_chunks, int64_t n_docs, int64_t doc_
                 MSE_CUDA_TRY(cudaGetLastError());
             }
             MSE_CUDA_TRY(cudaStreamSynchronize(st));
-            tmp.release();
         }
     }
     // doc-aligned scan tiles of ~kScanTileRows rows, and the row -> doc map
@@ -774,124 +953,197 @@ int mse_dense_load(mse_index* ix, int64_t n_chunks, int64_t n_docs, int64_t doc_
     return MSE_OK;
 }
 
+int mse_dense_set_url_groups(mse_index* ix, const int32_t* url_group, int64_t n, int where) {
+    if (!ix) { set_error("null index"); return MSE_ERR_INVALID; }
+    MSE_REQUIRE(where == MSE_HOST || where == MSE_DEVICE, "bad `where`");
+    MSE_REQUIRE(n >= 0 && (n == 0 || url_group), "null/negative argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    MSE_CUDA_TRY(cudaDeviceSynchronize());
+    ix->n_url_groups = 0;
+    if (n == 0) { ix->url_group.release(); return MSE_OK; }
+    int rc;
+    if ((rc = ix->url_group.ensure(sizeof(int32_t) * size_t(n)))) return rc;
+    MSE_CUDA_TRY(cudaMemcpy(ix->url_group.p, url_group, sizeof(int32_t) * size_t(n), where == MSE_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice));
+    ix->n_url_groups = n;
+    return MSE_OK;
+}
+
+namespace {
+// one pass of the scan + selection over queries [g0, g0 + gn) (enqueue-only)
+int dense_scan_pass(mse_index* ix, Lease& L, const float* d_q, int g0, int gn, int64_t rcap, int rtau, int32_t top_k,
+                    int32_t* o_doc, float* o_score, int32_t* o_count, uint64_t* o_key, bool mark, bool timed) {
+    Workspace* ws = L.ws;
+    cudaStream_t st = L.st;
+    const DenseDev& dn = ix->dn;
+    int r;
+    const int64_t gemm_min = ix->opt_gemm_min_batch > 0 ? ix->opt_gemm_min_batch : 8;
+    const bool use_gemm = ix->gemm_ok && gn >= gemm_min;
+    const int per_sm = ix->opt_scan_ctas > 0 ? int(ix->opt_scan_ctas) : 2;
+    const int grid = int(std::min<int64_t>((dn.n_tiles + kScanThreads / 32 - 1) / (kScanThreads / 32) + 1, int64_t(per_sm) * ix->sm_count));
+    if ((r = ws->tau.ensure(sizeof(uint32_t) * size_t(gn)))) return r;
+    if ((r = ws->hist.ensure(sizeof(uint32_t) * size_t(gn) * kHistBins))) return r;
+    if ((r = ws->maxbin.ensure(sizeof(uint32_t) * size_t(gn)))) return r;
+    if ((r = ws->cand.ensure(sizeof(uint64_t) * size_t(gn) * rcap))) return r;
+    if ((r = ws->cand_count.ensure(sizeof(int32_t) * size_t(gn)))) return r;
+    MSE_CUDA_TRY(cudaMemsetAsync(ws->cand_count.p, 0, sizeof(int32_t) * size_t(gn), st));
+    MSE_CUDA_TRY(cudaMemsetAsync(ws->tau.p, 0, sizeof(uint32_t) * size_t(gn), st));
+    if (rtau) {
+        MSE_CUDA_TRY(cudaMemsetAsync(ws->hist.p, 0, sizeof(uint32_t) * size_t(gn) * kHistBins, st));
+        MSE_CUDA_TRY(cudaMemsetAsync(ws->maxbin.p, 0, sizeof(uint32_t) * size_t(gn), st));
+    }
+    DenseWork w{};
+    w.q = d_q + size_t(g0) * kDim;
+    w.cand = ws->cand.as<uint64_t>(); w.cand_count = ws->cand_count.as<int32_t>();
+    w.overflow = ws->overflow.as<int32_t>() + g0;
+    w.ts = TauState{ws->tau.as<uint32_t>(), ws->hist.as<uint32_t>(), ws->maxbin.as<uint32_t>(), top_k};
+    w.cap = int32_t(rcap); w.use_tau = rtau;
+    int tscan = timed ? L.timer_begin(T_SCAN) : -1;
+    if (dn.n_chunks > 0 && use_gemm && rtau) {
+        // ---- tensor-core path: S = E * Q^T with the per-doc max / emit epilogue on TMEM ----
+        const int n_pad = round_up(gn, 32);
+        if ((r = ws->qb16.ensure(sizeof(__nv_bfloat16) * size_t(n_pad) * kDim))) return r;
+        gemm_pack_q_kernel<<<unsigned((int64_t(n_pad) * kDim + 255) / 256), 256, 0, st>>>(w.q, ws->qb16.as<__nv_bfloat16>(), gn, n_pad);
+        MSE_CUDA_TRY(cudaGetLastError());
+        CUtensorMap map_q;
+        if ((r = make_bf16_rowmajor_map(&map_q, ws->qb16.p, uint64_t(n_pad), uint32_t(n_pad)))) return r;
+        GemmWork gw{};
+        gw.group_row = ix->group_row.as<int64_t>(); gw.n_groups = ix->n_groups; gw.n_tiles = (ix->n_groups + 3) / 4;
+        gw.n_pad = n_pad; gw.n_real = gn; gw.q0 = 0; gw.debug = int(ix->opt_gemm_debug);
+        const size_t stage_bytes = gemm_stage_bytes(n_pad);
+        gw.stages = int(std::min<size_t>(8, (size_t(208) * 1024) / stage_bytes));
+        const size_t gsmem = stage_bytes * gw.stages + 1024;
+        MSE_CUDA_TRY(cudaFuncSetAttribute(dense_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gsmem)));
+        const int ggrid = int(std::min<int64_t>(gw.n_tiles, ix->sm_count));
+        const int64_t log_cap = std::min<int64_t>(int64_t(gn) * 65536, int64_t(64) << 20);
+        if ((r = ws->log_key.ensure(sizeof(uint64_t) * size_t(log_cap)))) return r;
+        if ((r = ws->log_q.ensure(sizeof(uint16_t) * size_t(log_cap)))) return r;
+        if ((r = ws->misc.ensure(64))) return r;
+        MSE_CUDA_TRY(cudaMemsetAsync(ws->misc.p, 0, 64, st));
+        w.log_key = ws->log_key.as<uint64_t>(); w.log_q = ws->log_q.as<uint16_t>();
+        w.log_count = reinterpret_cast<unsigned long long*>(ws->misc.as<char>() + 32);
+        w.log_cap = log_cap; w.n_log_queries = gn;
+        dense_gemm_kernel<<<ggrid, kGemmThreads, gsmem, st>>>(ix->map_e, map_q, dn, w, gw);
+        MSE_CUDA_TRY(cudaGetLastError());
+        gemm_bucket_kernel<<<ix->sm_count * 4, 256, 0, st>>>(w);
+        MSE_CUDA_TRY(cudaGetLastError());
+    } else if (dn.n_chunks > 0) {
+        int b = 0;
+        while (b < gn) {                                   // every pass streams the whole matrix once
+            if (gn - b >= 2) { dense_scan_kernel<2><<<grid, kScanThreads, 0, st>>>(dn, w, b); b += 2; }
+            else { dense_scan_kernel<1><<<grid, kScanThreads, 0, st>>>(dn, w, b); b += 1; }
+            MSE_CUDA_TRY(cudaGetLastError());
+        }
+    }
+    L.timer_end(tscan);
+    ListLoader ld{w.cand, w.cand_count, rcap, int32_t(rcap)};
+    int tsel = timed ? L.timer_begin(T_SELECT) : -1;
+    topk_select_kernel<ListLoader><<<gn, kSelectThreads, 0, st>>>(ld, top_k, o_doc, o_score, o_count, mark ? w.overflow : nullptr, nullptr, o_key);
+    MSE_CUDA_TRY(cudaGetLastError());
+    L.timer_end(tsel);
+    return MSE_OK;
+}
+
+// scan of the whole batch in groups of <= 256 queries; overflowed queries are marked in ws.overflow[B]
+int dense_scan_enqueue(mse_index* ix, Lease& L, int32_t B, const float* d_q, int32_t top_k, int32_t* d_doc, float* d_score,
+                       int32_t* d_count, uint64_t* d_key, int64_t* cap_out) {
+    Workspace* ws = L.ws;
+    int rc;
+    const int64_t D = std::max<int64_t>(ix->dn.n_docs, 1);
+    int64_t cap = ix->opt_cand_cap > 0 ? ix->opt_cand_cap : std::max<int64_t>(64 * int64_t(top_k), 262144);
+    cap = std::max<int64_t>(1, std::min<int64_t>(cap, D));
+    const int group = int(std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(B, 256), (int64_t(2) << 30) / (8 * cap))));
+    const int use_tau = ix->opt_use_tau ? 1 : 0;
+    if ((rc = ws->overflow.ensure(sizeof(int32_t) * size_t(B)))) return rc;
+    MSE_CUDA_TRY(cudaMemsetAsync(ws->overflow.p, 0, sizeof(int32_t) * size_t(B), L.st));
+    for (int g0 = 0; g0 < B; g0 += group) {
+        const int gn = std::min(group, B - g0);
+        if ((rc = dense_scan_pass(ix, L, d_q, g0, gn, cap, use_tau, top_k, d_doc ? d_doc + size_t(g0) * top_k : nullptr,
+                                  d_score ? d_score + size_t(g0) * top_k : nullptr, d_count ? d_count + g0 : nullptr,
+                                  d_key ? d_key + size_t(g0) * top_k : nullptr, true, g0 == 0))) return rc;
+    }
+    if (cap_out) *cap_out = cap;
+    return MSE_OK;
+}
+}  // namespace
+
 int mse_dense_scan_batch(mse_index* ix, int32_t B, const float* q, int32_t top_k, int32_t* out_doc, float* out_score,
                          int32_t* out_count, int where, void* stream) {
     if (!ix) { set_error("null index"); return MSE_ERR_INVALID; }
-    MSE_REQUIRE(where == MSE_HOST || where == MSE_DEVICE, "bad `where`");
+    MSE_REQUIRE(where == MSE_HOST || where == MSE_DEVICE, "bad `where` (MSE_HOST or MSE_DEVICE; see mse_dense_scan_batch_async)");
     MSE_REQUIRE(B >= 0 && out_count && (B == 0 || (q && out_doc && out_score)), "null/negative argument");
     if (top_k < 1 || top_k > MSE_MAX_TOPK) { set_error("top_k %d outside [1, %d]", top_k, MSE_MAX_TOPK); return MSE_ERR_UNSUPPORTED; }
-    std::lock_guard<std::mutex> lk(ix->mu);
     if (!ix->has_dense) { set_error("mse_dense_load has not been called"); return MSE_ERR_STATE; }
     if (B == 0) return MSE_OK;
     DeviceGuard g(ix->device);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const DenseDev& dn = ix->dn;
+    Lease L(&ix->pool, st);
+    Workspace* ws = L.ws;
     int rc;
     const float* d_q = q;
     int32_t* d_doc = out_doc; float* d_score = out_score; int32_t* d_count = out_count;
     if (where == MSE_HOST) {
-        if ((rc = ix->dq.ensure(sizeof(float) * size_t(B) * kDim))) return rc;
-        if ((rc = ix->o_doc.ensure(sizeof(int32_t) * size_t(B) * top_k))) return rc;
-        if ((rc = ix->o_score.ensure(sizeof(float) * size_t(B) * top_k))) return rc;
-        if ((rc = ix->o_count.ensure(sizeof(int32_t) * size_t(B)))) return rc;
-        if ((rc = copy_in(ix->dq.p, q, sizeof(float) * size_t(B) * kDim, where, st))) return rc;
-        d_q = ix->dq.as<float>(); d_doc = ix->o_doc.as<int32_t>(); d_score = ix->o_score.as<float>(); d_count = ix->o_count.as<int32_t>();
+        if ((rc = ws->dq.ensure(sizeof(float) * size_t(B) * kDim))) return rc;
+        if ((rc = ws->o_doc.ensure(sizeof(int32_t) * size_t(B) * top_k))) return rc;
+        if ((rc = ws->o_score.ensure(sizeof(float) * size_t(B) * top_k))) return rc;
+        if ((rc = ws->o_count.ensure(sizeof(int32_t) * size_t(B)))) return rc;
+        if ((rc = copy_in(ws->dq.p, q, sizeof(float) * size_t(B) * kDim, where, st))) return rc;
+        d_q = ws->dq.as<float>(); d_doc = ws->o_doc.as<int32_t>(); d_score = ws->o_score.as<float>(); d_count = ws->o_count.as<int32_t>();
     }
-    const int64_t D = std::max<int64_t>(dn.n_docs, 1);
-    int64_t cap = ix->opt_cand_cap > 0 ? ix->opt_cand_cap : std::max<int64_t>(64 * int64_t(top_k), 262144);
-    cap = std::max<int64_t>(1, std::min<int64_t>(cap, D));
-    const int64_t gemm_min = ix->opt_gemm_min_batch > 0 ? ix->opt_gemm_min_batch : 8;
-    const bool use_gemm = ix->gemm_ok && B >= gemm_min;
-    const int group = int(std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(B, 256), (int64_t(2) << 30) / (8 * cap))));
-    const int use_tau = ix->opt_use_tau ? 1 : 0;
-    const int per_sm = ix->opt_scan_ctas > 0 ? int(ix->opt_scan_ctas) : 2;
-    const int grid = int(std::min<int64_t>((dn.n_tiles + kScanThreads / 32 - 1) / (kScanThreads / 32) + 1, int64_t(per_sm) * ix->sm_count));
+    if ((rc = dense_scan_enqueue(ix, L, B, d_q, top_k, d_doc, d_score, d_count, nullptr, nullptr))) return rc;
     std::vector<int32_t> h_ovf;
     h_ovf.resize(size_t(B));
-    if ((rc = ix->overflow.ensure(sizeof(int32_t) * size_t(B)))) return rc;
-    MSE_CUDA_TRY(cudaMemsetAsync(ix->overflow.p, 0, sizeof(int32_t) * size_t(B), st));
-    auto run = [&](int g0, int gn, int64_t rcap, int rtau, int32_t* o_doc, float* o_score, int32_t* o_count, bool mark, bool timed) -> int {
-        int r;
-        if ((r = ix->tau.ensure(sizeof(uint32_t) * size_t(gn)))) return r;
-        if ((r = ix->hist.ensure(sizeof(uint32_t) * size_t(gn) * kHistBins))) return r;
-        if ((r = ix->maxbin.ensure(sizeof(uint32_t) * size_t(gn)))) return r;
-        if ((r = ix->cand.ensure(sizeof(uint64_t) * size_t(gn) * rcap))) return r;
-        if ((r = ix->cand_count.ensure(sizeof(int32_t) * size_t(gn)))) return r;
-        MSE_CUDA_TRY(cudaMemsetAsync(ix->cand_count.p, 0, sizeof(int32_t) * size_t(gn), st));
-        MSE_CUDA_TRY(cudaMemsetAsync(ix->tau.p, 0, sizeof(uint32_t) * size_t(gn), st));
-        if (rtau) {
-            MSE_CUDA_TRY(cudaMemsetAsync(ix->hist.p, 0, sizeof(uint32_t) * size_t(gn) * kHistBins, st));
-            MSE_CUDA_TRY(cudaMemsetAsync(ix->maxbin.p, 0, sizeof(uint32_t) * size_t(gn), st));
-        }
-        DenseWork w{};
-        w.q = d_q + size_t(g0) * kDim;
-        w.cand = ix->cand.as<uint64_t>(); w.cand_count = ix->cand_count.as<int32_t>();
-        w.overflow = ix->overflow.as<int32_t>() + g0;
-        w.ts = TauState{ix->tau.as<uint32_t>(), ix->hist.as<uint32_t>(), ix->maxbin.as<uint32_t>(), top_k};
-        w.cap = int32_t(rcap); w.use_tau = rtau;
-        if (timed) timer_begin(ix, T_SCAN, st);
-        if (dn.n_chunks > 0 && use_gemm && rtau) {
-            // ---- tensor-core path: S = E * Q^T with the per-doc max / emit epilogue on TMEM ----
-            const int n_pad = round_up(gn, 32);
-            if ((r = ix->qb16.ensure(sizeof(__nv_bfloat16) * size_t(n_pad) * kDim))) return r;
-            gemm_pack_q_kernel<<<unsigned((int64_t(n_pad) * kDim + 255) / 256), 256, 0, st>>>(w.q, ix->qb16.as<__nv_bfloat16>(), gn, n_pad);
-            MSE_CUDA_TRY(cudaGetLastError());
-            CUtensorMap map_q;
-            if ((r = make_bf16_rowmajor_map(&map_q, ix->qb16.p, uint64_t(n_pad), uint32_t(n_pad)))) return r;
-            GemmWork gw{};
-            gw.group_row = ix->group_row.as<int64_t>(); gw.n_groups = ix->n_groups; gw.n_tiles = (ix->n_groups + 3) / 4;
-            gw.n_pad = n_pad; gw.n_real = gn; gw.q0 = 0; gw.debug = int(ix->opt_gemm_debug);
-            const size_t stage_bytes = gemm_stage_bytes(n_pad);
-            gw.stages = int(std::min<size_t>(8, (size_t(208) * 1024) / stage_bytes));
-            const size_t gsmem = stage_bytes * gw.stages + 1024;
-            MSE_CUDA_TRY(cudaFuncSetAttribute(dense_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gsmem)));
-            const int ggrid = int(std::min<int64_t>(gw.n_tiles, ix->sm_count));
-            const int64_t log_cap = std::min<int64_t>(int64_t(gn) * 65536, int64_t(64) << 20);
-            if ((r = ix->log_key.ensure(sizeof(uint64_t) * size_t(log_cap)))) return r;
-            if ((r = ix->log_q.ensure(sizeof(uint16_t) * size_t(log_cap)))) return r;
-            if ((r = ix->misc.ensure(64))) return r;
-            MSE_CUDA_TRY(cudaMemsetAsync(ix->misc.p, 0, 64, st));
-            w.log_key = ix->log_key.as<uint64_t>(); w.log_q = ix->log_q.as<uint16_t>();
-            w.log_count = reinterpret_cast<unsigned long long*>(ix->misc.as<char>() + 32);
-            w.log_cap = log_cap; w.n_log_queries = gn;
-            dense_gemm_kernel<<<ggrid, kGemmThreads, gsmem, st>>>(ix->map_e, map_q, dn, w, gw);
-            MSE_CUDA_TRY(cudaGetLastError());
-            gemm_bucket_kernel<<<ix->sm_count * 4, 256, 0, st>>>(w);
-            MSE_CUDA_TRY(cudaGetLastError());
-        } else if (dn.n_chunks > 0) {
-            int b = 0;
-            while (b < gn) {                                   // every pass streams the whole matrix once
-                if (gn - b >= 2) { dense_scan_kernel<2><<<grid, kScanThreads, 0, st>>>(dn, w, b); b += 2; }
-                else { dense_scan_kernel<1><<<grid, kScanThreads, 0, st>>>(dn, w, b); b += 1; }
-                MSE_CUDA_TRY(cudaGetLastError());
-            }
-        }
-        if (timed) timer_end(ix, T_SCAN, st);
-        ListLoader ld{w.cand, w.cand_count, rcap, int32_t(rcap)};
-        if (timed) timer_begin(ix, T_SELECT, st);
-        topk_select_kernel<ListLoader><<<gn, kSelectThreads, 0, st>>>(ld, top_k, o_doc, o_score, o_count, mark ? w.overflow : nullptr);
-        MSE_CUDA_TRY(cudaGetLastError());
-        if (timed) timer_end(ix, T_SELECT, st);
-        return MSE_OK;
-    };
-    for (int g0 = 0; g0 < B; g0 += group) {
-        const int gn = std::min(group, B - g0);
-        if ((rc = run(g0, gn, cap, use_tau, d_doc + size_t(g0) * top_k, d_score + size_t(g0) * top_k, d_count + g0, true, g0 == 0))) return rc;
-    }
-    MSE_CUDA_TRY(cudaMemcpyAsync(h_ovf.data(), ix->overflow.p, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
+    MSE_CUDA_TRY(cudaMemcpyAsync(h_ovf.data(), ws->overflow.p, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
     MSE_CUDA_TRY(cudaStreamSynchronize(st));
-    timers_collect(ix);
+    const int64_t D = std::max<int64_t>(ix->dn.n_docs, 1);
     for (int i = 0; i < B; ++i) {
         if (!h_ovf[i]) continue;                               // candidate list overflowed: unbounded re-run of this query
-        if ((rc = run(i, 1, D, 0, d_doc + size_t(i) * top_k, d_score + size_t(i) * top_k, d_count + i, false, false))) return rc;
+        if ((rc = dense_scan_pass(ix, L, d_q, i, 1, D, 0, top_k, d_doc + size_t(i) * top_k, d_score + size_t(i) * top_k, d_count + i,
+                                  nullptr, false, false))) return rc;
     }
     if (where == MSE_HOST) {
-        MSE_CUDA_TRY(cudaMemcpyAsync(out_doc, d_doc, sizeof(int32_t) * size_t(B) * top_k, cudaMemcpyDeviceToHost, st));
-        MSE_CUDA_TRY(cudaMemcpyAsync(out_score, d_score, sizeof(float) * size_t(B) * top_k, cudaMemcpyDeviceToHost, st));
-        MSE_CUDA_TRY(cudaMemcpyAsync(out_count, d_count, sizeof(int32_t) * size_t(B), cudaMemcpyDeviceToHost, st));
+        if ((rc = copy_out(out_doc, d_doc, sizeof(int32_t) * size_t(B) * top_k, st))) return rc;
+        if ((rc = copy_out(out_score, d_score, sizeof(float) * size_t(B) * top_k, st))) return rc;
+        if ((rc = copy_out(out_count, d_count, sizeof(int32_t) * size_t(B), st))) return rc;
+        MSE_CUDA_TRY(cudaStreamSynchronize(st));
     }
-    MSE_CUDA_TRY(cudaStreamSynchronize(st));
-    timers_collect(ix);
+    return MSE_OK;
+}
+
+int mse_dense_scan_batch_async(mse_index* ix, int32_t B, const float* q, int32_t top_k, int32_t* out_doc, float* out_score,
+                               int32_t* out_count, int32_t* status, int where, void* stream) {
+    if (!ix) { set_error("null index"); return MSE_ERR_INVALID; }
+    MSE_REQUIRE(where == MSE_DEVICE || where == MSE_HOST_ASYNC, "bad `where` (MSE_DEVICE or MSE_HOST_ASYNC)");
+    MSE_REQUIRE(B >= 0 && out_count && (B == 0 || (q && out_doc && out_score)), "null/negative argument");
+    if (top_k < 1 || top_k > MSE_MAX_TOPK) { set_error("top_k %d outside [1, %d]", top_k, MSE_MAX_TOPK); return MSE_ERR_UNSUPPORTED; }
+    if (!ix->has_dense) { set_error("mse_dense_load has not been called"); return MSE_ERR_STATE; }
+    if (B == 0) return MSE_OK;
+    DeviceGuard g(ix->device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Lease L(&ix->pool, st);
+    Workspace* ws = L.ws;
+    int rc;
+    int32_t* d_status;
+    if ((rc = status_begin(L, status, where, &d_status))) return rc;
+    const float* d_q = q;
+    int32_t* d_doc = out_doc; float* d_score = out_score; int32_t* d_count = out_count;
+    if (where == MSE_HOST_ASYNC) {
+        if ((rc = ws->dq.ensure(sizeof(float) * size_t(B) * kDim))) return rc;
+        if ((rc = ws->o_doc.ensure(sizeof(int32_t) * size_t(B) * top_k))) return rc;
+        if ((rc = ws->o_score.ensure(sizeof(float) * size_t(B) * top_k))) return rc;
+        if ((rc = ws->o_count.ensure(sizeof(int32_t) * size_t(B)))) return rc;
+        if ((rc = copy_in(ws->dq.p, q, sizeof(float) * size_t(B) * kDim, where, st))) return rc;
+        d_q = ws->dq.as<float>(); d_doc = ws->o_doc.as<int32_t>(); d_score = ws->o_score.as<float>(); d_count = ws->o_count.as<int32_t>();
+    }
+    if ((rc = dense_scan_enqueue(ix, L, B, d_q, top_k, d_doc, d_score, d_count, nullptr, nullptr))) return rc;
+    status_add_flags_kernel<<<std::min(64, (B + 255) / 256), 256, 0, st>>>(ws->overflow.as<int32_t>(), B, d_status + 1);
+    MSE_CUDA_TRY(cudaGetLastError());
+    if (where == MSE_HOST_ASYNC) {
+        if ((rc = copy_out(out_doc, d_doc, sizeof(int32_t) * size_t(B) * top_k, st))) return rc;
+        if ((rc = copy_out(out_score, d_score, sizeof(float) * size_t(B) * top_k, st))) return rc;
+        if ((rc = copy_out(out_count, d_count, sizeof(int32_t) * size_t(B), st))) return rc;
+        if (status && (rc = copy_out(status, d_status, sizeof(int32_t) * MSE_STATUS_WORDS, st))) return rc;
+    }
     return MSE_OK;
 }
 
@@ -900,100 +1152,134 @@ int mse_rerank_batch(mse_index* ix, int32_t B, const int32_t* cand_off, const in
                      int32_t* out_doc, float* out_score, float* out_orig, int64_t* out_chunk, int32_t* out_count,
                      int32_t* out_rows, int where, void* stream) {
     if (!ix) { set_error("null index"); return MSE_ERR_INVALID; }
-    MSE_REQUIRE(where == MSE_HOST || where == MSE_DEVICE, "bad `where`");
+    MSE_REQUIRE(where == MSE_HOST || where == MSE_DEVICE || where == MSE_HOST_ASYNC, "bad `where`");
     MSE_REQUIRE(B >= 0 && cand_off && out_count && out_rows, "null/negative argument");
     MSE_REQUIRE(B == 0 || (q && out_doc && out_score && out_orig && out_chunk), "null argument");
     if (max_chunks < 1 || max_chunks > kRerankMaxChunks) { set_error("max_chunks %d outside [1, %d]", max_chunks, kRerankMaxChunks); return MSE_ERR_UNSUPPORTED; }
     if (max_out < 1 || max_out > kRerankMaxCand) { set_error("max_out %d outside [1, %d]", max_out, kRerankMaxCand); return MSE_ERR_UNSUPPORTED; }
     MSE_REQUIRE(smoothing >= 0.f && smoothing <= 1.f, "smoothing outside [0,1]");
-    std::lock_guard<std::mutex> lk(ix->mu);
     if (!ix->has_dense) { set_error("mse_dense_load has not been called"); return MSE_ERR_STATE; }
     if (B == 0) return MSE_OK;
     DeviceGuard g(ix->device);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     int rc;
-    std::vector<int32_t> h_off;
-    h_off.resize(size_t(B) + 1);
-    if (where == MSE_HOST) memcpy(h_off.data(), cand_off, sizeof(int32_t) * (B + 1));
-    else {
-        MSE_CUDA_TRY(cudaMemcpyAsync(h_off.data(), cand_off, sizeof(int32_t) * (B + 1), cudaMemcpyDeviceToHost, st));
-        MSE_CUDA_TRY(cudaStreamSynchronize(st));
-    }
-    MSE_REQUIRE(h_off[0] == 0, "cand_off[0] must be 0");
-    for (int i = 0; i < B; ++i) {
-        MSE_REQUIRE(h_off[i + 1] >= h_off[i], "cand_off not monotone at %d", i);
-        if (h_off[i + 1] - h_off[i] > kRerankMaxCand) { set_error("query %d has %d candidates (max %d)", i, h_off[i + 1] - h_off[i], kRerankMaxCand); return MSE_ERR_UNSUPPORTED; }
-    }
-    const int32_t C = h_off[B];
-    MSE_REQUIRE(C == 0 || (cand_doc && cand_bm25), "null candidate arrays");
-
     RerankArgs a{};
     a.smoothing = smoothing; a.max_chunks = max_chunks; a.max_out = max_out;
-    if (where == MSE_HOST) {
-        if ((rc = ix->r_in[0].ensure(sizeof(int32_t) * (B + 1)))) return rc;
-        if ((rc = ix->r_in[1].ensure(sizeof(int32_t) * std::max(C, 1)))) return rc;
-        if ((rc = ix->r_in[2].ensure(sizeof(float) * std::max(C, 1)))) return rc;
-        if ((rc = ix->r_in[3].ensure(sizeof(float) * size_t(B) * kDim))) return rc;
-        if (url_group && (rc = ix->r_in[4].ensure(sizeof(int32_t) * std::max<int64_t>(ix->dn.n_docs, 1)))) return rc;
-        if ((rc = ix->r_out[0].ensure(sizeof(int32_t) * size_t(B) * max_out))) return rc;
-        if ((rc = ix->r_out[1].ensure(sizeof(float) * size_t(B) * max_out))) return rc;
-        if ((rc = ix->r_out[2].ensure(sizeof(float) * size_t(B) * max_out))) return rc;
-        if ((rc = ix->r_out[3].ensure(sizeof(int64_t) * size_t(B) * max_out))) return rc;
-        if ((rc = ix->r_out[4].ensure(sizeof(int32_t) * size_t(B)))) return rc;
-        if ((rc = ix->r_out[5].ensure(sizeof(int32_t) * size_t(B)))) return rc;
-        if ((rc = copy_in(ix->r_in[0].p, cand_off, sizeof(int32_t) * (B + 1), where, st))) return rc;
-        if ((rc = copy_in(ix->r_in[1].p, cand_doc, sizeof(int32_t) * C, where, st))) return rc;
-        if ((rc = copy_in(ix->r_in[2].p, cand_bm25, sizeof(float) * C, where, st))) return rc;
-        if ((rc = copy_in(ix->r_in[3].p, q, sizeof(float) * size_t(B) * kDim, where, st))) return rc;
-        if (url_group && (rc = copy_in(ix->r_in[4].p, url_group, sizeof(int32_t) * ix->dn.n_docs, where, st))) return rc;
-        a.cand_off = ix->r_in[0].as<int32_t>(); a.cand_doc = ix->r_in[1].as<int32_t>(); a.cand_bm25 = ix->r_in[2].as<float>();
-        a.q = ix->r_in[3].as<float>(); a.url_group = url_group ? ix->r_in[4].as<int32_t>() : nullptr;
-        a.out_doc = ix->r_out[0].as<int32_t>(); a.out_score = ix->r_out[1].as<float>(); a.out_orig = ix->r_out[2].as<float>();
-        a.out_chunk = ix->r_out[3].as<int64_t>(); a.out_count = ix->r_out[4].as<int32_t>(); a.out_rows = ix->r_out[5].as<int32_t>();
+    Lease L(&ix->pool, st);
+    Workspace* ws = L.ws;
+    if (is_host(where)) {
+        // (a device caller's offsets are not read back: the kernels clamp a query to MSE_MAX_RERANK_CAND candidates)
+        MSE_REQUIRE(cand_off[0] == 0, "cand_off[0] must be 0");
+        for (int i = 0; i < B; ++i) {
+            MSE_REQUIRE(cand_off[i + 1] >= cand_off[i], "cand_off not monotone at %d", i);
+            if (cand_off[i + 1] - cand_off[i] > kRerankMaxCand) { set_error("query %d has %d candidates (max %d)", i, cand_off[i + 1] - cand_off[i], kRerankMaxCand); return MSE_ERR_UNSUPPORTED; }
+        }
+        const int32_t C = cand_off[B];
+        MSE_REQUIRE(C == 0 || (cand_doc && cand_bm25), "null candidate arrays");
+        if ((rc = ws->r_in[0].ensure(sizeof(int32_t) * (B + 1)))) return rc;
+        if ((rc = ws->r_in[1].ensure(sizeof(int32_t) * std::max(C, 1)))) return rc;
+        if ((rc = ws->r_in[2].ensure(sizeof(float) * std::max(C, 1)))) return rc;
+        if ((rc = ws->r_in[3].ensure(sizeof(float) * size_t(B) * kDim))) return rc;
+        if ((rc = rerank_out_buffers(ws, B, max_out, a))) return rc;
+        if ((rc = copy_in(ws->r_in[0].p, cand_off, sizeof(int32_t) * (B + 1), where, st))) return rc;
+        if ((rc = copy_in(ws->r_in[1].p, cand_doc, sizeof(int32_t) * C, where, st))) return rc;
+        if ((rc = copy_in(ws->r_in[2].p, cand_bm25, sizeof(float) * C, where, st))) return rc;
+        if ((rc = copy_in(ws->r_in[3].p, q, sizeof(float) * size_t(B) * kDim, where, st))) return rc;
+        a.cand_off = ws->r_in[0].as<int32_t>(); a.cand_doc = ws->r_in[1].as<int32_t>(); a.cand_bm25 = ws->r_in[2].as<float>();
+        a.q = ws->r_in[3].as<float>();
+        if (url_group) {                                   // host groups passed per call: staged (prefer mse_dense_set_url_groups)
+            if ((rc = ws->m_in[0].ensure(sizeof(int32_t) * std::max<int64_t>(ix->dn.n_docs, 1)))) return rc;
+            if ((rc = copy_in(ws->m_in[0].p, url_group, sizeof(int32_t) * ix->dn.n_docs, where, st))) return rc;
+            a.url_group = ws->m_in[0].as<int32_t>();
+        }
     } else {
         a.cand_off = cand_off; a.cand_doc = cand_doc; a.cand_bm25 = cand_bm25; a.q = q; a.url_group = url_group;
         a.out_doc = out_doc; a.out_score = out_score; a.out_orig = out_orig; a.out_chunk = out_chunk;
         a.out_count = out_count; a.out_rows = out_rows;
     }
-    const int slices = (B * 4 <= ix->sm_count && ix->dn.doc_base == 0) ? std::min(32, std::max(1, ix->sm_count / B)) : 1;
-    timer_begin(ix, T_RERANK, st);
-    if (slices > 1) {
-        // Small batch: one CTA per query would leave most SMs idle (batch-1 latency).  Same two kernels as the
-        // multi-GPU path: cosines by `slices` CTAs per query, then the pool-wide fusion from the gathered cosines.
-        const size_t slots = size_t(B) * kRerankMaxCand;
-        if ((rc = ix->r_split[0].ensure(sizeof(float) * slots * kRerankMaxChunks))) return rc;
-        if ((rc = ix->r_split[1].ensure(sizeof(int32_t) * slots))) return rc;
-        if ((rc = ix->r_split[2].ensure(sizeof(int64_t) * slots))) return rc;
-        if ((rc = ix->r_split[3].ensure(sizeof(int32_t) * slots))) return rc;
-        if ((rc = ix->r_split[4].ensure(sizeof(float) * slots))) return rc;
-        if ((rc = ix->r_split[5].ensure(sizeof(int32_t) * size_t(B)))) return rc;
-        MSE_CUDA_TRY(cudaMemsetAsync(ix->r_split[1].p, 0, sizeof(int32_t) * slots, st));      // rows: 0 = not fetched
-        RerankShardArgs sa{a.cand_off, a.cand_doc, a.cand_bm25, a.url_group, a.q, max_chunks, ix->dn.doc_base + ix->dn.n_docs,
-                           ix->r_split[0].as<float>(), ix->r_split[1].as<int32_t>(), ix->r_split[2].as<int64_t>(),
-                           ix->r_split[3].as<int32_t>(), ix->r_split[4].as<float>(), ix->r_split[5].as<int32_t>()};
-        rerank_shard_cos_kernel<<<dim3(unsigned(B), unsigned(slices)), kRerankThreads, 0, st>>>(ix->dn, sa);
-        MSE_CUDA_TRY(cudaGetLastError());
-        RerankFuseArgs fa{sa.cos, sa.rows, sa.chunk0, sa.surv_doc, sa.surv_bm25, sa.surv_count, smoothing, max_out,
-                          a.out_doc, a.out_score, a.out_orig, a.out_chunk, a.out_count, a.out_rows};
-        rerank_shard_fuse_kernel<<<B, kRerankThreads, 0, st>>>(fa);
-        MSE_CUDA_TRY(cudaGetLastError());
-    } else {
-        MSE_CUDA_TRY(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kRerankSmemBytes)));
-        rerank_kernel<<<B, kRerankThreads, kRerankSmemBytes, st>>>(ix->dn, a);
-        MSE_CUDA_TRY(cudaGetLastError());
+    if ((rc = rerank_enqueue(ix, L, B, a))) return rc;
+    if (is_host(where)) {
+        if ((rc = rerank_copy_out(a, B, max_out, out_doc, out_score, out_orig, out_chunk, out_count, out_rows, st))) return rc;
+        if (where == MSE_HOST) MSE_CUDA_TRY(cudaStreamSynchronize(st));
     }
-    timer_end(ix, T_RERANK, st);
+    return MSE_OK;
+}
+
+int mse_hybrid_search_batch(mse_index* ix, int32_t B, int32_t S, const int32_t* q_off, const int32_t* q_term, const int32_t* q_tf,
+                            const float* q_vec, int32_t top_k, float min_score, float smoothing, int32_t max_chunks, int32_t max_out,
+                            int32_t* out_doc, float* out_score, float* out_orig, int64_t* out_chunk, int32_t* out_count,
+                            int32_t* out_rows, int32_t* status, int where, void* stream) {
+    if (!ix) { set_error("null index"); return MSE_ERR_INVALID; }
+    MSE_REQUIRE(where == MSE_HOST || where == MSE_DEVICE || where == MSE_HOST_ASYNC, "bad `where`");
+    MSE_REQUIRE(B >= 0 && S >= 0 && q_off && out_count && out_rows && (S == 0 || (q_term && q_tf)), "null/negative argument");
+    MSE_REQUIRE(B == 0 || (q_vec && out_doc && out_score && out_orig && out_chunk), "null argument");
+    if (top_k < 1 || top_k > kRerankMaxCand) { set_error("top_k %d outside [1, %d]", top_k, kRerankMaxCand); return MSE_ERR_UNSUPPORTED; }
+    if (max_chunks < 1 || max_chunks > kRerankMaxChunks) { set_error("max_chunks %d outside [1, %d]", max_chunks, kRerankMaxChunks); return MSE_ERR_UNSUPPORTED; }
+    if (max_out < 1 || max_out > kRerankMaxCand) { set_error("max_out %d outside [1, %d]", max_out, kRerankMaxCand); return MSE_ERR_UNSUPPORTED; }
+    MSE_REQUIRE(smoothing >= 0.f && smoothing <= 1.f, "smoothing outside [0,1]");
+    MSE_REQUIRE(min_score == min_score, "min_score is NaN");
+    if (!ix->has_bm25) { set_error("mse_bm25_load has not been called"); return MSE_ERR_STATE; }
+    if (!ix->has_dense) { set_error("mse_dense_load has not been called"); return MSE_ERR_STATE; }
+    MSE_REQUIRE(ix->bm.doc_base == ix->dn.doc_base, "the BM25 and dense halves of the index must cover the same doc range");
+    if (B == 0) return MSE_OK;
+    DeviceGuard g(ix->device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int rc;
+    std::vector<int32_t> h_off;
     if (where == MSE_HOST) {
-        const size_t n = size_t(B) * max_out;
-        MSE_CUDA_TRY(cudaMemcpyAsync(out_doc, a.out_doc, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
-        MSE_CUDA_TRY(cudaMemcpyAsync(out_score, a.out_score, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
-        MSE_CUDA_TRY(cudaMemcpyAsync(out_orig, a.out_orig, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
-        MSE_CUDA_TRY(cudaMemcpyAsync(out_chunk, a.out_chunk, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, st));
-        MSE_CUDA_TRY(cudaMemcpyAsync(out_count, a.out_count, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
-        MSE_CUDA_TRY(cudaMemcpyAsync(out_rows, a.out_rows, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
+        int32_t S2 = 0;
+        if ((rc = check_host_csr(q_off, B, &S2))) return rc;
+        MSE_REQUIRE(S2 == S, "n_slots (%d) != q_off[n_queries] (%d)", S, S2);
+        h_off.assign(q_off, q_off + B + 1);
     }
+    Lease L(&ix->pool, st);
+    Workspace* ws = L.ws;
+    int32_t* d_status;
+    if ((rc = status_begin(L, status, where, &d_status))) return rc;
+    const int32_t *d_off, *d_term, *d_tf;
+    if ((rc = stage_queries(L, B, S, q_off, q_term, q_tf, where, where != MSE_HOST, d_status, &d_off, &d_term, &d_tf))) return rc;
+    // stage 1 -> candidates [B][top_k] in the workspace
+    if ((rc = ws->o_doc.ensure(sizeof(int32_t) * size_t(B) * top_k))) return rc;
+    if ((rc = ws->o_score.ensure(sizeof(float) * size_t(B) * top_k))) return rc;
+    if ((rc = ws->o_count.ensure(sizeof(int32_t) * size_t(B)))) return rc;
+    RerankArgs a{};
+    a.smoothing = smoothing; a.max_chunks = max_chunks; a.max_out = max_out;
+    a.cand_off = nullptr; a.cand_count = ws->o_count.as<int32_t>(); a.cand_stride = top_k;
+    a.cand_doc = ws->o_doc.as<int32_t>(); a.cand_bm25 = ws->o_score.as<float>();
+    a.q = q_vec;
+    if (is_host(where)) {
+        if ((rc = ws->r_in[3].ensure(sizeof(float) * size_t(B) * kDim))) return rc;
+        if ((rc = copy_in(ws->r_in[3].p, q_vec, sizeof(float) * size_t(B) * kDim, where, st))) return rc;
+        a.q = ws->r_in[3].as<float>();
+        if ((rc = rerank_out_buffers(ws, B, max_out, a))) return rc;
+    } else {
+        a.out_doc = out_doc; a.out_score = out_score; a.out_orig = out_orig; a.out_chunk = out_chunk;
+        a.out_count = out_count; a.out_rows = out_rows;
+    }
+    if ((rc = bm25_enqueue(ix, L, B, d_off, d_term, d_tf, S, top_k, min_score, bm25_default_cap(ix, B, top_k), ix->opt_use_tau ? 1 : 0,
+                           ws->o_doc.as<int32_t>(), ws->o_score.as<float>(), ws->o_count.as<int32_t>(), nullptr, true))) return rc;
+    status_add_counter_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const unsigned long long*>(ws->misc.as<char>() + 40), d_status + 1);
+    MSE_CUDA_TRY(cudaGetLastError());
+    if ((rc = rerank_enqueue(ix, L, B, a))) return rc;
+    if (where == MSE_DEVICE) return MSE_OK;
+    if ((rc = rerank_copy_out(a, B, max_out, out_doc, out_score, out_orig, out_chunk, out_count, out_rows, st))) return rc;
+    if (where == MSE_HOST_ASYNC) {
+        if (status && (rc = copy_out(status, d_status, sizeof(int32_t) * MSE_STATUS_WORDS, st))) return rc;
+        return MSE_OK;
+    }
+    // MSE_HOST: complete and exact on return — the optimistic pass above is final unless a candidate list overflowed
+    int32_t h_st[MSE_STATUS_WORDS] = {0, 0, 0, 0};
+    if ((rc = copy_out(h_st, d_status, sizeof(h_st), st))) return rc;
     MSE_CUDA_TRY(cudaStreamSynchronize(st));
-    timers_collect(ix);
+    if (h_st[1] > 0) {
+        if ((rc = bm25_search_exact(ix, L, B, S, h_off, d_off, d_term, d_tf, top_k, min_score, ws->o_doc.as<int32_t>(),
+                                    ws->o_score.as<float>(), ws->o_count.as<int32_t>()))) return rc;
+        if ((rc = rerank_enqueue(ix, L, B, a))) return rc;
+        if ((rc = rerank_copy_out(a, B, max_out, out_doc, out_score, out_orig, out_chunk, out_count, out_rows, st))) return rc;
+        MSE_CUDA_TRY(cudaStreamSynchronize(st));
+        h_st[1] = 0;
+    }
+    if (status) memcpy(status, h_st, sizeof(h_st));
     return MSE_OK;
 }
 
@@ -1005,7 +1291,6 @@ int mse_rerank_shard_cos(mse_index* ix, int32_t B, const int32_t* cand_off, cons
     MSE_REQUIRE(B >= 0 && cand_off && cos && rows && chunk0 && surv_doc && surv_bm25 && surv_count, "null/negative argument");
     MSE_REQUIRE(B == 0 || (q && cand_doc && cand_bm25), "null argument");
     if (max_chunks < 1 || max_chunks > kRerankMaxChunks) { set_error("max_chunks %d outside [1, %d]", max_chunks, kRerankMaxChunks); return MSE_ERR_UNSUPPORTED; }
-    std::lock_guard<std::mutex> lk(ix->mu);
     if (!ix->has_dense) { set_error("mse_dense_load has not been called"); return MSE_ERR_STATE; }
     if (B == 0) return MSE_OK;
     DeviceGuard g(ix->device);
@@ -1016,7 +1301,8 @@ int mse_rerank_shard_cos(mse_index* ix, int32_t B, const int32_t* cand_off, cons
     MSE_CUDA_TRY(cudaMemsetAsync(chunk0, 0, sizeof(int64_t) * slots, st));
     MSE_CUDA_TRY(cudaMemsetAsync(surv_doc, 0xff, sizeof(int32_t) * slots, st));
     MSE_CUDA_TRY(cudaMemsetAsync(surv_bm25, 0, sizeof(float) * slots, st));
-    RerankShardArgs a{cand_off, cand_doc, cand_bm25, url_group, q, max_chunks, n_docs_global, cos, rows, chunk0, surv_doc, surv_bm25, surv_count};
+    if (!url_group && ix->n_url_groups >= n_docs_global && ix->n_url_groups > 0) url_group = ix->url_group.as<int32_t>();
+    RerankShardArgs a{cand_off, nullptr, 0, cand_doc, cand_bm25, url_group, q, max_chunks, n_docs_global, cos, rows, chunk0, surv_doc, surv_bm25, surv_count};
     rerank_shard_cos_kernel<<<B, kRerankThreads, 0, st>>>(ix->dn, a);
     MSE_CUDA_TRY(cudaGetLastError());
     return MSE_OK;
@@ -1031,7 +1317,6 @@ int mse_rerank_shard_fuse(mse_index* ix, int32_t B, const float* cos, const int3
                 out_chunk && out_count && out_rows, "null/negative argument");
     if (max_out < 1 || max_out > kRerankMaxCand) { set_error("max_out %d outside [1, %d]", max_out, kRerankMaxCand); return MSE_ERR_UNSUPPORTED; }
     MSE_REQUIRE(smoothing >= 0.f && smoothing <= 1.f, "smoothing outside [0,1]");
-    std::lock_guard<std::mutex> lk(ix->mu);
     if (B == 0) return MSE_OK;
     DeviceGuard g(ix->device);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -1049,35 +1334,294 @@ int mse_topk_merge(mse_index* ix, int32_t B, int32_t n_lists, int32_t list_k, co
     MSE_REQUIRE(B >= 0 && n_lists >= 1 && list_k >= 1 && in_doc && in_score && in_count && out_doc && out_score && out_count,
                 "null/negative argument");
     if (top_k < 1 || top_k > MSE_MAX_TOPK) { set_error("top_k %d outside [1, %d]", top_k, MSE_MAX_TOPK); return MSE_ERR_UNSUPPORTED; }
-    std::lock_guard<std::mutex> lk(ix->mu);
     if (B == 0) return MSE_OK;
     DeviceGuard g(ix->device);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Lease L(&ix->pool, st);
+    Workspace* ws = L.ws;
     int rc;
     const size_t n_in = size_t(n_lists) * B * list_k;
     MergeLoader ld{in_doc, in_score, in_count, n_lists, B, list_k};
     int32_t* d_doc = out_doc; float* d_score = out_score; int32_t* d_count = out_count;
     if (where == MSE_HOST) {
-        if ((rc = ix->m_in[0].ensure(sizeof(int32_t) * n_in))) return rc;
-        if ((rc = ix->m_in[1].ensure(sizeof(float) * n_in))) return rc;
-        if ((rc = ix->m_in[2].ensure(sizeof(int32_t) * size_t(n_lists) * B))) return rc;
-        if ((rc = ix->o_doc.ensure(sizeof(int32_t) * size_t(B) * top_k))) return rc;
-        if ((rc = ix->o_score.ensure(sizeof(float) * size_t(B) * top_k))) return rc;
-        if ((rc = ix->o_count.ensure(sizeof(int32_t) * size_t(B)))) return rc;
-        if ((rc = copy_in(ix->m_in[0].p, in_doc, sizeof(int32_t) * n_in, where, st))) return rc;
-        if ((rc = copy_in(ix->m_in[1].p, in_score, sizeof(float) * n_in, where, st))) return rc;
-        if ((rc = copy_in(ix->m_in[2].p, in_count, sizeof(int32_t) * size_t(n_lists) * B, where, st))) return rc;
-        ld.doc = ix->m_in[0].as<int32_t>(); ld.score = ix->m_in[1].as<float>(); ld.count = ix->m_in[2].as<int32_t>();
-        d_doc = ix->o_doc.as<int32_t>(); d_score = ix->o_score.as<float>(); d_count = ix->o_count.as<int32_t>();
+        if ((rc = ws->m_in[0].ensure(sizeof(int32_t) * n_in))) return rc;
+        if ((rc = ws->m_in[1].ensure(sizeof(float) * n_in))) return rc;
+        if ((rc = ws->m_in[2].ensure(sizeof(int32_t) * size_t(n_lists) * B))) return rc;
+        if ((rc = ws->o_doc.ensure(sizeof(int32_t) * size_t(B) * top_k))) return rc;
+        if ((rc = ws->o_score.ensure(sizeof(float) * size_t(B) * top_k))) return rc;
+        if ((rc = ws->o_count.ensure(sizeof(int32_t) * size_t(B)))) return rc;
+        if ((rc = copy_in(ws->m_in[0].p, in_doc, sizeof(int32_t) * n_in, where, st))) return rc;
+        if ((rc = copy_in(ws->m_in[1].p, in_score, sizeof(float) * n_in, where, st))) return rc;
+        if ((rc = copy_in(ws->m_in[2].p, in_count, sizeof(int32_t) * size_t(n_lists) * B, where, st))) return rc;
+        ld.doc = ws->m_in[0].as<int32_t>(); ld.score = ws->m_in[1].as<float>(); ld.count = ws->m_in[2].as<int32_t>();
+        d_doc = ws->o_doc.as<int32_t>(); d_score = ws->o_score.as<float>(); d_count = ws->o_count.as<int32_t>();
     }
     topk_select_kernel<MergeLoader><<<B, kSelectThreads, 0, st>>>(ld, top_k, d_doc, d_score, d_count, nullptr);
     MSE_CUDA_TRY(cudaGetLastError());
     if (where == MSE_HOST) {
-        MSE_CUDA_TRY(cudaMemcpyAsync(out_doc, d_doc, sizeof(int32_t) * size_t(B) * top_k, cudaMemcpyDeviceToHost, st));
-        MSE_CUDA_TRY(cudaMemcpyAsync(out_score, d_score, sizeof(float) * size_t(B) * top_k, cudaMemcpyDeviceToHost, st));
-        MSE_CUDA_TRY(cudaMemcpyAsync(out_count, d_count, sizeof(int32_t) * size_t(B), cudaMemcpyDeviceToHost, st));
+        if ((rc = copy_out(out_doc, d_doc, sizeof(int32_t) * size_t(B) * top_k, st))) return rc;
+        if ((rc = copy_out(out_score, d_score, sizeof(float) * size_t(B) * top_k, st))) return rc;
+        if ((rc = copy_out(out_count, d_count, sizeof(int32_t) * size_t(B), st))) return rc;
         MSE_CUDA_TRY(cudaStreamSynchronize(st));
     }
+    return MSE_OK;
+}
+
+// ---- corpus sharded by document range: communicator ------------------------------------------------------------------
+int mse_comm_unique_id(void* id_bytes) {
+    MSE_REQUIRE(id_bytes, "null argument");
+    static_assert(sizeof(ncclUniqueId) <= MSE_COMM_ID_BYTES, "ncclUniqueId does not fit MSE_COMM_ID_BYTES");
+    NcclApi& n = nccl_api();
+    if (!n.ok) { set_error("NCCL (libnccl.so.2) could not be loaded"); return MSE_ERR_COMM; }
+    ncclUniqueId id;
+    MSE_NCCL_TRY(n.GetUniqueId(&id));
+    memset(id_bytes, 0, MSE_COMM_ID_BYTES);
+    memcpy(id_bytes, &id, sizeof(id));
+    return MSE_OK;
+}
+
+int mse_comm_init(mse_index* ix, const void* id_bytes, int32_t rank, int32_t world) {
+    if (!ix) { set_error("null index"); return MSE_ERR_INVALID; }
+    MSE_REQUIRE(world >= 1 && rank >= 0 && rank < world, "bad rank/world");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    if (ix->comm.owned && ix->comm.comm) { nccl_api().CommDestroy(ix->comm.comm); }
+    ix->comm = Comm{};
+    ix->comm.rank = rank; ix->comm.world = world;
+    if (world == 1) return MSE_OK;
+    MSE_REQUIRE(id_bytes, "null id");
+    NcclApi& n = nccl_api();
+    if (!n.ok) { set_error("NCCL (libnccl.so.2) could not be loaded"); return MSE_ERR_COMM; }
+    ncclUniqueId id;
+    memcpy(&id, id_bytes, sizeof(id));
+    MSE_NCCL_TRY(n.CommInitRank(&ix->comm.comm, world, id, rank));
+    ix->comm.owned = true;
+    return MSE_OK;
+}
+
+int mse_comm_attach(mse_index* ix, void* nccl_comm, int32_t rank, int32_t world) {
+    if (!ix) { set_error("null index"); return MSE_ERR_INVALID; }
+    MSE_REQUIRE(world >= 1 && rank >= 0 && rank < world && (world == 1 || nccl_comm), "bad communicator arguments");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    if (world > 1 && !nccl_api().ok) { set_error("NCCL (libnccl.so.2) could not be loaded"); return MSE_ERR_COMM; }
+    if (ix->comm.owned && ix->comm.comm) { DeviceGuard g(ix->device); nccl_api().CommDestroy(ix->comm.comm); }
+    ix->comm = Comm{};
+    ix->comm.comm = static_cast<ncclComm_t>(nccl_comm); ix->comm.rank = rank; ix->comm.world = world; ix->comm.owned = false;
+    return MSE_OK;
+}
+
+int mse_comm_destroy(mse_index* ix) {
+    if (!ix) return MSE_OK;
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaDeviceSynchronize();
+    if (ix->comm.owned && ix->comm.comm) nccl_api().CommDestroy(ix->comm.comm);
+    ix->comm = Comm{};
+    return MSE_OK;
+}
+
+namespace {
+// Sharded BM25 up to the exact merged top_k of this rank's block of the batch.  Leaves in the workspace:
+// x_merge[0..2] = doc / score / count [Bq][top_k], x_merge[3] = the same lists as keys.
+int bm25_sharded_core(mse_index* ix, Lease& L, int32_t GB, int32_t S, const int32_t* d_off, const int32_t* d_term, const int32_t* d_tf,
+                      int32_t top_k, float min_score, int32_t shard_list_len, int32_t* d_status) {
+    Workspace* ws = L.ws;
+    cudaStream_t st = L.st;
+    const Comm& c = ix->comm;
+    const int W = c.world, Bq = GB / W;
+    int rc;
+    int32_t m = shard_list_len > 0 ? std::min(shard_list_len, top_k) : std::min<int64_t>(top_k, 2 * int64_t(top_k) / W + 32);
+    if (W == 1) m = top_k;
+    if ((rc = ws->o_key.ensure(sizeof(uint64_t) * size_t(GB) * m))) return rc;
+    if ((rc = bm25_enqueue(ix, L, GB, d_off, d_term, d_tf, S, m, min_score, bm25_default_cap(ix, GB, m), ix->opt_use_tau ? 1 : 0,
+                           nullptr, nullptr, nullptr, ws->o_key.as<uint64_t>(), true))) return rc;
+    status_add_counter_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const unsigned long long*>(ws->misc.as<char>() + 40), d_status + 1);
+    MSE_CUDA_TRY(cudaGetLastError());
+    int tx = L.timer_begin(T_EXCHANGE);
+    const uint64_t* lists = ws->o_key.as<uint64_t>();
+    if (W > 1) {
+        if ((rc = ws->x_recv.ensure(sizeof(uint64_t) * size_t(GB) * m))) return rc;
+        if ((rc = comm_all_to_all(c, ws->o_key.p, ws->x_recv.p, sizeof(uint64_t) * size_t(Bq) * m, st))) return rc;
+        lists = ws->x_recv.as<uint64_t>();
+    }
+    if ((rc = ws->x_merge[0].ensure(sizeof(int32_t) * size_t(Bq) * top_k))) return rc;
+    if ((rc = ws->x_merge[1].ensure(sizeof(float) * size_t(Bq) * top_k))) return rc;
+    if ((rc = ws->x_merge[2].ensure(sizeof(int32_t) * size_t(Bq)))) return rc;
+    if ((rc = ws->x_merge[3].ensure(sizeof(uint64_t) * size_t(Bq) * top_k))) return rc;
+    KeyListLoader ld{lists, W, Bq, m};
+    topk_select_kernel<KeyListLoader><<<Bq, kSelectThreads, 0, st>>>(ld, top_k, ws->x_merge[0].as<int32_t>(), ws->x_merge[1].as<float>(),
+                                                                    ws->x_merge[2].as<int32_t>(), nullptr, nullptr, ws->x_merge[3].as<uint64_t>());
+    MSE_CUDA_TRY(cudaGetLastError());
+    if (W > 1 && m < top_k) {
+        const int64_t n = int64_t(W) * Bq;
+        shard_cut_check_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(lists, W, Bq, m, ws->x_merge[3].as<uint64_t>(), top_k, d_status);
+        MSE_CUDA_TRY(cudaGetLastError());
+    }
+    L.timer_end(tx);
+    return MSE_OK;
+}
+
+int sharded_common_checks(mse_index* ix, int32_t GB, int32_t* Bq) {
+    MSE_REQUIRE(ix->comm.world >= 1 && (ix->comm.world == 1 || ix->comm.comm), "no communicator attached (mse_comm_init / mse_comm_attach)");
+    MSE_REQUIRE(GB % ix->comm.world == 0, "n_queries (%d) must be a multiple of the world size (%d)", GB, ix->comm.world);
+    *Bq = GB / ix->comm.world;
+    return MSE_OK;
+}
+}  // namespace
+
+int mse_bm25_search_sharded(mse_index* ix, int32_t GB, int32_t S, const int32_t* q_off, const int32_t* q_term, const int32_t* q_tf,
+                            int32_t top_k, float min_score, int32_t shard_list_len, int32_t* out_doc, float* out_score,
+                            int32_t* out_count, int32_t* status, void* stream) {
+    if (!ix) { set_error("null index"); return MSE_ERR_INVALID; }
+    MSE_REQUIRE(GB >= 0 && S >= 0 && q_off && out_count && (GB == 0 || (out_doc && out_score)) && (S == 0 || (q_term && q_tf)), "null/negative argument");
+    if (top_k < 1 || top_k > MSE_MAX_TOPK) { set_error("top_k %d outside [1, %d]", top_k, MSE_MAX_TOPK); return MSE_ERR_UNSUPPORTED; }
+    MSE_REQUIRE(min_score == min_score, "min_score is NaN");
+    if (!ix->has_bm25) { set_error("mse_bm25_load has not been called"); return MSE_ERR_STATE; }
+    int32_t Bq = 0;
+    int rc;
+    if ((rc = sharded_common_checks(ix, GB, &Bq))) return rc;
+    if (GB == 0) return MSE_OK;
+    DeviceGuard g(ix->device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Lease L(&ix->pool, st);
+    Workspace* ws = L.ws;
+    int32_t* d_status;
+    if ((rc = status_begin(L, status, MSE_DEVICE, &d_status))) return rc;
+    const int32_t *d_off, *d_term, *d_tf;
+    if ((rc = stage_queries(L, GB, S, q_off, q_term, q_tf, MSE_DEVICE, true, d_status, &d_off, &d_term, &d_tf))) return rc;
+    if ((rc = bm25_sharded_core(ix, L, GB, S, d_off, d_term, d_tf, top_k, min_score, shard_list_len, d_status))) return rc;
+    MSE_CUDA_TRY(cudaMemcpyAsync(out_doc, ws->x_merge[0].p, sizeof(int32_t) * size_t(Bq) * top_k, cudaMemcpyDeviceToDevice, st));
+    MSE_CUDA_TRY(cudaMemcpyAsync(out_score, ws->x_merge[1].p, sizeof(float) * size_t(Bq) * top_k, cudaMemcpyDeviceToDevice, st));
+    MSE_CUDA_TRY(cudaMemcpyAsync(out_count, ws->x_merge[2].p, sizeof(int32_t) * size_t(Bq), cudaMemcpyDeviceToDevice, st));
+    return MSE_OK;
+}
+
+int mse_hybrid_search_sharded(mse_index* ix, int32_t GB, int32_t S, const int32_t* q_off, const int32_t* q_term, const int32_t* q_tf,
+                              const float* q_vec, int32_t top_k, float min_score, int32_t shard_list_len, float smoothing,
+                              int32_t max_chunks, int32_t max_out, int32_t* out_doc, float* out_score, float* out_orig,
+                              int64_t* out_chunk, int32_t* out_count, int32_t* out_rows, int32_t* status, void* stream) {
+    if (!ix) { set_error("null index"); return MSE_ERR_INVALID; }
+    MSE_REQUIRE(GB >= 0 && S >= 0 && q_off && out_count && out_rows && (S == 0 || (q_term && q_tf)), "null/negative argument");
+    MSE_REQUIRE(GB == 0 || (q_vec && out_doc && out_score && out_orig && out_chunk), "null argument");
+    if (top_k < 1 || top_k > kRerankMaxCand) { set_error("top_k %d outside [1, %d]", top_k, kRerankMaxCand); return MSE_ERR_UNSUPPORTED; }
+    if (max_chunks < 1 || max_chunks > kRerankMaxChunks) { set_error("max_chunks %d outside [1, %d]", max_chunks, kRerankMaxChunks); return MSE_ERR_UNSUPPORTED; }
+    if (max_out < 1 || max_out > kRerankMaxCand) { set_error("max_out %d outside [1, %d]", max_out, kRerankMaxCand); return MSE_ERR_UNSUPPORTED; }
+    MSE_REQUIRE(smoothing >= 0.f && smoothing <= 1.f, "smoothing outside [0,1]");
+    MSE_REQUIRE(min_score == min_score, "min_score is NaN");
+    if (!ix->has_bm25) { set_error("mse_bm25_load has not been called"); return MSE_ERR_STATE; }
+    if (!ix->has_dense) { set_error("mse_dense_load has not been called"); return MSE_ERR_STATE; }
+    MSE_REQUIRE(ix->bm.doc_base == ix->dn.doc_base && ix->bm.n_docs == ix->dn.n_docs, "the BM25 and dense halves of the shard must cover the same doc range");
+    int32_t Bq = 0;
+    int rc;
+    if ((rc = sharded_common_checks(ix, GB, &Bq))) return rc;
+    if (GB == 0) return MSE_OK;
+    DeviceGuard g(ix->device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const Comm& c = ix->comm;
+    const int W = c.world;
+    Lease L(&ix->pool, st);
+    Workspace* ws = L.ws;
+    int32_t* d_status;
+    if ((rc = status_begin(L, status, MSE_DEVICE, &d_status))) return rc;
+    const int32_t *d_off, *d_term, *d_tf;
+    if ((rc = stage_queries(L, GB, S, q_off, q_term, q_tf, MSE_DEVICE, true, d_status, &d_off, &d_term, &d_tf))) return rc;
+    // 1. exact global BM25 top_k of the owned queries
+    if ((rc = bm25_sharded_core(ix, L, GB, S, d_off, d_term, d_tf, top_k, min_score, shard_list_len, d_status))) return rc;
+
+    int tx = L.timer_begin(T_EXCHANGE);
+    // 2. survivors (doc order, URL dedupe) of the owned queries -> all ranks
+    const size_t blk = hyb_surv_block_bytes(Bq);
+    if ((rc = ws->x_surv.ensure(blk))) return rc;
+    if ((rc = ws->x_gath.ensure(blk * size_t(W)))) return rc;
+    HybPrepArgs pa{ws->x_merge[0].as<int32_t>(), ws->x_merge[1].as<float>(), ws->x_merge[2].as<int32_t>(), top_k,
+                   ix->n_url_groups > 0 ? ix->url_group.as<int32_t>() : nullptr,
+                   ix->n_url_groups > 0 ? ix->n_url_groups : (int64_t(1) << 31),
+                   ws->x_surv.as<unsigned char>(), Bq};
+    hyb_prep_kernel<<<Bq, kRerankThreads, 0, st>>>(pa);
+    MSE_CUDA_TRY(cudaGetLastError());
+    if ((rc = comm_all_gather(c, ws->x_surv.p, ws->x_gath.p, blk, st))) return rc;
+    L.timer_end(tx);
+
+    // 3. cosines of the survivors this rank owns + local bounds
+    const size_t slots = size_t(GB) * kHybSlots;
+    if ((rc = ws->x_cos.ensure(sizeof(float) * slots * kRerankMaxChunks))) return rc;
+    if ((rc = ws->x_rows.ensure(sizeof(int32_t) * slots))) return rc;
+    if ((rc = ws->x_own.ensure(sizeof(int2) * size_t(GB)))) return rc;
+    if ((rc = ws->x_mm.ensure(sizeof(uint32_t) * 4 * size_t(GB)))) return rc;
+    if ((rc = ws->x_rtot.ensure(sizeof(int32_t) * size_t(GB)))) return rc;
+    fill_u32_kernel<<<unsigned((int64_t(GB) * 4 + 255) / 256), 256, 0, st>>>(ws->x_mm.as<uint32_t>(), 0xffffffffu, int64_t(GB) * 4);
+    MSE_CUDA_TRY(cudaGetLastError());
+    MSE_CUDA_TRY(cudaMemsetAsync(ws->x_rtot.p, 0, sizeof(int32_t) * size_t(GB), st));
+    const int slices = std::max(1, std::min(32, (2 * ix->sm_count + GB - 1) / GB));
+    HybCosArgs ca{ws->x_gath.as<unsigned char>(), Bq, W, q_vec, max_chunks, ws->x_cos.as<float>(), ws->x_rows.as<int32_t>(),
+                  ws->x_own.as<int2>(), ws->x_mm.as<uint32_t>(), ws->x_rtot.as<int32_t>()};
+    int tr = L.timer_begin(T_RERANK);
+    hyb_cos_kernel<<<dim3(unsigned(GB), unsigned(slices)), kRerankThreads, 0, st>>>(ix->dn, ca);
+    MSE_CUDA_TRY(cudaGetLastError());
+    L.timer_end(tr);
+
+    // 4. pool-wide bounds
+    tx = L.timer_begin(T_EXCHANGE);
+    if ((rc = comm_all_reduce_min_u32(c, ws->x_mm.p, size_t(GB) * 4, st))) return rc;
+    L.timer_end(tx);
+
+    // 5. fuse own documents, local top max_out
+    const size_t rb = hyb_record_bytes(max_out);
+    if ((rc = ws->x_rec.ensure(rb * size_t(GB)))) return rc;
+    HybFuseArgs fa{ws->x_gath.as<unsigned char>(), Bq, W, ws->x_cos.as<float>(), ws->x_rows.as<int32_t>(), ws->x_own.as<int2>(),
+                   ws->x_mm.as<uint32_t>(), ws->x_rtot.as<int32_t>(), smoothing, max_out, ws->x_rec.as<unsigned char>()};
+    tr = L.timer_begin(T_RERANK);
+    hyb_fuse_kernel<<<GB, kRerankThreads, 0, st>>>(ix->dn, fa);
+    MSE_CUDA_TRY(cudaGetLastError());
+    L.timer_end(tr);
+
+    // 6. records -> query owner, merge
+    tx = L.timer_begin(T_EXCHANGE);
+    const unsigned char* recs = ws->x_rec.as<unsigned char>();
+    if (W > 1) {
+        if ((rc = ws->x_rrecv.ensure(rb * size_t(GB)))) return rc;
+        if ((rc = comm_all_to_all(c, ws->x_rec.p, ws->x_rrecv.p, rb * size_t(Bq), st))) return rc;
+        recs = ws->x_rrecv.as<unsigned char>();
+    }
+    HybFinalArgs na{recs, Bq, W, max_out, out_doc, out_score, out_orig, out_chunk, out_count, out_rows};
+    hyb_final_kernel<<<Bq, 128, 0, st>>>(na);
+    MSE_CUDA_TRY(cudaGetLastError());
+    L.timer_end(tx);
+    return MSE_OK;
+}
+
+int mse_dense_scan_sharded(mse_index* ix, int32_t B, const float* q, int32_t top_k, int32_t* out_doc, float* out_score,
+                           int32_t* out_count, int32_t* status, void* stream) {
+    if (!ix) { set_error("null index"); return MSE_ERR_INVALID; }
+    MSE_REQUIRE(B >= 0 && out_count && (B == 0 || (q && out_doc && out_score)), "null/negative argument");
+    if (top_k < 1 || top_k > MSE_MAX_TOPK) { set_error("top_k %d outside [1, %d]", top_k, MSE_MAX_TOPK); return MSE_ERR_UNSUPPORTED; }
+    if (!ix->has_dense) { set_error("mse_dense_load has not been called"); return MSE_ERR_STATE; }
+    MSE_REQUIRE(ix->comm.world >= 1 && (ix->comm.world == 1 || ix->comm.comm), "no communicator attached (mse_comm_init / mse_comm_attach)");
+    if (B == 0) return MSE_OK;
+    DeviceGuard g(ix->device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const Comm& c = ix->comm;
+    const int W = c.world;
+    Lease L(&ix->pool, st);
+    Workspace* ws = L.ws;
+    int rc;
+    int32_t* d_status;
+    if ((rc = status_begin(L, status, MSE_DEVICE, &d_status))) return rc;
+    if ((rc = ws->o_key.ensure(sizeof(uint64_t) * size_t(B) * top_k))) return rc;
+    if ((rc = dense_scan_enqueue(ix, L, B, q, top_k, nullptr, nullptr, nullptr, ws->o_key.as<uint64_t>(), nullptr))) return rc;
+    status_add_flags_kernel<<<std::min(64, (B + 255) / 256), 256, 0, st>>>(ws->overflow.as<int32_t>(), B, d_status + 1);
+    MSE_CUDA_TRY(cudaGetLastError());
+    int tx = L.timer_begin(T_EXCHANGE);
+    const uint64_t* lists = ws->o_key.as<uint64_t>();
+    if (W > 1) {
+        if ((rc = ws->x_recv.ensure(sizeof(uint64_t) * size_t(W) * B * top_k))) return rc;
+        if ((rc = comm_all_gather(c, ws->o_key.p, ws->x_recv.p, sizeof(uint64_t) * size_t(B) * top_k, st))) return rc;
+        lists = ws->x_recv.as<uint64_t>();
+    }
+    KeyListLoader ld{lists, W, B, top_k};
+    topk_select_kernel<KeyListLoader><<<B, kSelectThreads, 0, st>>>(ld, top_k, out_doc, out_score, out_count, nullptr);
+    MSE_CUDA_TRY(cudaGetLastError());
+    L.timer_end(tx);
     return MSE_OK;
 }
 

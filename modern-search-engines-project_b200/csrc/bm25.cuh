@@ -60,6 +60,9 @@ struct Bm25Dev {                                 // device-resident index of one
     const int64_t* skip_row;     //   first posting with doc >= g * skip_docs, g = 0..n_skip; skip_row[t] = first entry of term t, -1 = none
     int32_t skip_docs, n_skip;   //   granularity in docs (0 = no table) and ceil(n_docs / skip_docs)
     const float* imp_levels;     // [n_terms * kImpLevels] lower bound of the (64 << l)-th largest tf/(tf+norm) of a term, 0 = unknown
+    const int32_t* neg_row;      // [n_terms] row of the term in neg_imp, -1 = none.  Terms with idf < 0 (df > N/2) get a DENSE
+    const float* neg_imp;        //   impact row neg_imp[row * neg_stride + doc] (0 where the doc lacks the term): with
+    int64_t neg_stride;          //   min_score >= 0 their postings are never streamed, see bm25_score_kernel
     int64_t n_terms, n_docs, n_postings;
     uint32_t doc_base;
     float k1;
@@ -70,6 +73,7 @@ struct Bm25Work {                                // per-call workspace
     const int32_t* q_term;
     const int32_t* q_tf;
     float* slot_w;               // [S]  idf * qtf * (k1+1)
+    int32_t* slot_row;           // [S]  1 + dense row of a negative-weight slot that is looked up instead of streamed, else 0
     uint2* rec;                  // [n_sub * S] {first posting (absolute), count} of slot s in sub-range j
     TauState ts;                 // running per-query lower bound of the final k-th best score
     uint64_t* cand;              // [B * cap]
@@ -80,6 +84,7 @@ struct Bm25Work {                                // per-call workspace
     int32_t n_queries, n_slots, n_sub, sub_docs, queries_per_item, cap;
     uint32_t min_key;
     int32_t use_tau;
+    int32_t neg_lookup;          // 1: min_score >= 0, negative-weight terms with a dense row are looked up per candidate
 };
 
 // ---- prepare: slot weights, per-(sub-range, slot) task records, tau init ---------------------------
@@ -152,11 +157,22 @@ bm25_prepare_kernel(Bm25Dev ix, Bm25Work w) {
     const int t = w.q_term[s];
     int64_t a = 0, e = 0;
     if (t >= 0 && t < ix.n_terms) { a = ix.term_off[t]; e = ix.term_off[t + 1]; }
+    // A term with a negative weight (idf < 0: it is in more than half of the documents — the "tübingen" the reference
+    // appends to every query, search_api.py:160-165) can only LOWER a score.  With min_score >= 0 a document that holds
+    // no other query term ends below zero and is dropped (bm25_indexer.py:480), so such a term never creates a
+    // candidate: its postings are not streamed at all; the score kernel reads its contribution from the term's dense
+    // impact row for the few documents that reach the bound on their other terms.
+    const float idf_t = (t >= 0 && t < ix.n_terms) ? ix.idf[t] : 0.f;
+    const bool lookup = w.neg_lookup && e > a && idf_t < 0.f && w.q_tf[s] > 0 && ix.neg_row != nullptr && ix.neg_row[t] >= 0;
     if (tid == 0) {
-        const float idf = (t >= 0 && t < ix.n_terms) ? ix.idf[t] : 0.f;
         // idf * qtf * (k1+1) formed in double, rounded once (reference: float64 throughout)
-        w.slot_w[s] = float(double(idf) * double(w.q_tf[s]) * (double(ix.k1) + 1.0)) + 0.0f;
-        if (e > a) atomicAdd(w.stats, (unsigned long long)(e - a));
+        w.slot_w[s] = float(double(idf_t) * double(w.q_tf[s]) * (double(ix.k1) + 1.0)) + 0.0f;
+        w.slot_row[s] = lookup ? ix.neg_row[t] + 1 : 0;
+        if (e > a) atomicAdd(w.stats + (lookup ? 1 : 0), (unsigned long long)(e - a));
+    }
+    if (lookup) {
+        for (int j = tid; j < w.n_sub; j += kPrepThreads) w.rec[int64_t(j) * w.n_slots + s] = make_uint2(0u, 0u);
+        return;
     }
     const int2* __restrict__ pd = ix.post2;
     const uint32_t a32f = uint32_t(a);
@@ -299,6 +315,19 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
         if (w.use_tau) atomicAdd(&w.ts.hist[int64_t(q) * kHistBins + (key >> kHistShift)], 1u);   // maxbin[q] is preset
     };
 
+    // looked-up negative terms of the current query: staged slots [neg_lo, neg_hi) hold at least one (neg_hi == 0: none).
+    // The accumulator of a document that reached the bound on its streamed terms gets their contributions added (same
+    // round-down FMA as a streamed posting; a document the term does not hold reads impact 0).
+    int neg_lo = 0, neg_hi = 0;
+    auto neg_adjust = [&](uint32_t bits, int d) -> uint32_t {
+        float a = __uint_as_float(bits);
+        for (int sl = neg_lo; sl < neg_hi; ++sl) {
+            const uint4 m = s_meta[sl];
+            if (m.w) a = __fmaf_rd(-__uint_as_float(m.z), __ldg(ix.neg_imp + int64_t(m.w - 1u) * ix.neg_stride + (lo + d)), a);
+        }
+        return __float_as_uint(a);
+    };
+
     uint32_t hit_tau = 0xffffffffu;                  // bits of minus the bound of the current query (HITS), or "never"
     int hc = 0, hd = 0;                              // this lane's updates that reached the bound in the current task; doc of the last
     // one warp-round: up to 32 postings of one term; docs are unique inside a term (no race)
@@ -358,7 +387,7 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
             __syncwarp();
             for (int i = lane; i < ns; i += 32) {
                 const uint2 r = rec[sa + i];
-                s_meta[i] = make_uint4(r.x, r.y, __float_as_uint(w.slot_w[sa + i]), 0u);
+                s_meta[i] = make_uint4(r.x, r.y, __float_as_uint(w.slot_w[sa + i]), uint32_t(w.slot_row[sa + i]));
             }
             __syncwarp();
 
@@ -405,11 +434,13 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
                 uint32_t wneg = 0u;                             // sign bit set: a negative weight was applied (the last update
                                                                 // of a document need not be its largest then)
                 int touched = 0;
+                neg_lo = 0; neg_hi = 0;
 #pragma unroll
                 for (int t = 0; t < MP; ++t) {
                     if (o_cur + t < e_cur) {
                         const uint4 m = s_meta[o_cur + t];
                         const int n = int(m.y);
+                        if (m.w) { neg_lo = neg_hi ? neg_lo : o_cur + t; neg_hi = o_cur + t + 1; }
                         if (n > 0) {
                             const float wt = __uint_as_float(m.z);
                             touched = 1;
@@ -424,6 +455,7 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
                 for (int sl = o_cur + MP; sl < e_cur; ++sl) {               // queries with more than MP terms
                     const uint4 m = s_meta[sl];
                     const int n = int(m.y);
+                    if (m.w) { neg_lo = neg_hi ? neg_lo : sl; neg_hi = sl + 1; }
                     if (n == 0) continue;
                     const float wt = __uint_as_float(m.z);
                     touched = 1;
@@ -443,7 +475,10 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
                         if (__any_sync(0xffffffffu, hc == 1)) {
                             int d = -1 - lane;                               // idle lanes: distinct keys
                             uint32_t bits = 0u;
-                            if (hc == 1) { d = hd; bits = reinterpret_cast<const uint32_t*>(s_acc)[d]; }
+                            if (hc == 1) {
+                                d = hd; bits = reinterpret_cast<const uint32_t*>(s_acc)[d];
+                                if (neg_hi) bits = neg_adjust(bits, d);
+                            }
                             const unsigned same = __match_any_sync(0xffffffffu, d);
                             if (hc == 1 && (same & lt_mask) == 0u && bits >= tau_u) emit_one(q, int(bits), d);
                             __syncwarp();                                    // accumulators read before they are re-armed
@@ -483,7 +518,10 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
                         const int u = __ffs(int(pm)) - 1;
                         const uint32_t bits = u == 0 ? v.x : (u == 1 ? v.y : (u == 2 ? v.z : v.w));
                         const int d = (it * 32 + lane) * 4 + u;
-                        emit_one(q, int(bits), d);
+                        uint32_t fin = bits;
+                        bool ok = true;
+                        if (neg_hi) { fin = neg_adjust(bits, d); ok = fin >= tau_u; }     // (neg_hi != 0 implies `fast`)
+                        if (ok) emit_one(q, int(fin), d);
                         if (pm & (pm - 1u)) reinterpret_cast<uint32_t*>(s_acc)[d] = 0u;   // more in this group: come back for them
                         else { a4[it * 32] = z4; flag &= flag - 1u; }
                     }
@@ -507,6 +545,24 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
         }
     }
     complete_pending();
+}
+
+// Device-side validation of a query CSR (an enqueue-only call cannot look at it on the host).  q_off must start at 0,
+// be monotone, end at n_slots, and no query may hold more than MSE_MAX_QUERY_TERMS terms; otherwise the sanitised copy
+// describes a batch of EMPTY queries (no kernel then reads out of range) and MSE_ST_BAD_CSR is set.  One CTA.
+__global__ void __launch_bounds__(1024)
+bm25_sanitize_kernel(const int32_t* __restrict__ q_off, int32_t* __restrict__ safe_off, int32_t n_queries, int32_t n_slots,
+                     int32_t* __restrict__ status) {
+    int bad = 0;
+    for (int i = threadIdx.x; i <= n_queries; i += blockDim.x) {
+        const int v = q_off[i];
+        if (i == 0 && v != 0) bad = 1;
+        if (i == n_queries && v != n_slots) bad = 1;
+        if (i > 0) { const int n = v - q_off[i - 1]; if (n < 0 || n > MSE_MAX_QUERY_TERMS) bad = 1; }
+    }
+    bad = __syncthreads_or(bad);
+    for (int i = threadIdx.x; i <= n_queries; i += blockDim.x) safe_off[i] = bad ? 0 : q_off[i];
+    if (bad && threadIdx.x == 0 && status) atomicOr(status, MSE_ST_BAD_CSR);
 }
 
 // ---- load-time kernels ----------------------------------------------------------------------------------
@@ -589,6 +645,18 @@ bm25_impact_levels_kernel(const int64_t* __restrict__ term_off, const int32_t* _
         float v = 0.f;
         if (tid < 7 && s_bin[tid] >= 0 && s_low[tid] >= 0) v = float((s_bin[tid] << 8) | s_low[tid]) / 65536.0f;
         imp_levels[t * kImpLevels + tid] = v;
+    }
+}
+
+// Dense impact rows of the negative-idf terms (load time): one CTA per (row, slice of the term's postings).
+__global__ void bm25_neg_rows_kernel(const int64_t* __restrict__ term_off, const int2* __restrict__ post2,
+                                     const int32_t* __restrict__ row_term, float* __restrict__ neg_imp, int64_t stride) {
+    const int row = blockIdx.y;
+    const int t = row_term[row];
+    const int64_t a = term_off[t], e = term_off[t + 1];
+    for (int64_t i = a + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < e; i += int64_t(gridDim.x) * blockDim.x) {
+        const int2 p = post2[i];
+        neg_imp[int64_t(row) * stride + p.x] = __int_as_float(p.y);
     }
 }
 

@@ -26,7 +26,9 @@ constexpr int kRerankMaxChunks = 10;     // reranker_api.py:58
 constexpr int kRerankMaxRows = kRerankMaxCand * kRerankMaxChunks;
 
 struct RerankArgs {
-    const int32_t* cand_off;
+    const int32_t* cand_off;    // CSR offsets, or null: query i owns cand_doc[i*cand_stride .. +cand_count[i]) (count < 0 == 0)
+    const int32_t* cand_count;
+    int32_t cand_stride;
     const int32_t* cand_doc;
     const float* cand_bm25;
     const int32_t* url_group;   // may be null
@@ -68,6 +70,84 @@ __device__ __forceinline__ float block_reduce(float v, float* s_tmp, int op /*0 
     return r;
 }
 
+// Step 1 of every rerank kernel (reranker_api.py:38-47): the candidates of one query in ascending document order with
+// the URL-group dedupe applied (among the candidates of one group the lowest document survives).  A candidate id is
+// `cand_doc[i] - base`; ids outside [0, limit) are dropped (the -1 padding of a BM25 result, documents of another
+// index); `url_group` is indexed by that id (null: every document is its own group).  Writes the survivors to
+// s_doc[0..ns) / s_bm[0..ns) and returns ns.  Scratch: s_key, s_key2 [kRerankMaxCand] and s_dup [kRerankMaxCand];
+// s_key and s_doc / s_bm must not alias.  Ends with a block barrier.
+template <int NT>
+__device__ __forceinline__ int rerank_sort_dedupe(const int32_t* __restrict__ cand_doc, const float* __restrict__ cand_bm25, int nc,
+                                                  int64_t base, int64_t limit, const int32_t* __restrict__ url_group,
+                                                  uint64_t* s_key, uint64_t* s_key2, uint8_t* s_dup, int32_t* s_doc, float* s_bm,
+                                                  int* s_ns) {
+    const int tid = threadIdx.x;
+    int P = 1;
+    while (P < nc) P <<= 1;
+    // key layout (descending bitonic sort): valid<<63 | (0x7fffffff - major)<<10 | (0x3ff - minor)
+    for (int i = tid; i < P; i += NT) {
+        uint64_t k = 0;                                    // invalid entries sink to the end
+        if (i < nc) {
+            const int64_t d = int64_t(cand_doc[i]) - base;
+            if (d >= 0 && d < limit)
+                k = (1ull << 63) | (uint64_t(0x7fffffffu - uint32_t(d)) << 10) | uint64_t(0x3ff - i);
+        }
+        s_key[i] = k;
+    }
+    if (tid == 0) *s_ns = 0;
+    __syncthreads();
+    block_bitonic_desc<NT>(s_key, P);                      // ascending (doc, input slot)
+    for (int i = tid; i < P; i += NT) {
+        const uint64_t k = s_key[i];
+        uint64_t k2 = 0;
+        s_dup[i] = 0;
+        if (k >> 63) {
+            const uint32_t d = 0x7fffffffu - uint32_t((k >> 10) & 0x7fffffffu);
+            const uint32_t g = url_group ? uint32_t(url_group[d]) & 0x7fffffffu : d;
+            k2 = (1ull << 63) | (uint64_t(0x7fffffffu - g) << 10) | uint64_t(0x3ff - i);
+        }
+        s_key2[i] = k2;
+    }
+    __syncthreads();
+    if (url_group) {
+        block_bitonic_desc<NT>(s_key2, P);                 // ascending (group, position in doc order)
+        for (int j = tid; j < P; j += NT) {
+            const uint64_t k = s_key2[j];
+            if ((k >> 63) && j > 0) {
+                const uint64_t p = s_key2[j - 1];
+                if ((p >> 63) && ((p >> 10) == (k >> 10))) s_dup[0x3ff - int(k & 0x3ffull)] = 1;   // same group, higher doc
+            }
+        }
+        __syncthreads();
+    } else {
+        // every document is its own group: a duplicate can only be the same document listed twice (adjacent after the sort)
+        for (int j = tid + 1; j < P; j += NT) {
+            const uint64_t k = s_key[j], p = s_key[j - 1];
+            if ((k >> 63) && (p >> 63) && ((p >> 10) == (k >> 10))) s_dup[j] = 1;
+        }
+        __syncthreads();
+    }
+    if (tid < 32) {                                        // stable compaction of the survivors (one warp)
+        int carry = 0;
+        for (int b0 = 0; b0 < P; b0 += 32) {
+            const int i = b0 + tid;
+            const uint64_t k = i < P ? s_key[i] : 0ull;
+            const int keep = ((k >> 63) && !s_dup[i]) ? 1 : 0;
+            const int incl = warp_incl_scan(keep);
+            __syncwarp();
+            if (keep) {
+                const int o = carry + incl - 1;
+                s_doc[o] = int32_t(0x7fffffffu - uint32_t((k >> 10) & 0x7fffffffu));
+                s_bm[o] = cand_bm25[0x3ff - int(k & 0x3ffull)];
+            }
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (tid == 0) *s_ns = carry;
+    }
+    __syncthreads();
+    return *s_ns;
+}
+
 __global__ void __launch_bounds__(kRerankThreads)
 rerank_kernel(DenseDev dx, RerankArgs a) {
     constexpr int NT = kRerankThreads;
@@ -84,68 +164,21 @@ rerank_kernel(DenseDev dx, RerankArgs a) {
 
     const int qi = blockIdx.x;
     const int tid = threadIdx.x;
-    const int c0 = a.cand_off[qi];
-    int nc = a.cand_off[qi + 1] - c0;
+    int c0, nc;
+    if (a.cand_off) { c0 = a.cand_off[qi]; nc = a.cand_off[qi + 1] - c0; }
+    else { c0 = qi * a.cand_stride; nc = a.cand_count[qi]; }
+    if (nc < 0) nc = 0;
     if (nc > kRerankMaxCand) nc = kRerankMaxCand;
     const int max_chunks = a.max_chunks < kRerankMaxChunks ? a.max_chunks : kRerankMaxChunks;
-
-    // ---- 1. candidates in ascending doc order; URL-group dedupe (lowest doc of a group survives) ----
-    // key layout (descending bitonic sort): valid<<63 | (0x7fffffff - major)<<10 | (0x3ff - minor)
-    uint64_t* s_key2 = reinterpret_cast<uint64_t*>(s_cos);             // scratch, s_cos is free until step 3
-    uint8_t* s_dup = reinterpret_cast<uint8_t*>(s_key2 + kRerankMaxCand);
     int P = 1;
     while (P < nc) P <<= 1;
-    for (int i = tid; i < P; i += NT) {
-        uint64_t k = 0;                                    // invalid entries sink to the end
-        if (i < nc) {
-            const int64_t d = int64_t(a.cand_doc[c0 + i]) - int64_t(dx.doc_base);
-            if (d >= 0 && d < dx.n_docs)
-                k = (1ull << 63) | (uint64_t(0x7fffffffu - uint32_t(d)) << 10) | uint64_t(0x3ff - i);
-        }
-        s_key[i] = k;
-    }
-    if (tid == 0) { s_ns = 0; s_rows = 0; }
-    __syncthreads();
-    block_bitonic_desc<NT>(s_key, P);                      // ascending (doc, input slot)
-    for (int i = tid; i < P; i += NT) {
-        const uint64_t k = s_key[i];
-        uint64_t k2 = 0;
-        s_dup[i] = 0;
-        if (k >> 63) {
-            const uint32_t d = 0x7fffffffu - uint32_t((k >> 10) & 0x7fffffffu);
-            const uint32_t g = a.url_group ? uint32_t(a.url_group[d]) & 0x7fffffffu : d;
-            k2 = (1ull << 63) | (uint64_t(0x7fffffffu - g) << 10) | uint64_t(0x3ff - i);
-        }
-        s_key2[i] = k2;
-    }
-    __syncthreads();
-    block_bitonic_desc<NT>(s_key2, P);                     // ascending (group, position in doc order)
-    for (int j = tid; j < P; j += NT) {
-        const uint64_t k = s_key2[j];
-        if ((k >> 63) && j > 0) {
-            const uint64_t p = s_key2[j - 1];
-            if ((p >> 63) && ((p >> 10) == (k >> 10))) s_dup[0x3ff - int(k & 0x3ffull)] = 1;   // same group, higher doc
-        }
-    }
-    __syncthreads();
-    if (tid < 32) {                                        // stable compaction of the survivors (one warp)
-        int carry = 0;
-        for (int base = 0; base < P; base += 32) {
-            const int i = base + tid;
-            const uint64_t k = i < P ? s_key[i] : 0ull;
-            const int keep = ((k >> 63) && !s_dup[i]) ? 1 : 0;
-            const int incl = warp_incl_scan(keep);
-            __syncwarp();
-            if (keep) {
-                const int o = carry + incl - 1;            // o <= i: slots below i were consumed by earlier lanes/rounds
-                s_doc[o] = int32_t(0x7fffffffu - uint32_t((k >> 10) & 0x7fffffffu));
-                s_bm[o] = a.cand_bm25[c0 + (0x3ff - int(k & 0x3ffull))];
-            }
-            carry += __shfl_sync(0xffffffffu, incl, 31);
-        }
-        if (tid == 0) s_ns = carry;
-    }
-    __syncthreads();
+
+    // ---- 1. candidates in ascending doc order; URL-group dedupe (lowest doc of a group survives) ----
+    uint64_t* s_key2 = reinterpret_cast<uint64_t*>(s_cos);             // scratch, s_cos is free until step 3
+    uint8_t* s_dup = reinterpret_cast<uint8_t*>(s_key2 + kRerankMaxCand);
+    if (tid == 0) s_rows = 0;
+    rerank_sort_dedupe<NT>(a.cand_doc + c0, a.cand_bm25 + c0, nc, int64_t(dx.doc_base), dx.n_docs, a.url_group,
+                           s_key, s_key2, s_dup, s_doc, s_bm, &s_ns);
     const int ns = s_ns;                                   // survivors occupy s_doc[0..ns), ascending doc
 
     // ---- 2. rows per survivor (first <= max_chunks chunks), exclusive prefix ------------------

@@ -20,7 +20,9 @@
 namespace mse {
 
 struct RerankShardArgs {
-    const int32_t* cand_off;
+    const int32_t* cand_off;        // CSR offsets, or null: fixed stride + per-query counts (as RerankArgs)
+    const int32_t* cand_count;
+    int32_t cand_stride;
     const int32_t* cand_doc;        // GLOBAL dense doc index, BM25 order (replicated on all ranks)
     const float* cand_bm25;
     const int32_t* url_group;       // [n_docs_global] or null (replicated)
@@ -44,70 +46,25 @@ rerank_shard_cos_kernel(DenseDev dx, RerankShardArgs a) {
     __shared__ uint64_t s_key2[kRerankMaxCand];
     __shared__ uint8_t s_dup[kRerankMaxCand];
     __shared__ int32_t s_doc[kRerankMaxCand];
+    __shared__ float s_bm[kRerankMaxCand];
     __shared__ int s_ns;
     const int qi = blockIdx.x;
     const int tid = threadIdx.x;
-    const int c0 = a.cand_off[qi];
-    int nc = a.cand_off[qi + 1] - c0;
+    int c0, nc;
+    if (a.cand_off) { c0 = a.cand_off[qi]; nc = a.cand_off[qi + 1] - c0; }
+    else { c0 = qi * a.cand_stride; nc = a.cand_count[qi]; }
+    if (nc < 0) nc = 0;
     if (nc > kRerankMaxCand) nc = kRerankMaxCand;
-    int P = 1;
-    while (P < nc) P <<= 1;
-    // ascending (doc, input slot); docs outside [0, n_docs_global) are dropped (-1 padding of BM25 results)
-    for (int i = tid; i < P; i += NT) {
-        uint64_t k = 0;
-        if (i < nc) {
-            const int64_t g = a.cand_doc[c0 + i];
-            if (g >= 0 && g < a.n_docs_global)
-                k = (1ull << 63) | (uint64_t(0x7fffffffu - uint32_t(g)) << 10) | uint64_t(0x3ff - i);
+    // ascending (doc, input slot), URL-group dedupe; docs outside [0, n_docs_global) are dropped (-1 padding of BM25 results)
+    rerank_sort_dedupe<NT>(a.cand_doc + c0, a.cand_bm25 + c0, nc, 0, a.n_docs_global, a.url_group,
+                           s_key, s_key2, s_dup, s_doc, s_bm, &s_ns);
+    if (blockIdx.y == 0) {                                 // (every slice of a query computes the same list)
+        for (int i = tid; i < s_ns; i += NT) {
+            a.surv_doc[int64_t(qi) * kRerankMaxCand + i] = s_doc[i];
+            a.surv_bm25[int64_t(qi) * kRerankMaxCand + i] = s_bm[i];
         }
-        s_key[i] = k;
+        if (tid == 0) a.surv_count[qi] = s_ns;
     }
-    if (tid == 0) s_ns = 0;
-    __syncthreads();
-    block_bitonic_desc<NT>(s_key, P);
-    for (int i = tid; i < P; i += NT) {
-        const uint64_t k = s_key[i];
-        uint64_t k2 = 0;
-        s_dup[i] = 0;
-        if (k >> 63) {
-            const uint32_t g = 0x7fffffffu - uint32_t((k >> 10) & 0x7fffffffu);
-            const uint32_t grp = a.url_group ? uint32_t(a.url_group[g]) & 0x7fffffffu : g;
-            k2 = (1ull << 63) | (uint64_t(0x7fffffffu - grp) << 10) | uint64_t(0x3ff - i);
-        }
-        s_key2[i] = k2;
-    }
-    __syncthreads();
-    block_bitonic_desc<NT>(s_key2, P);
-    for (int j = tid; j < P; j += NT) {
-        const uint64_t k = s_key2[j];
-        if ((k >> 63) && j > 0) {
-            const uint64_t p = s_key2[j - 1];
-            if ((p >> 63) && ((p >> 10) == (k >> 10))) s_dup[0x3ff - int(k & 0x3ffull)] = 1;
-        }
-    }
-    __syncthreads();
-    if (tid < 32) {                                        // stable compaction (one warp)
-        int carry = 0;
-        for (int base = 0; base < P; base += 32) {
-            const int i = base + tid;
-            const uint64_t k = i < P ? s_key[i] : 0ull;
-            const int keep = ((k >> 63) && !s_dup[i]) ? 1 : 0;
-            const int incl = warp_incl_scan(keep);
-            __syncwarp();
-            if (keep) {
-                const int o = carry + incl - 1;
-                const int32_t g = int32_t(0x7fffffffu - uint32_t((k >> 10) & 0x7fffffffu));
-                s_doc[o] = g;
-                if (blockIdx.y == 0) {                     // (every slice of a query computes the same list)
-                    a.surv_doc[int64_t(qi) * kRerankMaxCand + o] = g;
-                    a.surv_bm25[int64_t(qi) * kRerankMaxCand + o] = a.cand_bm25[c0 + (0x3ff - int(k & 0x3ffull))];
-                }
-            }
-            carry += __shfl_sync(0xffffffffu, incl, 31);
-        }
-        if (tid == 0) { s_ns = carry; if (blockIdx.y == 0) a.surv_count[qi] = carry; }
-    }
-    __syncthreads();
     const int ns = s_ns;
     const int max_chunks = a.max_chunks < kRerankMaxChunks ? a.max_chunks : kRerankMaxChunks;
 

@@ -97,11 +97,24 @@ struct MergeLoader {         // all-gathered per-rank top-k lists, [n_lists][n_q
     }
 };
 
+struct KeyListLoader {       // per-shard lists of 64-bit keys exchanged between ranks, [n_lists][n_queries][list_k], 0 = empty slot
+    const uint64_t* keys;
+    int32_t n_lists, n_queries, list_k;
+    __device__ __forceinline__ int64_t n(int) const { return int64_t(n_lists) * list_k; }
+    __device__ __forceinline__ uint64_t get(int q, int64_t i) const {
+        const int l = int(i / list_k), j = int(i % list_k);
+        return keys[(int64_t(l) * n_queries + q) * list_k + j];
+    }
+};
+
+// Outputs: (out_doc, out_score, out_count) as the C ABI returns them and / or out_key, the same list as 64-bit keys
+// (0-padded) — the form the shard exchange moves.  Any of the two may be null.
 template <class Loader>
 __global__ void __launch_bounds__(kSelectThreads, 2)
 topk_select_kernel(Loader ld, int32_t top_k, int32_t* __restrict__ out_doc, float* __restrict__ out_score,
                    int32_t* __restrict__ out_count, const int32_t* __restrict__ skip_flag,
-                   unsigned long long* __restrict__ summary = nullptr) {   // [0] += elements selected from, [1] += skipped queries
+                   unsigned long long* __restrict__ summary = nullptr,   // [0] += elements selected from, [1] += skipped queries
+                   uint64_t* __restrict__ out_key = nullptr) {
     constexpr int NT = kSelectThreads;
     __shared__ uint64_t s_buf[kSortCap];
     __shared__ int s_hist[256];
@@ -111,10 +124,14 @@ topk_select_kernel(Loader ld, int32_t top_k, int32_t* __restrict__ out_doc, floa
 
     const int q = blockIdx.x;
     const int tid = threadIdx.x;
-    if (skip_flag && skip_flag[q]) {            // query re-run elsewhere (capacity overflow)
+    if (skip_flag && skip_flag[q]) {            // candidate list overflowed: the query is reported (count -1, no entries)
         if (tid == 0) {
-            out_count[q] = -1;
+            if (out_count) out_count[q] = -1;
             if (summary) atomicAdd(summary + 1, 1ull);
+        }
+        for (int i = tid; i < top_k; i += NT) {
+            if (out_doc) { out_doc[int64_t(q) * top_k + i] = -1; out_score[int64_t(q) * top_k + i] = 0.f; }
+            if (out_key) out_key[int64_t(q) * top_k + i] = 0ull;
         }
         return;
     }
@@ -148,8 +165,11 @@ topk_select_kernel(Loader ld, int32_t top_k, int32_t* __restrict__ out_doc, floa
 
     const int kk = n_valid < top_k ? n_valid : top_k;
     if (kk == 0) {
-        if (tid == 0) out_count[q] = 0;
-        for (int i = tid; i < top_k; i += NT) { out_doc[int64_t(q) * top_k + i] = -1; out_score[int64_t(q) * top_k + i] = 0.f; }
+        if (tid == 0 && out_count) out_count[q] = 0;
+        for (int i = tid; i < top_k; i += NT) {
+            if (out_doc) { out_doc[int64_t(q) * top_k + i] = -1; out_score[int64_t(q) * top_k + i] = 0.f; }
+            if (out_key) out_key[int64_t(q) * top_k + i] = 0ull;
+        }
         return;
     }
 
@@ -262,16 +282,28 @@ topk_select_kernel(Loader ld, int32_t top_k, int32_t* __restrict__ out_doc, floa
     const int out_n = m < kk ? m : kk;
     for (int i = tid; i < top_k; i += NT) {
         int64_t o = int64_t(q) * top_k + i;
-        if (i < out_n) {
-            uint64_t k = s_buf[i];
-            out_doc[o] = int32_t(key64_doc(k));
-            out_score[o] = key_to_float(key64_score_key(k));
-        } else {
-            out_doc[o] = -1;
-            out_score[o] = 0.f;
+        const uint64_t k = i < out_n ? s_buf[i] : 0ull;
+        if (out_key) out_key[o] = k;
+        if (out_doc) {
+            out_doc[o] = i < out_n ? int32_t(key64_doc(k)) : -1;
+            out_score[o] = i < out_n ? key_to_float(key64_score_key(k)) : 0.f;
         }
     }
-    if (tid == 0) out_count[q] = out_n;
+    if (tid == 0 && out_count) out_count[q] = out_n;
+}
+
+// Exactness check of a shard exchange that moved only the first list_k entries of every shard list (see sharding notes
+// in api.cu): a list that came back full (its last slot is used) may have been cut; if its last score is still >= the
+// merged k-th score, or the merge is short, it could hide a result of the exact top-k.  One thread per (list, query).
+__global__ void shard_cut_check_kernel(const uint64_t* __restrict__ keys, int32_t n_lists, int32_t n_queries, int32_t list_k,
+                                       const uint64_t* __restrict__ merged_key, int32_t top_k, int32_t* __restrict__ status) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= int64_t(n_lists) * n_queries) return;
+    const int q = int(i % n_queries);
+    const uint64_t last = keys[i * list_k + (list_k - 1)];
+    if (last == 0ull) return;                                   // the shard sent everything it had
+    const uint64_t kth = merged_key[int64_t(q) * top_k + (top_k - 1)];
+    if (kth == 0ull || key64_score_key(last) >= key64_score_key(kth)) atomicOr(status + 2, 1);
 }
 
 }  // namespace mse

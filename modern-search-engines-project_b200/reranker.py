@@ -140,6 +140,8 @@ class Reranker:
         self._urls = [url_map.get(int(d)) for d in self.doc_ids.tolist()] if url_map else None
         self.url_group = url_groups(self._urls) if self._urls is not None else None
         self._in_urls = np.asarray([u is not None for u in self._urls]) if self._urls is not None else None
+        if self.url_group is not None:                       # uploaded once; the rerank calls use the stored groups
+            self.native.set_url_groups(np.ascontiguousarray(self.url_group, dtype=np.int32))
 
     # ---- batched numeric core ------------------------------------------------------------------------
     def rerank_batch(self, cand_idx: Sequence[np.ndarray], cand_score: Sequence[np.ndarray], q_vecs: np.ndarray,
@@ -158,7 +160,7 @@ class Reranker:
         cs = np.concatenate(sims) if sims else np.zeros(0, np.float32)
         q = np.ascontiguousarray(q_vecs, dtype=np.float32).reshape(len(cand_idx), _native.EMB_DIM)
         o_doc, o_score, o_orig, o_chunk, o_count, o_rows = self.native.rerank(
-            off, np.ascontiguousarray(cd), np.ascontiguousarray(cs), q, self.url_group, self.smoothing,
+            off, np.ascontiguousarray(cd), np.ascontiguousarray(cs), q, None, self.smoothing,
             self.max_chunks, max_out)
         o_chunk = np.where(o_chunk >= 0, self.chunk_ids[np.maximum(o_chunk, 0)] if len(self.chunk_ids) else -1, -1)
         return o_doc, o_score, o_orig, o_chunk, o_count, o_rows

@@ -230,6 +230,39 @@ def make_dense_corpus(n_docs: int, dim: int = 768, seed: int = 1234, device="cpu
     return SyntheticDense(emb, torch.from_numpy(off).to(dev), torch.arange(n_chunks, dtype=torch.int64, device=dev))
 
 
+DENSE_SLAB_ROWS = 1 << 18
+
+
+def dense_rows(row_lo: int, row_hi: int, seed: int = 1234, dim: int = 768, device="cpu", dtype=torch.bfloat16) -> torch.Tensor:
+    """Rows [row_lo, row_hi) of the shardable synthetic chunk table: unit-norm Gaussian rows generated in slabs of
+    ``DENSE_SLAB_ROWS`` rows, slab s from its own generator seeded with (seed, s) — so ANY rank (or the CPU oracle)
+    regenerates exactly the rows it needs, whatever the sharding.  Values are identical on CPU
+    and CUDA only up to the generator implementation: regenerate on the device type the table was built on."""
+    dev = torch.device(device)
+    out = torch.empty((max(0, row_hi - row_lo), dim), dtype=dtype, device=dev)
+    s0, s1 = row_lo // DENSE_SLAB_ROWS, (max(row_hi, row_lo + 1) - 1) // DENSE_SLAB_ROWS
+    for sl in range(s0, s1 + 1):
+        a, e = sl * DENSE_SLAB_ROWS, (sl + 1) * DENSE_SLAB_ROWS
+        lo, hi = max(a, row_lo), min(e, row_hi)
+        if hi <= lo:
+            continue
+        g = torch.Generator(device=dev)
+        g.manual_seed((seed + 11) * 1_000_003 + sl)
+        x = torch.randn((DENSE_SLAB_ROWS, dim), generator=g, device=dev, dtype=torch.float32)[lo - a:hi - a]
+        out[lo - row_lo:hi - row_lo] = (x / x.norm(dim=1, keepdim=True)).to(dtype)
+    return out
+
+
+def make_dense_shard(doc_chunk_off_global: np.ndarray, doc_lo: int, doc_hi: int, seed: int = 1234, device="cpu",
+                     dtype=torch.bfloat16) -> SyntheticDense:
+    """The chunk rows of docs [doc_lo, doc_hi) of the shardable table (``dense_rows``): local offsets, global chunk ids."""
+    off = np.asarray(doc_chunk_off_global, dtype=np.int64)
+    r0, r1 = int(off[doc_lo]), int(off[doc_hi])
+    emb = dense_rows(r0, r1, seed, device=device, dtype=dtype)
+    return SyntheticDense(emb, torch.from_numpy(off[doc_lo:doc_hi + 1] - r0).to(device),
+                          torch.arange(r0, r1, dtype=torch.int64, device=device))
+
+
 def make_query_vectors(n: int, dim: int = 768, seed: int = 1235, normalize: bool = False) -> np.ndarray:
     """Standard-normal query vectors, float32; un-normalised for the rerank path
     (reranker_api.py:355), normalised for the exhaustive scan (embedder.py:58)."""

@@ -136,8 +136,9 @@ def test_rerank_golden_fixture():
     g = case["div"]
     assert resp.total_documents == g["total_documents"] and resp.total_windows == 100
     got = [int(d.doc_id) for d in resp.document_scores]
-    assert len(got) == len(g["doc_id"]) and len(set(got) ^ set(g["doc_id"])) <= 2
-    np.testing.assert_allclose([d.similarity_score for d in resp.document_scores], g["score"], atol=3e-3)
+    # tie-aware rule after diversification too: scores within the dense tolerance at every rank, a different doc only
+    # where the deciding scores tie inside it
+    helpers.assert_topk_matches(got, [d.similarity_score for d in resp.document_scores], g["doc_id"], g["score"], 0.0, atol=3e-3)
     rr.native.close()
 
 

@@ -28,7 +28,7 @@ def test_library_exports_every_symbol_declared_in_the_header():
     for name in declared:
         assert hasattr(L, name), name
     L.mse_abi_version.restype = ctypes.c_int
-    assert L.mse_abi_version() == 1
+    assert L.mse_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_gpu():
@@ -148,7 +148,7 @@ def test_reference_arm_of_bench_runs_on_cpu():
     assert r.returncode == 0, r.stderr[-2000:]
     d = json.loads(r.stdout.strip().splitlines()[-1])
     assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
-    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["metric"] == "bm25_queries_per_sec"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["metric"] == "hybrid_queries_per_sec"
 
 
 def test_synthetic_corpus_slab_path_is_a_valid_index():
@@ -177,6 +177,9 @@ class _OracleNative:
 
     def dense_load(self, emb, off):
         assert emb.shape[0] == int(off[-1])
+
+    def set_url_groups(self, groups):                  # the oracle dedupes from dense.urls itself
+        assert len(groups) == len(self.dense.doc_ids)
 
     def rerank(self, cand_off, cand_doc, cand_bm25, q, url_group, smoothing, max_chunks, max_out):
         B = len(cand_off) - 1
