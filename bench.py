@@ -338,6 +338,8 @@ def bm25_c2_supplement(dev, local_rank, peak, always: bool, steps=20, warmup=3, 
     c = synthetic.make_bm25_corpus(n_docs, vocab=VOCAB, seed=SEED, device=dev, always_frac=ALWAYS_FRAC if always else 0.0)
     nat = _native.NativeIndex(local_rank)
     nat.bm25_load(c.term_off, c.post_doc, c.post_tf, c.doc_len, c.idf, c.avgdl)
+    if always:
+        nat.set_option("bm25_class_term", c.always_term)
     df = torch.diff(c.term_off).cpu().numpy()
     host = [synthetic.make_bm25_queries(c, B, seed=SEED + 1 + i, add_always=always) for i in range(steps + warmup)]
     devb = [tuple(torch.from_numpy(a).to(dev) for a in b) for b in host]
@@ -539,6 +541,7 @@ def main():
     ap.add_argument("--shard-list-len", type=int, default=0)
     ap.add_argument("--neg-lookup", type=int, default=1)
     ap.add_argument("--range-docs", type=int, default=0)
+    ap.add_argument("--no-class-term", action="store_true", help="experiments: leave the posting class bits on the default term")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -582,6 +585,8 @@ def main():
     else:
         nat.comm_init(None, 0, 1)
     nat.set_option("bm25_neg_lookup", args.neg_lookup)
+    if corpus.always_term >= 0 and not args.no_class_term:
+        nat.set_option("bm25_class_term", corpus.always_term)       # the term appended to every query (search_api.py:160-165)
     if args.range_docs:
         nat.set_option("bm25_range_docs", args.range_docs)
     n_batches = args.steps + args.warmup

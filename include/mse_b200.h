@@ -104,6 +104,11 @@ int mse_index_destroy(mse_index* idx);
  *                            contribution is read from a dense per-term impact row for the documents that reach the
  *                            bound on their other terms.  0 = stream every posting list (identical results up to the
  *                            order of the float32 additions)
+ *   "bm25_class_term"        term id (idf < 0) whose per-document impact class is kept in every posting, so that a document that
+ *                            cannot reach the running bound once this term is charged is never looked up: set it to the term the
+ *                            caller appends to every query ("tübingen", search_api.py:160-165).  Default: the negative-idf term
+ *                            with the most postings.  Takes effect on the loaded index (rewrites 4 bits per posting); results
+ *                            never depend on it
  *   "dense_scan_ctas_per_sm" persistent CTAs per SM of the scan kernel
  *   "dense_gemm_min_batch"   smallest batch routed to the tcgen05 GEMM kernel
  *   "timers"                 1 (default) = bracket the kernels with CUDA events (mse_kernel_time), 0 = off

@@ -44,6 +44,8 @@ struct mse_index {
     Bm25Dev bm{};
     DevBuf term_off, post2, skip, skip_row, imp_levels, idf, neg_row, neg_imp;
     std::vector<int64_t> h_term_off;
+    std::vector<int32_t> h_neg_row;      // term -> dense row (-1: none), host copy
+    int64_t neg_stride = 0;
 
     bool has_dense = false;
     DenseDev dn{};
@@ -161,7 +163,7 @@ int bm25_enqueue(mse_index* ix, Lease& L, int32_t B, const int32_t* d_q_off, con
     const int qpi = int(std::min<int64_t>(31, ix->opt_qpi > 0 ? ix->opt_qpi : 8));
     int rc;
     if ((rc = ws->slot_w.ensure(sizeof(float) * size_t(S + 1)))) return rc;
-    if ((rc = ws->slot_row.ensure(sizeof(int32_t) * size_t(S + 1)))) return rc;
+    if ((rc = ws->slot_row.ensure(sizeof(float) * size_t(B + 1)))) return rc;              // cls_wq [B]
     if ((rc = ws->rec.ensure(sizeof(uint2) * (size_t(S) * n_sub + 1)))) return rc;
     if ((rc = ws->tau.ensure(sizeof(uint32_t) * size_t(B)))) return rc;
     if ((rc = ws->hist.ensure(sizeof(uint32_t) * size_t(B) * kHistBins))) return rc;
@@ -176,7 +178,7 @@ int bm25_enqueue(mse_index* ix, Lease& L, int32_t B, const int32_t* d_q_off, con
 
     Bm25Work w{};
     w.q_off = d_q_off; w.q_term = d_q_term; w.q_tf = d_q_tf;
-    w.slot_w = ws->slot_w.as<float>(); w.slot_row = ws->slot_row.as<int32_t>(); w.rec = ws->rec.as<uint2>();
+    w.slot_w = ws->slot_w.as<float>(); w.cls_wq = ws->slot_row.as<float>(); w.rec = ws->rec.as<uint2>();
     w.ts = TauState{ws->tau.as<uint32_t>(), ws->hist.as<uint32_t>(), ws->maxbin.as<uint32_t>(), top_k};
     w.cand = ws->cand.as<uint64_t>(); w.cand_count = ws->cand_count.as<int32_t>(); w.overflow = ws->cand_count.as<int32_t>() + B;
     w.item_counter = ws->misc.as<int32_t>();
@@ -473,6 +475,7 @@ int mse_index_create(int device, mse_index** out) {
     ix->sm_count = prop.multiProcessorCount;
     // function attributes are set once here, so that no search call touches them (calls may run inside a stream capture)
     cudaError_t e = cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kRerankSmemBytes));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dense_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemmStageBytes) * kGemmMaxStages + 1024);
     for (int hits = 0; hits < 2 && e == cudaSuccess; ++hits) {
         const void* kfn = score_kernel_fn(true, hits != 0);
         const size_t smem = size_t(kBm25Warps) * bm25_score_warp_bytes(kBm25DefaultRange);
@@ -505,6 +508,25 @@ int mse_index_set_option(mse_index* ix, const char* name, int64_t value) {
     if (!strcmp(name, "bm25_range_docs")) ix->opt_range_docs = value;
     else if (!strcmp(name, "bm25_readout")) ix->opt_readout = value;
     else if (!strcmp(name, "bm25_neg_lookup")) ix->opt_neg_lookup = value;
+    else if (!strcmp(name, "bm25_class_term")) {
+        // the negative-idf term whose per-document impact class rides in every posting (Bm25Dev::cls_row): the term the caller
+        // appends to every query (search_api.py:160-165).  Default after a load: the negative-idf term with the most postings.
+        if (!ix->has_bm25 || value < 0 || value >= ix->bm.n_terms || ix->h_neg_row.empty() || ix->h_neg_row[size_t(value)] < 0 ||
+            ix->bm.n_docs > int64_t(kDocMask)) {
+            set_error("bm25_class_term: term %lld has no dense impact row (it needs idf < 0 on a loaded index)", (long long)value);
+            return MSE_ERR_INVALID;
+        }
+        DeviceGuard g(ix->device);
+        MSE_CUDA_TRY(cudaDeviceSynchronize());               // no search may be reading the postings while their class bits change
+        const int32_t row = ix->h_neg_row[size_t(value)];
+        const int64_t P = ix->bm.n_postings;
+        if (P > 0) {
+            bm25_class_bits_kernel<<<unsigned((P + 255) / 256), 256>>>(ix->post2.as<int2>(), P, ix->neg_imp.as<float>() + int64_t(row) * ix->neg_stride);
+            MSE_CUDA_TRY(cudaGetLastError());
+            MSE_CUDA_TRY(cudaDeviceSynchronize());
+        }
+        ix->bm.cls_row = row;
+    }
     else if (!strcmp(name, "bm25_tau_init")) { ix->opt_tau_init = value; ix->bm.imp_levels = (value && ix->has_bm25) ? ix->imp_levels.as<float>() : nullptr; }
     else if (!strcmp(name, "bm25_queries_per_item")) ix->opt_qpi = value;
     else if (!strcmp(name, "bm25_cand_cap")) ix->opt_cand_cap = value;
@@ -647,7 +669,7 @@ int mse_bm25_load(mse_index* ix, int64_t n_terms, int64_t n_docs, int64_t doc_ba
         }
     }
     {   // dense impact rows of the negative-idf terms (df > N/2), largest first, within a memory budget
-        ix->bm.neg_row = nullptr; ix->bm.neg_imp = nullptr; ix->bm.neg_stride = 0;
+        ix->bm.neg_row = nullptr; ix->bm.neg_imp = nullptr; ix->bm.neg_stride = 0; ix->bm.cls_row = -1;
         std::vector<std::pair<int64_t, int32_t>> neg;          // (df, term)
         for (int64_t t = 0; t < n_terms; ++t)
             if (h_idf[t] < 0.f && ix->h_term_off[t + 1] > ix->h_term_off[t]) neg.emplace_back(ix->h_term_off[t + 1] - ix->h_term_off[t], int32_t(t));
@@ -659,8 +681,11 @@ int mse_bm25_load(mse_index* ix, int64_t n_terms, int64_t n_docs, int64_t doc_ba
         const int64_t max_rows = stride > 0 ? std::min<int64_t>(512, budget / (4 * stride)) : 0;
         const int64_t n_rows = std::min<int64_t>(int64_t(neg.size()), max_rows);
         if (n_rows > 0) {
-            std::vector<int32_t> h_neg_row(size_t(n_terms), -1), h_row_term(size_t(n_rows), 0);
+            std::vector<int32_t>& h_neg_row = ix->h_neg_row;
+            std::vector<int32_t> h_row_term(size_t(n_rows), 0);
+            h_neg_row.assign(size_t(n_terms), -1);
             for (int64_t r = 0; r < n_rows; ++r) { h_neg_row[neg[r].second] = int32_t(r); h_row_term[r] = neg[r].second; }
+            ix->neg_stride = stride;
             DevBuf d_row_term;
             if ((rc = ix->neg_row.ensure(sizeof(int32_t) * size_t(n_terms)))) return rc;
             if ((rc = ix->neg_imp.ensure(sizeof(float) * size_t(n_rows) * size_t(stride)))) return rc;
@@ -673,8 +698,15 @@ int mse_bm25_load(mse_index* ix, int64_t n_terms, int64_t n_docs, int64_t doc_ba
             MSE_CUDA_TRY(cudaGetLastError());
             MSE_CUDA_TRY(cudaStreamSynchronize(st));
             ix->bm.neg_row = ix->neg_row.as<int32_t>(); ix->bm.neg_imp = ix->neg_imp.as<float>(); ix->bm.neg_stride = stride;
+            if (n_docs <= int64_t(kDocMask) && P > 0) {          // class bits of the heaviest negative term (row 0) in every posting
+                bm25_class_bits_kernel<<<unsigned((P + 255) / 256), 256, 0, st>>>(ix->post2.as<int2>(), P, ix->neg_imp.as<float>());
+                MSE_CUDA_TRY(cudaGetLastError());
+                MSE_CUDA_TRY(cudaStreamSynchronize(st));
+                ix->bm.cls_row = 0;
+            }
         } else {
             ix->neg_row.release(); ix->neg_imp.release();
+            ix->h_neg_row.clear();
         }
     }
     ix->bm.post_doc = nullptr;
@@ -1000,21 +1032,19 @@ int dense_scan_pass(mse_index* ix, Lease& L, const float* d_q, int g0, int gn, i
     w.cap = int32_t(rcap); w.use_tau = rtau;
     int tscan = timed ? L.timer_begin(T_SCAN) : -1;
     if (dn.n_chunks > 0 && use_gemm && rtau) {
-        // ---- tensor-core path: S = E * Q^T with the per-doc max / emit epilogue on TMEM ----
-        const int n_pad = round_up(gn, 32);
+        // ---- tensor-core path: S = Q * E^T with the query panel in TMEM and the per-doc max / emit epilogue ----
+        const int n_panels = gn > kGemmPanel ? 2 : 1;
+        const int n_pad = n_panels * kGemmPanel;
         if ((r = ws->qb16.ensure(sizeof(__nv_bfloat16) * size_t(n_pad) * kDim))) return r;
         gemm_pack_q_kernel<<<unsigned((int64_t(n_pad) * kDim + 255) / 256), 256, 0, st>>>(w.q, ws->qb16.as<__nv_bfloat16>(), gn, n_pad);
         MSE_CUDA_TRY(cudaGetLastError());
-        CUtensorMap map_q;
-        if ((r = make_bf16_rowmajor_map(&map_q, ws->qb16.p, uint64_t(n_pad), uint32_t(n_pad)))) return r;
         GemmWork gw{};
-        gw.group_row = ix->group_row.as<int64_t>(); gw.n_groups = ix->n_groups; gw.n_tiles = (ix->n_groups + 3) / 4;
-        gw.n_pad = n_pad; gw.n_real = gn; gw.q0 = 0; gw.debug = int(ix->opt_gemm_debug);
-        const size_t stage_bytes = gemm_stage_bytes(n_pad);
-        gw.stages = int(std::min<size_t>(8, (size_t(208) * 1024) / stage_bytes));
-        const size_t gsmem = stage_bytes * gw.stages + 1024;
-        MSE_CUDA_TRY(cudaFuncSetAttribute(dense_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(gsmem)));
-        const int ggrid = int(std::min<int64_t>(gw.n_tiles, ix->sm_count));
+        gw.group_row = ix->group_row.as<int64_t>(); gw.n_groups = ix->n_groups;
+        gw.n_tiles = (ix->n_groups + kGemmTileGroups - 1) / kGemmTileGroups;
+        gw.qb16 = ws->qb16.as<__nv_bfloat16>(); gw.n_panels = n_panels; gw.n_real = gn; gw.q0 = 0; gw.debug = int(ix->opt_gemm_debug);
+        gw.stages = kGemmMaxStages;
+        const size_t gsmem = size_t(kGemmStageBytes) * gw.stages + 1024;
+        const int ggrid = int(std::max<int64_t>(1, std::min<int64_t>(gw.n_tiles, ix->sm_count / n_panels))) * n_panels;
         const int64_t log_cap = std::min<int64_t>(int64_t(gn) * 65536, int64_t(64) << 20);
         if ((r = ws->log_key.ensure(sizeof(uint64_t) * size_t(log_cap)))) return r;
         if ((r = ws->log_q.ensure(sizeof(uint16_t) * size_t(log_cap)))) return r;
@@ -1023,7 +1053,7 @@ int dense_scan_pass(mse_index* ix, Lease& L, const float* d_q, int g0, int gn, i
         w.log_key = ws->log_key.as<uint64_t>(); w.log_q = ws->log_q.as<uint16_t>();
         w.log_count = reinterpret_cast<unsigned long long*>(ws->misc.as<char>() + 32);
         w.log_cap = log_cap; w.n_log_queries = gn;
-        dense_gemm_kernel<<<ggrid, kGemmThreads, gsmem, st>>>(ix->map_e, map_q, dn, w, gw);
+        dense_gemm_kernel<<<ggrid, kGemmThreads, gsmem, st>>>(ix->map_e, dn, w, gw);
         MSE_CUDA_TRY(cudaGetLastError());
         gemm_bucket_kernel<<<ix->sm_count * 4, 256, 0, st>>>(w);
         MSE_CUDA_TRY(cudaGetLastError());

@@ -49,6 +49,9 @@ constexpr int kBm25DefaultRange = 1536;          // docs per sub-range (the comp
                                                  // 6 KB of accumulators per warp, 32 warps per SM
 constexpr int kBm25MaxPrefetchSlots = 8;         // terms per query whose postings are prefetched
 constexpr int kImpLevels = 8;                    // ranks 64, 128, ..., 4096 (7 used) of the per-term impact table
+constexpr uint32_t kDocMask = 0x0fffffffu;       // doc bits of a posting's first word (class bits above, see Bm25Dev::cls_row)
+constexpr int kClsShift = 28;
+constexpr uint32_t kRecRowShift = 16;            // task record .y = count | (1 + dense row) << 16 | classed << 31 (looked-up slots only)
 
 struct Bm25Dev {                                 // device-resident index of one shard
     const int64_t* term_off;
@@ -63,6 +66,9 @@ struct Bm25Dev {                                 // device-resident index of one
     const int32_t* neg_row;      // [n_terms] row of the term in neg_imp, -1 = none.  Terms with idf < 0 (df > N/2) get a DENSE
     const float* neg_imp;        //   impact row neg_imp[row * neg_stride + doc] (0 where the doc lacks the term): with
     int64_t neg_stride;          //   min_score >= 0 their postings are never streamed, see bm25_score_kernel
+    int32_t cls_row;             // row of neg_imp whose impact is ALSO summarised in every posting of every term: bits 28..31 of a
+                                 //   posting's doc word hold c = floor(16 * neg_imp[cls_row][doc]) (0 when the doc lacks the term), a
+                                 //   lower bound c/16 of that impact; -1 = postings carry no class (doc word == doc)
     int64_t n_terms, n_docs, n_postings;
     uint32_t doc_base;
     float k1;
@@ -73,7 +79,8 @@ struct Bm25Work {                                // per-call workspace
     const int32_t* q_term;
     const int32_t* q_tf;
     float* slot_w;               // [S]  idf * qtf * (k1+1)
-    int32_t* slot_row;           // [S]  1 + dense row of a negative-weight slot that is looked up instead of streamed, else 0
+    float* cls_wq;               // [B]  |weight| / 16 of the query's looked-up slot on the class row (0: none): class c of a posting
+                                 //      then says the document loses at least cls_wq * c from that term
     uint2* rec;                  // [n_sub * S] {first posting (absolute), count} of slot s in sub-range j
     TauState ts;                 // running per-query lower bound of the final k-th best score
     uint64_t* cand;              // [B * cap]
@@ -102,7 +109,7 @@ constexpr int kPrepCountMaxSub = 12000;          // the on-the-fly path keeps on
 __device__ __forceinline__ int64_t lower_bound_doc(const int2* __restrict__ pd, int64_t lo, int64_t hi, int64_t target) {
     while (lo < hi) {
         const int64_t mid = (lo + hi) >> 1;
-        if (int64_t(pd[mid].x) < target) lo = mid + 1; else hi = mid;
+        if (int64_t(uint32_t(pd[mid].x) & kDocMask) < target) lo = mid + 1; else hi = mid;
     }
     return lo;
 }
@@ -115,18 +122,18 @@ __device__ __forceinline__ int64_t lower_bound_doc(const int2* __restrict__ pd, 
 // Also sets maxbin[q], the top histogram bin the bound refresh starts from, to the bin of the query's score ceiling
 // (sum of the positive weights), so that the score kernel needs no atomicMax per candidate.
 __device__ __forceinline__ uint32_t bm25_initial_bound(const Bm25Dev& ix, const Bm25Work& w, int q) {
-    if (!w.use_tau) return w.min_key;
     int lv = 0;
     while (lv < 7 && (64 << lv) < w.ts.top_k) ++lv;
     const bool have_level = ix.imp_levels != nullptr && (64 << lv) >= w.ts.top_k;
     const int64_t need = int64_t(64) << lv;
-    float best = 0.f, neg = 0.f, mag = 0.f, pos = 0.f;
+    float best = 0.f, neg = 0.f, mag = 0.f, pos = 0.f, wq = 0.f;
     for (int s = w.q_off[q]; s < w.q_off[q + 1]; ++s) {
         const int t = w.q_term[s];
         if (t < 0 || t >= ix.n_terms) continue;
         const int64_t df = ix.term_off[t + 1] - ix.term_off[t];
         if (df == 0) continue;
         const float wt = float(double(ix.idf[t]) * double(w.q_tf[s]) * (double(ix.k1) + 1.0));
+        if (w.neg_lookup && wt < 0.f && ix.cls_row >= 0 && ix.neg_row[t] == ix.cls_row) wq = -wt * 0.0625f;   // (distinct terms: at most one such slot)
         mag += fabsf(wt);
         if (wt < 0.f) neg += wt;
         else {
@@ -135,8 +142,9 @@ __device__ __forceinline__ uint32_t bm25_initial_bound(const Bm25Dev& ix, const 
         }
     }
     w.ts.maxbin[q] = float_to_key(pos * 1.001f + 1e-30f) >> kHistShift;
+    w.cls_wq[q] = wq;
     const float bound = best * (1.0f - 1e-5f) + neg - 4e-6f * mag;     // slack for the fp32 summation of the score kernel
-    if (!(bound > 0.f)) return w.min_key;
+    if (!w.use_tau || !(bound > 0.f)) return w.min_key;
     const uint32_t key = float_to_key(bound);
     return key > w.min_key ? key : w.min_key;
 }
@@ -167,11 +175,12 @@ bm25_prepare_kernel(Bm25Dev ix, Bm25Work w) {
     if (tid == 0) {
         // idf * qtf * (k1+1) formed in double, rounded once (reference: float64 throughout)
         w.slot_w[s] = float(double(idf_t) * double(w.q_tf[s]) * (double(ix.k1) + 1.0)) + 0.0f;
-        w.slot_row[s] = lookup ? ix.neg_row[t] + 1 : 0;
         if (e > a) atomicAdd(w.stats + (lookup ? 1 : 0), (unsigned long long)(e - a));
     }
-    if (lookup) {
-        for (int j = tid; j < w.n_sub; j += kPrepThreads) w.rec[int64_t(j) * w.n_slots + s] = make_uint2(0u, 0u);
+    if (lookup) {                                              // no postings to stream: the record names the dense row instead
+        const uint32_t row = uint32_t(ix.neg_row[t]);
+        const uint32_t y = ((row + 1u) << kRecRowShift) | (int32_t(row) == ix.cls_row ? 0x80000000u : 0u);
+        for (int j = tid; j < w.n_sub; j += kPrepThreads) w.rec[int64_t(j) * w.n_slots + s] = make_uint2(0u, y);
         return;
     }
     const int2* __restrict__ pd = ix.post2;
@@ -193,7 +202,7 @@ bm25_prepare_kernel(Bm25Dev ix, Bm25Work w) {
         __shared__ int s_part[kPrepThreads];
         for (int j = tid; j < w.n_sub; j += kPrepThreads) s_cnt[j] = 0;
         __syncthreads();
-        for (int64_t i = a + tid; i < e; i += kPrepThreads) atomicAdd(&s_cnt[pd[i].x / w.sub_docs], 1);
+        for (int64_t i = a + tid; i < e; i += kPrepThreads) atomicAdd(&s_cnt[int(uint32_t(pd[i].x) & kDocMask) / w.sub_docs], 1);
         __syncthreads();
         const int per = (w.n_sub + kPrepThreads - 1) / kPrepThreads;     // contiguous sub-ranges per thread
         const int j0 = tid * per, j1 = (j0 + per) < w.n_sub ? (j0 + per) : w.n_sub;
@@ -331,15 +340,19 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
     uint32_t hit_tau = 0xffffffffu;                  // bits of minus the bound of the current query (HITS), or "never"
     int hc = 0, hd = 0;                              // this lane's updates that reached the bound in the current task; doc of the last
     // one warp-round: up to 32 postings of one term; docs are unique inside a term (no race)
+    float cwq = 0.f;                                  // class penalty unit of the current query (Bm25Work::cls_wq), 0 = none
     auto apply = [&](int dd, int tfi, bool valid, float wt) {
         if (valid) {
-            const int d = dd - lo;
+            const int d = int(uint32_t(dd) & kDocMask) - lo;
             // idf*qtf*(k1+1) * [tf / (tf + k1*(1-b+b*dl/avgdl))]: the bracket is the posting's precomputed impact.
             // The accumulator holds MINUS the score; round-down keeps "touched, score 0" at -0.0 (rest state: +0.0)
             const float nv = __fmaf_rd(-wt, __int_as_float(tfi), s_acc[d]);
             s_acc[d] = nv;
             if (HITS) {
-                const bool hit = __float_as_uint(nv) >= hit_tau;
+                // the looked-up class term takes at least cwq * c off this document's score: a document reaches the bound
+                // only if (minus score so far) + that penalty still does.  float(c) = (2^23 | c) - 2^23 (exact).
+                const float pen = __fmul_rd(cwq, __uint_as_float(0x4b000000u | (uint32_t(dd) >> kClsShift)) - 8388608.0f);
+                const bool hit = __float_as_uint(__fadd_rd(nv, pen)) >= hit_tau;
                 hd = hit ? d : hd;
                 hc += int(hit);
             }
@@ -375,6 +388,7 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
         const int nq = q1 - q0;
         const int qo_reg = (lane <= nq) ? w.q_off[q0 + lane] : 0;          // CSR offsets of the chunk (QC <= 31)
         const uint32_t tau_reg = (lane < nq && w.use_tau) ? ld_relaxed_u32(&w.ts.tau[q0 + lane]) : w.min_key;
+        const float wq_reg = (HITS && lane < nq) ? w.cls_wq[q0 + lane] : 0.f;
         const uint2* __restrict__ rec = w.rec + int64_t(j) * w.n_slots;
 
         int qa = 0;                                                         // queries are indexed relative to q0 below
@@ -387,7 +401,7 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
             __syncwarp();
             for (int i = lane; i < ns; i += 32) {
                 const uint2 r = rec[sa + i];
-                s_meta[i] = make_uint4(r.x, r.y, __float_as_uint(w.slot_w[sa + i]), uint32_t(w.slot_row[sa + i]));
+                s_meta[i] = make_uint4(r.x, r.y & 0xffffu, __float_as_uint(w.slot_w[sa + i]), (r.y >> kRecRowShift) & 0x7fffu);
             }
             __syncwarp();
 
@@ -430,20 +444,19 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
                 const bool fast = __float_as_int(tau_f) >= 0;   // tau is +0.0 or positive: the accumulators hold minus the
                                                                  // score, so "score >= tau" is one UNSIGNED compare that also
                                                                  // rejects 0 (untouched) and every negative score (sign bit clear)
-                if (HITS) { hit_tau = fast ? tau_u : 0xffffffffu; hc = 0; }
+                if (HITS) { hit_tau = fast ? tau_u : 0xffffffffu; hc = 0; cwq = __shfl_sync(0xffffffffu, wq_reg, qr); }
                 uint32_t wneg = 0u;                             // sign bit set: a negative weight was applied (the last update
                                                                 // of a document need not be its largest then)
-                int touched = 0;
-                neg_lo = 0; neg_hi = 0;
+                int touched = 0;                                // bit 0: postings were applied, bit 1: the query has looked-up slots
 #pragma unroll
                 for (int t = 0; t < MP; ++t) {
                     if (o_cur + t < e_cur) {
                         const uint4 m = s_meta[o_cur + t];
                         const int n = int(m.y);
-                        if (m.w) { neg_lo = neg_hi ? neg_lo : o_cur + t; neg_hi = o_cur + t + 1; }
+                        if (m.w) touched |= 2;                                  // a looked-up negative slot
                         if (n > 0) {
                             const float wt = __uint_as_float(m.z);
-                            touched = 1;
+                            touched |= 1;
                             if (HITS) wneg |= m.z;
                             apply(pd_cur[t], pt_cur[t], lane < n, wt);
                             if (n > 32) apply_rest(m.x, n, wt);
@@ -455,10 +468,10 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
                 for (int sl = o_cur + MP; sl < e_cur; ++sl) {               // queries with more than MP terms
                     const uint4 m = s_meta[sl];
                     const int n = int(m.y);
-                    if (m.w) { neg_lo = neg_hi ? neg_lo : sl; neg_hi = sl + 1; }
+                    if (m.w) touched |= 2;
                     if (n == 0) continue;
                     const float wt = __uint_as_float(m.z);
-                    touched = 1;
+                    touched |= 1;
                     if (HITS) wneg |= m.z;
                     int dd = 0, tfi = 0;
                     if (lane < n) { const int2 p = ldg_stream_i2(g_post + m.x + lane); dd = p.x; tfi = p.y; }
@@ -467,7 +480,8 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
                     __syncwarp();
                 }
                 // ---- read-out: scan the accumulators 128 per round, re-arm them, stage candidates >= tau ----
-                if (touched) {
+                if (touched & 1) {
+                    neg_lo = o_cur; neg_hi = (touched & 2) ? e_cur : 0;
                     uint4* a4 = reinterpret_cast<uint4*>(s_acc) + lane;
                     const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
                     if (HITS && fast && int(wneg) >= 0 && !__any_sync(0xffffffffu, hc > 1)) {
@@ -658,6 +672,18 @@ __global__ void bm25_neg_rows_kernel(const int64_t* __restrict__ term_off, const
         const int2 p = post2[i];
         neg_imp[int64_t(row) * stride + p.x] = __int_as_float(p.y);
     }
+}
+
+// Class bits (load time): every posting gets c = floor(16 * impact of its document in the class row) in bits 28..31 of its doc word.
+__global__ void bm25_class_bits_kernel(int2* __restrict__ post2, int64_t n, const float* __restrict__ cls_imp) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int2 p = post2[i];
+    const uint32_t d = uint32_t(p.x) & kDocMask;
+    int c = int(cls_imp[d] * 16.0f);                            // impact in [0, 1): c/16 <= impact
+    c = c < 0 ? 0 : (c > 15 ? 15 : c);
+    p.x = int(d | (uint32_t(c) << kClsShift));
+    post2[i] = p;
 }
 
 // The device-resident posting array: {doc, fp32 impact}, impact = tf / (tf + k1*(1 - b + b*dl/avgdl)) as in

@@ -7,23 +7,27 @@
 // Roles of the operands: the QUERIES are the M dimension (TMEM lanes), the chunk rows the N dimension (TMEM
 // columns).  A tcgen05.ld (32x32b) therefore hands every epilogue thread 32 consecutive chunk scores of ITS
 // query: the per-document max is a running max over registers with warp-uniform document boundaries — no
-// shuffles — and the query's running bound is one register.  (The first version of this kernel had the chunk
-// rows on the lanes and spent 20k warp-instructions per tile on segmented max-scans across lanes.)
+// shuffles — and the query's running bound is one register.
 //
-// Tiling: UMMA M=128 queries (one or two M tiles for B <= 128 / <= 256) x N=128 chunk rows x K=16, 12 k-blocks
-// of 64 elements (one 128-byte SWIZZLE_128B row per k-block).  A 128-row tile is assembled from FOUR
-// doc-aligned groups of <= 32 rows (four {64 x 32} TMA boxes per k-block, each starting at the first row of a
-// document), so a 32-column tcgen05.ld covers whole documents only.  (Rows past the end of a group belong to
-// the next group; they are computed twice and masked, ~8 % redundant L2 reads.)  Documents with more than 32
-// chunks do not fit a group: the caller falls back to the GEMV kernel for such corpora.
+// The query panel lives in TENSOR MEMORY for the whole kernel (tcgen05.mma with the A operand in TMEM): 128 queries
+// x 768 bf16 = 384 of the 512 TMEM columns (lane = query, two K elements per 32-bit column), written once with
+// tcgen05.st.  Only the chunk rows stream through shared memory, so the whole 200 KB ring buffers E tiles (24 stages
+// of 8 KB: ~190 KB of TMA loads in flight per SM) and the L2->SM path carries E only.  (Round 1 kept Q in shared
+// memory and re-fetched the 384 KB panel from L2 for every 128-row tile: 46 GB through L2->SM per 15.4 GB of E,
+// which pinned the kernel at the ~6300 B/cycle L2 limit, 4.7-5.0 ms at B=256.)
+// A CTA owns ONE panel of <= 128 queries; a batch of 129..256 queries runs as two interleaved sets of CTAs (even /
+// odd blockIdx) that walk the same tiles in the same order, so the second reader of an E tile hits L2.
+//
+// Tiling: UMMA M=128 queries x N=64 chunk rows x K=16, 12 k-blocks of 64 elements (one 128-byte SWIZZLE_128B row
+// per k-block), accumulators 2 x 64 TMEM columns (double-buffered: the epilogue of tile i overlaps the MMAs of
+// tile i+1).  A 64-row tile is assembled from TWO doc-aligned groups of <= 32 rows (two {64 x 32} TMA boxes per
+// k-block, each starting at the first row of a document), so a 32-column tcgen05.ld covers whole documents only.
+// (Rows past the end of a group belong to the next group; they are computed twice and masked, ~8 % redundant L2
+// reads.)  Documents with more than 32 chunks do not fit a group: the caller falls back to the GEMV kernel.
 //
 // Warp roles (320 threads, 1 CTA/SM, persistent over tiles): warp 0 = TMA producer (one lane),
 // warp 1 = TMEM allocator + MMA issuer (one lane), warps 2-9 = epilogue (warp w reads TMEM lane quarter w%4 =
-// queries 32*(w%4).. of an M tile; the two warps of a quarter take one M tile each, or two groups each when
-// there is a single M tile).
-// Pipelines: smem ring full/empty mbarriers (TMA <-> MMA, freed by tcgen05.commit) and a
-// double-buffered TMEM accumulator full/empty pair (MMA <-> epilogue), so the epilogue of tile i
-// overlaps the MMAs of tile i+1.
+// queries 32*(w%4).. of the panel; the two warps of a quarter take one group each).
 #pragma once
 #include <cuda.h>
 
@@ -33,26 +37,25 @@
 
 namespace mse {
 
-constexpr int kGemmEpiWarps = 8;                      // two per TMEM lane quarter, alternating 32-column chunks
+constexpr int kGemmEpiWarps = 8;                      // two per TMEM lane quarter, one doc-aligned group each
 constexpr int kGemmThreads = (2 + kGemmEpiWarps) * 32;
 constexpr int kGemmBlockK = 64;                        // elements per k-block (128 B of bf16)
 constexpr int kGemmKBlocks = kDim / kGemmBlockK;       // 12
-constexpr int kGemmTileRows = 128;
 constexpr int kGemmGroupRows = 32;
-constexpr int kGemmATileBytes = kGemmTileRows * 128;   // 16 KB per stage
+constexpr int kGemmTileGroups = 2;
+constexpr int kGemmTileRows = kGemmTileGroups * kGemmGroupRows;   // 64 chunk rows = N of the MMA
+constexpr int kGemmStageBytes = kGemmTileRows * 128;   // 8 KB per stage (one k-block of a tile)
+constexpr int kGemmMaxStages = 24;
+constexpr int kGemmPanel = 128;                        // queries per CTA
+constexpr int kGemmACols = kDim / 2;                   // TMEM columns of the query panel (2 bf16 per column)
 constexpr int kGemmStage = 96;                         // emissions staged per epilogue warp between flushes
-
-// shared-memory bytes of one pipeline stage: 128 chunk rows + one or two M tiles of 128 query rows, 128 B each (the
-// MMA addresses whole M tiles; rows past the padded batch are never loaded and only feed accumulator lanes nobody reads)
-__host__ __device__ inline uint32_t gemm_stage_bytes(int n_pad) {
-    return uint32_t(kGemmATileBytes) + uint32_t(n_pad > 128 ? 2 : 1) * 128u * 128u;
-}
 
 struct GemmWork {
     const int64_t* group_row;    // [n_groups + 1] first row of every doc-aligned group (<= 32 rows each)
     int64_t n_groups;
-    int64_t n_tiles;             // ceil(n_groups / 4)
-    int32_t n_pad;               // padded batch (multiple of 32)
+    int64_t n_tiles;             // ceil(n_groups / kGemmTileGroups)
+    const __nv_bfloat16* qb16;   // [n_panels * 128][768] bf16 queries, zero padded
+    int32_t n_panels;            // 1 or 2 panels of 128 queries
     int32_t n_real;              // real queries in this launch
     int32_t q0;                  // first query (index into cand / tau arrays)
     int32_t stages;
@@ -102,6 +105,23 @@ __device__ __forceinline__ void tcgen05_mma_bf16(uint32_t tmem_d, uint64_t adesc
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// A operand in tensor memory (lane = row of A, two 16-bit K elements per 32-bit column)
+__device__ __forceinline__ void tcgen05_mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
 // K-major, SWIZZLE_128B, 128-byte rows: LBO = 1 (16 B units, unused for swizzled K-major), SBO = 1024 B
 // (8-row atom), descriptor version 1 (sm_100), layout type 2.  (cute/arch/mma_sm100_desc.hpp)
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_byte_addr) {
@@ -127,24 +147,20 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
 }
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
-dense_gemm_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_constant__ CUtensorMap map_q,
-                  DenseDev dx, DenseWork w, GemmWork g) {
+dense_gemm_kernel(const __grid_constant__ CUtensorMap map_e, DenseDev dx, DenseWork w, GemmWork g) {
     extern __shared__ __align__(1024) unsigned char gemm_smem_raw[];
-    constexpr int kMaxStages = 8;
-    __shared__ __align__(8) uint64_t s_full[kMaxStages], s_empty[kMaxStages], s_tfull[2], s_tempty[2];
+    __shared__ __align__(8) uint64_t s_full[kGemmMaxStages], s_empty[kGemmMaxStages], s_tfull[2], s_tempty[2];
     __shared__ uint32_t s_tmem_base;
     __shared__ uint64_t s_stage_key[kGemmEpiWarps][kGemmStage];
     __shared__ uint16_t s_stage_q[kGemmEpiWarps][kGemmStage];
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int n_pad = g.n_pad;
-    const uint32_t tx_bytes = uint32_t(kGemmATileBytes) + uint32_t(n_pad) * 128u;        // bytes TMA delivers per stage
-    const uint32_t stage_bytes = gemm_stage_bytes(n_pad);                                // a whole M tile of query rows is addressable
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gemm_smem_raw) + 1023) & ~uintptr_t(1023));
-    const int MT = n_pad > 128 ? 2 : 1;                                   // M tiles of 128 queries
-    const uint32_t acc_cols = uint32_t(MT) * kGemmTileRows;               // accumulator columns per buffer
-    const uint32_t tmem_cols = 2 * acc_cols;                              // 256 or 512: a power of two
+    constexpr uint32_t tmem_cols = 512;                                   // 384 query panel + 2 x 64 accumulator
+    // CTAs of panel p are blockIdx p, p + n_panels, ...: both panels walk the same tiles in the same order
+    const int panel = int(blockIdx.x) % g.n_panels;
+    const int64_t cta = int64_t(blockIdx.x) / g.n_panels, n_cta = int64_t(gridDim.x) / g.n_panels;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < g.stages; ++s) { mbarrier_init(&s_full[s], 1); mbarrier_init(&s_empty[s], 1); }
@@ -159,27 +175,49 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_consta
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = s_tmem_base;
+    const uint32_t tmem_acc = tmem_base + uint32_t(kGemmACols);
+
+    if (warp >= 2) {
+        // query panel -> TMEM: thread = one query (TMEM lane), 32 columns (64 K elements) per tcgen05.st; the two warps
+        // of a lane quarter write one half of the columns each
+        const int quarter = warp & 3;
+        const int qrow = panel * kGemmPanel + quarter * 32 + lane;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(g.qb16) + int64_t(qrow) * kGemmACols;
+        const int c_lo = ((warp - 2) >> 2) * (kGemmACols / 2);
+        for (int c0 = c_lo; c0 < c_lo + kGemmACols / 2; c0 += 32) {
+            uint32_t r[32];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint4 v = *reinterpret_cast<const uint4*>(src + c0 + 4 * i);
+                r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+            }
+            tmem_st_32x32b_x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(c0), r);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int64_t tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
-                int rows[4];
+            for (int64_t tile = cta; tile < g.n_tiles; tile += n_cta) {
+                int rows[kGemmTileGroups];
 #pragma unroll
-                for (int gi = 0; gi < 4; ++gi) {
-                    const int64_t grp = tile * 4 + gi;
+                for (int gi = 0; gi < kGemmTileGroups; ++gi) {
+                    const int64_t grp = tile * kGemmTileGroups + gi;
                     rows[gi] = grp < g.n_groups ? int(g.group_row[grp]) : int(dx.n_chunks);     // past the end -> zero fill
                 }
                 for (int kb = 0; kb < kGemmKBlocks; ++kb) {
                     mbarrier_wait_backoff(&s_empty[stage], phase ^ 1u);
-                    unsigned char* sa = smem + size_t(stage) * stage_bytes;
-                    mbarrier_expect_tx(&s_full[stage], tx_bytes);
+                    unsigned char* sa = smem + size_t(stage) * kGemmStageBytes;
+                    mbarrier_expect_tx(&s_full[stage], uint32_t(kGemmStageBytes));
 #pragma unroll
-                    for (int gi = 0; gi < 4; ++gi)
+                    for (int gi = 0; gi < kGemmTileGroups; ++gi)
                         tma_load_2d(sa + gi * (kGemmGroupRows * 128), &map_e, kb * kGemmBlockK, rows[gi], &s_full[stage]);
-                    tma_load_2d(sa + kGemmATileBytes, &map_q, kb * kGemmBlockK, 0, &s_full[stage]);
                     if (++stage == g.stages) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -187,29 +225,26 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_consta
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16_f32(128, kGemmTileRows);   // M = 128 queries, N = 128 chunk rows
+            const uint32_t idesc = umma_idesc_bf16_f32(kGemmPanel, kGemmTileRows);   // M = 128 queries, N = 64 chunk rows
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int64_t tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++it) {
+            for (int64_t tile = cta; tile < g.n_tiles; tile += n_cta, ++it) {
                 const int buf = it & 1;
                 const uint32_t use = uint32_t(it >> 1);
                 mbarrier_wait_backoff(&s_tempty[buf], (use & 1u) ^ 1u);  // epilogue has drained this accumulator
                 tcgen05_fence_after();
-                const uint32_t tmem_d = tmem_base + uint32_t(buf) * acc_cols;
+                const uint32_t tmem_d = tmem_acc + uint32_t(buf) * kGemmTileRows;
                 for (int kb = 0; kb < kGemmKBlocks; ++kb) {
                     mbarrier_wait(&s_full[stage], phase);
                     tcgen05_fence_after();
-                    const uint32_t e_addr = smem_addr(smem + size_t(stage) * stage_bytes);   // 128 chunk rows x 64
-                    const uint32_t q_addr = e_addr + kGemmATileBytes;                        // n_pad queries x 64
-                    for (int mt = 0; mt < MT; ++mt) {
+                    const uint32_t e_addr = smem_addr(smem + size_t(stage) * kGemmStageBytes);   // 64 chunk rows x 64
 #pragma unroll
-                        for (int k = 0; k < kGemmBlockK / 16; ++k) {
-                            if (g.debug & 2) break;
-                            const uint64_t ad = umma_desc_sw128(q_addr + uint32_t(mt) * (128u * 128u) + k * 32);
-                            const uint64_t bd = umma_desc_sw128(e_addr + k * 32);
-                            tcgen05_mma_bf16(tmem_d + uint32_t(mt) * kGemmTileRows, ad, bd, idesc, (kb | k) ? 1u : 0u);
-                        }
+                    for (int k = 0; k < kGemmBlockK / 16; ++k) {
+                        if (g.debug & 2) break;
+                        const uint64_t bd = umma_desc_sw128(e_addr + k * 32);
+                        // A: 16 K elements = 8 TMEM columns per MMA
+                        tcgen05_mma_bf16_ts(tmem_d, tmem_base + uint32_t((kb * (kGemmBlockK / 16) + k) * 8), bd, idesc, (kb | k) ? 1u : 0u);
                     }
                     tcgen05_commit(&s_empty[stage]);                      // frees the smem slot when the MMAs retire
                     if (++stage == g.stages) { stage = 0; phase ^= 1u; }
@@ -218,20 +253,18 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_consta
             }
         }
     } else {
-        // ===================== epilogue (warp w -> TMEM lane quarter w % 4 = 32 queries of an M tile) ==========
+        // ===================== epilogue (warp w -> TMEM lane quarter w % 4 = 32 queries of the panel) ==========
         const int quarter = warp & 3;
         const int ew = warp - 2;                                          // 0..7
-        const int half = ew >> 2;                                         // which of the quarter's two warps
+        const int gi = ew >> 2;                                           // this warp's doc-aligned group of the tile
         const unsigned lt_mask = (1u << lane) - 1u;
         uint64_t* st_key = s_stage_key[ew];
         uint16_t* st_q = s_stage_q[ew];
         int staged = 0;                                                   // uniform
         int rr = int((blockIdx.x * kGemmEpiWarps + ew) % g.n_real);       // round-robin cursor for bound refreshes
-        const int mt = MT == 2 ? half : 0;                                // this warp's M tile
-        const int g_lo = MT == 2 ? 0 : 2 * half, g_hi = MT == 2 ? 4 : 2 * half + 2;   // and its doc-aligned groups
-        const int my_q = mt * 128 + quarter * 32 + lane;                  // this thread's query (may be padding)
+        const int my_q = panel * kGemmPanel + quarter * 32 + lane;        // this thread's query (may be padding)
         const bool q_real = my_q < g.n_real;
-        const bool warp_idle = mt * 128 + quarter * 32 >= g.n_real;       // no real query on these lanes
+        const bool warp_idle = panel * kGemmPanel + quarter * 32 >= g.n_real;   // no real query on these lanes
         auto flush = [&]() {
             if (staged == 0) return;
             unsigned long long base = 0;
@@ -246,7 +279,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_consta
             staged = 0;
         };
         int it = 0;
-        for (int64_t tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++it) {
+        for (int64_t tile = cta; tile < g.n_tiles; tile += n_cta, ++it) {
             const int buf = it & 1;
             const uint32_t use = uint32_t(it >> 1);
             if (warp_idle || (g.debug & 1)) {
@@ -260,32 +293,24 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_consta
                 const uint32_t tk = w.use_tau ? ld_relaxed_u32(&w.ts.tau[g.q0 + my_q]) : 0u;
                 tau = tk ? key_to_float(tk) : -INFINITY;
             }
-            // document layout of the warp's groups (lane i <-> row i of the group; warp-uniform masks)
-            int my_doc[4];
-            unsigned tails[4];
-#pragma unroll
-            for (int gi = 0; gi < 4; ++gi) {
-                my_doc[gi] = -1; tails[gi] = 0u;
-                if (gi >= g_lo && gi < g_hi) {
-                    const int64_t grp = tile * 4 + gi;
-                    int64_t r0 = dx.n_chunks, r1 = dx.n_chunks;
-                    if (grp < g.n_groups) { r0 = g.group_row[grp]; r1 = g.group_row[grp + 1]; }
-                    const bool valid = lane < int(r1 - r0);
-                    const int d = valid ? dx.row_doc[r0 + lane] : (-2 - lane);
-                    const int nd = __shfl_down_sync(0xffffffffu, d, 1);
-                    my_doc[gi] = d;
-                    tails[gi] = __ballot_sync(0xffffffffu, valid && (lane == 31 || nd != d));   // last row of every document
-                }
+            // document layout of the warp's group (lane i <-> row i of the group; warp-uniform masks)
+            int my_doc;
+            unsigned tl;
+            {
+                const int64_t grp = tile * kGemmTileGroups + gi;
+                int64_t r0 = dx.n_chunks, r1 = dx.n_chunks;
+                if (grp < g.n_groups) { r0 = g.group_row[grp]; r1 = g.group_row[grp + 1]; }
+                const bool valid = lane < int(r1 - r0);
+                const int d = valid ? dx.row_doc[r0 + lane] : (-2 - lane);
+                const int nd = __shfl_down_sync(0xffffffffu, d, 1);
+                my_doc = d;
+                tl = __ballot_sync(0xffffffffu, valid && (lane == 31 || nd != d));   // last row of every document
             }
             mbarrier_wait(&s_tfull[buf], use & 1u);
             tcgen05_fence_after();
-#pragma unroll
-            for (int gi = 0; gi < 4; ++gi) {
-                if (gi < g_lo || gi >= g_hi || tails[gi] == 0u) continue;  // uniform
+            if (tl != 0u) {                                               // uniform
                 uint32_t r[32];
-                tmem_ld_32x32b_x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(buf) * acc_cols +
-                                   uint32_t(mt * kGemmTileRows + gi * kGemmGroupRows), r);
-                const unsigned tl = tails[gi];
+                tmem_ld_32x32b_x32(tmem_acc + (uint32_t(quarter * 32) << 16) + uint32_t(buf * kGemmTileRows + gi * kGemmGroupRows), r);
                 // straight-line pass over the 32 columns: running max of the current document (boundaries are
                 // warp-uniform bits), bit i of passmask = "column i closes a document whose max reaches my bound"
                 float mm[32];
@@ -311,7 +336,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_consta
                     const unsigned pm = __ballot_sync(0xffffffffu, pass);
                     const int n = __popc(pm);
                     if (staged + n > kGemmStage) flush();
-                    const int doc = __shfl_sync(0xffffffffu, my_doc[gi], i);
+                    const int doc = __shfl_sync(0xffffffffu, my_doc, i);
                     if (pass) {
                         const int q = g.q0 + my_q;
                         const uint32_t key = float_to_key(vi);
