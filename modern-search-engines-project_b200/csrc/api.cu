@@ -179,7 +179,7 @@ int bm25_enqueue(mse_index* ix, Lease& L, int32_t B, const int32_t* d_q_off, con
     Bm25Work w{};
     w.q_off = d_q_off; w.q_term = d_q_term; w.q_tf = d_q_tf;
     w.slot_w = ws->slot_w.as<float>(); w.cls_wq = ws->slot_row.as<float>(); w.rec = ws->rec.as<uint2>();
-    w.ts = TauState{ws->tau.as<uint32_t>(), ws->hist.as<uint32_t>(), ws->maxbin.as<uint32_t>(), top_k};
+    w.ts = TauState{ws->tau.as<uint32_t>(), ws->hist.as<uint32_t>(), ws->maxbin.as<uint32_t>(), top_k, kHistShift};
     w.cand = ws->cand.as<uint64_t>(); w.cand_count = ws->cand_count.as<int32_t>(); w.overflow = ws->cand_count.as<int32_t>() + B;
     w.item_counter = ws->misc.as<int32_t>();
     w.stats = reinterpret_cast<unsigned long long*>(ws->misc.as<char>() + 16);
@@ -475,7 +475,7 @@ int mse_index_create(int device, mse_index** out) {
     ix->sm_count = prop.multiProcessorCount;
     // function attributes are set once here, so that no search call touches them (calls may run inside a stream capture)
     cudaError_t e = cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kRerankSmemBytes));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(dense_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemmStageBytes) * kGemmMaxStages + 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dense_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemmSmemBytes));
     for (int hits = 0; hits < 2 && e == cudaSuccess; ++hits) {
         const void* kfn = score_kernel_fn(true, hits != 0);
         const size_t smem = size_t(kBm25Warps) * bm25_score_warp_bytes(kBm25DefaultRange);
@@ -1014,21 +1014,21 @@ int dense_scan_pass(mse_index* ix, Lease& L, const float* d_q, int g0, int gn, i
     const int per_sm = ix->opt_scan_ctas > 0 ? int(ix->opt_scan_ctas) : 2;
     const int grid = int(std::min<int64_t>((dn.n_tiles + kScanThreads / 32 - 1) / (kScanThreads / 32) + 1, int64_t(per_sm) * ix->sm_count));
     if ((r = ws->tau.ensure(sizeof(uint32_t) * size_t(gn)))) return r;
-    if ((r = ws->hist.ensure(sizeof(uint32_t) * size_t(gn) * kHistBins))) return r;
+    if ((r = ws->hist.ensure(sizeof(uint32_t) * (size_t(gn) << kDenseHistBits)))) return r;
     if ((r = ws->maxbin.ensure(sizeof(uint32_t) * size_t(gn)))) return r;
     if ((r = ws->cand.ensure(sizeof(uint64_t) * size_t(gn) * rcap))) return r;
     if ((r = ws->cand_count.ensure(sizeof(int32_t) * size_t(gn)))) return r;
     MSE_CUDA_TRY(cudaMemsetAsync(ws->cand_count.p, 0, sizeof(int32_t) * size_t(gn), st));
     MSE_CUDA_TRY(cudaMemsetAsync(ws->tau.p, 0, sizeof(uint32_t) * size_t(gn), st));
     if (rtau) {
-        MSE_CUDA_TRY(cudaMemsetAsync(ws->hist.p, 0, sizeof(uint32_t) * size_t(gn) * kHistBins, st));
+        MSE_CUDA_TRY(cudaMemsetAsync(ws->hist.p, 0, sizeof(uint32_t) * (size_t(gn) << kDenseHistBits), st));
         MSE_CUDA_TRY(cudaMemsetAsync(ws->maxbin.p, 0, sizeof(uint32_t) * size_t(gn), st));
     }
     DenseWork w{};
     w.q = d_q + size_t(g0) * kDim;
     w.cand = ws->cand.as<uint64_t>(); w.cand_count = ws->cand_count.as<int32_t>();
     w.overflow = ws->overflow.as<int32_t>() + g0;
-    w.ts = TauState{ws->tau.as<uint32_t>(), ws->hist.as<uint32_t>(), ws->maxbin.as<uint32_t>(), top_k};
+    w.ts = TauState{ws->tau.as<uint32_t>(), ws->hist.as<uint32_t>(), ws->maxbin.as<uint32_t>(), top_k, 32 - kDenseHistBits};
     w.cap = int32_t(rcap); w.use_tau = rtau;
     int tscan = timed ? L.timer_begin(T_SCAN) : -1;
     if (dn.n_chunks > 0 && use_gemm && rtau) {
@@ -1043,7 +1043,9 @@ int dense_scan_pass(mse_index* ix, Lease& L, const float* d_q, int g0, int gn, i
         gw.n_tiles = (ix->n_groups + kGemmTileGroups - 1) / kGemmTileGroups;
         gw.qb16 = ws->qb16.as<__nv_bfloat16>(); gw.n_panels = n_panels; gw.n_real = gn; gw.q0 = 0; gw.debug = int(ix->opt_gemm_debug);
         gw.stages = kGemmMaxStages;
-        const size_t gsmem = size_t(kGemmStageBytes) * gw.stages + 1024;
+        const size_t gsmem = size_t(kGemmSmemBytes);
+        CUtensorMap map_q;                                               // {64 x 128 queries} boxes of the packed panel
+        if ((r = make_bf16_rowmajor_map(&map_q, ws->qb16.p, uint64_t(n_pad), uint32_t(kGemmPanel)))) return r;
         const int ggrid = int(std::max<int64_t>(1, std::min<int64_t>(gw.n_tiles, ix->sm_count / n_panels))) * n_panels;
         const int64_t log_cap = std::min<int64_t>(int64_t(gn) * 65536, int64_t(64) << 20);
         if ((r = ws->log_key.ensure(sizeof(uint64_t) * size_t(log_cap)))) return r;
@@ -1053,7 +1055,7 @@ int dense_scan_pass(mse_index* ix, Lease& L, const float* d_q, int g0, int gn, i
         w.log_key = ws->log_key.as<uint64_t>(); w.log_q = ws->log_q.as<uint16_t>();
         w.log_count = reinterpret_cast<unsigned long long*>(ws->misc.as<char>() + 32);
         w.log_cap = log_cap; w.n_log_queries = gn;
-        dense_gemm_kernel<<<ggrid, kGemmThreads, gsmem, st>>>(ix->map_e, dn, w, gw);
+        dense_gemm_kernel<<<ggrid, kGemmThreads, gsmem, st>>>(ix->map_e, map_q, dn, w, gw);
         MSE_CUDA_TRY(cudaGetLastError());
         gemm_bucket_kernel<<<ix->sm_count * 4, 256, 0, st>>>(w);
         MSE_CUDA_TRY(cudaGetLastError());

@@ -9,25 +9,31 @@
 // query: the per-document max is a running max over registers with warp-uniform document boundaries — no
 // shuffles — and the query's running bound is one register.
 //
-// The query panel lives in TENSOR MEMORY for the whole kernel (tcgen05.mma with the A operand in TMEM): 128 queries
-// x 768 bf16 = 384 of the 512 TMEM columns (lane = query, two K elements per 32-bit column), written once with
-// tcgen05.st.  Only the chunk rows stream through shared memory, so the whole 200 KB ring buffers E tiles (24 stages
-// of 8 KB: ~190 KB of TMA loads in flight per SM) and the L2->SM path carries E only.  (Round 1 kept Q in shared
-// memory and re-fetched the 384 KB panel from L2 for every 128-row tile: 46 GB through L2->SM per 15.4 GB of E,
-// which pinned the kernel at the ~6300 B/cycle L2 limit, 4.7-5.0 ms at B=256.)
+// Measured on B200 (tools/microbench/mma_rate.cu): a 128x256x16 tcgen05.mma runs at its arithmetic floor of 128 cycles
+// (2.2 PFLOP/s over 148 SMs on zero operands) ONLY when the issuing warp is converged; the same instruction issued
+// from inside `if (lane == 0)` costs ~300 cycles whatever its shape, because the compiler wraps every tcgen05 / TMA
+// instruction of a divergent region in an elect-broadcast-branch loop.  Issue overhead of the converged form is
+// ~110 cycles per MMA, so N = 256 chunk rows per instruction is the shape that keeps the tensor pipe busy.
+//
+// Operand placement: the query panel (128 queries x 768 bf16) stays on chip for the whole kernel — the first 512 K
+// elements in TENSOR MEMORY (256 columns, lane = query, two K elements per 32-bit column; tcgen05.mma with the A
+// operand in TMEM), the last 256 in shared memory (64 KB, K-major SWIZZLE_128B, loaded once by TMA) — because TMEM
+// also has to hold the 256-column accumulator.  Only the chunk rows stream: 4 stages of 32 KB (256 rows x one 64-element
+// k-block), so the L2->SM path carries E only.  (Round 1 re-fetched the 384 KB query panel from L2 for every 128-row
+// tile and issued 128x128x16 MMAs from a divergent lane: 4.7-5.0 ms at B=256.)
 // A CTA owns ONE panel of <= 128 queries; a batch of 129..256 queries runs as two interleaved sets of CTAs (even /
 // odd blockIdx) that walk the same tiles in the same order, so the second reader of an E tile hits L2.
 //
-// Tiling: UMMA M=128 queries x N=64 chunk rows x K=16, 12 k-blocks of 64 elements (one 128-byte SWIZZLE_128B row
-// per k-block), accumulators 2 x 64 TMEM columns (double-buffered: the epilogue of tile i overlaps the MMAs of
-// tile i+1).  A 64-row tile is assembled from TWO doc-aligned groups of <= 32 rows (two {64 x 32} TMA boxes per
-// k-block, each starting at the first row of a document), so a 32-column tcgen05.ld covers whole documents only.
-// (Rows past the end of a group belong to the next group; they are computed twice and masked, ~8 % redundant L2
-// reads.)  Documents with more than 32 chunks do not fit a group: the caller falls back to the GEMV kernel.
+// Tiling: UMMA M=128 queries x N=256 chunk rows x K=16, 12 k-blocks of 64 elements (one 128-byte SWIZZLE_128B row
+// per k-block), one 256-column accumulator (the loads of the next tile run under the epilogue).  A 256-row tile is
+// assembled from EIGHT doc-aligned groups of <= 32 rows (eight {64 x 32} TMA boxes per k-block, each starting at the
+// first row of a document), so a 32-column tcgen05.ld covers whole documents only.  (Rows past the end of a group
+// belong to the next group; they are computed twice and masked, ~8 % redundant L2 reads.)  Documents with more
+// than 32 chunks do not fit a group: the caller falls back to the GEMV kernel.
 //
-// Warp roles (320 threads, 1 CTA/SM, persistent over tiles): warp 0 = TMA producer (one lane),
-// warp 1 = TMEM allocator + MMA issuer (one lane), warps 2-9 = epilogue (warp w reads TMEM lane quarter w%4 =
-// queries 32*(w%4).. of the panel; the two warps of a quarter take one group each).
+// Warp roles (320 threads, 1 CTA/SM, persistent over tiles): warp 0 = TMA producer (converged, one elected lane issues),
+// warp 1 = TMEM allocator + MMA issuer (the same), warps 2-9 = epilogue (warp w reads TMEM lane quarter w%4 =
+// queries 32*(w%4).. of the panel; the two warps of a quarter take four groups each).
 #pragma once
 #include <cuda.h>
 
@@ -37,29 +43,33 @@
 
 namespace mse {
 
-constexpr int kGemmEpiWarps = 8;                      // two per TMEM lane quarter, one doc-aligned group each
+constexpr int kGemmEpiWarps = 8;                      // two per TMEM lane quarter, four doc-aligned groups each
 constexpr int kGemmThreads = (2 + kGemmEpiWarps) * 32;
 constexpr int kGemmBlockK = 64;                        // elements per k-block (128 B of bf16)
 constexpr int kGemmKBlocks = kDim / kGemmBlockK;       // 12
 constexpr int kGemmGroupRows = 32;
-constexpr int kGemmTileGroups = 2;
-constexpr int kGemmTileRows = kGemmTileGroups * kGemmGroupRows;   // 64 chunk rows = N of the MMA
-constexpr int kGemmStageBytes = kGemmTileRows * 128;   // 8 KB per stage (one k-block of a tile)
-constexpr int kGemmMaxStages = 24;
+constexpr int kGemmTileGroups = 8;
+constexpr int kGemmTileRows = kGemmTileGroups * kGemmGroupRows;   // 256 chunk rows = N of the MMA
+constexpr int kGemmStageBytes = kGemmTileRows * 128;   // 32 KB per stage (one k-block of a tile)
+constexpr int kGemmMaxStages = 4;                     // 12 k-blocks per tile = 3 turns of the ring: stage = kb & 3
 constexpr int kGemmPanel = 128;                        // queries per CTA
-constexpr int kGemmACols = kDim / 2;                   // TMEM columns of the query panel (2 bf16 per column)
+constexpr int kGemmKBlocksTmem = 8;                    // k-blocks of the query panel kept in TMEM (the rest in shared memory)
+constexpr int kGemmACols = kGemmKBlocksTmem * kGemmBlockK / 2;    // 256 TMEM columns (2 bf16 per column)
+constexpr int kGemmASmemBytes = (kGemmKBlocks - kGemmKBlocksTmem) * kGemmPanel * 128;   // 64 KB
+constexpr int kGemmDCol = 256;                         // first accumulator column
+constexpr int kGemmSmemBytes = kGemmASmemBytes + kGemmMaxStages * kGemmStageBytes + 1024;
 constexpr int kGemmStage = 96;                         // emissions staged per epilogue warp between flushes
 
 struct GemmWork {
     const int64_t* group_row;    // [n_groups + 1] first row of every doc-aligned group (<= 32 rows each)
     int64_t n_groups;
     int64_t n_tiles;             // ceil(n_groups / kGemmTileGroups)
-    const __nv_bfloat16* qb16;   // [n_panels * 128][768] bf16 queries, zero padded
+    const __nv_bfloat16* qb16;   // [n_panels * 128][768] bf16 queries, zero padded (map_q describes the same array)
     int32_t n_panels;            // 1 or 2 panels of 128 queries
     int32_t n_real;              // real queries in this launch
     int32_t q0;                  // first query (index into cand / tau arrays)
     int32_t stages;
-    int32_t debug;               // bit0: skip epilogue math, bit1: skip MMA issue (timing experiments only)
+    int32_t debug;               // bit0: skip epilogue math (timing experiments only)
 };
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -111,6 +121,67 @@ __device__ __forceinline__ void tcgen05_mma_bf16_ts(uint32_t tmem_d, uint32_t tm
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// ---- warp-converged issue -------------------------------------------------------------------------------------
+// tcgen05.mma / tcgen05.commit / cp.async.bulk.tensor take their operands from UNIFORM registers.  Issued from inside
+// `if (lane == 0)` the compiler cannot prove uniformity and wraps every instruction in an elect / broadcast / branch
+// loop: ~300 cycles per MMA on B200 whatever its shape (tools/microbench/mma_rate.cu), more than twice the 128 cycles a
+// 128x256x16 MMA takes on the tensor pipe.  The producer and MMA warps therefore run CONVERGED (all 32 lanes execute
+// the loop and the barrier waits) and one elected lane issues a whole k-block per asm block.
+//
+// One k-block of MMAs (4 x K=16) + the commit that frees the shared-memory stage.  A from tensor memory.
+__device__ __forceinline__ void umma_kblock_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate_first, uint64_t* empty_bar) {
+    asm volatile("{\n\t.reg .pred q, p, t;\n\t.reg .b32 a1, a2, a3;\n\t.reg .b64 b1, b2, b3;\n\t"
+                 "elect.sync _|q, 0xffffffff;\n\t"
+                 "setp.ne.b32 p, %4, 0;\n\tsetp.eq.b32 t, 0, 0;\n\t"
+                 "add.u32 a1, %1, 8;\n\tadd.u32 a2, %1, 16;\n\tadd.u32 a3, %1, 24;\n\t"
+                 "add.u64 b1, %2, 2;\n\tadd.u64 b2, %2, 4;\n\tadd.u64 b3, %2, 6;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], b1, %3, t;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], b2, %3, t;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [a3], b3, %3, t;\n\t"
+                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t}"
+                 ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate_first), "r"(smem_addr(empty_bar)) : "memory");
+}
+// the same with A from shared memory (descriptor; +32 bytes = +2 in the 16-byte address field per K=16 step)
+__device__ __forceinline__ void umma_kblock_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate_first, uint64_t* empty_bar) {
+    asm volatile("{\n\t.reg .pred q, p, t;\n\t.reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
+                 "elect.sync _|q, 0xffffffff;\n\t"
+                 "setp.ne.b32 p, %4, 0;\n\tsetp.eq.b32 t, 0, 0;\n\t"
+                 "add.u64 a1, %1, 2;\n\tadd.u64 a2, %1, 4;\n\tadd.u64 a3, %1, 6;\n\t"
+                 "add.u64 b1, %2, 2;\n\tadd.u64 b2, %2, 4;\n\tadd.u64 b3, %2, 6;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, t;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, t;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, t;\n\t"
+                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate_first), "r"(smem_addr(empty_bar)) : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_elect(uint64_t* bar) {
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_addr(bar)) : "memory");
+}
+// one stage of the E ring: expect_tx + eight {64 x 32-row} boxes (box i lands 4 KB after box i - 1), one elected lane
+__device__ __forceinline__ void tma_stage_elect(uint32_t dst, const CUtensorMap* map, int c0, const int (&rows)[8],
+                                                uint64_t* full_bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .pred q;\n\t.reg .b32 d1, d2, d3, d4, d5, d6, d7;\n\t"
+                 "elect.sync _|q, 0xffffffff;\n\t"
+                 "add.u32 d1, %0, 4096;\n\tadd.u32 d2, %0, 8192;\n\tadd.u32 d3, %0, 12288;\n\tadd.u32 d4, %0, 16384;\n\t"
+                 "add.u32 d5, %0, 20480;\n\tadd.u32 d6, %0, 24576;\n\tadd.u32 d7, %0, 28672;\n\t"
+                 "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %12;\n\t"
+                 "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %4}], [%3];\n\t"
+                 "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [d1], [%1, {%2, %5}], [%3];\n\t"
+                 "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [d2], [%1, {%2, %6}], [%3];\n\t"
+                 "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [d3], [%1, {%2, %7}], [%3];\n\t"
+                 "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [d4], [%1, {%2, %8}], [%3];\n\t"
+                 "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [d5], [%1, {%2, %9}], [%3];\n\t"
+                 "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [d6], [%1, {%2, %10}], [%3];\n\t"
+                 "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [d7], [%1, {%2, %11}], [%3];\n\t}"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(smem_addr(full_bar)),
+                   "r"(rows[0]), "r"(rows[1]), "r"(rows[2]), "r"(rows[3]), "r"(rows[4]), "r"(rows[5]), "r"(rows[6]), "r"(rows[7]),
+                   "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -143,28 +214,38 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
           "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// three-input maximum (one FMNMX3 on sm_100)
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
-dense_gemm_kernel(const __grid_constant__ CUtensorMap map_e, DenseDev dx, DenseWork w, GemmWork g) {
+dense_gemm_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_constant__ CUtensorMap map_q,
+                  DenseDev dx, DenseWork w, GemmWork g) {
     extern __shared__ __align__(1024) unsigned char gemm_smem_raw[];
-    __shared__ __align__(8) uint64_t s_full[kGemmMaxStages], s_empty[kGemmMaxStages], s_tfull[2], s_tempty[2];
+    __shared__ __align__(8) uint64_t s_full[kGemmMaxStages], s_empty[kGemmMaxStages], s_tfull, s_tempty, s_aready;
     __shared__ uint32_t s_tmem_base;
     __shared__ uint64_t s_stage_key[kGemmEpiWarps][kGemmStage];
     __shared__ uint16_t s_stage_q[kGemmEpiWarps][kGemmStage];
+    __shared__ __align__(16) uint32_t s_transpose[kGemmEpiWarps][32];     // one query's 32 scores of a group, lane <-> row
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gemm_smem_raw) + 1023) & ~uintptr_t(1023));
-    constexpr uint32_t tmem_cols = 512;                                   // 384 query panel + 2 x 64 accumulator
+    unsigned char* a_ss = smem;                                           // query panel, k-blocks 8..11: 4 x {128 rows x 128 B}
+    unsigned char* ring = smem + kGemmASmemBytes;                         // E stages
+    constexpr uint32_t tmem_cols = 512;                                   // 256 query panel + 256 accumulator
     // CTAs of panel p are blockIdx p, p + n_panels, ...: both panels walk the same tiles in the same order
     const int panel = int(blockIdx.x) % g.n_panels;
     const int64_t cta = int64_t(blockIdx.x) / g.n_panels, n_cta = int64_t(gridDim.x) / g.n_panels;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < g.stages; ++s) { mbarrier_init(&s_full[s], 1); mbarrier_init(&s_empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbarrier_init(&s_tfull[b], 1); mbarrier_init(&s_tempty[b], kGemmEpiWarps); }
+        for (int s = 0; s < kGemmMaxStages; ++s) { mbarrier_init(&s_full[s], 1); mbarrier_init(&s_empty[s], 1); }
+        mbarrier_init(&s_tfull, 1); mbarrier_init(&s_tempty, kGemmEpiWarps); mbarrier_init(&s_aready, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -175,14 +256,20 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_e, DenseDev dx, DenseW
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = s_tmem_base;
-    const uint32_t tmem_acc = tmem_base + uint32_t(kGemmACols);
+    const uint32_t tmem_acc = tmem_base + uint32_t(kGemmDCol);
 
+    if (warp == 0 && lane == 0) {
+        // second half of the query panel -> shared memory (resident): one TMA box per k-block
+        mbarrier_expect_tx(&s_aready, uint32_t(kGemmASmemBytes));
+        for (int kb = kGemmKBlocksTmem; kb < kGemmKBlocks; ++kb)
+            tma_load_2d(a_ss + (kb - kGemmKBlocksTmem) * (kGemmPanel * 128), &map_q, kb * kGemmBlockK, panel * kGemmPanel, &s_aready);
+    }
     if (warp >= 2) {
-        // query panel -> TMEM: thread = one query (TMEM lane), 32 columns (64 K elements) per tcgen05.st; the two warps
-        // of a lane quarter write one half of the columns each
+        // first half of the query panel -> TMEM: thread = one query (TMEM lane), 32 columns (64 K elements) per tcgen05.st;
+        // the two warps of a lane quarter write one half of the columns each
         const int quarter = warp & 3;
         const int qrow = panel * kGemmPanel + quarter * 32 + lane;
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(g.qb16) + int64_t(qrow) * kGemmACols;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(g.qb16) + int64_t(qrow) * (kDim / 2);
         const int c_lo = ((warp - 2) >> 2) * (kGemmACols / 2);
         for (int c0 = c_lo; c0 < c_lo + kGemmACols / 2; c0 += 32) {
             uint32_t r[32];
@@ -200,66 +287,63 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_e, DenseDev dx, DenseW
     tcgen05_fence_after();
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int64_t tile = cta; tile < g.n_tiles; tile += n_cta) {
-                int rows[kGemmTileGroups];
+        // ===================== TMA producer (converged warp, one elected lane issues) =====================
+        static_assert(kGemmTileGroups == 8 && kGemmGroupRows * 128 == 4096, "tma_stage_elect is written for 8 boxes of 4 KB");
+        static_assert(kGemmKBlocks % kGemmMaxStages == 0, "stage = kb % stages needs whole turns of the ring per tile");
+        const uint32_t ring_addr = smem_addr(ring);
+        int it = 0;
+        for (int64_t tile = cta; tile < g.n_tiles; tile += n_cta, ++it) {
+            int rows[kGemmTileGroups];
 #pragma unroll
-                for (int gi = 0; gi < kGemmTileGroups; ++gi) {
-                    const int64_t grp = tile * kGemmTileGroups + gi;
-                    rows[gi] = grp < g.n_groups ? int(g.group_row[grp]) : int(dx.n_chunks);     // past the end -> zero fill
-                }
-                for (int kb = 0; kb < kGemmKBlocks; ++kb) {
-                    mbarrier_wait_backoff(&s_empty[stage], phase ^ 1u);
-                    unsigned char* sa = smem + size_t(stage) * kGemmStageBytes;
-                    mbarrier_expect_tx(&s_full[stage], uint32_t(kGemmStageBytes));
+            for (int gi = 0; gi < kGemmTileGroups; ++gi) {
+                const int64_t grp = tile * kGemmTileGroups + gi;
+                rows[gi] = grp < g.n_groups ? int(g.group_row[grp]) : int(dx.n_chunks);     // past the end -> zero fill
+            }
 #pragma unroll
-                    for (int gi = 0; gi < kGemmTileGroups; ++gi)
-                        tma_load_2d(sa + gi * (kGemmGroupRows * 128), &map_e, kb * kGemmBlockK, rows[gi], &s_full[stage]);
-                    if (++stage == g.stages) { stage = 0; phase ^= 1u; }
-                }
+            for (int kb = 0; kb < kGemmKBlocks; ++kb) {
+                constexpr int turns = kGemmKBlocks / kGemmMaxStages;      // turns of the ring per tile
+                const int stage = kb % kGemmMaxStages;
+                const uint32_t phase = uint32_t(it * turns + kb / kGemmMaxStages) & 1u;
+                mbarrier_wait(&s_empty[stage], phase ^ 1u);
+                tma_stage_elect(ring_addr + uint32_t(stage) * kGemmStageBytes, &map_e, kb * kGemmBlockK, rows, &s_full[stage],
+                                uint32_t(kGemmStageBytes));
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16_f32(kGemmPanel, kGemmTileRows);   // M = 128 queries, N = 64 chunk rows
-            int stage = 0;
-            uint32_t phase = 0;
-            int it = 0;
-            for (int64_t tile = cta; tile < g.n_tiles; tile += n_cta, ++it) {
-                const int buf = it & 1;
-                const uint32_t use = uint32_t(it >> 1);
-                mbarrier_wait_backoff(&s_tempty[buf], (use & 1u) ^ 1u);  // epilogue has drained this accumulator
-                tcgen05_fence_after();
-                const uint32_t tmem_d = tmem_acc + uint32_t(buf) * kGemmTileRows;
-                for (int kb = 0; kb < kGemmKBlocks; ++kb) {
-                    mbarrier_wait(&s_full[stage], phase);
-                    tcgen05_fence_after();
-                    const uint32_t e_addr = smem_addr(smem + size_t(stage) * kGemmStageBytes);   // 64 chunk rows x 64
+        // ===================== MMA issuer (converged warp, one elected lane issues a k-block per asm block) ==========
+        const uint32_t idesc = umma_idesc_bf16_f32(kGemmPanel, kGemmTileRows);   // M = 128 queries, N = 256 chunk rows
+        const uint64_t e_desc0 = umma_desc_sw128(smem_addr(ring));
+        const uint64_t a_desc0 = umma_desc_sw128(smem_addr(a_ss));
+        mbarrier_wait(&s_aready, 0u);                                     // shared-memory part of the query panel has landed
+        int it = 0;
+        for (int64_t tile = cta; tile < g.n_tiles; tile += n_cta, ++it) {
+            mbarrier_wait(&s_tempty, (uint32_t(it) & 1u) ^ 1u);          // epilogue has drained the accumulator
+            tcgen05_fence_after();
 #pragma unroll
-                    for (int k = 0; k < kGemmBlockK / 16; ++k) {
-                        if (g.debug & 2) break;
-                        const uint64_t bd = umma_desc_sw128(e_addr + k * 32);
-                        // A: 16 K elements = 8 TMEM columns per MMA
-                        tcgen05_mma_bf16_ts(tmem_d, tmem_base + uint32_t((kb * (kGemmBlockK / 16) + k) * 8), bd, idesc, (kb | k) ? 1u : 0u);
-                    }
-                    tcgen05_commit(&s_empty[stage]);                      // frees the smem slot when the MMAs retire
-                    if (++stage == g.stages) { stage = 0; phase ^= 1u; }
-                }
-                tcgen05_commit(&s_tfull[buf]);                            // accumulator ready for the epilogue
+            for (int kb = 0; kb < kGemmKBlocks; ++kb) {
+                constexpr int turns = kGemmKBlocks / kGemmMaxStages;
+                const int stage = kb % kGemmMaxStages;
+                const uint32_t phase = uint32_t(it * turns + kb / kGemmMaxStages) & 1u;
+                mbarrier_wait(&s_full[stage], phase);
+                tcgen05_fence_after();
+                const uint64_t bd = e_desc0 + uint64_t(stage * (kGemmStageBytes >> 4));          // 256 chunk rows x 64
+                if (kb < kGemmKBlocksTmem)                                // A: 16 K elements = 8 TMEM columns per MMA
+                    umma_kblock_ts(tmem_acc, tmem_base + uint32_t(kb * (kGemmBlockK / 16) * 8), bd, idesc, kb ? 1u : 0u, &s_empty[stage]);
+                else
+                    umma_kblock_ss(tmem_acc, a_desc0 + uint64_t((kb - kGemmKBlocksTmem) * ((kGemmPanel * 128) >> 4)), bd, idesc, 1u,
+                                   &s_empty[stage]);
             }
+            tcgen05_commit_elect(&s_tfull);                               // accumulator ready for the epilogue
         }
     } else {
         // ===================== epilogue (warp w -> TMEM lane quarter w % 4 = 32 queries of the panel) ==========
         const int quarter = warp & 3;
         const int ew = warp - 2;                                          // 0..7
-        const int gi = ew >> 2;                                           // this warp's doc-aligned group of the tile
+        const int g_lo = (ew >> 2) * (kGemmTileGroups / 2);               // this warp's doc-aligned groups of the tile
         const unsigned lt_mask = (1u << lane) - 1u;
         uint64_t* st_key = s_stage_key[ew];
         uint16_t* st_q = s_stage_q[ew];
+        uint32_t* tr = s_transpose[ew];
         int staged = 0;                                                   // uniform
         int rr = int((blockIdx.x * kGemmEpiWarps + ew) % g.n_real);       // round-robin cursor for bound refreshes
         const int my_q = panel * kGemmPanel + quarter * 32 + lane;        // this thread's query (may be padding)
@@ -280,11 +364,10 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_e, DenseDev dx, DenseW
         };
         int it = 0;
         for (int64_t tile = cta; tile < g.n_tiles; tile += n_cta, ++it) {
-            const int buf = it & 1;
-            const uint32_t use = uint32_t(it >> 1);
+            const uint32_t par = uint32_t(it) & 1u;
             if (warp_idle || (g.debug & 1)) {
-                mbarrier_wait_backoff(&s_tfull[buf], use & 1u);
-                if (lane == 0) mbarrier_arrive(&s_tempty[buf]);
+                mbarrier_wait_backoff(&s_tfull, par);
+                if (lane == 0) mbarrier_arrive(&s_tempty);
                 continue;
             }
             // this thread's running bound (padding lanes never pass)
@@ -293,64 +376,88 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_e, DenseDev dx, DenseW
                 const uint32_t tk = w.use_tau ? ld_relaxed_u32(&w.ts.tau[g.q0 + my_q]) : 0u;
                 tau = tk ? key_to_float(tk) : -INFINITY;
             }
-            // document layout of the warp's group (lane i <-> row i of the group; warp-uniform masks)
-            int my_doc;
-            unsigned tl;
-            {
-                const int64_t grp = tile * kGemmTileGroups + gi;
+            // document layout of the warp's groups (lane i <-> row i of the group; warp-uniform masks)
+            int my_doc[kGemmTileGroups / 2];
+            unsigned tails[kGemmTileGroups / 2];
+#pragma unroll
+            for (int j = 0; j < kGemmTileGroups / 2; ++j) {
+                const int64_t grp = tile * kGemmTileGroups + g_lo + j;
                 int64_t r0 = dx.n_chunks, r1 = dx.n_chunks;
                 if (grp < g.n_groups) { r0 = g.group_row[grp]; r1 = g.group_row[grp + 1]; }
                 const bool valid = lane < int(r1 - r0);
                 const int d = valid ? dx.row_doc[r0 + lane] : (-2 - lane);
                 const int nd = __shfl_down_sync(0xffffffffu, d, 1);
-                my_doc = d;
-                tl = __ballot_sync(0xffffffffu, valid && (lane == 31 || nd != d));   // last row of every document
+                my_doc[j] = d;
+                tails[j] = __ballot_sync(0xffffffffu, valid && (lane == 31 || nd != d));   // last row of every document
             }
-            mbarrier_wait(&s_tfull[buf], use & 1u);
+            mbarrier_wait(&s_tfull, par);
             tcgen05_fence_after();
-            if (tl != 0u) {                                               // uniform
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(tmem_acc + (uint32_t(quarter * 32) << 16) + uint32_t(buf * kGemmTileRows + gi * kGemmGroupRows), r);
-                // straight-line pass over the 32 columns: running max of the current document (boundaries are
-                // warp-uniform bits), bit i of passmask = "column i closes a document whose max reaches my bound"
-                float mm[32];
-                unsigned passmask = 0u;
-                float m = -INFINITY;
+            // The accumulator is single-buffered (TMEM also holds half of the query panel): copy this warp's 4 x 32 columns
+            // to registers first and hand the accumulator back at once, so that the MMAs of the next tile run under the
+            // per-document pass below.
+            uint32_t racc[kGemmTileGroups / 2][32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    m = fmaxf(m, __uint_as_float(r[i]));
-                    mm[i] = m;
-                    if (m >= tau) passmask |= 1u << i;                    // masked with the document ends below
-                    m = ((tl >> i) & 1u) ? -INFINITY : m;
-                }
-                passmask &= tl;
-                unsigned colmask = __reduce_or_sync(0xffffffffu, passmask);
-                while (colmask) {                                         // stage (query, key) entries: no global round trip
-                    const int i = __ffs(colmask) - 1;
-                    colmask &= colmask - 1;
-                    float vi = 0.f;
+            for (int j = 0; j < kGemmTileGroups / 2; ++j)
+                if (tails[j] != 0u)                                       // uniform
+                    tmem_ld_32x32b_x32(tmem_acc + (uint32_t(quarter * 32) << 16) + uint32_t((g_lo + j) * kGemmGroupRows), racc[j]);
+            tmem_ld_wait();
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbarrier_arrive(&s_tempty);                    // accumulator may be overwritten
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) vi = (j == i) ? mm[j] : vi;
-                    vi += 0.0f;
-                    const bool pass = (passmask >> i) & 1u;
+            for (int j = 0; j < kGemmTileGroups / 2; ++j) {
+                if (tails[j] == 0u) continue;                             // uniform
+                uint32_t (&r)[32] = racc[j];
+                // Pre-filter: a document reaches the bound of a query iff one of its chunk scores does, so only lanes
+                // (queries) whose largest score of the group reaches their bound can emit: 16 three-input max + one
+                // vote per group.  (Columns past the end of the group only make the test conservative.)  Streaming a
+                // corpus of N documents for the best k emits ~k ln(N / k) candidates per query, i.e. for C3 less than
+                // one lane per group on average.
+                float gm = fmax3(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]));
+#pragma unroll
+                for (int i = 3; i + 1 < 32; i += 2) gm = fmax3(gm, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+                gm = fmaxf(gm, __uint_as_float(r[31]));
+                unsigned hm = __ballot_sync(0xffffffffu, gm >= tau);
+                if (hm == 0u) continue;                                   // uniform
+                // Exact pass, one hit lane at a time: the lane's 32 scores go through shared memory so that lane i holds
+                // the score of row i of the group, a segmented max over the lanes of each document (rows of a document
+                // are adjacent) leaves the document's max on its last row, and those rows test it against the bound.
+                const unsigned tl = tails[j];
+                const unsigned heads = (tl << 1) | 1u;                    // first row of every document
+                const int seg_start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+                const bool is_tail = (tl >> lane) & 1u;
+                while (hm) {                                              // uniform
+                    const int hl = __ffs(hm) - 1;
+                    hm &= hm - 1;
+                    __syncwarp();
+                    if (lane == hl) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) *reinterpret_cast<uint4*>(&tr[i]) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
+                    }
+                    __syncwarp();
+                    float v = __uint_as_float(tr[lane]);
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const float t = __shfl_up_sync(0xffffffffu, v, d);
+                        if (lane - d >= seg_start) v = fmaxf(v, t);
+                    }
+                    const float tau_hl = __shfl_sync(0xffffffffu, tau, hl);
+                    const bool pass = is_tail && v >= tau_hl;
                     const unsigned pm = __ballot_sync(0xffffffffu, pass);
+                    if (pm == 0u) continue;                               // uniform
                     const int n = __popc(pm);
                     if (staged + n > kGemmStage) flush();
-                    const int doc = __shfl_sync(0xffffffffu, my_doc, i);
                     if (pass) {
-                        const int q = g.q0 + my_q;
-                        const uint32_t key = float_to_key(vi);
+                        const int q = g.q0 + panel * kGemmPanel + quarter * 32 + hl;
+                        const uint32_t key = float_to_key(v + 0.0f);
                         const int e = staged + __popc(pm & lt_mask);
-                        st_key[e] = make_key64(key, dx.doc_base + uint32_t(doc));
+                        st_key[e] = make_key64(key, dx.doc_base + uint32_t(my_doc[j]));
                         st_q[e] = uint16_t(q);
                         if (w.use_tau) tau_count(w.ts, q, key);           // fire-and-forget histogram update
                     }
                     staged += n;
                 }
             }
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbarrier_arrive(&s_tempty[buf]);               // accumulator may be overwritten
             if (staged > kGemmStage / 2) flush();
             // refresh the bound of ONE query per tile, round-robin over warps and tiles
             if (w.use_tau) { tau_raise(w.ts, g.q0 + rr); rr = (rr + 1 == g.n_real) ? 0 : rr + 1; }

@@ -19,20 +19,25 @@ namespace mse {
 constexpr int kHistBits = 12;                    // sign + exponent + 3 mantissa bits of the score key
 constexpr int kHistBins = 1 << kHistBits;
 constexpr int kHistShift = 32 - kHistBits;
+// The dense scans bin finer (sign + exponent + 6 mantissa bits: bins 1.6 % wide in score, 128 KB per query): their
+// scores crowd just above the k-th best (cosines of a large corpus), where 12.5 %-wide bins leave the bound so far below
+// the true k-th score that most 32-row groups of the GEMM epilogue still hold a passing document.
+constexpr int kDenseHistBits = 15;
 
 // Running lower bound of the final k-th best score of every query (see bm25.cuh / dense.cuh):
 // producers count each emitted candidate in hist[q][score bin]; tau[q] is the largest bin edge with
 // >= top_k emitted candidates at or above it.  Any value tau ever took is a valid bound.
 struct TauState {
     uint32_t* tau;      // [B] score key
-    uint32_t* hist;     // [B * kHistBins]
+    uint32_t* hist;     // [B << (32 - shift)]
     uint32_t* maxbin;   // [B]
     int32_t top_k;
+    int32_t shift;      // score-key bits dropped by a bin (kHistShift for BM25)
 };
 
 __device__ __forceinline__ void tau_count(const TauState& ts, int q, uint32_t key) {
-    const uint32_t bin = key >> kHistShift;
-    atomicAdd(&ts.hist[int64_t(q) * kHistBins + bin], 1u);
+    const uint32_t bin = key >> ts.shift;
+    atomicAdd(&ts.hist[(int64_t(q) << (32 - ts.shift)) + bin], 1u);
     atomicMax(&ts.maxbin[q], bin);
 }
 
@@ -40,10 +45,10 @@ __device__ __forceinline__ void tau_count(const TauState& ts, int q, uint32_t ke
 __device__ __forceinline__ void tau_raise(const TauState& ts, int q) {
     const int lane = lane_id();
     const uint32_t cur = ld_relaxed_u32(&ts.tau[q]);
-    const int cur_bin = int(cur >> kHistShift);
+    const int cur_bin = int(cur >> ts.shift);
     int b = int(ld_relaxed_u32(&ts.maxbin[q]));
     int acc = 0;
-    const uint32_t* h = ts.hist + int64_t(q) * kHistBins;
+    const uint32_t* h = ts.hist + (int64_t(q) << (32 - ts.shift));
     while (b >= cur_bin) {
         const int bin = b - lane;
         const int c = (bin >= cur_bin && bin >= 0) ? int(ld_relaxed_u32(&h[bin])) : 0;
@@ -51,7 +56,7 @@ __device__ __forceinline__ void tau_raise(const TauState& ts, int q) {
         const unsigned hit = __ballot_sync(0xffffffffu, acc + incl >= ts.top_k);
         if (hit) {
             const int tb = b - (__ffs(hit) - 1);
-            if (lane == 0 && tb > cur_bin) atomicMax(&ts.tau[q], uint32_t(tb) << kHistShift);
+            if (lane == 0 && tb > cur_bin) atomicMax(&ts.tau[q], uint32_t(tb) << ts.shift);
             return;
         }
         acc += __shfl_sync(0xffffffffu, incl, 31);
