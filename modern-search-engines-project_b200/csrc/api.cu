@@ -475,7 +475,8 @@ int mse_index_create(int device, mse_index** out) {
     ix->sm_count = prop.multiProcessorCount;
     // function attributes are set once here, so that no search call touches them (calls may run inside a stream capture)
     cudaError_t e = cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kRerankSmemBytes));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(dense_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemmSmemBytes));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dense_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemmSmemBytes));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dense_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemmSmemBytes));
     for (int hits = 0; hits < 2 && e == cudaSuccess; ++hits) {
         const void* kfn = score_kernel_fn(true, hits != 0);
         const size_t smem = size_t(kBm25Warps) * bm25_score_warp_bytes(kBm25DefaultRange);
@@ -1055,7 +1056,18 @@ int dense_scan_pass(mse_index* ix, Lease& L, const float* d_q, int g0, int gn, i
         w.log_key = ws->log_key.as<uint64_t>(); w.log_q = ws->log_q.as<uint16_t>();
         w.log_count = reinterpret_cast<unsigned long long*>(ws->misc.as<char>() + 32);
         w.log_cap = log_cap; w.n_log_queries = gn;
-        dense_gemm_kernel<<<ggrid, kGemmThreads, gsmem, st>>>(ix->map_e, map_q, dn, w, gw);
+        if (n_panels == 2) {
+            // two panels: clusters of two CTAs (panel = rank in the cluster) that share every E tile by TMA multicast
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(unsigned(ggrid)); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = gsmem; cfg.stream = st;
+            cudaLaunchAttribute attr{};
+            attr.id = cudaLaunchAttributeClusterDimension;
+            attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+            cfg.attrs = &attr; cfg.numAttrs = 1;
+            MSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, dense_gemm_kernel<true>, ix->map_e, map_q, dn, w, gw));
+        } else {
+            dense_gemm_kernel<false><<<ggrid, kGemmThreads, gsmem, st>>>(ix->map_e, map_q, dn, w, gw);
+        }
         MSE_CUDA_TRY(cudaGetLastError());
         gemm_bucket_kernel<<<ix->sm_count * 4, 256, 0, st>>>(w);
         MSE_CUDA_TRY(cudaGetLastError());

@@ -31,8 +31,8 @@
 // belong to the next group; they are computed twice and masked, ~8 % redundant L2 reads.)  Documents with more
 // than 32 chunks do not fit a group: the caller falls back to the GEMV kernel.
 //
-// Warp roles (320 threads, 1 CTA/SM, persistent over tiles): warp 0 = TMA producer (converged, one elected lane issues),
-// warp 1 = TMEM allocator + MMA issuer (the same), warps 2-9 = epilogue (warp w reads TMEM lane quarter w%4 =
+// Warp roles (352 threads, 1 CTA/SM, persistent over tiles): warp 0 = TMA producer (converged, one elected lane issues),
+// warp 1 = TMEM allocator + MMA issuer (the same), warps 2-9 = epilogue, warp 10 = bound refresher (warp w reads TMEM lane quarter w%4 =
 // queries 32*(w%4).. of the panel; the two warps of a quarter take four groups each).
 #pragma once
 #include <cuda.h>
@@ -44,7 +44,7 @@
 namespace mse {
 
 constexpr int kGemmEpiWarps = 8;                      // two per TMEM lane quarter, four doc-aligned groups each
-constexpr int kGemmThreads = (2 + kGemmEpiWarps) * 32;
+constexpr int kGemmThreads = (3 + kGemmEpiWarps) * 32;   // + TMA producer, MMA issuer, bound warp
 constexpr int kGemmBlockK = 64;                        // elements per k-block (128 B of bf16)
 constexpr int kGemmKBlocks = kDim / kGemmBlockK;       // 12
 constexpr int kGemmGroupRows = 32;
@@ -129,8 +129,24 @@ __device__ __forceinline__ void tcgen05_mma_bf16_ts(uint32_t tmem_d, uint32_t tm
 // the loop and the barrier waits) and one elected lane issues a whole k-block per asm block.
 //
 // One k-block of MMAs (4 x K=16) + the commit that frees the shared-memory stage.  A from tensor memory.
+template <bool PAIR>
 __device__ __forceinline__ void umma_kblock_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
                                                uint32_t accumulate_first, uint64_t* empty_bar) {
+    if constexpr (PAIR) {
+    asm volatile("{\n\t.reg .pred q, p, t;\n\t.reg .b32 a1, a2, a3;\n\t.reg .b64 b1, b2, b3;\n\t.reg .b16 m;\n\t"
+                 "elect.sync _|q, 0xffffffff;\n\t"
+                 "mov.b16 m, 3;\n\t"
+                 "setp.ne.b32 p, %4, 0;\n\tsetp.eq.b32 t, 0, 0;\n\t"
+                 "add.u32 a1, %1, 8;\n\tadd.u32 a2, %1, 16;\n\tadd.u32 a3, %1, 24;\n\t"
+                 "add.u64 b1, %2, 2;\n\tadd.u64 b2, %2, 4;\n\tadd.u64 b3, %2, 6;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], b1, %3, t;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], b2, %3, t;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [a3], b3, %3, t;\n\t"
+                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%5], m;\n\t}"
+                 ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate_first), "r"(smem_addr(empty_bar)) : "memory");
+    return;
+    }
     asm volatile("{\n\t.reg .pred q, p, t;\n\t.reg .b32 a1, a2, a3;\n\t.reg .b64 b1, b2, b3;\n\t"
                  "elect.sync _|q, 0xffffffff;\n\t"
                  "setp.ne.b32 p, %4, 0;\n\tsetp.eq.b32 t, 0, 0;\n\t"
@@ -144,8 +160,24 @@ __device__ __forceinline__ void umma_kblock_ts(uint32_t tmem_d, uint32_t tmem_a,
                  ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate_first), "r"(smem_addr(empty_bar)) : "memory");
 }
 // the same with A from shared memory (descriptor; +32 bytes = +2 in the 16-byte address field per K=16 step)
+template <bool PAIR>
 __device__ __forceinline__ void umma_kblock_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                                uint32_t accumulate_first, uint64_t* empty_bar) {
+    if constexpr (PAIR) {
+    asm volatile("{\n\t.reg .pred q, p, t;\n\t.reg .b64 a1, a2, a3, b1, b2, b3;\n\t.reg .b16 m;\n\t"
+                 "elect.sync _|q, 0xffffffff;\n\t"
+                 "mov.b16 m, 3;\n\t"
+                 "setp.ne.b32 p, %4, 0;\n\tsetp.eq.b32 t, 0, 0;\n\t"
+                 "add.u64 a1, %1, 2;\n\tadd.u64 a2, %1, 4;\n\tadd.u64 a3, %1, 6;\n\t"
+                 "add.u64 b1, %2, 2;\n\tadd.u64 b2, %2, 4;\n\tadd.u64 b3, %2, 6;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, t;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, t;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, t;\n\t"
+                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%5], m;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate_first), "r"(smem_addr(empty_bar)) : "memory");
+    return;
+    }
     asm volatile("{\n\t.reg .pred q, p, t;\n\t.reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
                  "elect.sync _|q, 0xffffffff;\n\t"
                  "setp.ne.b32 p, %4, 0;\n\tsetp.eq.b32 t, 0, 0;\n\t"
@@ -181,6 +213,32 @@ __device__ __forceinline__ void tma_stage_elect(uint32_t dst, const CUtensorMap*
                  ::"r"(dst), "l"(map), "r"(c0), "r"(smem_addr(full_bar)),
                    "r"(rows[0]), "r"(rows[1]), "r"(rows[2]), "r"(rows[3]), "r"(rows[4]), "r"(rows[5]), "r"(rows[6]), "r"(rows[7]),
                    "r"(bytes) : "memory");
+}
+// ---- CTA pair (cluster of 2): the two query panels of a 129..256-query batch share every E tile ----------------------
+// Each CTA of the pair loads HALF of a stage (four of the eight boxes) and multicasts it into the shared memory of
+// both, so a chunk row leaves HBM / L2 once per pair instead of once per panel.  A stage is free when BOTH CTAs'
+// MMAs have read it: the commit that frees it is multicast to the empty barrier of both CTAs (arrival count 2).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_half_stage_multicast_elect(uint32_t dst, const CUtensorMap* map, int c0, const int (&rows)[4],
+                                                               uint64_t* full_bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .pred q;\n\t.reg .b32 d1, d2, d3;\n\t.reg .b16 m;\n\t"
+                 "elect.sync _|q, 0xffffffff;\n\t"
+                 "mov.b16 m, 3;\n\t"
+                 "add.u32 d1, %0, 4096;\n\tadd.u32 d2, %0, 8192;\n\tadd.u32 d3, %0, 12288;\n\t"
+                 "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %8;\n\t"
+                 "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %4}], [%3], m;\n\t"
+                 "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [d1], [%1, {%2, %5}], [%3], m;\n\t"
+                 "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [d2], [%1, {%2, %6}], [%3], m;\n\t"
+                 "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [d3], [%1, {%2, %7}], [%3], m;\n\t}"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(smem_addr(full_bar)),
+                   "r"(rows[0]), "r"(rows[1]), "r"(rows[2]), "r"(rows[3]), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
     asm volatile(
@@ -223,12 +281,14 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+template <bool PAIR>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 dense_gemm_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_constant__ CUtensorMap map_q,
                   DenseDev dx, DenseWork w, GemmWork g) {
     extern __shared__ __align__(1024) unsigned char gemm_smem_raw[];
     __shared__ __align__(8) uint64_t s_full[kGemmMaxStages], s_empty[kGemmMaxStages], s_tfull, s_tempty, s_aready;
     __shared__ uint32_t s_tmem_base;
+    __shared__ int s_epi_done;                                            // epilogue warps that have finished (stops the bound warp)
     __shared__ uint64_t s_stage_key[kGemmEpiWarps][kGemmStage];
     __shared__ uint16_t s_stage_q[kGemmEpiWarps][kGemmStage];
     __shared__ __align__(16) uint32_t s_transpose[kGemmEpiWarps][32];     // one query's 32 scores of a group, lane <-> row
@@ -240,11 +300,13 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_consta
     unsigned char* ring = smem + kGemmASmemBytes;                         // E stages
     constexpr uint32_t tmem_cols = 512;                                   // 256 query panel + 256 accumulator
     // CTAs of panel p are blockIdx p, p + n_panels, ...: both panels walk the same tiles in the same order
-    const int panel = int(blockIdx.x) % g.n_panels;
+    // (PAIR: the two CTAs of a cluster are the two panels and share the E loads; otherwise a single panel)
+    const int panel = PAIR ? int(cluster_ctarank()) : int(blockIdx.x) % g.n_panels;
     const int64_t cta = int64_t(blockIdx.x) / g.n_panels, n_cta = int64_t(gridDim.x) / g.n_panels;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kGemmMaxStages; ++s) { mbarrier_init(&s_full[s], 1); mbarrier_init(&s_empty[s], 1); }
+        s_epi_done = 0;
+        for (int s = 0; s < kGemmMaxStages; ++s) { mbarrier_init(&s_full[s], 1); mbarrier_init(&s_empty[s], PAIR ? 2 : 1); }
         mbarrier_init(&s_tfull, 1); mbarrier_init(&s_tempty, kGemmEpiWarps); mbarrier_init(&s_aready, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -254,6 +316,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_consta
     }
     tcgen05_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();                               // the peer's barriers are initialised too
     tcgen05_fence_after();
     const uint32_t tmem_base = s_tmem_base;
     const uint32_t tmem_acc = tmem_base + uint32_t(kGemmDCol);
@@ -264,7 +327,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_consta
         for (int kb = kGemmKBlocksTmem; kb < kGemmKBlocks; ++kb)
             tma_load_2d(a_ss + (kb - kGemmKBlocksTmem) * (kGemmPanel * 128), &map_q, kb * kGemmBlockK, panel * kGemmPanel, &s_aready);
     }
-    if (warp >= 2) {
+    if (warp >= 2 && warp < 2 + kGemmEpiWarps) {
         // first half of the query panel -> TMEM: thread = one query (TMEM lane), 32 columns (64 K elements) per tcgen05.st;
         // the two warps of a lane quarter write one half of the columns each
         const int quarter = warp & 3;
@@ -293,10 +356,12 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_consta
         const uint32_t ring_addr = smem_addr(ring);
         int it = 0;
         for (int64_t tile = cta; tile < g.n_tiles; tile += n_cta, ++it) {
-            int rows[kGemmTileGroups];
+            constexpr int n_rows = PAIR ? kGemmTileGroups / 2 : kGemmTileGroups;   // boxes this CTA loads per stage
+            const int gi0 = PAIR ? panel * n_rows : 0;
+            int rows[n_rows];
 #pragma unroll
-            for (int gi = 0; gi < kGemmTileGroups; ++gi) {
-                const int64_t grp = tile * kGemmTileGroups + gi;
+            for (int gi = 0; gi < n_rows; ++gi) {
+                const int64_t grp = tile * kGemmTileGroups + gi0 + gi;
                 rows[gi] = grp < g.n_groups ? int(g.group_row[grp]) : int(dx.n_chunks);     // past the end -> zero fill
             }
 #pragma unroll
@@ -304,9 +369,12 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_consta
                 constexpr int turns = kGemmKBlocks / kGemmMaxStages;      // turns of the ring per tile
                 const int stage = kb % kGemmMaxStages;
                 const uint32_t phase = uint32_t(it * turns + kb / kGemmMaxStages) & 1u;
-                mbarrier_wait(&s_empty[stage], phase ^ 1u);
-                tma_stage_elect(ring_addr + uint32_t(stage) * kGemmStageBytes, &map_e, kb * kGemmBlockK, rows, &s_full[stage],
-                                uint32_t(kGemmStageBytes));
+                mbarrier_wait(&s_empty[stage], phase ^ 1u);               // PAIR: both CTAs have consumed the stage
+                const uint32_t dst = ring_addr + uint32_t(stage) * kGemmStageBytes + uint32_t(gi0) * (kGemmGroupRows * 128);
+                if constexpr (PAIR)                                       // the other half arrives from the peer's multicast
+                    tma_half_stage_multicast_elect(dst, &map_e, kb * kGemmBlockK, rows, &s_full[stage], uint32_t(kGemmStageBytes));
+                else
+                    tma_stage_elect(dst, &map_e, kb * kGemmBlockK, rows, &s_full[stage], uint32_t(kGemmStageBytes));
             }
         }
     } else if (warp == 1) {
@@ -328,12 +396,25 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_consta
                 tcgen05_fence_after();
                 const uint64_t bd = e_desc0 + uint64_t(stage * (kGemmStageBytes >> 4));          // 256 chunk rows x 64
                 if (kb < kGemmKBlocksTmem)                                // A: 16 K elements = 8 TMEM columns per MMA
-                    umma_kblock_ts(tmem_acc, tmem_base + uint32_t(kb * (kGemmBlockK / 16) * 8), bd, idesc, kb ? 1u : 0u, &s_empty[stage]);
+                    umma_kblock_ts<PAIR>(tmem_acc, tmem_base + uint32_t(kb * (kGemmBlockK / 16) * 8), bd, idesc, kb ? 1u : 0u, &s_empty[stage]);
                 else
-                    umma_kblock_ss(tmem_acc, a_desc0 + uint64_t((kb - kGemmKBlocksTmem) * ((kGemmPanel * 128) >> 4)), bd, idesc, 1u,
+                    umma_kblock_ss<PAIR>(tmem_acc, a_desc0 + uint64_t((kb - kGemmKBlocksTmem) * ((kGemmPanel * 128) >> 4)), bd, idesc, 1u,
                                    &s_empty[stage]);
             }
             tcgen05_commit_elect(&s_tfull);                               // accumulator ready for the epilogue
+        }
+    } else if (warp == 2 + kGemmEpiWarps) {
+        // ===================== bound warp: raises the running bounds of the queries, four at a time, for as long as the
+        // epilogue runs (kept off the epilogue warps: a refresh is three dependent L2 round trips, ~2.5k cycles that
+        // would sit between two tiles of every epilogue warp) =====================
+        if (w.use_tau && !(g.debug & 1)) {
+            int q = int((int64_t(blockIdx.x) * 4) % g.n_real);
+            while (*reinterpret_cast<volatile int*>(&s_epi_done) < kGemmEpiWarps) {
+                int qs[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { qs[i] = g.q0 + q; q = (q + 1 == g.n_real) ? 0 : q + 1; }
+                tau_raise_multi<4>(w.ts, qs);
+            }
         }
     } else {
         // ===================== epilogue (warp w -> TMEM lane quarter w % 4 = 32 queries of the panel) ==========
@@ -345,7 +426,6 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_consta
         uint16_t* st_q = s_stage_q[ew];
         uint32_t* tr = s_transpose[ew];
         int staged = 0;                                                   // uniform
-        int rr = int((blockIdx.x * kGemmEpiWarps + ew) % g.n_real);       // round-robin cursor for bound refreshes
         const int my_q = panel * kGemmPanel + quarter * 32 + lane;        // this thread's query (may be padding)
         const bool q_real = my_q < g.n_real;
         const bool warp_idle = panel * kGemmPanel + quarter * 32 >= g.n_real;   // no real query on these lanes
@@ -459,13 +539,13 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_consta
                 }
             }
             if (staged > kGemmStage / 2) flush();
-            // refresh the bound of ONE query per tile, round-robin over warps and tiles
-            if (w.use_tau) { tau_raise(w.ts, g.q0 + rr); rr = (rr + 1 == g.n_real) ? 0 : rr + 1; }
         }
         flush();
+        if (lane == 0) atomicAdd(&s_epi_done, 1);
     }
     tcgen05_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();                               // no exit while the peer may still signal this CTA's barriers
     if (warp == 1) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");

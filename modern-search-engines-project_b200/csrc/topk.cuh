@@ -41,13 +41,9 @@ __device__ __forceinline__ void tau_count(const TauState& ts, int q, uint32_t ke
     atomicMax(&ts.maxbin[q], bin);
 }
 
-// one full warp
-__device__ __forceinline__ void tau_raise(const TauState& ts, int q) {
+// one full warp; continues the scan of query q's histogram at bin b with `acc` candidates already counted above it
+__device__ __forceinline__ void tau_raise_from(const TauState& ts, int q, int b, int acc, int cur_bin) {
     const int lane = lane_id();
-    const uint32_t cur = ld_relaxed_u32(&ts.tau[q]);
-    const int cur_bin = int(cur >> ts.shift);
-    int b = int(ld_relaxed_u32(&ts.maxbin[q]));
-    int acc = 0;
     const uint32_t* h = ts.hist + (int64_t(q) << (32 - ts.shift));
     while (b >= cur_bin) {
         const int bin = b - lane;
@@ -61,6 +57,36 @@ __device__ __forceinline__ void tau_raise(const TauState& ts, int q) {
         }
         acc += __shfl_sync(0xffffffffu, incl, 31);
         b -= 32;
+    }
+}
+__device__ __forceinline__ void tau_raise(const TauState& ts, int q) {
+    const int cur_bin = int(ld_relaxed_u32(&ts.tau[q]) >> ts.shift);
+    tau_raise_from(ts, q, int(ld_relaxed_u32(&ts.maxbin[q])), 0, cur_bin);
+}
+// NQ queries at once: the dependent loads (bound and top bin, then the first 32 bins) of all of them are in flight
+// together; a query whose k-th candidate lies further down continues alone
+template <int NQ>
+__device__ __forceinline__ void tau_raise_multi(const TauState& ts, const int (&q)[NQ]) {
+    const int lane = lane_id();
+    int cur_bin[NQ], b[NQ], c[NQ];
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) { cur_bin[i] = int(ld_relaxed_u32(&ts.tau[q[i]]) >> ts.shift); b[i] = int(ld_relaxed_u32(&ts.maxbin[q[i]])); }
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+        const int bin = b[i] - lane;
+        c[i] = (bin >= cur_bin[i] && bin >= 0) ? int(ld_relaxed_u32(&ts.hist[(int64_t(q[i]) << (32 - ts.shift)) + bin])) : 0;
+    }
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+        if (b[i] < cur_bin[i]) continue;                                  // uniform
+        const int incl = warp_incl_scan(c[i]);
+        const unsigned hit = __ballot_sync(0xffffffffu, incl >= ts.top_k);
+        if (hit) {
+            const int tb = b[i] - (__ffs(hit) - 1);
+            if (lane == 0 && tb > cur_bin[i]) atomicMax(&ts.tau[q[i]], uint32_t(tb) << ts.shift);
+        } else {
+            tau_raise_from(ts, q[i], b[i] - 32, __shfl_sync(0xffffffffu, incl, 31), cur_bin[i]);
+        }
     }
 }
 
