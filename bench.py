@@ -575,6 +575,10 @@ def main():
 
     sampler = ClockSampler(local_rank)
     sampler.start()
+    t_start = time.perf_counter()
+
+    def note(what):                                       # progress on stderr: a stuck phase is then visible in the log
+        print(f"[bench rank {rank}] {time.perf_counter() - t_start:7.1f}s {what}", file=sys.stderr, flush=True)
 
     # ---- corpus + index ------------------------------------------------------------------------
     t0 = time.perf_counter()
@@ -631,6 +635,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    note(f"corpus + index ready ({setup_s:.1f}s)")
     # ---- value: inputs resident in HBM ----------------------------------------------------------------
     for i in range(args.warmup):
         step_device(i)
@@ -653,6 +658,7 @@ def main():
     rows_per_query = float(out[5].float().mean().item())
     gpu_doc, gpu_score, gpu_count = (x.cpu().numpy() for x in (out[0], out[1], out[4]))     # last step (not the parity batch)
 
+    note(f"value leg done: {value:.0f} {UNIT}")
     # ---- e2e: pinned host buffers through the C ABI, two streams alternating ---------------------------------
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     host_pinned = [tuple(pin(a) for a in b) for b in host_batches]
@@ -698,6 +704,7 @@ def main():
     d2h = world * (B * MAX_OUT * (4 + 4 + 4 + 8) + B * 8 + 16)
     sampler.stop()
 
+    note(f"e2e leg done: {e2e_value:.0f} {UNIT}")
     # ---- batch-1 latency (N=1): synchronous MSE_HOST call per query ---------------------------------------------
     latency = None
     if lat_batches:
@@ -738,14 +745,17 @@ def main():
                    "algorithmic_bytes_per_launch": alg_rerank, "kernel_ms": rerank_ms, "rows_per_query": rows_per_query,
                    "basis": "2*768 B per fetched chunk row + 12 B per candidate + 8 B per result"}
 
+    note("parity / cpu legs")
     # ---- parity at this size (rank 0): GPU vs oracle pipeline on sampled queries of one timed batch ------------------
     parity = None
     cpu_baseline = None
+    if max(n_par, n_cpu) > 0:
+        # every rank runs the step (the sharded call holds collectives); rank 0 alone checks it
+        step_device(args.warmup)
+        sync_all()
     if rank == 0 and par_ix is not None:
         fetch = fetch_rows_fn(corpus, dev)
         i = args.warmup
-        step_device(i)
-        torch.cuda.synchronize()
         g_doc, g_score, g_count = (x.cpu().numpy() for x in (out[0], out[1], out[4]))
         qv = host_batches[i][3]
         if n_par:
@@ -772,6 +782,7 @@ def main():
     gc.collect()
     gc.freeze()
 
+    note("supplements")
     # ---- supplements -------------------------------------------------------------------------------------------------------
     supplements = {}
     if not args.no_supplements:
