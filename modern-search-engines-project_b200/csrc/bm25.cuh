@@ -328,8 +328,12 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
     // The accumulator of a document that reached the bound on its streamed terms gets their contributions added (same
     // round-down FMA as a streamed posting; a document the term does not hold reads impact 0).
     int neg_lo = 0, neg_hi = 0;
+    int look_n = 0;                                  // looked-up slots of the current query; when there is exactly one (the
+    uint32_t look_w = 0u, look_row = 0u;             // usual case: the always-term) its weight bits and 1 + dense row
     auto neg_adjust = [&](uint32_t bits, int d) -> uint32_t {
         float a = __uint_as_float(bits);
+        if (look_n == 1)
+            return __float_as_uint(__fmaf_rd(-__uint_as_float(look_w), __ldg(ix.neg_imp + int64_t(look_row - 1u) * ix.neg_stride + (lo + d)), a));
         for (int sl = neg_lo; sl < neg_hi; ++sl) {
             const uint4 m = s_meta[sl];
             if (m.w) a = __fmaf_rd(-__uint_as_float(m.z), __ldg(ix.neg_imp + int64_t(m.w - 1u) * ix.neg_stride + (lo + d)), a);
@@ -351,8 +355,8 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
             if (HITS) {
                 // the looked-up class term takes at least cwq * c off this document's score: a document reaches the bound
                 // only if (minus score so far) + that penalty still does.  float(c) = (2^23 | c) - 2^23 (exact).
-                const float pen = __fmul_rd(cwq, __uint_as_float(0x4b000000u | (uint32_t(dd) >> kClsShift)) - 8388608.0f);
-                const bool hit = __float_as_uint(__fadd_rd(nv, pen)) >= hit_tau;
+                // (one round-down FMA: the rounded value is <= the exact one, i.e. the test errs towards "hit")
+                const bool hit = __float_as_uint(__fmaf_rd(cwq, __uint_as_float(0x4b000000u | (uint32_t(dd) >> kClsShift)) - 8388608.0f, nv)) >= hit_tau;
                 hd = hit ? d : hd;
                 hc += int(hit);
             }
@@ -448,12 +452,13 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
                 uint32_t wneg = 0u;                             // sign bit set: a negative weight was applied (the last update
                                                                 // of a document need not be its largest then)
                 int touched = 0;                                // bit 0: postings were applied, bit 1: the query has looked-up slots
+                look_n = 0;
 #pragma unroll
                 for (int t = 0; t < MP; ++t) {
                     if (o_cur + t < e_cur) {
                         const uint4 m = s_meta[o_cur + t];
                         const int n = int(m.y);
-                        if (m.w) touched |= 2;                                  // a looked-up negative slot
+                        if (m.w) { touched |= 2; ++look_n; look_w = m.z; look_row = m.w; }   // a looked-up negative slot
                         if (n > 0) {
                             const float wt = __uint_as_float(m.z);
                             touched |= 1;
@@ -468,7 +473,7 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
                 for (int sl = o_cur + MP; sl < e_cur; ++sl) {               // queries with more than MP terms
                     const uint4 m = s_meta[sl];
                     const int n = int(m.y);
-                    if (m.w) touched |= 2;
+                    if (m.w) { touched |= 2; ++look_n; look_w = m.z; look_row = m.w; }
                     if (n == 0) continue;
                     const float wt = __uint_as_float(m.z);
                     touched |= 1;
