@@ -342,24 +342,54 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
     };
 
     uint32_t hit_tau = 0xffffffffu;                  // bits of minus the bound of the current query (HITS), or "never"
-    int hc = 0, hd = 0;                              // this lane's updates that reached the bound in the current task; doc of the last
+    int hc = 0;                                      // this lane's updates that reached the bound in the current task
+    uint32_t hd = 0u;                                // shared-memory address of the accumulator the last of them wrote
     // one warp-round: up to 32 postings of one term; docs are unique inside a term (no race)
     float cwq = 0.f;                                  // class penalty unit of the current query (Bm25Work::cls_wq), 0 = none
-    auto apply = [&](int dd, int tfi, bool valid, float wt) {
-        if (valid) {
-            const int d = int(uint32_t(dd) & kDocMask) - lo;
-            // idf*qtf*(k1+1) * [tf / (tf + k1*(1-b+b*dl/avgdl))]: the bracket is the posting's precomputed impact.
-            // The accumulator holds MINUS the score; round-down keeps "touched, score 0" at -0.0 (rest state: +0.0)
-            const float nv = __fmaf_rd(-wt, __int_as_float(tfi), s_acc[d]);
-            s_acc[d] = nv;
-            if (HITS) {
-                // the looked-up class term takes at least cwq * c off this document's score: a document reaches the bound
-                // only if (minus score so far) + that penalty still does.  float(c) = (2^23 | c) - 2^23 (exact).
-                // (one round-down FMA: the rounded value is <= the exact one, i.e. the test errs towards "hit")
-                const bool hit = __float_as_uint(__fmaf_rd(cwq, __uint_as_float(0x4b000000u | (uint32_t(dd) >> kClsShift)) - 8388608.0f, nv)) >= hit_tau;
-                hd = hit ? d : hd;
-                hc += int(hit);
-            }
+    // Written as ONE predicated instruction sequence (no branch around the body: the compiler's version of
+    // `if (valid) {...}` cost a BSSY / BRA / BSYNC triple and five instructions for the two hit registers per round):
+    // mask + multiply-add for the shared-memory address, LDS, FMA, STS, class -> float (2), FMA, compare, two predicated
+    // moves.  The hit register holds the ADDRESS of the document's accumulator.  (asm volatile without a memory clobber:
+    // the blocks keep their order among themselves and against __syncwarp, which separates them from every C++ access
+    // to the accumulators; with the clobber the compiler moved the prefetch arrays to local memory.)
+    const uint32_t acc_addr = uint32_t(__cvta_generic_to_shared(s_acc));
+    uint32_t acc_lo = acc_addr;                       // acc_addr - 4 * lo: accumulator address of global doc 0 (per item)
+    auto apply = [&](int dd, int tfi, float wt) {       // dd == -1: no posting on this lane
+        // idf*qtf*(k1+1) * [tf / (tf + k1*(1-b+b*dl/avgdl))]: the bracket is the posting's precomputed impact.
+        // The accumulator holds MINUS the score; round-down keeps "touched, score 0" at -0.0 (rest state: +0.0)
+        if (HITS) {
+            // the looked-up class term takes at least cwq * c off this document's score: a document reaches the bound
+            // only if (minus score so far) + that penalty still does.  float(c) = (2^23 | c) - 2^23 (exact); one
+            // round-down FMA: the rounded value is <= the exact one, i.e. the test errs towards "hit"
+            asm volatile("{\n\t.reg .pred v, h;\n\t.reg .b32 a, c;\n\t.reg .f32 o, n, x, cf;\n\t"
+                         "setp.ne.b32 v, %2, -1;\n\t"
+                         "and.b32 a, %2, 0x0fffffff;\n\t"
+                         "mad.lo.u32 a, a, 4, %4;\n\t"
+                         "mov.f32 o, 0f00000000;\n\t"          // (a full definition: a predicated-only one keeps the register live across rounds)
+                         "@v ld.shared.f32 o, [a];\n\t"
+                         "fma.rm.f32 n, %5, %3, o;\n\t"
+                         "@v st.shared.f32 [a], n;\n\t"
+                         "shr.u32 c, %2, 28;\n\t"
+                         "or.b32 c, c, 0x4b000000;\n\t"
+                         "mov.b32 cf, c;\n\t"
+                         "sub.rn.f32 cf, cf, 0f4B000000;\n\t"
+                         "fma.rm.f32 x, %6, cf, n;\n\t"
+                         "mov.b32 c, x;\n\t"
+                         "setp.ge.and.u32 h, c, %7, v;\n\t"
+                         "@h add.s32 %0, %0, 1;\n\t"
+                         "@h mov.b32 %1, a;\n\t}"
+                         : "+r"(hc), "+r"(hd)
+                         : "r"(dd), "f"(__int_as_float(tfi)), "r"(acc_lo), "f"(-wt), "f"(cwq), "r"(hit_tau));
+        } else {
+            asm volatile("{\n\t.reg .pred v;\n\t.reg .b32 a;\n\t.reg .f32 o, n;\n\t"
+                         "setp.ne.b32 v, %0, -1;\n\t"
+                         "and.b32 a, %0, 0x0fffffff;\n\t"
+                         "mad.lo.u32 a, a, 4, %2;\n\t"
+                         "mov.f32 o, 0f00000000;\n\t"
+                         "@v ld.shared.f32 o, [a];\n\t"
+                         "fma.rm.f32 n, %3, %1, o;\n\t"
+                         "@v st.shared.f32 [a], n;\n\t}"
+                         :: "r"(dd), "f"(__int_as_float(tfi)), "r"(acc_lo), "f"(-wt));
         }
     };
     // postings 32.. of a slice: the loads of up to four rounds are issued before the first is applied
@@ -369,14 +399,14 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
             int dd[4], tt[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                dd[u] = 0; tt[u] = 0;
+                dd[u] = -1; tt[u] = 0;
                 if (i0 + 32 * u + lane < n) {
                     const int2 p = ldg_stream_i2(g_post + begin + i0 + 32 * u + lane);
                     dd[u] = p.x; tt[u] = p.y;
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) apply(dd[u], tt[u], i0 + 32 * u + lane < n, wt);
+            for (int u = 0; u < 4; ++u) apply(dd[u], tt[u], wt);
         }
     };
 
@@ -387,6 +417,7 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
         if (item >= n_items) break;
         const int j = item / chunks, c = item - j * chunks;
         lo = j * RS;
+        acc_lo = acc_addr - 4u * uint32_t(lo);
         const int q0 = c * QC;
         const int q1 = (q0 + QC) < w.n_queries ? (q0 + QC) : w.n_queries;
         const int nq = q1 - q0;
@@ -415,7 +446,7 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
             // prefetch of the first query of the group
 #pragma unroll
             for (int t = 0; t < MP; ++t) {
-                pd_nxt[t] = 0; pt_nxt[t] = 0;
+                pd_nxt[t] = -1; pt_nxt[t] = 0;
                 if (o_nxt + t < e_nxt) {
                     const uint4 m = s_meta[o_nxt + t];
                     if (lane < int(m.y)) { const int2 p = ldg_stream_i2(g_post + m.x + lane); pd_nxt[t] = p.x; pt_nxt[t] = p.y; }
@@ -438,6 +469,7 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
                     for (int t = 0; t < MP; ++t) {
                         if (o_nxt + t < e_nxt) {
                             const uint4 m = s_meta[o_nxt + t];
+                            pd_nxt[t] = -1;                                 // lanes past the end of the slice: no posting
                             if (lane < int(m.y)) { const int2 p = ldg_stream_i2(g_post + m.x + lane); pd_nxt[t] = p.x; pt_nxt[t] = p.y; }
                         }
                     }
@@ -463,7 +495,7 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
                             const float wt = __uint_as_float(m.z);
                             touched |= 1;
                             if (HITS) wneg |= m.z;
-                            apply(pd_cur[t], pt_cur[t], lane < n, wt);
+                            apply(pd_cur[t], pt_cur[t], wt);
                             if (n > 32) apply_rest(m.x, n, wt);
                             __syncwarp();                                   // next term may touch the same docs
                         }
@@ -478,9 +510,9 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
                     const float wt = __uint_as_float(m.z);
                     touched |= 1;
                     if (HITS) wneg |= m.z;
-                    int dd = 0, tfi = 0;
+                    int dd = -1, tfi = 0;
                     if (lane < n) { const int2 p = ldg_stream_i2(g_post + m.x + lane); dd = p.x; tfi = p.y; }
-                    apply(dd, tfi, lane < n, wt);
+                    apply(dd, tfi, wt);
                     if (n > 32) apply_rest(m.x, n, wt);
                     __syncwarp();
                 }
@@ -495,7 +527,7 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
                             int d = -1 - lane;                               // idle lanes: distinct keys
                             uint32_t bits = 0u;
                             if (hc == 1) {
-                                d = hd; bits = reinterpret_cast<const uint32_t*>(s_acc)[d];
+                                d = int(hd - acc_addr) >> 2; bits = reinterpret_cast<const uint32_t*>(s_acc)[d];
                                 if (neg_hi) bits = neg_adjust(bits, d);
                             }
                             const unsigned same = __match_any_sync(0xffffffffu, d);
