@@ -62,7 +62,7 @@ struct mse_index {
     Comm comm;
 
     int64_t opt_readout = 1, opt_tau_init = 1, opt_neg_lookup = 1;
-    int64_t opt_range_docs = 0, opt_qpi = 0, opt_cand_cap = 0, opt_use_tau = 1, opt_scan_ctas = 0, opt_gemm_min_batch = 0, opt_gemm_debug = 0;
+    int64_t opt_range_docs = 0, opt_qpi = 0, opt_cand_cap = 0, opt_use_tau = 1, opt_scan_ctas = 0, opt_gemm_min_batch = 0, opt_gemm_debug = 0, opt_gemm_pair_mode = 1;
     int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int score_ctas_per_sm[2] = {0, 0};            // occupancy of the score kernel (scan / hit read-out) at the default range
 };
@@ -475,8 +475,9 @@ int mse_index_create(int device, mse_index** out) {
     ix->sm_count = prop.multiProcessorCount;
     // function attributes are set once here, so that no search call touches them (calls may run inside a stream capture)
     cudaError_t e = cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kRerankSmemBytes));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(dense_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemmSmemBytes));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(dense_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemmSmemBytes));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dense_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemmSmemBytes));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dense_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemmSmemBytes));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dense_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemmSmemBytes));
     for (int hits = 0; hits < 2 && e == cudaSuccess; ++hits) {
         const void* kfn = score_kernel_fn(true, hits != 0);
         const size_t smem = size_t(kBm25Warps) * bm25_score_warp_bytes(kBm25DefaultRange);
@@ -535,6 +536,7 @@ int mse_index_set_option(mse_index* ix, const char* name, int64_t value) {
     else if (!strcmp(name, "dense_scan_ctas_per_sm")) ix->opt_scan_ctas = value;
     else if (!strcmp(name, "dense_gemm_min_batch")) ix->opt_gemm_min_batch = value;
     else if (!strcmp(name, "dense_gemm_debug")) ix->opt_gemm_debug = value;
+    else if (!strcmp(name, "dense_gemm_pair_mode")) ix->opt_gemm_pair_mode = value;     // 1 (default): multicast pair (cta_group::1), 2: cta_group::2 pair (measured slower: 4.7 vs 3.9 ms at C3 B=256)
     else if (!strcmp(name, "timers")) { std::lock_guard<std::mutex> lp(ix->pool.mu); ix->pool.timers_on = value != 0; }
     else if (!strcmp(name, "reset_timers")) {
         DeviceGuard g(ix->device);
@@ -1064,9 +1066,10 @@ int dense_scan_pass(mse_index* ix, Lease& L, const float* d_q, int g0, int gn, i
             attr.id = cudaLaunchAttributeClusterDimension;
             attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
             cfg.attrs = &attr; cfg.numAttrs = 1;
-            MSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, dense_gemm_kernel<true>, ix->map_e, map_q, dn, w, gw));
+            if (ix->opt_gemm_pair_mode == 1) MSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, dense_gemm_kernel<1>, ix->map_e, map_q, dn, w, gw));
+            else MSE_CUDA_TRY(cudaLaunchKernelEx(&cfg, dense_gemm_kernel<2>, ix->map_e, map_q, dn, w, gw));
         } else {
-            dense_gemm_kernel<false><<<ggrid, kGemmThreads, gsmem, st>>>(ix->map_e, map_q, dn, w, gw);
+            dense_gemm_kernel<0><<<ggrid, kGemmThreads, gsmem, st>>>(ix->map_e, map_q, dn, w, gw);
         }
         MSE_CUDA_TRY(cudaGetLastError());
         gemm_bucket_kernel<<<ix->sm_count * 4, 256, 0, st>>>(w);

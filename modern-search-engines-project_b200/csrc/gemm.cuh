@@ -58,6 +58,7 @@ constexpr int kGemmACols = kGemmKBlocksTmem * kGemmBlockK / 2;    // 256 TMEM co
 constexpr int kGemmASmemBytes = (kGemmKBlocks - kGemmKBlocksTmem) * kGemmPanel * 128;   // 64 KB
 constexpr int kGemmDCol = 256;                         // first accumulator column
 constexpr int kGemmSmemBytes = kGemmASmemBytes + kGemmMaxStages * kGemmStageBytes + 1024;
+constexpr int kGemmCg2Stages = 8;                      // MODE 2: stages of 16 KB per CTA (half a k-block of the tile each)
 constexpr int kGemmStage = 96;                         // emissions staged per epilogue warp between flushes
 
 struct GemmWork {
@@ -240,6 +241,74 @@ __device__ __forceinline__ void tma_half_stage_multicast_elect(uint32_t dst, con
                  ::"r"(dst), "l"(map), "r"(c0), "r"(smem_addr(full_bar)),
                    "r"(rows[0]), "r"(rows[1]), "r"(rows[2]), "r"(rows[3]), "r"(bytes) : "memory");
 }
+// ---- CTA pair with cta_group::2 MMAs (kernel MODE 2) ---------------------------------------------------------------
+// One tcgen05.mma.cta_group::2 (M = 256: 128 queries per CTA, N = 256 chunk rows) is issued by the leader CTA (rank 0) for
+// the pair.  Each CTA keeps its own query panel (tensor + shared memory) and its own 128 x 256 accumulator; the E tile
+// is SPLIT: CTA r holds rows [128 r, 128 r + 128) of the tile, so a ring stage is 16 KB per CTA instead of 32 KB and the
+// same shared memory holds twice as many k-blocks in flight.  Barriers: every TMA load of the pair completes on the
+// LEADER's full barrier; the leader's commits are multicast to the empty / accumulator-full barriers of both CTAs; the
+// epilogue warps of both CTAs arrive on the leader's accumulator-empty barrier.
+__device__ __forceinline__ uint32_t mapa_rank0(uint32_t local_addr) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(local_addr));
+    return r;
+}
+__device__ __forceinline__ void mbarrier_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// four {64 x 32-row} boxes into this CTA's half stage; completion counted on the leader's barrier (cluster address)
+__device__ __forceinline__ void tma_half_stage_cg2_elect(uint32_t dst, const CUtensorMap* map, int c0, const int (&rows)[4],
+                                                         uint32_t leader_full_bar) {
+    asm volatile("{\n\t.reg .pred q;\n\t.reg .b32 d1, d2, d3;\n\t"
+                 "elect.sync _|q, 0xffffffff;\n\t"
+                 "add.u32 d1, %0, 4096;\n\tadd.u32 d2, %0, 8192;\n\tadd.u32 d3, %0, 12288;\n\t"
+                 "@q cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %4}], [%3];\n\t"
+                 "@q cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [d1], [%1, {%2, %5}], [%3];\n\t"
+                 "@q cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [d2], [%1, {%2, %6}], [%3];\n\t"
+                 "@q cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [d3], [%1, {%2, %7}], [%3];\n\t}"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(leader_full_bar),
+                   "r"(rows[0]), "r"(rows[1]), "r"(rows[2]), "r"(rows[3]) : "memory");
+}
+__device__ __forceinline__ void mbarrier_expect_tx_elect(uint64_t* bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+                 "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+// one k-block of cta_group::2 MMAs + the multicast commit that frees the stage in both CTAs
+__device__ __forceinline__ void umma_kblock_ts_cg2(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                                   uint32_t accumulate_first, uint64_t* empty_bar) {
+    asm volatile("{\n\t.reg .pred q, p, t;\n\t.reg .b32 a1, a2, a3;\n\t.reg .b64 b1, b2, b3;\n\t.reg .b16 m;\n\t"
+                 "elect.sync _|q, 0xffffffff;\n\t"
+                 "mov.b16 m, 3;\n\t"
+                 "setp.ne.b32 p, %4, 0;\n\tsetp.eq.b32 t, 0, 0;\n\t"
+                 "add.u32 a1, %1, 8;\n\tadd.u32 a2, %1, 16;\n\tadd.u32 a3, %1, 24;\n\t"
+                 "add.u64 b1, %2, 2;\n\tadd.u64 b2, %2, 4;\n\tadd.u64 b3, %2, 6;\n\t"
+                 "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+                 "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [a1], b1, %3, t;\n\t"
+                 "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [a2], b2, %3, t;\n\t"
+                 "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [a3], b3, %3, t;\n\t"
+                 "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%5], m;\n\t}"
+                 ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate_first), "r"(smem_addr(empty_bar)) : "memory");
+}
+__device__ __forceinline__ void umma_kblock_ss_cg2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                   uint32_t accumulate_first, uint64_t* empty_bar) {
+    asm volatile("{\n\t.reg .pred q, p, t;\n\t.reg .b64 a1, a2, a3, b1, b2, b3;\n\t.reg .b16 m;\n\t"
+                 "elect.sync _|q, 0xffffffff;\n\t"
+                 "mov.b16 m, 3;\n\t"
+                 "setp.ne.b32 p, %4, 0;\n\tsetp.eq.b32 t, 0, 0;\n\t"
+                 "add.u64 a1, %1, 2;\n\tadd.u64 a2, %1, 4;\n\tadd.u64 a3, %1, 6;\n\t"
+                 "add.u64 b1, %2, 2;\n\tadd.u64 b2, %2, 4;\n\tadd.u64 b3, %2, 6;\n\t"
+                 "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+                 "@q tcgen05.mma.cta_group::2.kind::f16 [%0], a1, b1, %3, t;\n\t"
+                 "@q tcgen05.mma.cta_group::2.kind::f16 [%0], a2, b2, %3, t;\n\t"
+                 "@q tcgen05.mma.cta_group::2.kind::f16 [%0], a3, b3, %3, t;\n\t"
+                 "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%5], m;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate_first), "r"(smem_addr(empty_bar)) : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_cg2_multicast_elect(uint64_t* bar) {
+    asm volatile("{\n\t.reg .pred q;\n\t.reg .b16 m;\n\telect.sync _|q, 0xffffffff;\n\tmov.b16 m, 3;\n\t"
+                 "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}"
+                 ::"r"(smem_addr(bar)) : "memory");
+}
 __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -281,12 +350,18 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-template <bool PAIR>
+// MODE 0: one panel per CTA, no cluster.  MODE 1: cluster of two CTAs = two panels, cta_group::1 MMAs, every E stage
+// multicast into both CTAs.  MODE 2: cluster of two CTAs = two panels, cta_group::2 MMAs issued by rank 0, E stages split.
+template <int MODE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 dense_gemm_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_constant__ CUtensorMap map_q,
                   DenseDev dx, DenseWork w, GemmWork g) {
+    constexpr bool PAIR = MODE != 0;
+    constexpr bool CG2 = MODE == 2;
+    constexpr int kStages = CG2 ? kGemmCg2Stages : kGemmMaxStages;
+    constexpr int kStageBytes = CG2 ? kGemmStageBytes / 2 : kGemmStageBytes;
     extern __shared__ __align__(1024) unsigned char gemm_smem_raw[];
-    __shared__ __align__(8) uint64_t s_full[kGemmMaxStages], s_empty[kGemmMaxStages], s_tfull, s_tempty, s_aready;
+    __shared__ __align__(8) uint64_t s_full[kGemmCg2Stages], s_empty[kGemmCg2Stages], s_tfull, s_tempty, s_aready;
     __shared__ uint32_t s_tmem_base;
     __shared__ int s_epi_done;                                            // epilogue warps that have finished (stops the bound warp)
     __shared__ uint64_t s_stage_key[kGemmEpiWarps][kGemmStage];
@@ -306,13 +381,20 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_consta
 
     if (threadIdx.x == 0) {
         s_epi_done = 0;
-        for (int s = 0; s < kGemmMaxStages; ++s) { mbarrier_init(&s_full[s], 1); mbarrier_init(&s_empty[s], PAIR ? 2 : 1); }
-        mbarrier_init(&s_tfull, 1); mbarrier_init(&s_tempty, kGemmEpiWarps); mbarrier_init(&s_aready, 1);
+        // MODE 1: a stage is free when the MMAs of both CTAs have read it (two multicast commits); MODE 2: one multicast
+        // commit of the leader per CTA, and the leader's accumulator-empty barrier collects the epilogue warps of both CTAs
+        for (int s = 0; s < kStages; ++s) { mbarrier_init(&s_full[s], 1); mbarrier_init(&s_empty[s], MODE == 1 ? 2 : 1); }
+        mbarrier_init(&s_tfull, 1); mbarrier_init(&s_tempty, CG2 ? 2 * kGemmEpiWarps : kGemmEpiWarps); mbarrier_init(&s_aready, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&s_tmem_base)), "r"(tmem_cols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (CG2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&s_tmem_base)), "r"(tmem_cols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&s_tmem_base)), "r"(tmem_cols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -345,8 +427,10 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_consta
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
+    if constexpr (CG2) mbarrier_wait(&s_aready, 0u);                      // this CTA's shared-memory part of the panel has landed
     tcgen05_fence_before();
     __syncthreads();
+    if constexpr (CG2) cluster_sync_all();                                // ... and so has the peer's: the leader's MMAs read both
     tcgen05_fence_after();
 
     if (warp == 0) {
@@ -355,6 +439,8 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_consta
         static_assert(kGemmKBlocks % kGemmMaxStages == 0, "stage = kb % stages needs whole turns of the ring per tile");
         const uint32_t ring_addr = smem_addr(ring);
         int it = 0;
+        int rstage = 0;                                                   // MODE 2: running stage / phase (12 k-blocks over 8 stages)
+        uint32_t rphase = 0;
         for (int64_t tile = cta; tile < g.n_tiles; tile += n_cta, ++it) {
             constexpr int n_rows = PAIR ? kGemmTileGroups / 2 : kGemmTileGroups;   // boxes this CTA loads per stage
             const int gi0 = PAIR ? panel * n_rows : 0;
@@ -366,42 +452,68 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_consta
             }
 #pragma unroll
             for (int kb = 0; kb < kGemmKBlocks; ++kb) {
-                constexpr int turns = kGemmKBlocks / kGemmMaxStages;      // turns of the ring per tile
-                const int stage = kb % kGemmMaxStages;
-                const uint32_t phase = uint32_t(it * turns + kb / kGemmMaxStages) & 1u;
-                mbarrier_wait(&s_empty[stage], phase ^ 1u);               // PAIR: both CTAs have consumed the stage
-                const uint32_t dst = ring_addr + uint32_t(stage) * kGemmStageBytes + uint32_t(gi0) * (kGemmGroupRows * 128);
-                if constexpr (PAIR)                                       // the other half arrives from the peer's multicast
-                    tma_half_stage_multicast_elect(dst, &map_e, kb * kGemmBlockK, rows, &s_full[stage], uint32_t(kGemmStageBytes));
-                else
-                    tma_stage_elect(dst, &map_e, kb * kGemmBlockK, rows, &s_full[stage], uint32_t(kGemmStageBytes));
+                if constexpr (CG2) {
+                    // this CTA's four groups = its half of the tile's rows; the pair's bytes are counted on the leader's barrier
+                    mbarrier_wait(&s_empty[rstage], rphase ^ 1u);         // the leader's MMAs have read the stage (in both CTAs)
+                    if (panel == 0) mbarrier_expect_tx_elect(&s_full[rstage], uint32_t(kGemmStageBytes));
+                    tma_half_stage_cg2_elect(ring_addr + uint32_t(rstage) * kStageBytes, &map_e, kb * kGemmBlockK, rows,
+                                             mapa_rank0(smem_addr(&s_full[rstage])));
+                    if (++rstage == kStages) { rstage = 0; rphase ^= 1u; }
+                } else {
+                    constexpr int turns = kGemmKBlocks / kGemmMaxStages;  // turns of the ring per tile
+                    const int stage = kb % kGemmMaxStages;
+                    const uint32_t phase = uint32_t(it * turns + kb / kGemmMaxStages) & 1u;
+                    mbarrier_wait(&s_empty[stage], phase ^ 1u);           // MODE 1: both CTAs have consumed the stage
+                    const uint32_t dst = ring_addr + uint32_t(stage) * kGemmStageBytes + uint32_t(gi0) * (kGemmGroupRows * 128);
+                    if constexpr (PAIR)                                   // the other half arrives from the peer's multicast
+                        tma_half_stage_multicast_elect(dst, &map_e, kb * kGemmBlockK, rows, &s_full[stage], uint32_t(kGemmStageBytes));
+                    else
+                        tma_stage_elect(dst, &map_e, kb * kGemmBlockK, rows, &s_full[stage], uint32_t(kGemmStageBytes));
+                }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (converged warp, one elected lane issues a k-block per asm block) ==========
-        const uint32_t idesc = umma_idesc_bf16_f32(kGemmPanel, kGemmTileRows);   // M = 128 queries, N = 256 chunk rows
+        // M = 128 queries (MODE 2: 256 over the pair), N = 256 chunk rows
+        const uint32_t idesc = umma_idesc_bf16_f32(CG2 ? 2 * kGemmPanel : kGemmPanel, kGemmTileRows);
         const uint64_t e_desc0 = umma_desc_sw128(smem_addr(ring));
         const uint64_t a_desc0 = umma_desc_sw128(smem_addr(a_ss));
-        mbarrier_wait(&s_aready, 0u);                                     // shared-memory part of the query panel has landed
+        if constexpr (!CG2) mbarrier_wait(&s_aready, 0u);                 // shared-memory part of the query panel has landed
         int it = 0;
-        for (int64_t tile = cta; tile < g.n_tiles; tile += n_cta, ++it) {
-            mbarrier_wait(&s_tempty, (uint32_t(it) & 1u) ^ 1u);          // epilogue has drained the accumulator
+        int rstage = 0;
+        uint32_t rphase = 0;
+        const bool issuer = !CG2 || panel == 0;                           // MODE 2: the leader CTA issues for the pair
+        for (int64_t tile = cta; issuer && tile < g.n_tiles; tile += n_cta, ++it) {
+            mbarrier_wait(&s_tempty, (uint32_t(it) & 1u) ^ 1u);          // epilogue has drained the accumulator (MODE 2: of both CTAs)
             tcgen05_fence_after();
 #pragma unroll
             for (int kb = 0; kb < kGemmKBlocks; ++kb) {
-                constexpr int turns = kGemmKBlocks / kGemmMaxStages;
-                const int stage = kb % kGemmMaxStages;
-                const uint32_t phase = uint32_t(it * turns + kb / kGemmMaxStages) & 1u;
-                mbarrier_wait(&s_full[stage], phase);
-                tcgen05_fence_after();
-                const uint64_t bd = e_desc0 + uint64_t(stage * (kGemmStageBytes >> 4));          // 256 chunk rows x 64
-                if (kb < kGemmKBlocksTmem)                                // A: 16 K elements = 8 TMEM columns per MMA
-                    umma_kblock_ts<PAIR>(tmem_acc, tmem_base + uint32_t(kb * (kGemmBlockK / 16) * 8), bd, idesc, kb ? 1u : 0u, &s_empty[stage]);
-                else
-                    umma_kblock_ss<PAIR>(tmem_acc, a_desc0 + uint64_t((kb - kGemmKBlocksTmem) * ((kGemmPanel * 128) >> 4)), bd, idesc, 1u,
-                                   &s_empty[stage]);
+                if constexpr (CG2) {
+                    mbarrier_wait(&s_full[rstage], rphase);               // both halves of the stage have landed
+                    tcgen05_fence_after();
+                    const uint64_t bd = e_desc0 + uint64_t(rstage * (kStageBytes >> 4));       // this CTA's 128 rows x 64; the peer's at the same offset
+                    if (kb < kGemmKBlocksTmem)
+                        umma_kblock_ts_cg2(tmem_acc, tmem_base + uint32_t(kb * (kGemmBlockK / 16) * 8), bd, idesc, kb ? 1u : 0u, &s_empty[rstage]);
+                    else
+                        umma_kblock_ss_cg2(tmem_acc, a_desc0 + uint64_t((kb - kGemmKBlocksTmem) * ((kGemmPanel * 128) >> 4)), bd, idesc, 1u,
+                                           &s_empty[rstage]);
+                    if (++rstage == kStages) { rstage = 0; rphase ^= 1u; }
+                } else {
+                    constexpr int turns = kGemmKBlocks / kGemmMaxStages;
+                    const int stage = kb % kGemmMaxStages;
+                    const uint32_t phase = uint32_t(it * turns + kb / kGemmMaxStages) & 1u;
+                    mbarrier_wait(&s_full[stage], phase);
+                    tcgen05_fence_after();
+                    const uint64_t bd = e_desc0 + uint64_t(stage * (kGemmStageBytes >> 4));      // 256 chunk rows x 64
+                    if (kb < kGemmKBlocksTmem)                            // A: 16 K elements = 8 TMEM columns per MMA
+                        umma_kblock_ts<MODE == 1>(tmem_acc, tmem_base + uint32_t(kb * (kGemmBlockK / 16) * 8), bd, idesc, kb ? 1u : 0u, &s_empty[stage]);
+                    else
+                        umma_kblock_ss<MODE == 1>(tmem_acc, a_desc0 + uint64_t((kb - kGemmKBlocksTmem) * ((kGemmPanel * 128) >> 4)), bd, idesc, 1u,
+                                                  &s_empty[stage]);
+                }
             }
-            tcgen05_commit_elect(&s_tfull);                               // accumulator ready for the epilogue
+            if constexpr (CG2) tcgen05_commit_cg2_multicast_elect(&s_tfull);     // accumulators of both CTAs ready
+            else tcgen05_commit_elect(&s_tfull);                          // accumulator ready for the epilogue
         }
     } else if (warp == 2 + kGemmEpiWarps) {
         // ===================== bound warp: raises the running bounds of the queries, four at a time, for as long as the
@@ -429,6 +541,10 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_consta
         const int my_q = panel * kGemmPanel + quarter * 32 + lane;        // this thread's query (may be padding)
         const bool q_real = my_q < g.n_real;
         const bool warp_idle = panel * kGemmPanel + quarter * 32 >= g.n_real;   // no real query on these lanes
+        const uint32_t tempty_leader = CG2 ? mapa_rank0(smem_addr(&s_tempty)) : 0u;
+        auto tempty_arrive = [&]() {                                      // MODE 2: the leader CTA's barrier collects both CTAs
+            if constexpr (CG2) mbarrier_arrive_cluster(tempty_leader); else mbarrier_arrive(&s_tempty);
+        };
         auto flush = [&]() {
             if (staged == 0) return;
             unsigned long long base = 0;
@@ -447,7 +563,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_consta
             const uint32_t par = uint32_t(it) & 1u;
             if (warp_idle || (g.debug & 1)) {
                 mbarrier_wait_backoff(&s_tfull, par);
-                if (lane == 0) mbarrier_arrive(&s_tempty);
+                if (lane == 0) tempty_arrive();
                 continue;
             }
             // this thread's running bound (padding lanes never pass)
@@ -483,7 +599,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_consta
             tmem_ld_wait();
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbarrier_arrive(&s_tempty);                    // accumulator may be overwritten
+            if (lane == 0) tempty_arrive();                    // accumulator may be overwritten
 #pragma unroll
             for (int j = 0; j < kGemmTileGroups / 2; ++j) {
                 if (tails[j] == 0u) continue;                             // uniform
@@ -548,7 +664,8 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_consta
     if constexpr (PAIR) cluster_sync_all();                               // no exit while the peer may still signal this CTA's barriers
     if (warp == 1) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+        if constexpr (CG2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
     }
 }
 

@@ -71,6 +71,15 @@ def test_dense_gemm_path_vs_oracle(dense_small, B, top_k):
     d3, s3, c3 = nat.dense_scan(q[:6], min(top_k, 100))
     for i in range(6):
         helpers.assert_topk_matches(d3[i, :c3[i]], s3[i, :c3[i]], d2[i, :c2[i]], s2[i, :c2[i]], DENSE_RTOL, atol=2e-4)
+    if B > 128:
+        # two query panels run as a cluster of two CTAs: the default shares every E tile by TMA multicast (cta_group::1
+        # MMAs); the cta_group::2 variant (one MMA stream for the pair, split E stages) must give the same lists
+        nat.set_option("dense_gemm_min_batch", 0)
+        nat.set_option("dense_gemm_pair_mode", 2)
+        d4, s4, c4 = nat.dense_scan(q, top_k)
+        assert np.array_equal(c4, count)
+        for i in range(B):
+            helpers.assert_topk_matches(d4[i, :c4[i]], s4[i, :c4[i]], doc[i, :count[i]], score[i, :count[i]], 1e-6, atol=1e-7)
     nat.close()
 
 
