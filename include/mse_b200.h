@@ -94,7 +94,7 @@ int mse_index_destroy(mse_index* idx);
 
 /* Tuning knobs (all optional; 0 restores the automatic choice unless stated):
  *   "bm25_range_docs"        docs per shared-memory accumulator range (rounded up to a multiple of 128, default 1536)
- *   "bm25_queries_per_item"  queries a warp scores per scheduled work item (<= 31, default 8)
+ *   "bm25_queries_per_item"  queries a warp scores per scheduled work item (<= 8, default 8)
  *   "bm25_cand_cap"          per-query capacity of the candidate list between scoring and selection
  *   "bm25_use_tau"           1 (default) = running k-th-score bound filters candidates, 0 = emit all
  *   "bm25_tau_init"          1 (default) = seed the bound from the per-term impact table built at load time, 0 = off
@@ -110,7 +110,7 @@ int mse_index_destroy(mse_index* idx);
  *                            with the most postings.  Takes effect on the loaded index (rewrites 4 bits per posting); results
  *                            never depend on it
  *   "dense_scan_ctas_per_sm" persistent CTAs per SM of the scan kernel
- *   "dense_gemm_min_batch"   smallest batch routed to the tcgen05 GEMM kernel
+ *   "dense_gemm_min_batch"   smallest batch routed to the tcgen05 GEMM kernel (default 3)
  *   "timers"                 1 (default) = bracket the kernels with CUDA events (mse_kernel_time), 0 = off
  *   "reset_timers"           any value: zero the accumulated kernel timers
  * Environment: MSE_DEBUG_SYNC=1 synchronises after every BM25 kernel so that a device fault names its kernel. */

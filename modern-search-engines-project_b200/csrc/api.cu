@@ -160,10 +160,11 @@ int bm25_enqueue(mse_index* ix, Lease& L, int32_t B, const int32_t* d_q_off, con
     int RS = ix->opt_range_docs > 0 ? round_up(std::min<int64_t>(ix->opt_range_docs, 4096), 128) : kBm25DefaultRange;
     if (bm.n_docs < RS) RS = std::max(128, round_up(bm.n_docs, 128));
     const int n_sub = int((bm.n_docs + RS - 1) / RS);
-    const int qpi = int(std::min<int64_t>(31, ix->opt_qpi > 0 ? ix->opt_qpi : 8));
+    const int qpi = int(std::min<int64_t>(kBm25MaxQueriesPerItem, ix->opt_qpi > 0 ? ix->opt_qpi : 8));
     int rc;
     if ((rc = ws->slot_w.ensure(sizeof(float) * size_t(S + 1)))) return rc;
     if ((rc = ws->slot_row.ensure(sizeof(float) * size_t(B + 1)))) return rc;              // cls_wq [B]
+    if ((rc = ws->qinfo.ensure(sizeof(uint4) * size_t(B + 1)))) return rc;
     if ((rc = ws->rec.ensure(sizeof(uint2) * (size_t(S) * n_sub + 1)))) return rc;
     if ((rc = ws->tau.ensure(sizeof(uint32_t) * size_t(B)))) return rc;
     if ((rc = ws->hist.ensure(sizeof(uint32_t) * size_t(B) * kHistBins))) return rc;
@@ -178,7 +179,7 @@ int bm25_enqueue(mse_index* ix, Lease& L, int32_t B, const int32_t* d_q_off, con
 
     Bm25Work w{};
     w.q_off = d_q_off; w.q_term = d_q_term; w.q_tf = d_q_tf;
-    w.slot_w = ws->slot_w.as<float>(); w.cls_wq = ws->slot_row.as<float>(); w.rec = ws->rec.as<uint2>();
+    w.slot_w = ws->slot_w.as<float>(); w.cls_wq = ws->slot_row.as<float>(); w.qinfo = ws->qinfo.as<uint4>(); w.rec = ws->rec.as<uint2>();
     w.ts = TauState{ws->tau.as<uint32_t>(), ws->hist.as<uint32_t>(), ws->maxbin.as<uint32_t>(), top_k, kHistShift};
     w.cand = ws->cand.as<uint64_t>(); w.cand_count = ws->cand_count.as<int32_t>(); w.overflow = ws->cand_count.as<int32_t>() + B;
     w.item_counter = ws->misc.as<int32_t>();
@@ -1012,7 +1013,9 @@ int dense_scan_pass(mse_index* ix, Lease& L, const float* d_q, int g0, int gn, i
     cudaStream_t st = L.st;
     const DenseDev& dn = ix->dn;
     int r;
-    const int64_t gemm_min = ix->opt_gemm_min_batch > 0 ? ix->opt_gemm_min_batch : 8;
+    // batches of 1-2 queries: one GEMV pass; from 3 queries on the GEMV kernel would stream the matrix ceil(B/2) times (B=7: 9 ms
+    // against 2.4 ms for one GEMM pass at C3)
+    const int64_t gemm_min = ix->opt_gemm_min_batch > 0 ? ix->opt_gemm_min_batch : 3;
     const bool use_gemm = ix->gemm_ok && gn >= gemm_min;
     const int per_sm = ix->opt_scan_ctas > 0 ? int(ix->opt_scan_ctas) : 2;
     const int grid = int(std::min<int64_t>((dn.n_tiles + kScanThreads / 32 - 1) / (kScanThreads / 32) + 1, int64_t(per_sm) * ix->sm_count));

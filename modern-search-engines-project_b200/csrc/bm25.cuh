@@ -81,6 +81,9 @@ struct Bm25Work {                                // per-call workspace
     float* slot_w;               // [S]  idf * qtf * (k1+1)
     float* cls_wq;               // [B]  |weight| / 16 of the query's looked-up slot on the class row (0: none): class c of a posting
                                  //      then says the document loses at least cls_wq * c from that term
+    uint4* qinfo;                // [B]  per-query facts the score kernel needs in every task, formed once by the prepare kernel:
+                                 //      x = number of looked-up slots | 0x100 when a STREAMED slot has a negative weight,
+                                 //      y = weight bits and z = 1 + dense row of the (last) looked-up slot, w = bits of cls_wq
     uint2* rec;                  // [n_sub * S] {first posting (absolute), count} of slot s in sub-range j
     TauState ts;                 // running per-query lower bound of the final k-th best score
     uint64_t* cand;              // [B * cap]
@@ -127,12 +130,19 @@ __device__ __forceinline__ uint32_t bm25_initial_bound(const Bm25Dev& ix, const 
     const bool have_level = ix.imp_levels != nullptr && (64 << lv) >= w.ts.top_k;
     const int64_t need = int64_t(64) << lv;
     float best = 0.f, neg = 0.f, mag = 0.f, pos = 0.f, wq = 0.f;
+    uint32_t look_n = 0u, look_w = 0u, look_row = 0u, neg_streamed = 0u;
     for (int s = w.q_off[q]; s < w.q_off[q + 1]; ++s) {
         const int t = w.q_term[s];
         if (t < 0 || t >= ix.n_terms) continue;
         const int64_t df = ix.term_off[t + 1] - ix.term_off[t];
         if (df == 0) continue;
         const float wt = float(double(ix.idf[t]) * double(w.q_tf[s]) * (double(ix.k1) + 1.0));
+        // (the same condition as `lookup` in bm25_prepare_kernel: this slot's postings are not streamed)
+        if (w.neg_lookup && ix.idf[t] < 0.f && w.q_tf[s] > 0 && ix.neg_row != nullptr && ix.neg_row[t] >= 0) {
+            ++look_n; look_w = __float_as_uint(wt + 0.0f); look_row = uint32_t(ix.neg_row[t]) + 1u;
+        } else if (wt < 0.f) {
+            neg_streamed = 0x100u;
+        }
         if (w.neg_lookup && wt < 0.f && ix.cls_row >= 0 && ix.neg_row[t] == ix.cls_row) wq = -wt * 0.0625f;   // (distinct terms: at most one such slot)
         mag += fabsf(wt);
         if (wt < 0.f) neg += wt;
@@ -143,6 +153,7 @@ __device__ __forceinline__ uint32_t bm25_initial_bound(const Bm25Dev& ix, const 
     }
     w.ts.maxbin[q] = float_to_key(pos * 1.001f + 1e-30f) >> kHistShift;
     w.cls_wq[q] = wq;
+    w.qinfo[q] = make_uint4(look_n | neg_streamed, look_w, look_row, __float_as_uint(wq));
     const float bound = best * (1.0f - 1e-5f) + neg - 4e-6f * mag;     // slack for the fp32 summation of the score kernel
     if (!w.use_tau || !(bound > 0.f)) return w.min_key;
     const uint32_t key = float_to_key(bound);
@@ -250,10 +261,11 @@ bm25_prepare_kernel(Bm25Dev ix, Bm25Work w) {
 // ---- scoring ------------------------------------------------------------------------------------------
 constexpr int kMetaSlots = 32;                   // slot records staged per warp at a time (16 B each)
 constexpr int kPrefetchSlots = 4;                // terms per query whose first 32 postings are prefetched
-constexpr int kEmitStage = 24;                   // candidates of one task staged in shared memory (deferred write-out)
+constexpr int kEmitStage = 16;                   // candidates of one task staged in shared memory (deferred write-out)
 
+constexpr int kBm25MaxQueriesPerItem = 8;        // per-query facts of an item staged per warp (16 B each)
 __host__ __device__ inline size_t bm25_score_warp_bytes(int rs) {
-    return size_t(kMetaSlots) * 16 + size_t(2 * kEmitStage) * 8 + 16 + size_t(rs) * 4;
+    return size_t(kMetaSlots) * 16 + size_t(2 * kEmitStage) * 8 + 16 + size_t(kBm25MaxQueriesPerItem) * 16 + size_t(rs) * 4;
 }
 
 // RS_T: sub-range size known at compile time (0 = take it from the workspace).
@@ -274,7 +286,8 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
     uint4* s_meta = reinterpret_cast<uint4*>(my);                                  // {begin, count, weight bits, -}
     uint64_t* s_emit = reinterpret_cast<uint64_t*>(my + kMetaSlots * 16);          // [2][kEmitStage] staged candidates
     int* s_cnt = reinterpret_cast<int*>(my + kMetaSlots * 16 + size_t(2 * kEmitStage) * 8);   // candidates staged by the current task
-    unsigned char* body = my + kMetaSlots * 16 + size_t(2 * kEmitStage) * 8 + 16;
+    uint4* s_qinfo = reinterpret_cast<uint4*>(my + kMetaSlots * 16 + size_t(2 * kEmitStage) * 8 + 16);   // Bm25Work::qinfo of the item's queries
+    unsigned char* body = my + kMetaSlots * 16 + size_t(2 * kEmitStage) * 8 + 16 + size_t(kBm25MaxQueriesPerItem) * 16;
     float* s_acc = reinterpret_cast<float*>(body);
 
     const int QC = w.queries_per_item;
@@ -423,7 +436,9 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
         const int nq = q1 - q0;
         const int qo_reg = (lane <= nq) ? w.q_off[q0 + lane] : 0;          // CSR offsets of the chunk (QC <= 31)
         const uint32_t tau_reg = (lane < nq && w.use_tau) ? ld_relaxed_u32(&w.ts.tau[q0 + lane]) : w.min_key;
-        const float wq_reg = (HITS && lane < nq) ? w.cls_wq[q0 + lane] : 0.f;
+        __syncwarp();
+        if (lane < nq) s_qinfo[lane] = w.qinfo[q0 + lane];
+        __syncwarp();
         const uint2* __restrict__ rec = w.rec + int64_t(j) * w.n_slots;
 
         int qa = 0;                                                         // queries are indexed relative to q0 below
@@ -480,21 +495,20 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
                 const bool fast = __float_as_int(tau_f) >= 0;   // tau is +0.0 or positive: the accumulators hold minus the
                                                                  // score, so "score >= tau" is one UNSIGNED compare that also
                                                                  // rejects 0 (untouched) and every negative score (sign bit clear)
-                if (HITS) { hit_tau = fast ? tau_u : 0xffffffffu; hc = 0; cwq = __shfl_sync(0xffffffffu, wq_reg, qr); }
-                uint32_t wneg = 0u;                             // sign bit set: a negative weight was applied (the last update
-                                                                // of a document need not be its largest then)
-                int touched = 0;                                // bit 0: postings were applied, bit 1: the query has looked-up slots
-                look_n = 0;
+                const uint4 qi = s_qinfo[qr];                  // per-query facts (one broadcast read)
+                look_n = int(qi.x & 0xffu); look_w = qi.y; look_row = qi.z;
+                if (HITS) { hit_tau = fast ? tau_u : 0xffffffffu; hc = 0; cwq = __uint_as_float(qi.w); }
+                const bool wneg = (qi.x & 0x100u) != 0u;        // a streamed slot has a negative weight (the last update of a
+                                                                // document need not be its largest then)
+                int touched = 0;                                // bit 0: postings were applied
 #pragma unroll
                 for (int t = 0; t < MP; ++t) {
                     if (o_cur + t < e_cur) {
                         const uint4 m = s_meta[o_cur + t];
                         const int n = int(m.y);
-                        if (m.w) { touched |= 2; ++look_n; look_w = m.z; look_row = m.w; }   // a looked-up negative slot
                         if (n > 0) {
                             const float wt = __uint_as_float(m.z);
                             touched |= 1;
-                            if (HITS) wneg |= m.z;
                             apply(pd_cur[t], pt_cur[t], wt);
                             if (n > 32) apply_rest(m.x, n, wt);
                             __syncwarp();                                   // next term may touch the same docs
@@ -505,11 +519,9 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
                 for (int sl = o_cur + MP; sl < e_cur; ++sl) {               // queries with more than MP terms
                     const uint4 m = s_meta[sl];
                     const int n = int(m.y);
-                    if (m.w) { touched |= 2; ++look_n; look_w = m.z; look_row = m.w; }
                     if (n == 0) continue;
                     const float wt = __uint_as_float(m.z);
                     touched |= 1;
-                    if (HITS) wneg |= m.z;
                     int dd = -1, tfi = 0;
                     if (lane < n) { const int2 p = ldg_stream_i2(g_post + m.x + lane); dd = p.x; tfi = p.y; }
                     apply(dd, tfi, wt);
@@ -518,10 +530,10 @@ bm25_score_kernel(Bm25Dev ix, Bm25Work w) {
                 }
                 // ---- read-out: scan the accumulators 128 per round, re-arm them, stage candidates >= tau ----
                 if (touched & 1) {
-                    neg_lo = o_cur; neg_hi = (touched & 2) ? e_cur : 0;
+                    neg_lo = o_cur; neg_hi = look_n ? e_cur : 0;
                     uint4* a4 = reinterpret_cast<uint4*>(s_acc) + lane;
                     const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
-                    if (HITS && fast && int(wneg) >= 0 && !__any_sync(0xffffffffu, hc > 1)) {
+                    if (HITS && fast && !wneg && !__any_sync(0xffffffffu, hc > 1)) {
                         // hit read-out: the remembered documents are the only ones that can reach the bound
                         if (__any_sync(0xffffffffu, hc == 1)) {
                             int d = -1 - lane;                               // idle lanes: distinct keys
