@@ -421,7 +421,7 @@ def dense_c3_supplement(dev, local_rank, peak, tf_peak, n_chunks=10_000_000, chu
         scan_ms /= max(n, 1)
         alg = 2.0 * 768 * n_chunks + 8.0 * (n_docs + 1) + 4.0 * 768 * B + 8.0 * top_k * B
         tfl = 2.0 * 768 * n_chunks * B / (scan_ms * 1e-3) / 1e12
-        results.append({"batch": B, "kernel": "dense_gemm_kernel (tcgen05)" if B >= 3 else "dense_scan_kernel (GEMV)",
+        results.append({"batch": B, "kernel": "dense_gemm_kernel (tcgen05)" if B >= 8 else "dense_scan_kernel (GEMV)",
                         "ms_per_batch": ms, "queries_per_s": B / (ms / 1e3), "scan_kernel_ms": scan_ms,
                         "hbm_GBps_algorithmic": alg / (scan_ms * 1e-3) / 1e9, "frac_of_hbm_peak": alg / (scan_ms * 1e-3) / 1e9 / peak,
                         "bf16_TFLOPs": tfl, "frac_of_bf16_peak": tfl / tf_peak})

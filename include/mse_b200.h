@@ -110,7 +110,7 @@ int mse_index_destroy(mse_index* idx);
  *                            with the most postings.  Takes effect on the loaded index (rewrites 4 bits per posting); results
  *                            never depend on it
  *   "dense_scan_ctas_per_sm" persistent CTAs per SM of the scan kernel
- *   "dense_gemm_min_batch"   smallest batch routed to the tcgen05 GEMM kernel (default 3)
+ *   "dense_gemm_min_batch"   smallest batch routed to the tcgen05 GEMM kernel (default 8; faster from 3 on, but queries are rounded to bf16 there)
  *   "timers"                 1 (default) = bracket the kernels with CUDA events (mse_kernel_time), 0 = off
  *   "reset_timers"           any value: zero the accumulated kernel timers
  * Environment: MSE_DEBUG_SYNC=1 synchronises after every BM25 kernel so that a device fault names its kernel. */

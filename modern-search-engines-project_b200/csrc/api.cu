@@ -1013,9 +1013,10 @@ int dense_scan_pass(mse_index* ix, Lease& L, const float* d_q, int g0, int gn, i
     cudaStream_t st = L.st;
     const DenseDev& dn = ix->dn;
     int r;
-    // batches of 1-2 queries: one GEMV pass; from 3 queries on the GEMV kernel would stream the matrix ceil(B/2) times (B=7: 9 ms
-    // against 2.4 ms for one GEMM pass at C3)
-    const int64_t gemm_min = ix->opt_gemm_min_batch > 0 ? ix->opt_gemm_min_batch : 3;
+    // The GEMM kernel rounds the queries to bf16, which by itself can use up the 2e-3 tolerance of the dense scores when a
+    // score is small against the sum of its terms' magnitudes; batches below 8 therefore stay on the fp32-query GEMV kernel
+    // (ceil(B/2) passes) unless the caller lowers `dense_gemm_min_batch` (one GEMM pass is faster from B = 3 on).
+    const int64_t gemm_min = ix->opt_gemm_min_batch > 0 ? ix->opt_gemm_min_batch : 8;
     const bool use_gemm = ix->gemm_ok && gn >= gemm_min;
     const int per_sm = ix->opt_scan_ctas > 0 ? int(ix->opt_scan_ctas) : 2;
     const int grid = int(std::min<int64_t>((dn.n_tiles + kScanThreads / 32 - 1) / (kScanThreads / 32) + 1, int64_t(per_sm) * ix->sm_count));

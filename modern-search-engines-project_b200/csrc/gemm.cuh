@@ -538,6 +538,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_consta
         uint16_t* st_q = s_stage_q[ew];
         uint32_t* tr = s_transpose[ew];
         int staged = 0;                                                   // uniform
+        int rr2 = int((blockIdx.x * kGemmEpiWarps + ew) % g.n_real);
         const int my_q = panel * kGemmPanel + quarter * 32 + lane;        // this thread's query (may be padding)
         const bool q_real = my_q < g.n_real;
         const bool warp_idle = panel * kGemmPanel + quarter * 32 >= g.n_real;   // no real query on these lanes
@@ -655,6 +656,9 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_consta
                 }
             }
             if (staged > kGemmStage / 2) flush();
+            // two panels (129..256 queries): the bound warp alone does not keep 256 bounds fresh enough; every epilogue warp adds
+            // one refresh per tile (A/B on one board: 4.65 -> 4.40 ms at B=256, but 2.96 -> 3.00 ms at B=128, so one panel skips it)
+            if (g.n_panels == 2 && w.use_tau) { tau_raise(w.ts, g.q0 + rr2); rr2 = (rr2 + 1 == g.n_real) ? 0 : rr2 + 1; }
         }
         flush();
         if (lane == 0) atomicAdd(&s_epi_done, 1);

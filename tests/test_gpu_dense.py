@@ -51,7 +51,7 @@ def test_dense_scan_vs_oracle(dense_small, B, top_k):
 
 @pytest.mark.parametrize("B,top_k", [(8, 100), (40, 1000), (256, 10), (33, 4096)])
 def test_dense_gemm_path_vs_oracle(dense_small, B, top_k):
-    """Batches >= 3 take the tcgen05 GEMM kernel (queries rounded to bf16 there): same documents and
+    """Batches >= 8 take the tcgen05 GEMM kernel (queries rounded to bf16 there): same documents and
     scores within the dense tolerance."""
     emb, off, ids, urls, oracle = dense_small
     nat = _native.NativeIndex(0)

@@ -17,15 +17,23 @@ ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--top-k", type=int, default=1000)
 ap.add_argument("--ctas-per-sm", type=int, default=0)
 ap.add_argument("--gemm-debug", type=int, default=0)
+ap.add_argument("--pair-mode", type=int, default=0, help="dense_gemm_pair_mode (1: multicast pair, 2: cta_group::2 pair)")
+ap.add_argument("--slab-rows", action="store_true", help="the slab-seeded row generator bench.py's C3 supplement uses")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 n_docs = a.chunks // a.chunks_per_doc
 t0 = time.time()
-d = synthetic.make_dense_corpus(n_docs, seed=1234, device=dev, dtype=torch.bfloat16, chunks_per_doc=a.chunks_per_doc)
 nat = _native.NativeIndex(0)
-nat.dense_load(d.emb, d.doc_chunk_off)
-del d.emb
+if a.slab_rows:
+    emb = synthetic.dense_rows(0, a.chunks, 1234, device=dev, dtype=torch.bfloat16)
+    nat.dense_load(emb, torch.arange(n_docs + 1, dtype=torch.int64, device=dev) * a.chunks_per_doc, borrow=True)
+else:
+    d = synthetic.make_dense_corpus(n_docs, seed=1234, device=dev, dtype=torch.bfloat16, chunks_per_doc=a.chunks_per_doc)
+    nat.dense_load(d.emb, d.doc_chunk_off)
+    del d.emb
 torch.cuda.empty_cache()
+if a.pair_mode:
+    nat.set_option("dense_gemm_pair_mode", a.pair_mode)
 if a.gemm_debug:
     nat.set_option("dense_gemm_debug", a.gemm_debug)
 if a.ctas_per_sm:
