@@ -722,7 +722,9 @@ def main():
     share = corpus.local_postings / max(1, corpus.n_postings)
     streamed = float(stats["postings"])                                  # this rank, last step
     looked = float(stats["postings_looked_up"])
-    m_local = TOP_K if world == 1 else (args.shard_list_len or min(TOP_K, 2 * TOP_K // world + 32))
+    # (the library's automatic shard list length: mean + 6 sigma + 16 of Binomial(top_k, 1/world), a multiple of 8)
+    m_auto = (int(TOP_K / world + 6.0 * (TOP_K / world * (1.0 - 1.0 / world)) ** 0.5 + 16.0) + 7) // 8 * 8
+    m_local = TOP_K if world == 1 else (args.shard_list_len or min(TOP_K, m_auto))
     score_ms = kt["bm25_score"][0] / max(1, kt["bm25_score"][1])
     rerank_ms = kt["rerank"][0] / max(1, kt["rerank"][1]) * (1 if world == 1 else 2)     # sharded: cos + fuse kernels per step
     alg_score = 12.0 * streamed + 8.0 * m_local * GB

@@ -267,7 +267,7 @@ int mse_comm_attach(mse_index* idx, void* nccl_comm /* ncclComm_t owned by the c
 int mse_comm_destroy(mse_index* idx);
 
 /* BM25 over the sharded corpus.  Every rank scores all n_queries against its shard and keeps shard_list_len
- * entries per query (0 = automatic: 2*top_k/world + 32; a shard owns ~top_k/world of a global top-k); block w of the
+ * entries per query (0 = automatic: mean + 6 sigma + 16 of Binomial(top_k, 1/world); a shard owns ~top_k/world of a global top-k); block w of the
  * lists travels to rank w (one grouped send/receive per peer), which merges the `world` lists of its queries to the
  * exact top_k.  status[2] reports a cut that could have hidden a result.  Outputs: [queries_per_rank * top_k]. */
 int mse_bm25_search_sharded(mse_index* idx, int32_t n_queries, int32_t n_slots, const int32_t* q_off,

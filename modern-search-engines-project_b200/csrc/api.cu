@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
 #include <mutex>
 #include <vector>
 
@@ -577,8 +578,10 @@ int mse_bm25_load(mse_index* ix, int64_t n_terms, int64_t n_docs, int64_t doc_ba
                   const int64_t* term_off, const int32_t* post_doc, const int32_t* post_tf,
                   const int32_t* doc_len, const float* idf, float avgdl, float k1, float b, int where) {
     if (!ix) { set_error("null index"); return MSE_ERR_INVALID; }
-    MSE_REQUIRE(n_terms >= 0 && n_docs >= 0 && n_docs < (int64_t(1) << 31) && doc_base >= 0 &&
-                doc_base + n_docs < (int64_t(1) << 31), "n_terms/n_docs/doc_base out of range");
+    // a posting's doc word holds 28 bits of (shard-local) document index below 4 class bits, and the all-ones word marks "no
+    // posting" in the score kernel: a shard holds at most 2^28 - 1 documents (far beyond what its postings fit in HBM)
+    MSE_REQUIRE(n_terms >= 0 && n_docs >= 0 && n_docs <= int64_t(kDocMask) && doc_base >= 0 &&
+                doc_base + n_docs < (int64_t(1) << 31), "n_terms/n_docs/doc_base out of range (docs per shard <= 2^28 - 1)");
     MSE_REQUIRE(term_off && doc_len && idf, "null array");
     MSE_REQUIRE(avgdl > 0.f, "avgdl must be positive (got %g)", double(avgdl));
     MSE_REQUIRE(where == MSE_HOST || where == MSE_DEVICE, "bad `where`");
@@ -1481,7 +1484,13 @@ int bm25_sharded_core(mse_index* ix, Lease& L, int32_t GB, int32_t S, const int3
     const Comm& c = ix->comm;
     const int W = c.world, Bq = GB / W;
     int rc;
-    int32_t m = shard_list_len > 0 ? std::min(shard_list_len, top_k) : std::min<int64_t>(top_k, 2 * int64_t(top_k) / W + 32);
+    // Automatic list length: a shard holds Binomial(top_k, 1/W) of a global top-k when results spread evenly over the doc
+    // ranges — mean + 6 sigma + 16, a multiple of 8.  (Round 1 kept 2 top_k / W + 32; the shorter list raises the shard's
+    // running bound, i.e. fewer candidates per task.)  A corpus whose hits cluster in one doc range trips the cut check
+    // (status[2]) and the caller repeats with shard_list_len = top_k.
+    const double mean = double(top_k) / W;
+    const int32_t m_auto = int32_t((int64_t(mean + 6.0 * std::sqrt(mean * (1.0 - 1.0 / W)) + 16.0) + 7) / 8 * 8);
+    int32_t m = shard_list_len > 0 ? std::min(shard_list_len, top_k) : std::min(top_k, m_auto);
     if (W == 1) m = top_k;
     if ((rc = ws->o_key.ensure(sizeof(uint64_t) * size_t(GB) * m))) return rc;
     if ((rc = bm25_enqueue(ix, L, GB, d_off, d_term, d_tf, S, m, min_score, bm25_default_cap(ix, GB, m), ix->opt_use_tau ? 1 : 0,
