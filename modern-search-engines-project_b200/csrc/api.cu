@@ -167,6 +167,7 @@ int bm25_enqueue(mse_index* ix, Lease& L, int32_t B, const int32_t* d_q_off, con
     if ((rc = ws->slot_row.ensure(sizeof(float) * size_t(B + 1)))) return rc;              // cls_wq [B]
     if ((rc = ws->qinfo.ensure(sizeof(uint4) * size_t(B + 1)))) return rc;
     if ((rc = ws->rec.ensure(sizeof(uint2) * (size_t(S) * n_sub + 1)))) return rc;
+    if ((rc = ws->rec_t.ensure(sizeof(uint2) * (size_t(S) * n_sub + 1)))) return rc;
     if ((rc = ws->tau.ensure(sizeof(uint32_t) * size_t(B)))) return rc;
     if ((rc = ws->hist.ensure(sizeof(uint32_t) * size_t(B) * kHistBins))) return rc;
     if ((rc = ws->maxbin.ensure(sizeof(uint32_t) * size_t(B)))) return rc;
@@ -180,7 +181,7 @@ int bm25_enqueue(mse_index* ix, Lease& L, int32_t B, const int32_t* d_q_off, con
 
     Bm25Work w{};
     w.q_off = d_q_off; w.q_term = d_q_term; w.q_tf = d_q_tf;
-    w.slot_w = ws->slot_w.as<float>(); w.cls_wq = ws->slot_row.as<float>(); w.qinfo = ws->qinfo.as<uint4>(); w.rec = ws->rec.as<uint2>();
+    w.slot_w = ws->slot_w.as<float>(); w.cls_wq = ws->slot_row.as<float>(); w.qinfo = ws->qinfo.as<uint4>(); w.rec = ws->rec.as<uint2>(); w.rec_t = ws->rec_t.as<uint2>();
     w.ts = TauState{ws->tau.as<uint32_t>(), ws->hist.as<uint32_t>(), ws->maxbin.as<uint32_t>(), top_k, kHistShift};
     w.cand = ws->cand.as<uint64_t>(); w.cand_count = ws->cand_count.as<int32_t>(); w.overflow = ws->cand_count.as<int32_t>() + B;
     w.item_counter = ws->misc.as<int32_t>();
@@ -197,6 +198,10 @@ int bm25_enqueue(mse_index* ix, Lease& L, int32_t B, const int32_t* d_q_off, con
         if (psm > 48 * 1024) MSE_CUDA_TRY(cudaFuncSetAttribute(bm25_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(psm)));
         bm25_prepare_kernel<<<unsigned(S + tau_ctas), kPrepThreads, psm, st>>>(bm, w);
         MSE_CUDA_TRY(cudaGetLastError());
+        if (S > 0 && n_sub > 0) {
+            bm25_rec_transpose_kernel<<<dim3(unsigned((n_sub + 31) / 32), unsigned((S + 31) / 32)), 256, 0, st>>>(w.rec_t, w.rec, S, n_sub);
+            MSE_CUDA_TRY(cudaGetLastError());
+        }
     }
     L.timer_end(tp);
     if ((rc = debug_sync(st, "bm25_prepare_kernel"))) return rc;

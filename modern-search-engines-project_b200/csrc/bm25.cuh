@@ -85,6 +85,8 @@ struct Bm25Work {                                // per-call workspace
                                  //      x = number of looked-up slots | 0x100 when a STREAMED slot has a negative weight,
                                  //      y = weight bits and z = 1 + dense row of the (last) looked-up slot, w = bits of cls_wq
     uint2* rec;                  // [n_sub * S] {first posting (absolute), count} of slot s in sub-range j
+    uint2* rec_t;                // [S * n_sub] the same slot-major: what the prepare kernel writes (one CTA per slot, coalesced);
+                                 //             bm25_rec_transpose_kernel turns it into `rec`
     TauState ts;                 // running per-query lower bound of the final k-th best score
     uint64_t* cand;              // [B * cap]
     int32_t* cand_count;         // [B]
@@ -191,7 +193,7 @@ bm25_prepare_kernel(Bm25Dev ix, Bm25Work w) {
     if (lookup) {                                              // no postings to stream: the record names the dense row instead
         const uint32_t row = uint32_t(ix.neg_row[t]);
         const uint32_t y = ((row + 1u) << kRecRowShift) | (int32_t(row) == ix.cls_row ? 0x80000000u : 0u);
-        for (int j = tid; j < w.n_sub; j += kPrepThreads) w.rec[int64_t(j) * w.n_slots + s] = make_uint2(0u, y);
+        for (int j = tid; j < w.n_sub; j += kPrepThreads) w.rec_t[int64_t(s) * w.n_sub + j] = make_uint2(0u, y);
         return;
     }
     const int2* __restrict__ pd = ix.post2;
@@ -203,7 +205,7 @@ bm25_prepare_kernel(Bm25Dev ix, Bm25Work w) {
         for (int j = tid; j < w.n_sub; j += kPrepThreads) {
             const int g0 = j * m, g1 = (j + 1) * m < ix.n_skip ? (j + 1) * m : ix.n_skip;
             const uint32_t o0 = row[g0], o1 = row[g1];
-            w.rec[int64_t(j) * w.n_slots + s] = make_uint2(a32f + o0, o1 - o0);
+            w.rec_t[int64_t(s) * w.n_sub + j] = make_uint2(a32f + o0, o1 - o0);
         }
         return;
     }
@@ -233,7 +235,7 @@ bm25_prepare_kernel(Bm25Dev ix, Bm25Work w) {
         uint32_t run = a32f + uint32_t(s_part[tid]);
         for (int j = j0; j < j1; ++j) {
             const int c = s_cnt[j];
-            w.rec[int64_t(j) * w.n_slots + s] = make_uint2(run, uint32_t(c));
+            w.rec_t[int64_t(s) * w.n_sub + j] = make_uint2(run, uint32_t(c));
             run += uint32_t(c);
         }
         return;
@@ -255,7 +257,24 @@ bm25_prepare_kernel(Bm25Dev ix, Bm25Work w) {
     __syncthreads();
     const uint32_t a32 = uint32_t(a);                          // n_postings < 2^32 (checked at load)
     for (int j = tid; j < w.n_sub; j += kPrepThreads)
-        w.rec[int64_t(j) * w.n_slots + s] = make_uint2(a32 + s_pos[j], s_pos[j + 1] - s_pos[j]);
+        w.rec_t[int64_t(s) * w.n_sub + j] = make_uint2(a32 + s_pos[j], s_pos[j + 1] - s_pos[j]);
+}
+
+// Slot-major task records -> sub-range-major (what a scoring warp reads: the consecutive slots of a query group in one
+// sub-range).  The prepare kernel used to write sub-range-major itself: isolated 8-byte stores 8 * n_slots bytes apart,
+// 2.5 GB of DRAM writes for 1.07 GB of records at C5 and a kernel that did nothing but wait for them (2.2 ms).
+__global__ void __launch_bounds__(256)
+bm25_rec_transpose_kernel(const uint2* __restrict__ in, uint2* __restrict__ out, int n_slots, int n_sub) {
+    __shared__ uint2 tile[32][33];
+    const int j0 = blockIdx.x * 32, s0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;               // 32 x 8 threads
+#pragma unroll
+    for (int r = ty; r < 32; r += 8)
+        if (s0 + r < n_slots && j0 + tx < n_sub) tile[r][tx] = in[int64_t(s0 + r) * n_sub + (j0 + tx)];
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8)
+        if (j0 + r < n_sub && s0 + tx < n_slots) out[int64_t(j0 + r) * n_slots + (s0 + tx)] = tile[tx][r];
 }
 
 // ---- scoring ------------------------------------------------------------------------------------------

@@ -63,7 +63,7 @@ struct TimerSlot {
 
 struct Workspace {
     // BM25
-    DevBuf q_off, q_term, q_tf, q_safe, slot_w, slot_row, qinfo, rec, tau, hist, maxbin, cand, cand_count, misc, status;
+    DevBuf q_off, q_term, q_tf, q_safe, slot_w, slot_row, qinfo, rec, rec_t, tau, hist, maxbin, cand, cand_count, misc, status;
     DevBuf o_doc, o_score, o_count, o_key;   // device staging of results (host callers, hybrid hand-over, shard lists)
     DevBuf fb_q[3], fb_out[3];               // re-run of overflowed queries
     // dense scan
