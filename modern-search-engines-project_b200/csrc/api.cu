@@ -50,7 +50,7 @@ struct mse_index {
 
     bool has_dense = false;
     DenseDev dn{};
-    DevBuf emb, doc_chunk_off, row_doc, tile_row, group_row, url_group;
+    DevBuf emb, doc_chunk_off, row_doc, row_sq, tile_row, group_row, url_group;
     int64_t n_url_groups = 0;
     bool gemm_ok = false;
     int64_t n_groups = 0;
@@ -966,6 +966,11 @@ int mse_dense_load(mse_index* ix, int64_t n_chunks, int64_t n_docs, int64_t doc_
         dense_row_doc_kernel<<<unsigned((n_docs + 255) / 256), 256, 0, st>>>(ix->doc_chunk_off.as<int64_t>(), ix->row_doc.as<int32_t>(), n_docs);
         MSE_CUDA_TRY(cudaGetLastError());
     }
+    if ((rc = ix->row_sq.ensure(sizeof(float) * std::max<int64_t>(n_chunks, 1)))) return rc;
+    if (n_chunks > 0) {                                   // squared row norms for the cosine kernels (one pass over the table)
+        dense_row_sq_kernel<<<unsigned(ix->sm_count * 8), 256, 0, st>>>(emb_dev, ix->row_sq.as<float>(), n_chunks);
+        MSE_CUDA_TRY(cudaGetLastError());
+    }
     // doc-aligned groups of <= 32 rows for the tensor-core scan (a longer document disables that path)
     {
         std::vector<int64_t> groups;
@@ -990,6 +995,7 @@ int mse_dense_load(mse_index* ix, int64_t n_chunks, int64_t n_docs, int64_t doc_
     ix->dn.emb = emb_dev;
     ix->dn.doc_chunk_off = ix->doc_chunk_off.as<int64_t>();
     ix->dn.row_doc = ix->row_doc.as<int32_t>();
+    ix->dn.row_sq = ix->row_sq.as<float>();
     ix->dn.tile_row = ix->tile_row.as<int64_t>();
     ix->dn.n_tiles = n_tiles;
     ix->dn.n_chunks = n_chunks; ix->dn.n_docs = n_docs; ix->dn.doc_base = uint32_t(doc_base); ix->dn.chunk_base = chunk_base;

@@ -33,6 +33,8 @@ struct DenseDev {
     const __nv_bfloat16* emb;
     const int64_t* doc_chunk_off;
     const int32_t* row_doc;
+    const float* row_sq;         // [n_chunks] sum of squares of every stored (bf16) row, formed at load by dense_row_sq_kernel in
+                                 // exactly the order the rerank kernels used to accumulate it per fetch (same bits)
     const int64_t* tile_row;
     int64_t n_chunks, n_docs, n_tiles;
     uint32_t doc_base;
@@ -180,6 +182,27 @@ dense_scan_kernel(DenseDev dx, DenseWork w, int q0) {
 #pragma unroll
             for (int b = 0; b < QB; ++b) tau_raise(w.ts, q0 + b);
         }
+    }
+}
+
+// Squared norm of every row (load time): lane l holds elements (l + 32 j) * 8 .. + 8 of the row, j = 0..2, accumulates them
+// in that order with FMAs and the warp adds the 32 partial sums by butterfly — the arithmetic the rerank kernels did per
+// fetched row (24 FMAs + 5 shuffles per lane and row: a third of their instructions), so the cosine keeps its bits.
+__global__ void __launch_bounds__(256)
+dense_row_sq_kernel(const __nv_bfloat16* __restrict__ emb, float* __restrict__ row_sq, int64_t n_chunks) {
+    const int64_t warps = int64_t(gridDim.x) * (blockDim.x >> 5);
+    for (int64_t r = int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n_chunks; r += warps) {
+        const uint4* p = reinterpret_cast<const uint4*>(emb + r * kDim) + lane_id();
+        float ee = 0.f;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            float f[8];
+            bf16x8_to_float(ldg_stream(p + j * 32), f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) ee = fmaf(f[e], f[e], ee);
+        }
+        ee = warp_sum(ee);
+        if (lane_id() == 0) row_sq[r] = ee;
     }
 }
 

@@ -232,26 +232,35 @@ rerank_kernel(DenseDev dx, RerankArgs a) {
         const int64_t row0 = s_rowstart[i];
         for (int b = 0; b < n; b += RIF) {
             uint4 v[RIF][3];
+            float ee[RIF];                                 // squared norm of the row, formed at load (DenseDev::row_sq)
 #pragma unroll
             for (int k = 0; k < RIF; ++k) {
-                const int kk = (b + k) < n ? (b + k) : (n - 1);
-                const uint4* p = reinterpret_cast<const uint4*>(dx.emb + (row0 + kk) * kDim) + lane_id();
+                // rows past the end of the document are NOT fetched (the streaming loads bypass L1: re-reading the last row, as
+                // this loop did before, cost L2 bandwidth for ~40 % more rows than the documents hold)
+                if ((b + k) < n) {                         // uniform
+                    const uint4* p = reinterpret_cast<const uint4*>(dx.emb + (row0 + b + k) * kDim) + lane_id();
 #pragma unroll
-                for (int j = 0; j < 3; ++j) v[k][j] = ldg_stream(p + j * 32);
+                    for (int j = 0; j < 3; ++j) v[k][j] = ldg_stream(p + j * 32);
+                    ee[k] = __ldg(dx.row_sq + row0 + b + k);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) v[k][j] = make_uint4(0u, 0u, 0u, 0u);
+                    ee[k] = 1.f;
+                }
             }
 #pragma unroll
             for (int k = 0; k < RIF; ++k) {
-                float dot = 0.f, ee = 0.f;
+                if ((b + k) >= n) break;                   // uniform
+                float dot = 0.f;
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
                     float f[8];
                     bf16x8_to_float(v[k][j], f);
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) { dot = fmaf(f[e], qf[j * 8 + e], dot); ee = fmaf(f[e], f[e], ee); }
+                    for (int e = 0; e < 8; ++e) dot = fmaf(f[e], qf[j * 8 + e], dot);
                 }
                 dot = warp_sum(dot);
-                ee = warp_sum(ee);
-                if (lane_id() == 0 && (b + k) < n) s_cos[r_begin + b + k] = dot / (sqrtf(ee) * qn);
+                if (lane_id() == 0 && (b + k) < n) s_cos[r_begin + b + k] = dot / (sqrtf(ee[k]) * qn);
             }
         }
     }

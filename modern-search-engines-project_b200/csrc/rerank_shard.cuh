@@ -91,16 +91,16 @@ rerank_shard_cos_kernel(DenseDev dx, RerankShardArgs a) {
         if (lane_id() == 0) { a.rows[slot] = n; a.chunk0[slot] = dx.chunk_base + ra; }
         for (int j = 0; j < n; ++j) {
             const uint4* p = reinterpret_cast<const uint4*>(dx.emb + (ra + j) * kDim) + lane_id();
-            float dot = 0.f, ee = 0.f;
+            float dot = 0.f;
+            const float ee = __ldg(dx.row_sq + ra + j);    // squared norm of the row, formed at load
 #pragma unroll
             for (int t = 0; t < 3; ++t) {
                 float f[8];
                 bf16x8_to_float(ldg_stream(p + t * 32), f);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) { dot = fmaf(f[e], qf[t * 8 + e], dot); ee = fmaf(f[e], f[e], ee); }
+                for (int e = 0; e < 8; ++e) dot = fmaf(f[e], qf[t * 8 + e], dot);
             }
             dot = warp_sum(dot);
-            ee = warp_sum(ee);
             if (lane_id() == 0) a.cos[slot * kRerankMaxChunks + j] = dot / (sqrtf(ee) * qn);
         }
     }
