@@ -10,6 +10,7 @@
 
 #include <cstdlib>
 #include "bm25.cuh"
+#include "bm25_u16.cuh"
 #include "build.cuh"
 #include "comm.cuh"
 #include "common.cuh"
@@ -62,10 +63,10 @@ struct mse_index {
 
     Comm comm;
 
-    int64_t opt_readout = 1, opt_tau_init = 1, opt_neg_lookup = 1;
+    int64_t opt_readout = 1, opt_tau_init = 1, opt_neg_lookup = 1, opt_accum = 0;
     int64_t opt_range_docs = 0, opt_qpi = 0, opt_cand_cap = 0, opt_use_tau = 1, opt_scan_ctas = 0, opt_gemm_min_batch = 0, opt_gemm_debug = 0, opt_gemm_pair_mode = 1;
     int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    int score_ctas_per_sm[2] = {0, 0};            // occupancy of the score kernel (scan / hit read-out) at the default range
+    int score_ctas_per_sm[3] = {0, 0, 0};         // occupancy of the score kernel (fp32 scan / fp32 hit read-out / two-phase) at its default range
 };
 
 namespace {
@@ -158,13 +159,21 @@ int bm25_enqueue(mse_index* ix, Lease& L, int32_t B, const int32_t* d_q_off, con
     Workspace* ws = L.ws;
     cudaStream_t st = L.st;
     const Bm25Dev& bm = ix->bm;
-    int RS = ix->opt_range_docs > 0 ? round_up(std::min<int64_t>(ix->opt_range_docs, 4096), 128) : kBm25DefaultRange;
-    if (bm.n_docs < RS) RS = std::max(128, round_up(bm.n_docs, 128));
+    // two-phase kernel with 16-bit upper-bound accumulators (bm25_u16.cuh): default whenever min_score >= 0 (the reference's
+    // 0.0), the hit read-out is on and no sub-range size was asked for; otherwise the fp32 kernel of bm25.cuh
+    // and the corpus is long enough for the bound to work: with fewer than ~1.5 * top_k sub-ranges per query a task holds
+    // several documents of the final list, most tasks end in exact mode and the fp32 kernel is the faster one (C2: 326
+    // sub-ranges of 3072 docs for k = 1000: 0.73 vs 0.53 ms; C5: 3256 sub-ranges: 15.6 vs 18.3 ms).  bm25_accum = 16 forces it.
+    const bool u16 = ix->opt_accum != 32 && ix->opt_readout != 0 && ix->opt_range_docs <= 0 &&
+                     float_to_key(min_score + 0.0f) >= float_to_key(0.0f) &&
+                     (ix->opt_accum == 16 || 2 * (bm.n_docs / kBm25Range16) >= 3 * int64_t(top_k));
+    int RS = u16 ? kBm25Range16 : ix->opt_range_docs > 0 ? round_up(std::min<int64_t>(ix->opt_range_docs, 4096), 128) : kBm25DefaultRange;
+    if (!u16 && bm.n_docs < RS) RS = std::max(128, round_up(bm.n_docs, 128));
     const int n_sub = int((bm.n_docs + RS - 1) / RS);
     const int qpi = int(std::min<int64_t>(kBm25MaxQueriesPerItem, ix->opt_qpi > 0 ? ix->opt_qpi : 8));
     int rc;
     if ((rc = ws->slot_w.ensure(sizeof(float) * size_t(S + 1)))) return rc;
-    if ((rc = ws->slot_row.ensure(sizeof(float) * size_t(B + 1)))) return rc;              // cls_wq [B]
+    if ((rc = ws->slot_row.ensure(sizeof(float) * 2 * size_t(B + 1)))) return rc;          // cls_wq [B], then inv_unit [B]
     if ((rc = ws->qinfo.ensure(sizeof(uint4) * size_t(B + 1)))) return rc;
     if ((rc = ws->rec.ensure(sizeof(uint2) * (size_t(S) * n_sub + 1)))) return rc;
     if ((rc = ws->rec_t.ensure(sizeof(uint2) * (size_t(S) * n_sub + 1)))) return rc;
@@ -181,7 +190,7 @@ int bm25_enqueue(mse_index* ix, Lease& L, int32_t B, const int32_t* d_q_off, con
 
     Bm25Work w{};
     w.q_off = d_q_off; w.q_term = d_q_term; w.q_tf = d_q_tf;
-    w.slot_w = ws->slot_w.as<float>(); w.cls_wq = ws->slot_row.as<float>(); w.qinfo = ws->qinfo.as<uint4>(); w.rec = ws->rec.as<uint2>(); w.rec_t = ws->rec_t.as<uint2>();
+    w.slot_w = ws->slot_w.as<float>(); w.cls_wq = ws->slot_row.as<float>(); w.inv_unit = ws->slot_row.as<float>() + (B + 1); w.qinfo = ws->qinfo.as<uint4>(); w.rec = ws->rec.as<uint2>(); w.rec_t = ws->rec_t.as<uint2>();
     w.ts = TauState{ws->tau.as<uint32_t>(), ws->hist.as<uint32_t>(), ws->maxbin.as<uint32_t>(), top_k, kHistShift};
     w.cand = ws->cand.as<uint64_t>(); w.cand_count = ws->cand_count.as<int32_t>(); w.overflow = ws->cand_count.as<int32_t>() + B;
     w.item_counter = ws->misc.as<int32_t>();
@@ -210,11 +219,11 @@ int bm25_enqueue(mse_index* ix, Lease& L, int32_t B, const int32_t* d_q_off, con
     const int64_t n_items = int64_t(n_sub) * chunks;
     int grid = 0;
     {
-        const size_t smem = size_t(kBm25Warps) * bm25_score_warp_bytes(RS);
+        const size_t smem = size_t(kBm25Warps) * bm25_score_warp_bytes(u16 ? RS / 2 : RS);
         const bool hits = ix->opt_readout != 0;        // candidates found while the postings are applied (default) or by a scan
-        const bool dflt = RS == kBm25DefaultRange;
-        const void* kfn = score_kernel_fn(dflt, hits);
-        int per_sm = dflt ? ix->score_ctas_per_sm[hits ? 1 : 0] : 0;
+        const bool dflt = !u16 && RS == kBm25DefaultRange;
+        const void* kfn = u16 ? (const void*)bm25_score16_kernel : score_kernel_fn(dflt, hits);
+        int per_sm = u16 ? ix->score_ctas_per_sm[2] : dflt ? ix->score_ctas_per_sm[hits ? 1 : 0] : 0;
         if (per_sm == 0) {
             MSE_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
             MSE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kBm25Threads, smem));
@@ -319,7 +328,7 @@ int bm25_search_exact(mse_index* ix, Lease& L, int32_t B, int32_t S, const std::
     if ((rc = bm25_enqueue(ix, L, B, d_off, d_term, d_tf, S, top_k, min_score, cap, use_tau, d_doc, d_score, d_count, nullptr, true))) return rc;
 
     // one 32-byte status read: {postings streamed, postings looked up, candidates handed to the selection, overflowed queries}
-    unsigned long long h_status[4] = {0, 0, 0, 0};
+    unsigned long long h_status[6] = {0, 0, 0, 0, 0, 0};     // + {tasks rescored in exact mode, replay passes} of the two-phase kernel
     MSE_CUDA_TRY(cudaMemcpyAsync(h_status, ws->misc.as<char>() + 16, sizeof(h_status), cudaMemcpyDeviceToHost, st));
     MSE_CUDA_TRY(cudaStreamSynchronize(st));
     std::vector<int32_t> redo;
@@ -335,6 +344,7 @@ int bm25_search_exact(mse_index* ix, Lease& L, int32_t B, int32_t S, const std::
         ix->stats[5] = int64_t(h_status[1]);
         ix->stats[1] = int64_t(h_status[2]);
         ix->stats[2] = int64_t(redo.size());
+        ix->stats[6] = int64_t(h_status[4]); ix->stats[7] = int64_t(h_status[5]);
         ix->last_bm25_ws = nullptr;                  // the snapshot above is the answer of mse_bm25_last_stats
     }
     if (redo.empty()) return MSE_OK;
@@ -491,6 +501,11 @@ int mse_index_create(int device, mse_index** out) {
         e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ix->score_ctas_per_sm[hits], kfn, kBm25Threads, smem);
     }
+    if (e == cudaSuccess) {
+        const size_t smem = size_t(kBm25Warps) * bm25_score_warp_bytes(kBm25Range16 / 2);
+        e = cudaFuncSetAttribute(bm25_score16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ix->score_ctas_per_sm[2], bm25_score16_kernel, kBm25Threads, smem);
+    }
     if (e != cudaSuccess) {
         set_error("kernel attribute setup failed: %s", cudaGetErrorString(e));
         (void)cudaGetLastError();
@@ -516,6 +531,7 @@ int mse_index_set_option(mse_index* ix, const char* name, int64_t value) {
     std::lock_guard<std::mutex> lk(ix->mu);
     if (!strcmp(name, "bm25_range_docs")) ix->opt_range_docs = value;
     else if (!strcmp(name, "bm25_readout")) ix->opt_readout = value;
+    else if (!strcmp(name, "bm25_accum")) ix->opt_accum = value;                  // 0 (default): two-phase kernel where it pays, 16: wherever it applies, 32: always the fp32 kernel
     else if (!strcmp(name, "bm25_neg_lookup")) ix->opt_neg_lookup = value;
     else if (!strcmp(name, "bm25_class_term")) {
         // the negative-idf term whose per-document impact class rides in every posting (Bm25Dev::cls_row): the term the caller
@@ -569,10 +585,11 @@ int mse_bm25_last_stats(mse_index* ix, int64_t stats[8]) {
     DeviceGuard g(ix->device);
     std::lock_guard<std::mutex> lk(ix->mu);
     if (ix->last_bm25_ws) {                       // the last call was enqueue-only: fetch its counters now
-        unsigned long long h[4] = {0, 0, 0, 0};
+        unsigned long long h[6] = {0, 0, 0, 0, 0, 0};
         MSE_CUDA_TRY(cudaDeviceSynchronize());
         MSE_CUDA_TRY(cudaMemcpy(h, ix->last_bm25_ws->misc.as<char>() + 16, sizeof(h), cudaMemcpyDeviceToHost));
         ix->stats[0] = int64_t(h[0]); ix->stats[5] = int64_t(h[1]); ix->stats[1] = int64_t(h[2]); ix->stats[2] = int64_t(h[3]);
+        ix->stats[6] = int64_t(h[4]); ix->stats[7] = int64_t(h[5]);
     }
     memcpy(stats, ix->stats, sizeof(ix->stats));
     return MSE_OK;

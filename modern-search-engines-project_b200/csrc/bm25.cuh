@@ -81,6 +81,8 @@ struct Bm25Work {                                // per-call workspace
     float* slot_w;               // [S]  idf * qtf * (k1+1)
     float* cls_wq;               // [B]  |weight| / 16 of the query's looked-up slot on the class row (0: none): class c of a posting
                                  //      then says the document loses at least cls_wq * c from that term
+    float* inv_unit;             // [B]  16-bit accumulator units per unit of score (bm25_u16.cuh): 60000 / sum of the query's positive
+                                 //      weights, 0 when it has none
     uint4* qinfo;                // [B]  per-query facts the score kernel needs in every task, formed once by the prepare kernel:
                                  //      x = number of looked-up slots | 0x100 when a STREAMED slot has a negative weight,
                                  //      y = weight bits and z = 1 + dense row of the (last) looked-up slot, w = bits of cls_wq
@@ -155,6 +157,7 @@ __device__ __forceinline__ uint32_t bm25_initial_bound(const Bm25Dev& ix, const 
     }
     w.ts.maxbin[q] = float_to_key(pos * 1.001f + 1e-30f) >> kHistShift;
     w.cls_wq[q] = wq;
+    w.inv_unit[q] = pos > 0.f ? 60000.0f / pos : 0.f;
     w.qinfo[q] = make_uint4(look_n | neg_streamed, look_w, look_row, __float_as_uint(wq));
     const float bound = best * (1.0f - 1e-5f) + neg - 4e-6f * mag;     // slack for the fp32 summation of the score kernel
     if (!w.use_tau || !(bound > 0.f)) return w.min_key;

@@ -21,8 +21,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 KEYS = {"range": "bm25_range_docs", "readout": "bm25_readout", "qpi": "bm25_queries_per_item", "tau": "bm25_use_tau",
-        "candcap": "bm25_cand_cap", "init": "bm25_tau_init"}
-DEFAULTS = {"range": 0, "readout": 1, "qpi": 0, "tau": 1, "candcap": 0, "init": 1}
+        "candcap": "bm25_cand_cap", "init": "bm25_tau_init", "accum": "bm25_accum"}
+DEFAULTS = {"range": 0, "readout": 1, "qpi": 0, "tau": 1, "candcap": 0, "init": 1, "accum": 0}
 
 
 def main():
@@ -33,20 +33,23 @@ def main():
     ap.add_argument("--docs", type=int, default=1_000_000)
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--top-k", type=int, default=1000)
+    ap.add_argument("--always", type=float, default=0.0, help="fraction of docs holding the always-term appended to every query (C5: 0.95)")
     a = ap.parse_args()
 
     import torch
     import mse_b200  # noqa: F401
     from mse_b200 import _native, synthetic
     dev = torch.device("cuda", 0)
-    c = synthetic.make_bm25_corpus(a.docs, vocab=200_000, seed=1234, device=dev)
+    c = synthetic.make_bm25_corpus(a.docs, vocab=200_000, seed=1234, device=dev, always_frac=a.always)
     nat = _native.NativeIndex(0)
     nat.bm25_load(c.term_off, c.post_doc, c.post_tf, c.doc_len, c.idf, c.avgdl)
+    if a.always > 0:
+        nat.set_option("bm25_class_term", c.always_term)      # as bench.py / the pipeline do for the appended term
     df = torch.diff(c.term_off).cpu().numpy()
     n = a.steps + a.warmup
     batches, posts = [], []
     for i in range(n):
-        q_off, q_term, q_tf = synthetic.make_bm25_queries(c, a.batch, seed=1235 + i)
+        q_off, q_term, q_tf = synthetic.make_bm25_queries(c, a.batch, seed=1235 + i, add_always=a.always > 0)
         batches.append(tuple(torch.from_numpy(x).to(dev) for x in (q_off, q_term, q_tf)))
         posts.append(int(df[q_term].sum()))
     alg = 12.0 * float(np.mean(posts[a.warmup:])) + 8.0 * a.top_k * a.batch
@@ -80,7 +83,7 @@ def main():
             rec.update(step_ms=e0.elapsed_time(e1) / a.steps, score_ms=sc / max(1, scn), prepare_ms=pr / max(1, scn),
                        select_ms=se / max(1, scn), score_GBps=alg / (sc / max(1, scn) * 1e-3) / 1e9,
                        emitted_per_query=st.get("emitted", 0) / a.batch, reruns=st.get("rerun_queries", 0),
-                       ctas=st.get("ctas"))
+                       ctas=st.get("ctas"), exact_tasks=st.get("exact_mode_tasks"), replays=st.get("replay_passes"))
             # comparison on the LAST timed batch
             ids, scores, cnt = (t.clone().cpu().numpy() for t in out)
             if base is None:
