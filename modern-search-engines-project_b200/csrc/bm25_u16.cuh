@@ -114,22 +114,25 @@ bm25_score16_kernel(Bm25Dev ix, Bm25Work w) {
         const uint2* __restrict__ rec = w.rec + int64_t(sub) * w.n_slots + s0;
         float ex = 0.f;
 #pragma unroll 1
-        for (int k = 0; k < maxs; ++k) {                               // the query's terms in order; streamed slots only
-            uint32_t begin = 0u;
-            int hi = 0;
-            float wt = 0.f;
-            if (on && k < ns) { const uint2 r = rec[k]; begin = r.x; hi = int(r.y & 0xffffu); wt = w.slot_w[s0 + k]; }
-            int lw = 0, ci = 0;
-            uint32_t cd = kNoDoc;
-            while (__any_sync(0xffffffffu, lw < hi)) {                 // lower bound of the document in the slice
-                if (lw < hi) {
-                    const int mid = (lw + hi) >> 1;
-                    const int2 p = __ldg(g_post + begin + mid);
-                    const uint32_t dm = uint32_t(p.x) & kDocMask;
-                    if (dm < ldoc) lw = mid + 1; else { hi = mid; cd = dm; ci = p.y; }
-                }
+        for (int k = 0; k < maxs; k += 2) {                            // the query's terms in order, two searches in flight
+            uint32_t bA = 0u, bB = 0u;
+            int hA = 0, hB = 0;
+            float wA = 0.f, wB = 0.f;
+            if (on && k < ns) { const uint2 r = rec[k]; bA = r.x; hA = int(r.y & 0xffffu); wA = w.slot_w[s0 + k]; }
+            if (on && k + 1 < ns) { const uint2 r = rec[k + 1]; bB = r.x; hB = int(r.y & 0xffffu); wB = w.slot_w[s0 + k + 1]; }
+            int lA = 0, lB = 0, iA = 0, iB = 0;
+            uint32_t cA = kNoDoc, cB = kNoDoc;
+            while (__any_sync(0xffffffffu, (lA < hA) | (lB < hB))) {   // lower bound of the document in each slice
+                const bool a = lA < hA, b = lB < hB;
+                const int mA = (lA + hA) >> 1, mB = (lB + hB) >> 1;
+                int2 pA = make_int2(0, 0), pB = make_int2(0, 0);
+                if (a) pA = __ldg(g_post + bA + mA);
+                if (b) pB = __ldg(g_post + bB + mB);
+                if (a) { const uint32_t dm = uint32_t(pA.x) & kDocMask; if (dm < ldoc) lA = mA + 1; else { hA = mA; cA = dm; iA = pA.y; } }
+                if (b) { const uint32_t dm = uint32_t(pB.x) & kDocMask; if (dm < ldoc) lB = mB + 1; else { hB = mB; cB = dm; iB = pB.y; } }
             }
-            if (cd == ldoc) ex = __fmaf_rd(-wt, __int_as_float(ci), ex);
+            if (cA == ldoc) ex = __fmaf_rd(-wA, __int_as_float(iA), ex);
+            if (cB == ldoc) ex = __fmaf_rd(-wB, __int_as_float(iB), ex);
         }
         // looked-up negative terms: after the streamed ones, in slot order (as bm25_score_kernel)
         const int look = int(qi.x & 0xffu);
@@ -269,37 +272,29 @@ bm25_score16_kernel(Bm25Dev ix, Bm25Work w) {
             }
             __syncwarp();
 
-            int pd_cur[MP], pt_cur[MP], pd_nxt[MP], pt_nxt[MP];
+            // first round (<= 32 postings) of the first MP terms of a query: loaded one query ahead, into the registers the
+            // current query has just consumed; a longer slice is announced to L2 at the same time (one 128-byte line per lane)
+            int pd[MP], pt[MP];
             int o_nxt = 0;                                                  // first staged slot of the next query
             int e_nxt = __shfl_sync(0xffffffffu, qo_reg, qa + 1) - sa;
-#pragma unroll
-            for (int t = 0; t < MP; ++t) {                                  // prefetch of the first query of the group
-                pd_nxt[t] = -1; pt_nxt[t] = 0;
+            auto fetch_first = [&](int t) {                                // term t of the query whose staged slots are [o_nxt, e_nxt)
+                pd[t] = -1; pt[t] = 0;
                 if (o_nxt + t < e_nxt) {
                     const uint4 m = s_meta[o_nxt + t];
-                    if (lane < int(m.y)) { const int2 p = ldg_stream_i2(g_post + m.x + lane); pd_nxt[t] = p.x; pt_nxt[t] = p.y; }
+                    if (lane < int(m.y)) { const int2 p = ldg_stream_i2(g_post + m.x + lane); pd[t] = p.x; pt[t] = p.y; }
+                    if (int(m.y) > 32 + 16 * lane) asm volatile("prefetch.global.L2 [%0];" :: "l"(g_post + m.x + 32 + 16 * lane));
                 }
-            }
+            };
+#pragma unroll
+            for (int t = 0; t < MP; ++t) fetch_first(t);                    // the first query of the group
 #pragma unroll 1
             for (int qr = qa; qr < qb; ++qr) {
                 const int o_cur = o_nxt, e_cur = e_nxt;
-#pragma unroll
-                for (int t = 0; t < MP; ++t) { pd_cur[t] = pd_nxt[t]; pt_cur[t] = pt_nxt[t]; }
                 const int q = q0 + qr;
                 const uint32_t tau_key = __shfl_sync(0xffffffffu, tau_reg, qr);
                 const float invU = __shfl_sync(0xffffffffu, inv_reg, qr);
                 o_nxt = e_cur;
-                if (qr + 1 < qb) {                                          // prefetch the next query of the group
-                    e_nxt = __shfl_sync(0xffffffffu, qo_reg, qr + 2) - sa;
-#pragma unroll
-                    for (int t = 0; t < MP; ++t) {
-                        if (o_nxt + t < e_nxt) {
-                            const uint4 m = s_meta[o_nxt + t];
-                            pd_nxt[t] = -1;
-                            if (lane < int(m.y)) { const int2 p = ldg_stream_i2(g_post + m.x + lane); pd_nxt[t] = p.x; pt_nxt[t] = p.y; }
-                        }
-                    }
-                }
+                e_nxt = (qr + 1 < qb) ? __shfl_sync(0xffffffffu, qo_reg, qr + 2) - sa : e_cur;      // last query of the group: nothing to fetch
                 // ---- phase 1 -----------------------------------------------------------------------------------
                 const float tau_f = key_to_float(tau_key);                      // >= +0.0: the host sends min_score >= 0 here
                 const uint32_t tau_u = __float_as_uint(tau_f) | 0x80000000u;    // bits of -tau
@@ -309,27 +304,32 @@ bm25_score16_kernel(Bm25Dev ix, Bm25Work w) {
                 npen = -__float2int_rd(__fmul_rd(__uint_as_float(qi.w), invU));
                 hc = 0;
                 int touched = 0;
+                // no bound yet (the first tasks of a query): every touched document would be a hit, phase 1 is skipped
+                const bool direct = tau_key == float_to_key(0.0f);
 #pragma unroll
                 for (int t = 0; t < MP; ++t) {
                     if (o_cur + t < e_cur) {
                         const uint4 m = s_meta[o_cur + t];
                         const int n = int(m.y);
-                        if (n > 0) {
+                        if (n > 0 && direct) touched = 1;
+                        else if (n > 0) {
                             const float ws = __fmul_ru(fmaxf(__uint_as_float(m.z), 0.f), invU);
                             touched = 1;
-                            apply(pd_cur[t], pt_cur[t], ws);
+                            apply(pd[t], pt[t], ws);
                             if (n > 32) apply_rest(m.x, n, ws);
                             __syncwarp();                                   // next term may touch the same docs
                         }
                     }
+                    fetch_first(t);                                         // the same term of the next query
                 }
 #pragma unroll 1
                 for (int sl = o_cur + MP; sl < e_cur; ++sl) {               // queries with more than MP terms
                     const uint4 m = s_meta[sl];
                     const int n = int(m.y);
                     if (n == 0) continue;
-                    const float ws = __fmul_ru(fmaxf(__uint_as_float(m.z), 0.f), invU);
                     touched = 1;
+                    if (direct) continue;
+                    const float ws = __fmul_ru(fmaxf(__uint_as_float(m.z), 0.f), invU);
                     int dd = -1, tfi = 0;
                     if (lane < n) { const int2 p = ldg_stream_i2(g_post + m.x + lane); dd = p.x; tfi = p.y; }
                     apply(dd, tfi, ws);
@@ -339,9 +339,9 @@ bm25_score16_kernel(Bm25Dev ix, Bm25Work w) {
                 if (!touched) continue;
                 // ---- hit documents -----------------------------------------------------------------------------
                 const unsigned ev1 = __ballot_sync(0xffffffffu, hc > 0);
-                if (ev1) {
+                if (ev1 | unsigned(direct)) {
                     const int n_events = __popc(ev1) + __popc(__ballot_sync(0xffffffffu, hc > 1));
-                    if (n_events <= kExactModeEvents && !__any_sync(0xffffffffu, hc > 2)) {
+                    if (!direct && n_events <= kExactModeEvents && !__any_sync(0xffffffffu, hc > 2)) {
                         // the remembered events name every document that can reach the bound: queue them.  A document's
                         // accumulator is cleared when it is taken, so that a second event of the same document finds it done
                         if (qcount + n_events > kQueueMax) flush();
