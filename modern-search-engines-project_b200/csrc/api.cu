@@ -170,7 +170,8 @@ int bm25_enqueue(mse_index* ix, Lease& L, int32_t B, const int32_t* d_q_off, con
     int RS = u16 ? kBm25Range16 : ix->opt_range_docs > 0 ? round_up(std::min<int64_t>(ix->opt_range_docs, 4096), 128) : kBm25DefaultRange;
     if (!u16 && bm.n_docs < RS) RS = std::max(128, round_up(bm.n_docs, 128));
     const int n_sub = int((bm.n_docs + RS - 1) / RS);
-    const int qpi = int(std::min<int64_t>(kBm25MaxQueriesPerItem, ix->opt_qpi > 0 ? ix->opt_qpi : 8));
+    // queries per work item: 8; 6 for the two-phase kernel (6 queries x 5 terms fit the 32 staged slot records: one group per item)
+    const int qpi = int(std::min<int64_t>(kBm25MaxQueriesPerItem, ix->opt_qpi > 0 ? ix->opt_qpi : (u16 ? 6 : 8)));
     int rc;
     if ((rc = ws->slot_w.ensure(sizeof(float) * size_t(S + 1)))) return rc;
     if ((rc = ws->slot_row.ensure(sizeof(float) * 2 * size_t(B + 1)))) return rc;          // cls_wq [B], then inv_unit [B]

@@ -27,12 +27,17 @@
 
 namespace mse {
 
-constexpr int kBm25Range16 = 3072;               // docs per sub-range: 6 KB of 16-bit accumulators per warp
+#ifndef MSE_BM25_RANGE16
+#define MSE_BM25_RANGE16 3072
+#endif
+constexpr int kBm25Range16 = MSE_BM25_RANGE16;   // docs per sub-range: 6 KB of 16-bit accumulators per warp
+constexpr int kBm25Ctas16 = kBm25Range16 <= 3072 ? 4 : 3;
+constexpr int kQueueDocBits = 13;                // doc within the sub-range
 constexpr int kQueueMax = 32;                    // hit documents a warp collects before it forms their exact scores
 constexpr int kExactModeEvents = 12;             // more hit events than this in one task: exact mode
 static_assert(kQueueMax * 8 == 2 * kEmitStage * 8, "the queue takes the place of the fp32 kernel's emission stage");
 
-__global__ void __launch_bounds__(kBm25Threads, 4)
+__global__ void __launch_bounds__(kBm25Threads, kBm25Ctas16)
 bm25_score16_kernel(Bm25Dev ix, Bm25Work w) {
     extern __shared__ __align__(16) unsigned char bm25_smem[];
     constexpr int RS = kBm25Range16;
@@ -41,7 +46,7 @@ bm25_score16_kernel(Bm25Dev ix, Bm25Work w) {
     asm volatile("shr.u32 %0, %1, 5;" : "=r"(wid) : "r"(threadIdx.x));
     unsigned char* my = bm25_smem + bm25_score_warp_bytes(RS / 2) * wid;
     uint4* s_meta = reinterpret_cast<uint4*>(my);                                  // {begin, count, weight bits, 1 + dense row}
-    uint64_t* s_queue = reinterpret_cast<uint64_t*>(my + kMetaSlots * 16);         // [kQueueMax] query << 32 | sub-range << 12 | doc in it
+    uint64_t* s_queue = reinterpret_cast<uint64_t*>(my + kMetaSlots * 16);         // [kQueueMax] query << 32 | sub-range << 13 | doc in it
     uint4* s_qinfo = reinterpret_cast<uint4*>(my + kMetaSlots * 16 + size_t(kQueueMax) * 8 + 16);
     uint16_t* s_acc = reinterpret_cast<uint16_t*>(my + kMetaSlots * 16 + size_t(kQueueMax) * 8 + 16 + size_t(kBm25MaxQueriesPerItem) * 16);
 
@@ -105,8 +110,8 @@ bm25_score16_kernel(Bm25Dev ix, Bm25Work w) {
         const bool on = lane < qcount;
         const uint64_t e = on ? s_queue[lane] : 0ull;
         const int q = int(e >> 32);
-        const uint32_t sub = uint32_t(e) >> 12;
-        const uint32_t ldoc = sub * uint32_t(RS) + (uint32_t(e) & 0xfffu);
+        const uint32_t sub = uint32_t(e) >> kQueueDocBits;
+        const uint32_t ldoc = sub * uint32_t(RS) + (uint32_t(e) & ((1u << kQueueDocBits) - 1u));
         int s0 = 0, ns = 0;
         uint4 qi = make_uint4(0u, 0u, 0u, 0u);
         if (on) { s0 = w.q_off[q]; ns = w.q_off[q + 1] - s0; qi = w.qinfo[q]; }
@@ -282,7 +287,9 @@ bm25_score16_kernel(Bm25Dev ix, Bm25Work w) {
                 if (o_nxt + t < e_nxt) {
                     const uint4 m = s_meta[o_nxt + t];
                     if (lane < int(m.y)) { const int2 p = ldg_stream_i2(g_post + m.x + lane); pd[t] = p.x; pt[t] = p.y; }
+#ifndef MSE_BM25_NO_L2_PREFETCH
                     if (int(m.y) > 32 + 16 * lane) asm volatile("prefetch.global.L2 [%0];" :: "l"(g_post + m.x + 32 + 16 * lane));
+#endif
                 }
             };
 #pragma unroll
@@ -357,7 +364,7 @@ bm25_score16_kernel(Bm25Dev ix, Bm25Work w) {
                             __syncwarp();
                             if (act) s_acc[d] = 0;
                             const unsigned tm = __ballot_sync(0xffffffffu, act);
-                            if (act) s_queue[qcount + __popc(tm & lt_mask)] = (uint64_t(uint32_t(q)) << 32) | uint64_t((uint32_t(j) << 12) | uint32_t(d));
+                            if (act) s_queue[qcount + __popc(tm & lt_mask)] = (uint64_t(uint32_t(q)) << 32) | uint64_t((uint32_t(j) << kQueueDocBits) | uint32_t(d));
                             qcount += __popc(tm);
                             __syncwarp();
                         }

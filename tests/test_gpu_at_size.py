@@ -67,6 +67,12 @@ def test_c5_hybrid_10m_docs_sampled_parity_and_properties():
     b_doc, b_score, b_count = nat.bm25_search(q_off, q_term, q_tf, 1000, 0.0)
     st = nat.bm25_stats()
     assert st["rerun_queries"] == 0 and st["postings_looked_up"] > st["postings"]
+    assert st["ranges"] == -(-bench.N_DOCS // 3072)                      # a corpus of this length gets the two-phase kernel (bm25_u16.cuh)
+    nat.set_option("bm25_accum", 32)                                     # ... whose lists equal the fp32 kernel's, bit for bit
+    f_doc, f_score, f_count = nat.bm25_search(q_off, q_term, q_tf, 1000, 0.0)
+    assert nat.bm25_stats()["ranges"] == -(-bench.N_DOCS // 1536)
+    assert np.array_equal(f_doc, b_doc) and np.array_equal(f_score, b_score) and np.array_equal(f_count, b_count)
+    nat.set_option("bm25_accum", 0)
     bres = sampled.check_bm25(par_ix, par_queries, b_doc[:n_par], b_score[:n_par], b_count[:n_par], 1000)
     assert bres["queries_failing"] == 0, bres
     assert (o_count == 100).all() and (b_count == 1000).all()

@@ -64,11 +64,13 @@ def test_appendix_e_through_sql_store_and_facade():
     bm.close()
 
 
-@pytest.mark.parametrize("range_docs,qpi,use_tau", [(0, 0, 1), (256, 1, 1), (256, 3, 0)])
-def test_golden_small_corpus(range_docs, qpi, use_tau):
-    """tests/golden/bm25_small: results of the unmodified reference search()."""
+@pytest.mark.parametrize("range_docs,qpi,use_tau,accum", [(0, 0, 1, 0), (256, 1, 1, 0), (256, 3, 0, 0), (0, 0, 1, 16), (0, 2, 0, 16)])
+def test_golden_small_corpus(range_docs, qpi, use_tau, accum):
+    """tests/golden/bm25_small: results of the unmodified reference search().  accum = 16 forces the two-phase kernel
+    (bm25_u16.cuh) wherever it applies (min_score >= 0), which a corpus this small would not get by default."""
     ix, j, _ = helpers.load_bm25_small()
     bm = _facade(ix)
+    bm.native.set_option("bm25_accum", accum)
     bm.native.set_option("bm25_range_docs", range_docs)
     bm.native.set_option("bm25_queries_per_item", qpi)
     bm.native.set_option("bm25_use_tau", use_tau)
@@ -95,6 +97,9 @@ def corpus20k():
     dict(bm25_range_docs=2048, bm25_queries_per_item=5, bm25_use_tau=0),
     dict(bm25_cand_cap=64),                                   # forces the overflow re-run path
     dict(bm25_range_docs=24576),                              # one range holds the whole corpus
+    dict(bm25_accum=16),                                      # two-phase kernel (16-bit bounds, exact rescoring); fp32 kernel at min_score < 0
+    dict(bm25_accum=16, bm25_queries_per_item=1, bm25_use_tau=0),   # no running bound: every task ends in its exact mode
+    dict(bm25_accum=16, bm25_cand_cap=64),                    # two-phase kernel + the overflow re-run path
 ])
 @pytest.mark.parametrize("top_k,min_score", [(10, 0.0), (1000, 0.0), (100, -50.0)])
 def test_synthetic_batch_vs_oracle(corpus20k, opts, top_k, min_score):
@@ -121,6 +126,8 @@ def test_synthetic_batch_vs_oracle(corpus20k, opts, top_k, min_score):
     dict(bm25_readout=0, bm25_range_docs=512, bm25_queries_per_item=3),
     dict(bm25_range_docs=1536),                               # sub-ranges that are not a power of two
     dict(bm25_range_docs=2048),                               # skip table with two entries per sub-range
+    dict(bm25_accum=16),                                      # two-phase kernel: the same fp32 scores bit for bit
+    dict(bm25_accum=16, bm25_tau_init=0, bm25_queries_per_item=3),
 ])
 def test_kernel_variants_agree(corpus20k, opts):
     """Every variant returns what the default configuration returns (same summation order)."""
@@ -133,6 +140,9 @@ def test_kernel_variants_agree(corpus20k, opts):
         bm.native.set_option(k, v)
     got = bm.search_batch_terms(q_off, q_term, q_tf, 200, 0.0)
     assert np.array_equal(ref[2], got[2])
+    if opts.get("bm25_accum") == 16:                          # same terms, same order, same round-down FMAs
+        assert np.array_equal(got[1], ref[1]) and np.array_equal(got[0], ref[0])
+        assert bm.native.bm25_stats()["exact_mode_tasks"] > 0
     np.testing.assert_allclose(got[1], ref[1], rtol=2e-6, atol=4e-6)
     assert np.mean(ref[0] == got[0]) > 0.995
     _check_batch(ix, q_off, q_term, q_tf, got[0], got[1], got[2], 200, 0.0)
