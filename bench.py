@@ -20,7 +20,7 @@ the compute stream inside the library.
 Prints ONE JSON line (rank 0).  `value` = hybrid queries/s with the inputs resident in HBM (CUDA events, max over
 ranks); `e2e` = the same through the C ABI with PINNED HOST buffers (H2D of query CSR + query vectors and D2H of the
 top-100 inside the timed region, two streams alternating); `roofline` describes the dominant kernel
-(bm25_score_kernel) — algorithmic bytes 12 B per STREAMED posting + 8*k per query over the kernel's mean duration —
+(bm25_score16_kernel, the two-phase BM25 score kernel) — algorithmic bytes 12 B per STREAMED posting + 8*k per query over the kernel's mean duration —
 and `rooflines` lists every hot kernel; `cpu_baseline` = the oracle port of the reference's per-query path
 (bm25_indexer.py:435-485 -> reranker_api.py:336-372) timed on this box's host cores on a bounded sample; `parity` =
 GPU vs oracle on sampled queries AT THIS SIZE.  Supplements (N=1): C2 BM25-only (with and without the always-term) and
@@ -740,16 +740,20 @@ def main():
     alg_score_def = 12.0 * timed_all * share + 8.0 * m_local * GB
     rows_local = rows_per_query * (B if world == 1 else GB / world)
     alg_rerank = 2.0 * 768 * rows_local + 12.0 * TOP_K * (B if world == 1 else GB / world) + 8.0 * MAX_OUT * B
-    tr_score, tr_src = committed_traffic("bm25_score_kernel")
+    # which score kernel ran: the two-phase one (bm25_u16.cuh) cuts the corpus into 3072-doc sub-ranges, the fp32 one into 1536
+    two_phase = int(stats["ranges"]) == -(-(corpus.hi - corpus.lo) // 3072)
+    score_kernel = "bm25_score16_kernel" if two_phase else "bm25_score_kernel"
+    tr_score, tr_src = committed_traffic(score_kernel)
     tr_rr, tr_rr_src = committed_traffic("rerank_kernel")
-    roof_score = {"bound": "hbm", "kernel": "bm25_score_kernel", "achieved": alg_score / (score_ms * 1e-3) / 1e9 if score_ms else 0.0,
+    roof_score = {"bound": "hbm", "kernel": score_kernel, "achieved": alg_score / (score_ms * 1e-3) / 1e9 if score_ms else 0.0,
                   "peak": peak, "unit": "GB/s", "frac": (alg_score / (score_ms * 1e-3) / 1e9 / peak) if score_ms else 0.0,
                   "traffic": tr_score, "traffic_source": tr_src, "peak_source": peak_src,
                   "algorithmic_bytes_per_launch": alg_score, "kernel_ms": score_ms,
                   "basis": "12 B per posting STREAMED by the kernel + 8 B per emitted result (postings of the negative-idf always-term "
                            "are not streamed: their contribution is read from a dense impact row per candidate)",
                   "achieved_on_all_query_postings": alg_score_def / (score_ms * 1e-3) / 1e9 if score_ms else 0.0,
-                  "postings_streamed_per_query": streamed / GB, "postings_not_streamed_per_query": looked / GB}
+                  "postings_streamed_per_query": streamed / GB, "postings_not_streamed_per_query": looked / GB,
+                  "tasks_rescored_in_exact_mode": int(stats.get("exact_mode_tasks", 0))}
     roof_rerank = {"bound": "hbm", "kernel": "rerank_kernel" if world == 1 else "hyb_cos_kernel + hyb_fuse_kernel",
                    "achieved": alg_rerank / (rerank_ms * 1e-3) / 1e9 if rerank_ms else 0.0, "peak": peak, "unit": "GB/s",
                    "frac": (alg_rerank / (rerank_ms * 1e-3) / 1e9 / peak) if rerank_ms else 0.0, "traffic": tr_rr, "traffic_source": tr_rr_src,

@@ -159,14 +159,15 @@ int bm25_enqueue(mse_index* ix, Lease& L, int32_t B, const int32_t* d_q_off, con
     Workspace* ws = L.ws;
     cudaStream_t st = L.st;
     const Bm25Dev& bm = ix->bm;
-    // two-phase kernel with 16-bit upper-bound accumulators (bm25_u16.cuh): default whenever min_score >= 0 (the reference's
-    // 0.0), the hit read-out is on and no sub-range size was asked for; otherwise the fp32 kernel of bm25.cuh
-    // and the corpus is long enough for the bound to work: with fewer than ~1.5 * top_k sub-ranges per query a task holds
-    // several documents of the final list, most tasks end in exact mode and the fp32 kernel is the faster one (C2: 326
-    // sub-ranges of 3072 docs for k = 1000: 0.73 vs 0.53 ms; C5: 3256 sub-ranges: 15.6 vs 18.3 ms).  bm25_accum = 16 forces it.
+    // two-phase kernel with 16-bit upper-bound accumulators (bm25_u16.cuh): whenever min_score >= 0 (the reference's 0.0), the
+    // hit read-out is on, no sub-range size was asked for, and the corpus is long enough for the bound to work: with fewer
+    // sub-ranges per query than top_k a task holds several documents of the final list, most tasks end in exact mode and the
+    // fp32 kernel of bm25.cuh is the faster one.  Measured (score kernel, ms, fp32 / two-phase; always-term queries, batch 4096):
+    // 1M docs k=1000 0.53 / 0.65 (per 1024); 3M k=1000 6.85 / 6.51; 5M k=1000 10.3 / 9.0; 10M k=1000 18.3 / 14.5; shard shapes
+    // 5M k=608 9.6 / 7.9, 2.5M k=344 4.9 / 4.2, 1.25M k=208 2.6 / 2.3.  bm25_accum = 16 forces it, 32 forbids it.
     const bool u16 = ix->opt_accum != 32 && ix->opt_readout != 0 && ix->opt_range_docs <= 0 &&
                      float_to_key(min_score + 0.0f) >= float_to_key(0.0f) &&
-                     (ix->opt_accum == 16 || 2 * (bm.n_docs / kBm25Range16) >= 3 * int64_t(top_k));
+                     (ix->opt_accum == 16 || bm.n_docs / kBm25Range16 >= int64_t(top_k));
     int RS = u16 ? kBm25Range16 : ix->opt_range_docs > 0 ? round_up(std::min<int64_t>(ix->opt_range_docs, 4096), 128) : kBm25DefaultRange;
     if (!u16 && bm.n_docs < RS) RS = std::max(128, round_up(bm.n_docs, 128));
     const int n_sub = int((bm.n_docs + RS - 1) / RS);

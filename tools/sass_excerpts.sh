@@ -1,6 +1,6 @@
 #!/bin/bash
 # SASS evidence of the built library for profiles/: which Blackwell instructions the hot kernels hold, and the inner loops.
-# usage: tools/sass_excerpts.sh <tag>      (writes profiles/sass_dense_gemm_<tag>.txt and profiles/sass_bm25_score_<tag>.txt)
+# usage: tools/sass_excerpts.sh <tag>      (writes profiles/sass_dense_gemm_<tag>.txt, sass_bm25_score_<tag>.txt, sass_bm25_score16_<tag>.txt)
 set -eu
 TAG=${1:-r02}
 LIB=modern-search-engines-project_b200/csrc/libmsegpu.so
@@ -38,5 +38,20 @@ kernel() { awk -v k="$1" '/Function : /{f=(index($0,k)>0)} f' $TMP; }
   L=$(kernel bm25_score_kernelILi1536ELb1 | grep -n 'FFMA.RM' | sed -n 9p | cut -d: -f1)
   kernel bm25_score_kernelILi1536ELb1 | sed -n "$((L-46)),$((L+14))p" | cut -c1-118
 } > profiles/sass_bm25_score_$TAG.txt
+{
+  echo "# cuobjdump -sass $LIB — bm25_score16_kernel (two-phase BM25 score kernel, bm25_u16.cuh)"
+  echo "# instruction counts:"
+  kernel bm25_score16_kernel | grep -o 'FFMA\.RP\|FFMA\.RM\|LDG\.E\.NA\.64\.CONSTANT\|LDG\.E\.64\.CONSTANT\|CCTL[.A-Z0-9]*\|LDS\(\.U16\|\.128\)\?\|STS\(\.U16\|\.128\)\?\|MATCH\.ANY\|ATOMG[.A-Z0-9]*\|RED[.A-Z0-9]*\|VOTE[.A-Z]*\|SHFL\.[A-Z]*\|BSSY\|STL\|LDL' | sort | uniq -c | sort -rn
+  echo
+  echo "# phase 1, four interleaved rounds of one term (apply4): per posting LOP3 (doc bits) + IMAD (accumulator address) +"
+  echo "# LDS.U16, FFMA.RP onto 2^23 + 1 (rounded-up 16-bit contribution), IADD3 (accumulate), STS.U16, SHF + IMAD (class penalty),"
+  echo "# ISETP (hit test against the 16-bit bound), SEL / VIADD (the two hit registers) — no branch inside a round"
+  L=$(kernel bm25_score16_kernel | grep -n 'FFMA.RP' | sed -n 2p | cut -d: -f1)
+  kernel bm25_score16_kernel | sed -n "$((L-12)),$((L+66))p" | cut -c1-118
+  echo
+  echo "# phase 2 (flush): two binary searches in flight per lane, round-down FMA of the found impacts"
+  L=$(kernel bm25_score16_kernel | grep -n 'LDG.E.64.CONSTANT' | sed -n 1p | cut -d: -f1)
+  kernel bm25_score16_kernel | sed -n "$((L-14)),$((L+40))p" | cut -c1-118
+} > profiles/sass_bm25_score16_$TAG.txt
 rm -f $TMP
 wc -l profiles/sass_dense_gemm_$TAG.txt profiles/sass_bm25_score_$TAG.txt
