@@ -93,8 +93,13 @@ int mse_index_create(int device, mse_index** out);
 int mse_index_destroy(mse_index* idx);
 
 /* Tuning knobs (all optional; 0 restores the automatic choice unless stated):
- *   "bm25_range_docs"        docs per shared-memory accumulator range (rounded up to a multiple of 128, default 1536)
- *   "bm25_queries_per_item"  queries a warp scores per scheduled work item (<= 8, default 8)
+ *   "bm25_range_docs"        docs per shared-memory accumulator range of the fp32 score kernel (rounded up to a multiple of
+ *                            128, default 1536); asking for a size selects that kernel
+ *   "bm25_accum"             0 (default) = the two-phase score kernel (16-bit upper-bound accumulators over 3072-doc ranges, exact
+ *                            fp32 rescoring of the documents that reach the bound: the same scores bit for bit) whenever
+ *                            min_score >= 0 and the shard holds at least top_k such ranges, the fp32 kernel otherwise;
+ *                            16 = the two-phase kernel wherever min_score >= 0; 32 = always the fp32 kernel
+ *   "bm25_queries_per_item"  queries a warp scores per scheduled work item (<= 8, default 8; 6 in the two-phase kernel)
  *   "bm25_cand_cap"          per-query capacity of the candidate list between scoring and selection
  *   "bm25_use_tau"           1 (default) = running k-th-score bound filters candidates, 0 = emit all
  *   "bm25_tau_init"          1 (default) = seed the bound from the per-term impact table built at load time, 0 = off
@@ -172,7 +177,8 @@ int mse_bm25_search_batch_async(mse_index* idx, int32_t n_queries, int32_t n_slo
  * stats[0] = postings traversed (sum of df over the streamed query terms), stats[1] = candidates
  * emitted to the selection stage, stats[2] = queries re-run through the unbounded-capacity path,
  * stats[3] = doc ranges, stats[4] = score-kernel CTAs launched, stats[5] = postings of looked-up
- * (negative-idf) terms that were NOT streamed. */
+ * (negative-idf) terms that were NOT streamed, stats[6] = (sub-range, query) tasks the two-phase score
+ * kernel rescored in its exact fp32 mode (0 when the fp32 kernel ran). */
 int mse_bm25_last_stats(mse_index* idx, int64_t stats[8]);
 
 /* Timing hooks: every call brackets its kernels with CUDA events on the launching stream (not while the stream is

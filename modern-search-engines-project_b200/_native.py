@@ -220,7 +220,7 @@ class NativeIndex:
         arr = (C.c_int64 * 8)()
         _check(lib().mse_bm25_last_stats(self._h, arr))
         return {"postings": arr[0], "emitted": arr[1], "rerun_queries": arr[2], "ranges": arr[3], "ctas": arr[4],
-                "postings_looked_up": arr[5], "exact_mode_tasks": arr[6], "replay_passes": arr[7]}
+                "postings_looked_up": arr[5], "exact_mode_tasks": arr[6]}
 
     # ---- BM25 --------------------------------------------------------------------------------
     def bm25_load(self, term_off, post_doc, post_tf, doc_len, idf, avgdl, k1=1.2, b=0.75, doc_base=0):

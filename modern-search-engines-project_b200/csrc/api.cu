@@ -330,7 +330,7 @@ int bm25_search_exact(mse_index* ix, Lease& L, int32_t B, int32_t S, const std::
     if ((rc = bm25_enqueue(ix, L, B, d_off, d_term, d_tf, S, top_k, min_score, cap, use_tau, d_doc, d_score, d_count, nullptr, true))) return rc;
 
     // one 32-byte status read: {postings streamed, postings looked up, candidates handed to the selection, overflowed queries}
-    unsigned long long h_status[6] = {0, 0, 0, 0, 0, 0};     // + {tasks rescored in exact mode, replay passes} of the two-phase kernel
+    unsigned long long h_status[6] = {0, 0, 0, 0, 0, 0};     // + {tasks rescored in exact mode, -} of the two-phase kernel
     MSE_CUDA_TRY(cudaMemcpyAsync(h_status, ws->misc.as<char>() + 16, sizeof(h_status), cudaMemcpyDeviceToHost, st));
     MSE_CUDA_TRY(cudaStreamSynchronize(st));
     std::vector<int32_t> redo;

@@ -83,7 +83,7 @@ def main():
             rec.update(step_ms=e0.elapsed_time(e1) / a.steps, score_ms=sc / max(1, scn), prepare_ms=pr / max(1, scn),
                        select_ms=se / max(1, scn), score_GBps=alg / (sc / max(1, scn) * 1e-3) / 1e9,
                        emitted_per_query=st.get("emitted", 0) / a.batch, reruns=st.get("rerun_queries", 0),
-                       ctas=st.get("ctas"), exact_tasks=st.get("exact_mode_tasks"), replays=st.get("replay_passes"))
+                       ctas=st.get("ctas"), exact_tasks=st.get("exact_mode_tasks"))
             # comparison on the LAST timed batch
             ids, scores, cnt = (t.clone().cpu().numpy() for t in out)
             if base is None:

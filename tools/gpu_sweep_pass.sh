@@ -21,6 +21,6 @@ for f in ("gpurun_out/sweep_c5.log", "gpurun_out/sweep_c2.log"):
         if l.startswith("{"):
             j = json.loads(l)
             v = j.get("vs_first")
-            print(" ", j["config"], "score", round(j.get("score_ms", -1), 3), "step", round(j.get("step_ms", -1), 3), "emit", round(j.get("emitted_per_query", -1)), "exact", j.get("exact_tasks"), "replays", j.get("replays"),
+            print(" ", j["config"], "score", round(j.get("score_ms", -1), 3), "step", round(j.get("step_ms", -1), 3), "emit", round(j.get("emitted_per_query", -1)), "exact", j.get("exact_tasks"),
                   v if isinstance(v, str) else (v and (v["counts_equal"], v["max_rel_score_diff"], v["id_match_frac"])), j.get("error", ""))
 PY
