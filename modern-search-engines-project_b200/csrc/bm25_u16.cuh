@@ -53,6 +53,7 @@ bm25_score16_kernel(Bm25Dev ix, Bm25Work w) {
     const int QC = w.queries_per_item;
     const int chunks = (w.n_queries + QC - 1) / QC;
     const int n_items = w.n_sub * chunks;
+    const uint32_t ulane = uint32_t(lane);
     const unsigned lt_mask = (1u << lane) - 1u;
     const int2* __restrict__ g_post = ix.post2;
     constexpr int MP = kPrefetchSlots;
@@ -131,8 +132,8 @@ bm25_score16_kernel(Bm25Dev ix, Bm25Work w) {
                 const bool a = lA < hA, b = lB < hB;
                 const int mA = (lA + hA) >> 1, mB = (lB + hB) >> 1;
                 int2 pA = make_int2(0, 0), pB = make_int2(0, 0);
-                if (a) pA = __ldg(g_post + bA + mA);
-                if (b) pB = __ldg(g_post + bB + mB);
+                if (a) pA = __ldg(g_post + (bA + uint32_t(mA)));
+                if (b) pB = __ldg(g_post + (bB + uint32_t(mB)));
                 if (a) { const uint32_t dm = uint32_t(pA.x) & kDocMask; if (dm < ldoc) lA = mA + 1; else { hA = mA; cA = dm; iA = pA.y; } }
                 if (b) { const uint32_t dm = uint32_t(pB.x) & kDocMask; if (dm < ldoc) lB = mB + 1; else { hB = mB; cB = dm; iB = pB.y; } }
             }
@@ -229,7 +230,7 @@ bm25_score16_kernel(Bm25Dev ix, Bm25Work w) {
         }
     };
     auto apply_rest = [&](uint32_t begin, int n, float ws) {
-        const int2* __restrict__ p = g_post + begin + 32 + lane;
+        const int2* __restrict__ p = g_post + (begin + 32u + ulane);    // (posting indices fit 32 bits: one widening add)
 #pragma unroll 1
         for (int rem = n - 32; rem > 0; rem -= 128, p += 128) {
             if (rem <= 32) {
@@ -286,9 +287,9 @@ bm25_score16_kernel(Bm25Dev ix, Bm25Work w) {
                 pd[t] = -1; pt[t] = 0;
                 if (o_nxt + t < e_nxt) {
                     const uint4 m = s_meta[o_nxt + t];
-                    if (lane < int(m.y)) { const int2 p = ldg_stream_i2(g_post + m.x + lane); pd[t] = p.x; pt[t] = p.y; }
+                    if (lane < int(m.y)) { const int2 p = ldg_stream_i2(g_post + (m.x + ulane)); pd[t] = p.x; pt[t] = p.y; }
 #ifndef MSE_BM25_NO_L2_PREFETCH
-                    if (int(m.y) > 32 + 16 * lane) asm volatile("prefetch.global.L2 [%0];" :: "l"(g_post + m.x + 32 + 16 * lane));
+                    if (int(m.y) > 32 + 16 * lane) asm volatile("prefetch.global.L2 [%0];" :: "l"(g_post + (m.x + 32u + 16u * ulane)));
 #endif
                 }
             };
@@ -338,7 +339,7 @@ bm25_score16_kernel(Bm25Dev ix, Bm25Work w) {
                     if (direct) continue;
                     const float ws = __fmul_ru(fmaxf(__uint_as_float(m.z), 0.f), invU);
                     int dd = -1, tfi = 0;
-                    if (lane < n) { const int2 p = ldg_stream_i2(g_post + m.x + lane); dd = p.x; tfi = p.y; }
+                    if (lane < n) { const int2 p = ldg_stream_i2(g_post + (m.x + ulane)); dd = p.x; tfi = p.y; }
                     apply(dd, tfi, ws);
                     if (n > 32) apply_rest(m.x, n, ws);
                     __syncwarp();
@@ -392,7 +393,7 @@ bm25_score16_kernel(Bm25Dev ix, Bm25Work w) {
                                 const int n = int(m.y);
                                 if (n == 0) continue;
                                 const float wt = __uint_as_float(m.z);
-                                const int2* __restrict__ p = g_post + m.x + lane;
+                                const int2* __restrict__ p = g_post + (m.x + ulane);
 #pragma unroll 1
                                 for (int rem = n; rem > 0; rem -= 128, p += 128) {
                                     int dd[4], tt[4];
