@@ -376,6 +376,7 @@ bm25_score16_kernel(Bm25Dev ix, Bm25Work w) {
                         float* acc32 = reinterpret_cast<float*>(s_acc);
                         if (lane == 0) atomicAdd(w.stats + 4, 1ull);
                         neg_lo = o_cur; neg_hi = look_n ? e_cur : 0;
+                        int split = 0;                                       // lane k: where slot o_cur + k's postings of the second half begin
 #pragma unroll 1
                         for (int half = 0; half < 2; ++half) {
                             __syncwarp();
@@ -383,6 +384,7 @@ bm25_score16_kernel(Bm25Dev ix, Bm25Work w) {
                             for (int it = 0; it < kSweep; ++it) a4[it * 32] = z4;
                             __syncwarp();
                             const uint32_t base = uint32_t(lo + half * (RS / 2));
+                            const uint32_t mid_doc = uint32_t(lo + RS / 2);
                             auto apply32 = [&](int dd, int tfi, float wt) {
                                 const uint32_t l = (uint32_t(dd) & kDocMask) - base;
                                 if (dd != -1 && l < uint32_t(RS / 2)) acc32[l] = __fmaf_rd(-wt, __int_as_float(tfi), acc32[l]);
@@ -393,14 +395,24 @@ bm25_score16_kernel(Bm25Dev ix, Bm25Work w) {
                                 const int n = int(m.y);
                                 if (n == 0) continue;
                                 const float wt = __uint_as_float(m.z);
-                                const int2* __restrict__ p = g_post + (m.x + ulane);
+                                // the first half stops at the group of 128 postings that reaches the middle of the sub-range
+                                // (a slice is sorted by document), the second half starts there
+                                const int start = half ? __shfl_sync(0xffffffffu, split, sl - o_cur) : 0;
+                                const int2* __restrict__ p = g_post + (m.x + uint32_t(start) + ulane);
+                                int done = n;
 #pragma unroll 1
-                                for (int rem = n; rem > 0; rem -= 128, p += 128) {
+                                for (int rem = n - start; rem > 0; rem -= 128, p += 128) {
                                     int dd[4], tt[4];
                                     load4(p, rem, dd, tt);
+                                    bool ge = false;
 #pragma unroll
-                                    for (int u = 0; u < 4; ++u) apply32(dd[u], tt[u], wt);
+                                    for (int u = 0; u < 4; ++u) {
+                                        apply32(dd[u], tt[u], wt);
+                                        ge = ge || (dd[u] != -1 && (uint32_t(dd[u]) & kDocMask) >= mid_doc);
+                                    }
+                                    if (half == 0 && __any_sync(0xffffffffu, ge)) { done = n - rem; break; }
                                 }
+                                if (half == 0 && lane == sl - o_cur) split = done;
                                 __syncwarp();
                             }
                             // read-out: lane's accumulators 4 * (it * 32 + lane) + u; bit (it * 4 + u) of `fl` = reaches the bound
