@@ -178,10 +178,13 @@ def test_hybrid_call_equals_the_two_stages_and_the_oracle(hybrid_index, B):
     assert res["queries_failing"] == 0, res
 
 
-def test_bm25_step_captured_in_a_cuda_graph(hybrid_index):
-    """One BM25 step (sanitize, prepare, score, select, status) captured and replayed: the call enqueues only."""
+@pytest.mark.parametrize("accum", [0, 16])
+def test_bm25_step_captured_in_a_cuda_graph(hybrid_index, accum):
+    """One BM25 step (sanitize, prepare, score, select, status) captured and replayed: the call enqueues only.  accum = 16:
+    the same with the two-phase score kernel forced on this small corpus."""
     h = hybrid_index
     nat, c = h["nat"], h["c"]
+    nat.set_option("bm25_accum", accum)
     q_off, q_term, q_tf, qv = _batch(c, 64, 17)
     d_off, d_term, d_tf, d_qv = _dev(q_off, q_term, q_tf, qv)
     out = tuple(torch.empty_like(t) for t in nat.bm25_search_async(d_off, d_term, d_tf, int(q_off[-1]), 100, 0.0))   # also grows the workspace
@@ -210,6 +213,7 @@ def test_bm25_step_captured_in_a_cuda_graph(hybrid_index):
         ref2 = nat.bm25_search(q2[0], q2[1], q2[2], 100, 0.0)
         for got, r in zip(out, ref2):
             assert np.array_equal(got.cpu().numpy(), r)
+    nat.set_option("bm25_accum", 0)
 
 
 def test_concurrent_host_callers_get_their_own_workspace(hybrid_index):

@@ -149,6 +149,37 @@ def test_kernel_variants_agree(corpus20k, opts):
     bm.close()
 
 
+@pytest.mark.parametrize("top_k,use_tau", [(10, 1), (300, 1), (40, 0)])
+def test_two_phase_kernel_queue_path_long_queries(top_k, use_tau):
+    """The two-phase kernel where its normal path runs: 300k docs = 98 sub-ranges of 3072, small k, so that thousands of tasks
+    queue their hits instead of ending in exact mode; queries of 9 terms (more than the four prefetched slots), several
+    of them with negative idf (the generic looked-up path of the rescoring pass), one term twice.  Against the fp32
+    kernel bit for bit, and against the oracle."""
+    c = synthetic.make_bm25_corpus(300_000, vocab=20_000, mean_len=48, seed=5, always_frac=0.95)
+    ix = _oracle_arrays(c)
+    # (480 queries: 47k tasks = ten waves of warps — in the first wave no query has a bound yet and every task runs in exact mode)
+    q_off, q_term, q_tf = synthetic.make_bm25_queries(c, 480, terms_per_query=9, min_rank=2, seed=41, repeat_frac=0.3, add_always=True)
+    neg_per_query = np.add.reduceat((np.asarray(ix.idf)[q_term] < 0).astype(np.int64), q_off[:-1])
+    assert neg_per_query.max() >= 2                                      # some query holds a second negative-idf term
+    bm = _facade(ix)
+    bm.native.set_option("bm25_use_tau", use_tau)
+    bm.native.set_option("bm25_accum", 32)
+    ref = bm.search_batch_terms(q_off, q_term, q_tf, top_k, 0.0)
+    assert bm.native.bm25_stats()["exact_mode_tasks"] == 0
+    bm.native.set_option("bm25_accum", 16)
+    got = bm.search_batch_terms(q_off, q_term, q_tf, top_k, 0.0)
+    st = bm.native.bm25_stats()
+    assert st["ranges"] == -(-300_000 // 3072)
+    if use_tau:
+        assert 0 < st["exact_mode_tasks"] <= 480 * st["ranges"]
+        if top_k == 10:
+            assert st["exact_mode_tasks"] < 0.8 * 480 * st["ranges"]     # the queue path took the rest (thousands of tasks)
+    for r, g in zip(ref, got):
+        assert np.array_equal(r, g)
+    _check_batch(ix, q_off[:9], q_term, q_tf, got[0], got[1], got[2], top_k, 0.0)
+    bm.close()
+
+
 def test_impact_table_matches_checker(corpus20k):
     """The seed of the candidate filter: GPU results with and without it are identical, and the bound the oracle-side
     restatement derives for these queries is below the k-th returned score."""
