@@ -34,7 +34,10 @@ constexpr int kBm25Range16 = MSE_BM25_RANGE16;   // docs per sub-range: 6 KB of 
 constexpr int kBm25Ctas16 = kBm25Range16 <= 3072 ? 4 : 3;
 constexpr int kQueueDocBits = 13;                // doc within the sub-range
 constexpr int kQueueMax = 32;                    // hit documents a warp collects before it forms their exact scores
-constexpr int kExactModeEvents = 12;             // more hit events than this in one task: exact mode
+#ifndef MSE_BM25_EXACT_EVENTS
+#define MSE_BM25_EXACT_EVENTS 12
+#endif
+constexpr int kExactModeEvents = MSE_BM25_EXACT_EVENTS;   // more hit events than this in one task: exact mode
 static_assert(kQueueMax * 8 == 2 * kEmitStage * 8, "the queue takes the place of the fp32 kernel's emission stage");
 
 __global__ void __launch_bounds__(kBm25Threads, kBm25Ctas16)
