@@ -16,7 +16,12 @@
 
 namespace mse {
 
-constexpr int kHistBits = 12;                    // sign + exponent + 3 mantissa bits of the score key
+#ifndef MSE_BM25_HIST_BITS
+#define MSE_BM25_HIST_BITS 13
+#endif
+constexpr int kHistBits = MSE_BM25_HIST_BITS;    // sign + exponent + 4 mantissa bits of the score key: bins 6 % wide in score (32 KB per
+                                                 // query).  Measured at C5: 12 bits 5789 candidates per query / 14.33 ms score kernel,
+                                                 // 13 and 14 bits 5209 / 14.16 ms (the refresh cadence, not the bin width, limits it then)
 constexpr int kHistBins = 1 << kHistBits;
 constexpr int kHistShift = 32 - kHistBits;
 // The dense scans bin finer (sign + exponent + 6 mantissa bits: bins 1.6 % wide in score, 128 KB per query): their
