@@ -125,3 +125,35 @@ def test_initial_bound_never_exceeds_the_kth_score():
             assert cand.size >= k and cand[k - 1] >= bound, (k, i, bound, cand[k - 1] if cand.size >= k else None)
             useful += 1
     assert useful > 20
+
+
+def test_two_phase_bound_cannot_miss_a_document():
+    """Phase 1 of the two-phase GPU score kernel (oracle.two_phase_upper_bound restates csrc/bm25_u16.cuh) keeps a 16-bit
+    upper bound per document and rescoring is spent only on documents whose bound reaches the running k-th score.  For the
+    results to stay exact the bound, in units of 1 / invU, must not fall below the exact score of any document that can be
+    returned (score >= 0 at min_score 0): here it stays at least 3/4 of a unit above it (every touching term adds one
+    unit beyond its rounded-up contribution, which also absorbs the fp32 rounding of the exact score), and it fits 16 bits."""
+    import torch  # noqa: F401
+    from mse_b200 import synthetic
+    c = synthetic.make_bm25_corpus(6000, vocab=800, mean_len=48, seed=5, always_frac=0.9)
+    ix = bo.Bm25Arrays(c.term_off.numpy(), c.post_doc.numpy(), c.post_tf.numpy(), c.doc_len.numpy(), c.idf.numpy(),
+                       c.avgdl, c.total_docs, c.doc_ids.numpy())
+    assert float(ix.idf[c.always_term]) < 0
+    checked = 0
+    for seed, tpq, always in ((9, 3, True), (10, 6, True), (11, 4, False)):
+        q_off, q_term, q_tf = synthetic.make_bm25_queries(c, 25, terms_per_query=tpq, min_rank=2, seed=seed, repeat_frac=0.4,
+                                                           add_always=always)
+        for i in range(25):
+            terms = [int(t) for s in range(q_off[i], q_off[i + 1]) for t in [q_term[s]] * int(q_tf[s])]
+            ub = bo.two_phase_upper_bound(ix, terms, class_term=c.always_term)
+            score, touched = bo.score_all_fast(ix, terms)
+            assert ub["acc16"].max() < 65536 and ub["penalty16"].min() >= 0
+            live = ub["touched"] & (score >= 0.0)                 # what min_score = 0 can return
+            assert live.any() or not always
+            slack = (ub["acc16"] - ub["penalty16"])[live] - score[live] * float(ub["inv_unit"])
+            assert slack.size == 0 or slack.min() >= 0.75, (seed, i, slack.min())
+            # and a document only the looked-up (negative-idf) terms touch can never be returned at min_score 0
+            only_neg = touched & ~ub["touched"]
+            assert not (score[only_neg] >= 0.0).any()
+            checked += int(live.sum())
+    assert checked > 10000
