@@ -97,7 +97,9 @@ int mse_index_destroy(mse_index* idx);
  *                            128, default 1536); asking for a size selects that kernel
  *   "bm25_accum"             0 (default) = the two-phase score kernel (16-bit upper-bound accumulators over 3072-doc ranges, exact
  *                            fp32 rescoring of the documents that reach the bound: the same scores bit for bit) whenever
- *                            min_score >= 0 and the shard holds at least top_k such ranges, the fp32 kernel otherwise;
+ *                            min_score >= 0, the shard holds at least top_k such ranges and the batch is large enough for a bound
+ *                            to form while it runs (>= 64 tasks per resident warp: ~100 queries at 10 M docs), the fp32 kernel
+ *                            otherwise — also for the 64 calls that follow an exact call in which > 45 % of the tasks needed exact mode;
  *                            16 = the two-phase kernel wherever min_score >= 0; 32 = always the fp32 kernel
  *   "bm25_queries_per_item"  queries a warp scores per scheduled work item (<= 8, default 8; 6 in the two-phase kernel)
  *   "bm25_cand_cap"          per-query capacity of the candidate list between scoring and selection

@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <mutex>
 #include <vector>
@@ -66,6 +67,7 @@ struct mse_index {
     int64_t opt_readout = 1, opt_tau_init = 1, opt_neg_lookup = 1, opt_accum = 0;
     int64_t opt_range_docs = 0, opt_qpi = 0, opt_cand_cap = 0, opt_use_tau = 1, opt_scan_ctas = 0, opt_gemm_min_batch = 0, opt_gemm_debug = 0, opt_gemm_pair_mode = 1;
     int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    std::atomic<int> u16_backoff{0};              // calls the fp32 score kernel still serves after a hostile batch (bm25_enqueue)
     int score_ctas_per_sm[3] = {0, 0, 0};         // occupancy of the score kernel (fp32 scan / fp32 hit read-out / two-phase) at its default range
 };
 
@@ -165,9 +167,20 @@ int bm25_enqueue(mse_index* ix, Lease& L, int32_t B, const int32_t* d_q_off, con
     // fp32 kernel of bm25.cuh is the faster one.  Measured (score kernel, ms, fp32 / two-phase; always-term queries, batch 4096):
     // 1M docs k=1000 0.53 / 0.65 (per 1024); 3M k=1000 6.85 / 6.51; 5M k=1000 10.3 / 9.0; 10M k=1000 18.3 / 14.5; shard shapes
     // 5M k=608 9.6 / 7.9, 2.5M k=344 4.9 / 4.2, 1.25M k=208 2.6 / 2.3.  bm25_accum = 16 forces it, 32 forbids it.
-    const bool u16 = ix->opt_accum != 32 && ix->opt_readout != 0 && ix->opt_range_docs <= 0 &&
-                     float_to_key(min_score + 0.0f) >= float_to_key(0.0f) &&
-                     (ix->opt_accum == 16 || bm.n_docs / kBm25Range16 >= int64_t(top_k));
+    // Two more conditions for the automatic choice: the batch must be large enough for a bound to form while it runs (the
+    // first tasks of a query run without one, in exact mode, and a small batch has little else; measured at 10 M docs, score
+    // kernel ms fp32 / two-phase: B=1 0.058 / 0.068, B=8 0.147 / 0.197, B=64 0.394 / 0.435, B=128 0.677 / 0.626, B=256 1.28 / 1.09,
+    // B=1024 4.78 / 3.88 — the crossover lies near 64 tasks per resident warp), and the
+    // last exact call must not have found the workload hostile to it (more than 45 % of the tasks in exact mode: queries of
+    // many heavy terms on a dense corpus — the fp32 kernel then serves the next 64 calls before the two-phase one is tried again).
+    bool u16 = ix->opt_accum != 32 && ix->opt_readout != 0 && ix->opt_range_docs <= 0 &&
+               float_to_key(min_score + 0.0f) >= float_to_key(0.0f);
+    if (u16 && ix->opt_accum != 16) {
+        const int64_t n_sub16 = (bm.n_docs + kBm25Range16 - 1) / kBm25Range16;
+        const int64_t resident = int64_t(std::max(1, ix->score_ctas_per_sm[2])) * ix->sm_count * kBm25Warps;
+        u16 = bm.n_docs / kBm25Range16 >= int64_t(top_k) && n_sub16 * B >= 64 * resident;
+        if (u16 && ix->u16_backoff.load(std::memory_order_relaxed) > 0) { ix->u16_backoff.fetch_sub(1, std::memory_order_relaxed); u16 = false; }
+    }
     int RS = u16 ? kBm25Range16 : ix->opt_range_docs > 0 ? round_up(std::min<int64_t>(ix->opt_range_docs, 4096), 128) : kBm25DefaultRange;
     if (!u16 && bm.n_docs < RS) RS = std::max(128, round_up(bm.n_docs, 128));
     const int n_sub = int((bm.n_docs + RS - 1) / RS);
@@ -348,6 +361,8 @@ int bm25_search_exact(mse_index* ix, Lease& L, int32_t B, int32_t S, const std::
         ix->stats[2] = int64_t(redo.size());
         ix->stats[6] = int64_t(h_status[4]); ix->stats[7] = int64_t(h_status[5]);
         ix->last_bm25_ws = nullptr;                  // the snapshot above is the answer of mse_bm25_last_stats
+        // (stats[3] = sub-ranges of this call; exact-mode tasks are counted by the two-phase kernel only)
+        if (double(h_status[4]) > 0.45 * double(ix->stats[3]) * double(B)) ix->u16_backoff.store(64, std::memory_order_relaxed);
     }
     if (redo.empty()) return MSE_OK;
 
