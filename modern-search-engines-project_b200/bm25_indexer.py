@@ -70,7 +70,8 @@ MAX_QUERY_TERMS = 32          # distinct valid terms per query the score kernel 
 class BM25:
     def __init__(self, db_path: Optional[str], k1: float = 1.2, b: float = 0.75, read_only: bool = True, *,
                  store=None, tokenizer: Optional[Callable[[str], List[str]]] = None, device: int = 0,
-                 doc_range: Optional[Tuple[int, int]] = None, load: bool = True, cache_path: Optional[str] = None):
+                 doc_range: Optional[Tuple[int, int]] = None, load: bool = True, cache_path: Optional[str] = None,
+                 appended_term: Optional[str] = "tübingen"):
         self.db_path = db_path
         self.k1 = k1
         self.b = b
@@ -81,6 +82,7 @@ class BM25:
         self.device = device
         self.doc_range = doc_range
         self.cache_path = cache_path                      # optional .npz of the CSR arrays (skips the SQL scan)
+        self.appended_term = appended_term                # the term search_api.py:160-165 appends to every query
         self.tables: Optional[Bm25Tables] = None
         self.native: Optional[_native.NativeIndex] = None
         self._term_index: Dict[str, int] = {}
@@ -120,6 +122,16 @@ class BM25:
                               np.ascontiguousarray(t.doc_len, dtype=np.int32),
                               np.ascontiguousarray(t.idf, dtype=np.float32),
                               t.avgdl, self.k1, self.b, doc_base=self.doc_base)
+        # The term the caller appends to every query is in nearly every document (negative idf): the library keeps its
+        # per-document impact class in every posting, so that documents it sinks below the bound are never looked up.  Its
+        # default is the negative-idf term with the most postings; name the right one when the dictionary holds it.
+        # (Speed only: results never depend on it.)
+        j = self._term_index.get(self.appended_term, -1) if self.appended_term else -1
+        if j >= 0 and float(t.idf[j]) < 0 and hasattr(self.native, "set_option"):
+            try:
+                self.native.set_option("bm25_class_term", j)
+            except _native.NativeError:
+                pass                                      # no dense impact row for it (row budget): the default stays
 
     def refresh(self) -> bool:
         """Reloads the index when the bm25_* tables have changed since it was read (new ``processed_at`` /
