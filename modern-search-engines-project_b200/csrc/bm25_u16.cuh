@@ -17,7 +17,9 @@
 //   invU = 60000 / (sum of the query's positive weights), so an accumulator cannot overflow 16 bits; the "+ 1" keeps a
 //   touched document apart from an untouched one (score exactly 0.0 is kept by the reference, bm25_indexer.py:480).
 //   With U = 1 / invU:  exact score <= (acc16 - class * pen16) * U  and  tau16 <= tau / U, i.e. a document that
-//   reaches the bound is always a hit (no false negative); false positives fall out at the exact test of phase 2.
+//   reaches the bound is always a hit (no false negative); false positives fall out at the exact test of phase 2.  (The
+//   "+ 1" of every touching term also absorbs the fp32 rounding of the exact score, a fraction of a unit; the arithmetic
+//   is restated in oracle/bm25_oracle.py::two_phase_upper_bound and checked on CPU by tests/test_oracle_bm25.py.)
 //   An accumulator only grows, so a document reaches the bound iff its LAST update does: every lane remembers its last
 //   two hit events.  A task with a third event on one lane, or with more than kExactModeEvents in all (the first tasks
 //   of a query, while its bound is still low), is rescored in EXACT MODE: the 6 KB become fp32 accumulators of half the
