@@ -78,6 +78,23 @@ def measured_peaks():
     return 6650.0, 1600.0, "fallback (B200_PROFILING.md)"
 
 
+def hosted_reference_c1():
+    """The UNMODIFIED reference timed on BASELINE.json configs[0] (C1) under oracle/stub_harness.py in the build container
+    (`oracle/time_hosted_reference.py` -> profiles/hosted_reference_c1.json): the provenance of the CPU baseline.  A cited
+    figure — the reference is not on the GPU box — beside which the same file holds the oracle port's speed on the same
+    queries and their agreement with the hosted reference."""
+    p = os.path.join(ROOT, "profiles", "hosted_reference_c1.json")
+    try:
+        j = json.load(open(p))
+        return {"queries_per_s": j["hosted_reference"]["queries_per_s"], "bm25_search_ms": j["hosted_reference"]["bm25_search_ms_per_query"],
+                "rerank_ms": j["hosted_reference"]["rerank_ms_per_query"], "workload": j["workload"], "host_cores": j["host"]["cpu_count"],
+                "oracle_port_on_the_same_queries": {k: j["oracle_port"][k] for k in ("faithful_queries_per_s", "fast_queries_per_s",
+                                                                                   "queries_identical_to_the_hosted_reference", "queries")},
+                "source": "profiles/hosted_reference_c1.json (measured in the build container, not by this run)"}
+    except Exception:
+        return None
+
+
 def committed_traffic(kernel):
     """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture of this workload (a cited figure,
     not measured by this run)."""
@@ -329,7 +346,8 @@ def run_reference_arm(args, rank, world):
         "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(n_docs, n_chunks, BATCH), "queries_per_step": per_step},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": min(procs, per_step), "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": min(procs, per_step), "kind": "port", "sample": sample,
+                         "hosted_reference_c1": hosted_reference_c1()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -793,7 +811,8 @@ def main():
             cpu_baseline = {"value": n_cpu / dt, "unit": UNIT, "cores": 1, "kind": "port",
                             "sample": f"{n_cpu} hybrid queries of one batch on 1 core, full {n_docs}-doc index: faithful Python-loop port of "
                                       f"bm25_indexer.py:435-485 (~{int(timed_all / GB)} posting rows per query incl. the always-term) -> "
-                                      f"reranker_api.py:336-372 (sklearn cosine, 32-row batches); no SQL / spaCy / HTTP cost"}
+                                      f"reranker_api.py:336-372 (sklearn cosine, 32-row batches); no SQL / spaCy / HTTP cost",
+                            "hosted_reference_c1": hosted_reference_c1()}
     gc.collect()
     gc.freeze()
 

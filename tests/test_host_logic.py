@@ -492,3 +492,16 @@ def test_bm25_facade_returns_the_references_known_answers():
     hit = [g for g in bm.search("gamma delta", top_k=10) if g["doc_id"] == long_id]
     assert hit and hit[0]["text_snippet"] == "T: " + "x" * 200 + "..."          # (:508-510)
     assert bm.get_term_stats("beta")["document_frequency"] == 4 and bm.get_term_stats("nosuchterm") is None
+
+
+def test_hosted_reference_timing_record():
+    """profiles/hosted_reference_c1.json (oracle/time_hosted_reference.py): the unmodified reference timed on C1 under the stub
+    harness, with the oracle port beside it — every one of its queries must have matched the hosted reference, and bench.py
+    must be able to cite the record."""
+    import json
+    import bench
+    rec = json.load(open(os.path.join(ROOT, "profiles", "hosted_reference_c1.json")))
+    assert rec["oracle_port"]["queries_identical_to_the_hosted_reference"] == rec["oracle_port"]["queries"] >= 16
+    assert 0 < rec["hosted_reference"]["queries_per_s"] < rec["oracle_port"]["faithful_queries_per_s"] < rec["oracle_port"]["fast_queries_per_s"]
+    cited = bench.hosted_reference_c1()
+    assert cited is not None and cited["queries_per_s"] == rec["hosted_reference"]["queries_per_s"] and "not by this run" in cited["source"]
