@@ -157,3 +157,41 @@ def test_two_phase_bound_cannot_miss_a_document():
             assert not (score[only_neg] >= 0.0).any()
             checked += int(live.sum())
     assert checked > 10000
+
+
+def test_two_phase_selection_model_returns_the_oracle_top_k():
+    """Model of the two-phase kernel's selection on CPU: sub-ranges of 3072 docs in order, a document is rescored only when
+    its 16-bit bound reaches floor(tau / U), tau being the k-th best exact score seen so far (the TIGHTEST bound the running
+    histogram of the kernel could ever reach — the kernel's is looser and lets more through).  The survivors' top-k must be
+    the oracle's top-k: the filter may never drop a document of the final list."""
+    import torch  # noqa: F401
+    from mse_b200 import synthetic
+    c = synthetic.make_bm25_corpus(20000, vocab=3000, mean_len=40, seed=8, always_frac=0.95)
+    ix = bo.Bm25Arrays(c.term_off.numpy(), c.post_doc.numpy(), c.post_tf.numpy(), c.doc_len.numpy(), c.idf.numpy(),
+                       c.avgdl, c.total_docs, c.doc_ids.numpy())
+    q_off, q_term, q_tf = synthetic.make_bm25_queries(c, 30, terms_per_query=4, min_rank=4, seed=12, repeat_frac=0.3, add_always=True)
+    rescored_total = touched_total = 0
+    for k in (10, 200):
+        for i in range(30):
+            terms = [int(t) for s in range(q_off[i], q_off[i + 1]) for t in [q_term[s]] * int(q_tf[s])]
+            ub = bo.two_phase_upper_bound(ix, terms, class_term=c.always_term)
+            score, touched = bo.score_all_fast(ix, terms)
+            bound16 = ub["acc16"] - ub["penalty16"]
+            inv_u = float(ub["inv_unit"])
+            tau, best, kept = 0.0, [], []
+            for lo in range(0, ix.n_docs, 3072):
+                sl = slice(lo, min(lo + 3072, ix.n_docs))
+                tau16 = int(np.floor(np.float32(tau) * np.float32(inv_u)))          # (rounding down twice only lowers it)
+                hit = np.flatnonzero(ub["touched"][sl] & (bound16[sl] >= tau16)) + lo
+                rescored_total += len(hit)
+                ok = hit[score[hit] >= tau]
+                kept.extend(ok.tolist())
+                best = sorted(best + score[ok].tolist(), reverse=True)[:k]
+                if len(best) == k:
+                    tau = max(tau, best[-1])
+            touched_total += int(ub["touched"].sum())
+            ref = bo.search_fast(ix, terms, top_k=k, min_score=0.0)
+            kept = np.asarray(kept, dtype=np.int64)
+            got = [(int(d), float(score[d])) for d in np.sort(kept)[np.argsort(-score[np.sort(kept)], kind="stable")[:k]]] if len(kept) else []
+            assert got == ref, (k, i)
+    assert rescored_total < 0.5 * touched_total                   # and it does filter
