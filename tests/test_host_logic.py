@@ -494,6 +494,45 @@ def test_bm25_facade_returns_the_references_known_answers():
     assert bm.get_term_stats("beta")["document_frequency"] == 4 and bm.get_term_stats("nosuchterm") is None
 
 
+def test_facade_names_the_appended_term_to_the_library():
+    """After every load `BM25` tells the library which negative-idf term the caller appends to every query
+    (search_api.py:160-165; option bm25_class_term: speed only): here "beta" plays the part (idf < 0 in Appendix E);
+    a term with idf >= 0, an unknown term or `None` leave the library's default alone, and a library that has no dense
+    row for the term (NativeError) is not an error."""
+    from mse_b200.bm25_indexer import BM25, whitespace_tokenizer
+    ix, e = helpers.load_appendix_e()
+    conn = sqlite3.connect(":memory:")
+    conn.execute("CREATE TABLE urlsDB (id BIGINT PRIMARY KEY, url TEXT, title TEXT, text TEXT)")
+    conn.executemany("INSERT INTO urlsDB VALUES (?,?,?,?)", [(i, f"http://x/{i}", "", t) for i, t in e["docs"]])
+    st = store.SqlStore(conn)
+    st.write_bm25(e["doc_stats"], [(r[1], r[0], r[2]) for r in e["term_freq"]], [(r[0], r[1], r[2]) for r in e["term_stats"]],
+                  e["corpus_stats"]["avg_doc_length"], int(e["corpus_stats"]["total_docs"]),
+                  lambda df: float(np.float32(np.log10((float(np.float32(e["corpus_stats"]["total_docs"])) - df + 0.5) / (df + 0.5)))))
+
+    class Recording(_OracleBm25Native):
+        def __init__(self, fail=False):
+            self.options, self.fail = [], fail
+
+        def set_option(self, name, value):
+            if self.fail:
+                raise _native.NativeError(-2, "no dense impact row")
+            self.options.append((name, int(value)))
+
+    for term, expect in (("beta", True), ("gamma", False), ("nosuchterm", False), (None, False)):
+        bm = BM25(None, store=st, tokenizer=whitespace_tokenizer, load=False, appended_term=term)
+        bm.native = Recording()
+        bm.reload()
+        if expect:
+            assert bm.native.options == [("bm25_class_term", bm._term_index["beta"])]
+            assert float(bm.tables.idf[bm._term_index["beta"]]) < 0
+        else:
+            assert bm.native.options == []
+    bm = BM25(None, store=st, tokenizer=whitespace_tokenizer, load=False, appended_term="beta")
+    bm.native = Recording(fail=True)
+    bm.reload()                                                                  # the default class term stays; no exception
+    assert [g["doc_id"] for g in bm.search("gamma delta", top_k=10)]
+
+
 def test_hosted_reference_timing_record():
     """profiles/hosted_reference_c1.json (oracle/time_hosted_reference.py): the unmodified reference timed on C1 under the stub
     harness, with the oracle port beside it — every one of its queries must have matched the hosted reference, and bench.py
